@@ -1,0 +1,156 @@
+/*
+ * wfd_b200.h — C ABI of libwfd_b200.so, the B200 (sm_100a) implementation of WaveFunctionDiffusion's WFC-guidance
+ * hot path. Plain pointers and sizes only; no torch types. The reference has no FFI of its own: these entry points are
+ * what a ctypes binding placed behind the reference's Python objects calls. Each block cites the
+ * reference code it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; wfd_last_error() gives the message (thread local)
+ *   - all tensor arguments are device pointers owned by the caller unless stated otherwise; nothing is freed or
+ *     retained past the call except inside an explicit handle
+ *   - `stream` is a cudaStream_t passed as void*; no call synchronises the device
+ *   - internal activations are channels-last [B, H*W, C] 16-bit ("nhwc16"); dtype16: 0 = fp16, 1 = bf16
+ *   - handles are not thread safe individually; distinct handles may be used from distinct threads/streams
+ */
+#ifndef WFD_B200_H
+#define WFD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WFD_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define WFD_API __attribute__((visibility("default")))
+#else
+#define WFD_API
+#endif
+
+WFD_API int wfd_version(void);
+WFD_API const char* wfd_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py reports it as gpu_launches) */
+WFD_API long long wfd_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Tile-VAE decoder: AutoencoderTile._decode = post_quant_conv + DecoderTile.forward
+ *   wfd/wf_diffusers/wf_vae.py:151-232 (DecoderTile), :592-599 (_decode), :617-627 (decode)
+ *   wfd/wf_diffusers/resnet.py:369-499 (ResnetBlock2D), :147-192 (Downsample2D)
+ *   wfd/wf_diffusers/attention.py:247-380 (AttentionBlock), wf_unet_2d_blocks.py:388-464, :1771-1883
+ *   configs/tilenet/tilenet_sc_space_{64x64,32x32}.json
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct wfd_decoder wfd_decoder;
+
+typedef struct {
+    int latent_channels;        /* 4 */
+    int out_channels;           /* T_pad = round_up(shrink_count, 128), train_tile_vae.py:141-144 */
+    int n_blocks;               /* len(block_out_channels) */
+    int block_out_channels[8];  /* config order, e.g. 3072,1536,768,384 (reversed inside, wf_vae.py:185) */
+    int conv_groups[8];         /* config order, e.g. 64,16,4,1 (reversed inside, wf_vae.py:206) */
+    int block_down[8];          /* decoder order: 1 where up_block_types[i] == "DownDecoderBlock2D" */
+    int conv_init_groups;       /* groups of conv_out, 128 */
+    int layers_per_block;       /* config value (decoder uses +1, wf_vae.py:195) */
+    int norm_num_groups;        /* 8 */
+} wfd_decoder_config;
+
+/* h, w: latent plane; B_max: largest batch one call will carry; dtype16: operand/activation type */
+WFD_API int wfd_decoder_create(const wfd_decoder_config* cfg, int h, int w, int B_max, int dtype16, wfd_decoder** out);
+WFD_API void wfd_decoder_destroy(wfd_decoder* d);
+/* output plane (H, W) = (h, w) or halved per DownDecoderBlock2D */
+WFD_API int wfd_decoder_out_hw(const wfd_decoder* d, int* H, int* W);
+
+/* Weights by state_dict key (e.g. "decoder.up_blocks.1.resnets.0.conv1.weight"), fp32, HOST memory, `numel` floats.
+ * Keys not on the decode path (encoder.*, quant_conv.*) are accepted and ignored (returns 1). */
+WFD_API int wfd_decoder_set_weight(wfd_decoder* d, const char* key, const float* host_data, long long numel);
+/* Packs weights for the tensor-core kernels (forward and backward-data forms) and uploads them. */
+WFD_API int wfd_decoder_finalize_weights(wfd_decoder* d);
+
+/* Activation / scratch memory is caller owned: query, allocate (256-byte aligned), bind. */
+WFD_API size_t wfd_decoder_workspace_bytes(const wfd_decoder* d);
+WFD_API int wfd_decoder_bind_workspace(wfd_decoder* d, void* ws, size_t bytes);
+
+/* z: NCHW [B, 4, h, w], z_dtype 0 = fp32, 1 = fp16. Computes logits = decode(z * in_scale) into the plan's internal
+ * nhwc16 logits buffer and keeps what backward needs. */
+WFD_API int wfd_decoder_forward(wfd_decoder* d, const void* z, int z_dtype, int B, float in_scale, void* stream);
+/* device pointer to the internal logits [B, H*W, T_pad] nhwc16 */
+WFD_API void* wfd_decoder_logits(wfd_decoder* d);
+/* copies logits out as NCHW-shaped data: layout 0 = NCHW contiguous, 1 = channels-last (NHWC memory);
+ * out_dtype 0 = fp32, 1 = fp16, 2 = bf16 */
+WFD_API int wfd_decoder_export_logits(wfd_decoder* d, int B, void* out, int out_dtype, int layout, void* stream);
+/* data gradient only (autograd.grad w.r.t. latents, pipeline_wfd.py:613): dlogits nhwc16 [B, H*W, T_pad] ->
+ * dz fp32 NCHW [B, 4, h, w], already multiplied by in_scale (and by scale_b[b] if given). dlogits == NULL uses the
+ * internal dlogits buffer (wfd_decoder_dlogits). */
+WFD_API int wfd_decoder_backward(wfd_decoder* d, const void* dlogits, int B, const float* scale_b, float* dz, void* stream);
+WFD_API void* wfd_decoder_dlogits(wfd_decoder* d);
+/* imports a gradient given in NCHW-shaped form (layout/dtype as in export) into the internal dlogits buffer */
+WFD_API int wfd_decoder_import_dlogits(wfd_decoder* d, int B, const void* in, int in_dtype, int layout, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * WFC transition-rule loss: WFCLossEinsum
+ *   wfd/wfdf/losses.py:43-75; buffers built from wfc_mats of wfd/scmap/tile_data/wfc/*.npz (pipeline_wfd.py:180-182)
+ *   softmax over all T_pad channels: pipeline_wfd.py:405
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct wfd_wfc wfd_wfc;
+
+/* mat_x[i*T+j] != 0 <=> tile j allowed to the right of i; mat_y[i*T+j] != 0 <=> j allowed below i (HOST memory) */
+WFD_API int wfd_wfc_create(const uint8_t* mat_x, const uint8_t* mat_y, int T, int T_pad, int dtype16, wfd_wfc** out);
+WFD_API void wfd_wfc_destroy(wfd_wfc* h);
+/* bytes of the `saved` block one forward needs for (B, H, W) */
+WFD_API size_t wfd_wfc_saved_bytes(const wfd_wfc* h, int B, int H, int W);
+/* in: nhwc16 [B, H*W, T_pad]; is_logits != 0: softmax is applied first (decode_latents_tile), else `in` is the wave.
+ * loss[b] = strength * WFCLossEinsum(wave)[b]. `in` must stay valid until backward when is_logits == 0. */
+WFD_API int wfd_wfc_forward(wfd_wfc* h, const void* in, int is_logits, int B, int H, int W, float strength, void* saved,
+                    float* loss, void* stream);
+/* dout nhwc16 [B, H*W, T_pad]: gradient of sum_b dloss[b]*loss[b] w.r.t. `in` of the matching forward
+ * (dloss == NULL means ones). */
+WFD_API int wfd_wfc_backward(wfd_wfc* h, void* saved, const float* dloss, void* dout, void* stream);
+/* device pointer to the wave [B, H*W, T_pad] nhwc16 held in `saved` after a forward with is_logits != 0 */
+WFD_API void* wfd_wfc_saved_wave(const wfd_wfc* h, void* saved, int B, int H, int W);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * One whole guidance step: decode + softmax + loss + backward to the latents
+ *   pipeline_wfd.py:609-613 minus scheduler.step (its scalar chain factor stays with the caller)
+ * loss[b] = strength * loss_b ; dz = d(sum_b loss[b]) / d z   (fp32 NCHW, includes in_scale)
+ * ---------------------------------------------------------------------------------------------------------------- */
+WFD_API int wfd_guidance_step(wfd_decoder* d, wfd_wfc* h, const void* z, int z_dtype, int B, float in_scale, float strength,
+                      void* wfc_saved, float* loss, float* dz, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Wave argmax into tiles: numpy.argmax(wave, axis=-1) (wfd/webui/ui.py:228, README.md:90-91)
+ * x: [rows, n] contiguous, dtype 0 = fp32, 1 = fp16, 2 = bf16; out: int64 [rows]. First maximum wins, NaN is maximal.
+ * ---------------------------------------------------------------------------------------------------------------- */
+WFD_API int wfd_argmax_tiles(const void* x, int dtype, long long rows, int n, long long* out, void* stream);
+
+/* layout helpers used by the Python layer: NCHW (fp32/fp16) <-> nhwc16, 16-bit -> fp32 */
+WFD_API int wfd_nchw_to_nhwc16(const void* in, int in_dtype, void* out, int B, int C, int HW, int dtype16, void* stream);
+WFD_API int wfd_nhwc16_to_nchw(const void* in, void* out, int out_dtype, int B, int C, int HW, int dtype16, void* stream);
+WFD_API int wfd_cvt16_to_f32(const void* in, float* out, long long n, int dtype16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Test hooks (used by tests/ only): run one tapgemm contraction described field by field, either on the tcgen05
+ * kernel (use_ref = 0) or on the CUDA-core checking kernel (use_ref = 1).
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* a; int a_C, a_W, a_H, a_B; long long a_ld;     /* channels-last input [a_B, a_H, a_W, a_ld] */
+    const void* b; int b_rows; long long ldb, b_zstride; int b_Z; /* K-major matrix [b_Z][b_rows][ldb] */
+    int n_taps, cpt; int tap_dx[9], tap_dy[9];
+    const int* a_c0;
+    int BN, N, W, H, B, w_box, h_box, in_stride;
+    int z_count, a_zmul, b_zmul, b_bbmul;
+    void* out; int out_fp32; long long ldc, c_zstride;
+    const float* bias; const void* residual; float alpha;
+    float* rowdot; const void* dotsrc; long long ld_dot;
+    float* gn_sums; int gn_cpg;
+    int dtype16;
+} wfd_tapgemm_desc;
+WFD_API int wfd_test_tapgemm(const wfd_tapgemm_desc* desc, int use_ref, void* stream);
+/* when set to 1 every tensor-core contraction is routed to the CUDA-core checking kernel (debug bisecting only) */
+WFD_API int wfd_debug_set_ref_gemm(int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WFD_B200_H */

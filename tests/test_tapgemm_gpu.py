@@ -1,0 +1,197 @@
+"""tapgemm (tcgen05/TMA/TMEM contraction kernel) against torch fp32 on the same rounded operands.
+
+The kernel is reached through the C ABI test hook wfd_test_tapgemm; use_ref=1 runs the CUDA-core checking kernel on the
+same descriptors, which separates descriptor/packing mistakes from tensor-core mistakes.
+"""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from wavefunctiondiffusion_b200 import _native as nat
+
+pytestmark = pytest.mark.gpu
+
+
+def _desc(**kw):
+    d = nat.TapGemmDesc()
+    for k, v in kw.items():
+        if k in ("tap_dx", "tap_dy"):
+            arr = getattr(d, k)
+            for i, t in enumerate(v):
+                arr[i] = t
+        else:
+            setattr(d, k, v)
+    return d
+
+
+def _run(d, use_ref):
+    nat.check(nat.lib().wfd_test_tapgemm(C.byref(d), use_ref, nat.stream_ptr()), "wfd_test_tapgemm")
+    torch.cuda.synchronize()
+
+
+def _dt(bf16):
+    return torch.bfloat16 if bf16 else torch.float16
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-30)).item()
+
+
+@pytest.mark.parametrize("use_ref", [1, 0])
+@pytest.mark.parametrize("bf16", [1, 0])
+@pytest.mark.parametrize("M,K,N,BN", [(256, 128, 64, 64), (1024, 384, 384, 192), (512, 64, 48, 48), (384, 1152, 256, 256)])
+def test_plain_gemm(M, K, N, BN, bf16, use_ref):
+    torch.manual_seed(0)
+    dt = _dt(bf16)
+    A = torch.randn(M, K, device="cuda").to(dt)
+    Bm = torch.randn(N, K, device="cuda").to(dt)
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda").to(dt)
+    out = torch.zeros(M, N, device="cuda", dtype=dt)
+    d = _desc(a=A.data_ptr(), a_C=K, a_W=M, a_H=1, a_B=1, a_ld=K, b=Bm.data_ptr(), b_rows=N, ldb=K, b_zstride=0, b_Z=1,
+              n_taps=1, cpt=K // 64, tap_dx=[0], tap_dy=[0], a_c0=None, BN=BN, N=N, W=M, H=1, B=1, w_box=128, h_box=1,
+              in_stride=1, z_count=1, out=out.data_ptr(), out_fp32=0, ldc=N, bias=bias.data_ptr(),
+              residual=res.data_ptr(), alpha=0.5, dtype16=bf16)
+    _run(d, use_ref)
+    want = 0.5 * (A.float() @ Bm.float().t()) + bias + res.float()
+    assert _rel(out, want) < (6e-3 if bf16 else 1e-3)
+
+
+@pytest.mark.parametrize("use_ref", [1, 0])
+def test_fp32_out_rowdot_batched(use_ref):
+    """scores-style: per-sample B operand, fp32 output, plus the row-dot epilogue used by the WFC contraction."""
+    torch.manual_seed(1)
+    Bz, M, K, N = 3, 256, 128, 256
+    A = torch.randn(Bz, M, K, device="cuda").bfloat16()
+    Bm = torch.randn(Bz, N, K, device="cuda").bfloat16()
+    dots = torch.randn(Bz, M, N, device="cuda").bfloat16()
+    out = torch.zeros(Bz, M, N, device="cuda")
+    rowdot = torch.zeros(Bz * M, device="cuda")
+    d = _desc(a=A.data_ptr(), a_C=K, a_W=M, a_H=1, a_B=Bz, a_ld=K, b=Bm.data_ptr(), b_rows=N, ldb=K, b_zstride=N * K,
+              b_Z=Bz, n_taps=1, cpt=K // 64, tap_dx=[0], tap_dy=[0], BN=128, N=N, W=M, H=1, B=Bz, w_box=128, h_box=1,
+              in_stride=1, z_count=1, b_bbmul=1, out=out.data_ptr(), out_fp32=1, ldc=N, alpha=1.0,
+              rowdot=rowdot.data_ptr(), dotsrc=dots.data_ptr(), ld_dot=N, dtype16=1)
+    _run(d, use_ref)
+    want = torch.bmm(A.float(), Bm.float().transpose(1, 2))
+    assert _rel(out, want) < 1e-4
+    assert _rel(rowdot.view(Bz, M), (want * dots.float()).sum(-1)) < 1e-3
+
+
+@pytest.mark.parametrize("use_ref", [1, 0])
+def test_shared_a_z_batch(use_ref):
+    """v^T-style: A (weights) shared by every z, B operand and output indexed by z."""
+    torch.manual_seed(2)
+    Z, M, K, N = 2, 384, 384, 512
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    Bm = torch.randn(Z, N, K, device="cuda").bfloat16()
+    out = torch.zeros(Z, M, N, device="cuda", dtype=torch.bfloat16)
+    d = _desc(a=A.data_ptr(), a_C=K, a_W=M, a_H=1, a_B=1, a_ld=K, b=Bm.data_ptr(), b_rows=N, ldb=K, b_zstride=N * K,
+              b_Z=Z, n_taps=1, cpt=K // 64, tap_dx=[0], tap_dy=[0], BN=256, N=N, W=M, H=1, B=1, w_box=128, h_box=1,
+              in_stride=1, z_count=Z, b_zmul=1, out=out.data_ptr(), out_fp32=0, ldc=N, c_zstride=M * N, alpha=1.0,
+              dtype16=1)
+    _run(d, use_ref)
+    want = torch.einsum("mk,znk->zmn", A.float(), Bm.float())
+    assert _rel(out, want) < 6e-3
+
+
+def _pack_conv(w, groups, BN, bwd=False):
+    """Python restatement of the C++ packer for the test: returns (Bm [n_tiles*BN, taps*cpt*64], a_c0, cpt, N)."""
+    cout, cin_g, k, _ = w.shape
+    cin = cin_g * groups
+    cout_g = cout // groups
+    N = cin if bwd else cout
+    rpg = cin_g if bwd else cout_g
+    kpg = cout_g if bwd else cin_g
+    n_tiles = (N + BN - 1) // BN
+    c0, cpt = [], 1
+    for t in range(n_tiles):
+        n0, n1 = t * BN, min(N, (t + 1) * BN)
+        g_lo, g_hi = n0 // rpg, (n1 - 1) // rpg
+        c0.append(g_lo * kpg)
+        cpt = max(cpt, ((g_hi + 1) * kpg - c0[-1] + 63) // 64)
+    taps = k * k
+    Bm = torch.zeros(n_tiles * BN, taps * cpt * 64)
+    wf = w.reshape(cout, cin_g, taps)
+    for n in range(N):
+        g, t = n // rpg, n // BN
+        for kk in range(kpg):
+            pos = g * kpg + kk - c0[t]
+            if not bwd:
+                vals = wf[n, kk, :]
+            else:
+                vals = wf[g * cout_g + kk, n - g * cin_g, :]
+            Bm[n, torch.arange(taps) * cpt * 64 + pos] = vals
+    return Bm, torch.tensor(c0, dtype=torch.int32), cpt, N
+
+
+@pytest.mark.parametrize("use_ref", [1, 0])
+@pytest.mark.parametrize("cin,cout,groups,BN,H,W", [(64, 64, 1, 64, 16, 16), (192, 96, 4, 48, 8, 64), (96, 192, 2, 96, 32, 32),
+                                                   (384, 384, 1, 192, 64, 64)])
+def test_conv3x3_forward_and_backward_data(cin, cout, groups, BN, H, W, use_ref):
+    torch.manual_seed(3)
+    Bn = 2
+    x = torch.randn(Bn, cin, H, W, device="cuda").bfloat16()
+    w = (torch.randn(cout, cin // groups, 3, 3) * 0.1).bfloat16().float()
+    bias = torch.randn(cout, device="cuda")
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    w_box = min(W, 128)
+    h_box = 128 // w_box
+    # forward
+    Bm, c0, cpt, N = _pack_conv(w, groups, BN)
+    Bm = Bm.cuda().bfloat16()
+    c0 = c0.cuda()
+    out = torch.zeros(Bn, H, W, cout, device="cuda", dtype=torch.bfloat16)
+    gn = torch.zeros(Bn * 8 * 2, device="cuda")
+    taps = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+    d = _desc(a=x_nhwc.data_ptr(), a_C=cin, a_W=W, a_H=H, a_B=Bn, a_ld=cin, b=Bm.data_ptr(), b_rows=Bm.shape[0],
+              ldb=Bm.shape[1], b_zstride=0, b_Z=1, n_taps=9, cpt=cpt, tap_dx=[t[1] for t in taps],
+              tap_dy=[t[0] for t in taps], a_c0=c0.data_ptr(), BN=BN, N=N, W=W, H=H, B=Bn, w_box=w_box, h_box=h_box,
+              in_stride=1, z_count=1, out=out.data_ptr(), out_fp32=0, ldc=cout, bias=bias.data_ptr(), alpha=1.0,
+              gn_sums=gn.data_ptr(), gn_cpg=cout // 8, dtype16=1)
+    _run(d, use_ref)
+    want = F.conv2d(x.float(), w.cuda(), bias, padding=1, groups=groups)
+    got = out.permute(0, 3, 1, 2).float()
+    assert _rel(got, want) < 6e-3
+    # fused GroupNorm statistics of the stored (rounded) output
+    g8 = got.view(Bn, 8, -1)
+    assert _rel(gn.view(Bn, 8, 2)[..., 0], g8.sum(-1)) < 2e-3 or g8.sum(-1).abs().max() < 50
+    assert _rel(gn.view(Bn, 8, 2)[..., 1], (g8 * g8).sum(-1)) < 2e-3
+    # backward data: dX = conv_transpose(dY, w)
+    dy = torch.randn(Bn, cout, H, W, device="cuda").bfloat16()
+    dy_nhwc = dy.permute(0, 2, 3, 1).contiguous()
+    BNb = BN if (cin // groups) % 16 == 0 and (cin // groups) <= 256 and BN % (cin // groups) == 0 else 64
+    Bm2, c02, cpt2, N2 = _pack_conv(w, groups, BNb, bwd=True)
+    Bm2 = Bm2.cuda().bfloat16()
+    c02 = c02.cuda()
+    dx = torch.zeros(Bn, H, W, cin, device="cuda", dtype=torch.bfloat16)
+    d = _desc(a=dy_nhwc.data_ptr(), a_C=cout, a_W=W, a_H=H, a_B=Bn, a_ld=cout, b=Bm2.data_ptr(), b_rows=Bm2.shape[0],
+              ldb=Bm2.shape[1], b_zstride=0, b_Z=1, n_taps=9, cpt=cpt2, tap_dx=[-t[1] for t in taps],
+              tap_dy=[-t[0] for t in taps], a_c0=c02.data_ptr(), BN=BNb, N=N2, W=W, H=H, B=Bn, w_box=w_box, h_box=h_box,
+              in_stride=1, z_count=1, out=dx.data_ptr(), out_fp32=0, ldc=cin, alpha=1.0, dtype16=1)
+    _run(d, use_ref)
+    want = F.conv_transpose2d(dy.float(), w.cuda(), padding=1, groups=groups)
+    assert _rel(dx.permute(0, 3, 1, 2), want) < 6e-3
+
+
+@pytest.mark.parametrize("use_ref", [1, 0])
+def test_four_tap_neighbour_contraction(use_ref):
+    """WFC-style: 4 taps (right, left, below, above) with zero fill at the map border."""
+    torch.manual_seed(4)
+    Bn, H, W, T = 2, 16, 16, 128
+    p = torch.rand(Bn, H, W, T, device="cuda").bfloat16()
+    mats = (torch.rand(4, T, T, device="cuda") < 0.05).bfloat16()  # [tap][i][j]
+    Bm = torch.cat([mats[t] for t in range(4)], dim=1).contiguous()  # [T, 4T]
+    out = torch.zeros(Bn, H, W, T, device="cuda", dtype=torch.bfloat16)
+    d = _desc(a=p.data_ptr(), a_C=T, a_W=W, a_H=H, a_B=Bn, a_ld=T, b=Bm.data_ptr(), b_rows=T, ldb=4 * T, b_zstride=0,
+              b_Z=1, n_taps=4, cpt=T // 64, tap_dx=[1, -1, 0, 0], tap_dy=[0, 0, 1, -1], BN=128, N=T, W=W, H=H, B=Bn,
+              w_box=16, h_box=8, in_stride=1, z_count=1, out=out.data_ptr(), out_fp32=0, ldc=T, alpha=1.0, dtype16=1)
+    _run(d, use_ref)
+    pf = p.float()
+    want = torch.zeros(Bn, H, W, T, device="cuda")
+    want[:, :, :-1] += torch.einsum("ij,bhwj->bhwi", mats[0].float(), pf[:, :, 1:])
+    want[:, :, 1:] += torch.einsum("ij,bhwj->bhwi", mats[1].float(), pf[:, :, :-1])
+    want[:, :-1] += torch.einsum("ij,bhwj->bhwi", mats[2].float(), pf[:, 1:])
+    want[:, 1:] += torch.einsum("ij,bhwj->bhwi", mats[3].float(), pf[:, :-1])
+    assert _rel(out, want) < 6e-3

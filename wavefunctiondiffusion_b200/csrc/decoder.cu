@@ -1,0 +1,930 @@
+// Tile-VAE decoder plan: weight packing for the tapgemm kernel, forward, backward-data.
+// Mirrors AutoencoderTile._decode (reference wf_vae.py:592-599) = post_quant_conv -> DecoderTile.forward (:216-232):
+// conv_in, UNetMidBlock2D (resnet, single-head attention, resnet), 4 decoder blocks of 3 ResnetBlock2D each
+// (resnet.py:458-499; grouped 3x3 convs, GroupNorm(8)+SiLU, 1x1 grouped shortcut), GroupNorm+SiLU, grouped conv_out.
+// Backward is the data gradient only (torch.autograd.grad w.r.t. latents, pipeline_wfd.py:613).
+#include "decoder.cuh"
+#include "kernels.cuh"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+
+namespace wfd {
+
+static int g_debug_ref_gemm = 0;
+void debug_set_ref_gemm(int on) { g_debug_ref_gemm = on; }
+int debug_ref_gemm() { return g_debug_ref_gemm; }
+
+#define CK(expr)                      \
+    do {                              \
+        int rc__ = (expr);            \
+        if (rc__ < 0) return rc__;    \
+    } while (0)
+#define CUDA_CK(expr)                                                           \
+    do {                                                                        \
+        cudaError_t e__ = (expr);                                               \
+        if (e__ != cudaSuccess) {                                               \
+            set_error("%s: %s", #expr, cudaGetErrorString(e__));                \
+            return -8;                                                          \
+        }                                                                       \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ host 16-bit
+static uint16_t host_f_to_16(float f, bool bf16) {
+    if (bf16) {
+        uint32_t u;
+        memcpy(&u, &f, 4);
+        if ((u & 0x7FFFFFFFu) > 0x7F800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
+        u += 0x7FFFu + ((u >> 16) & 1u);
+        return static_cast<uint16_t>(u >> 16);
+    }
+    __half h = __float2half_rn(f);
+    uint16_t r;
+    memcpy(&r, &h, 2);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+static int choose_bn(int rpg) {
+    if (rpg % 16 == 0) {
+        if (rpg <= 256) {
+            if (rpg >= 48) return rpg;
+            return rpg == 16 ? 48 : 64;  // 16 -> 3 groups, 32 -> 2 groups
+        }
+        for (int d = 256; d >= 16; d -= 16)
+            if (rpg % d == 0) return d;
+    }
+    if ((2 * rpg) % 16 == 0 && 2 * rpg <= 256) return 2 * rpg;
+    return 64;
+}
+
+void PackedB::release() {
+    if (Bm) cudaFree(Bm);
+    if (a_c0) cudaFree(a_c0);
+    Bm = nullptr;
+    a_c0 = nullptr;
+}
+
+// w: [cout][cin/groups][k][k] fp32 (torch Conv2d / Linear layout). mode 0: forward, pad (k-1)/2; mode 1: backward-data of
+// mode 0; mode 2: forward of the stride-2 downsample conv applied after F.pad(x, (0,1,0,1)) (resnet.py:185-190).
+int pack_conv(const float* w, int cout, int cin, int groups, int k, int mode, bool bf16, int bn_override, PackedB* out) {
+    const bool bwd = (mode == 1);
+    const int cin_g = cin / groups, cout_g = cout / groups;
+    const int N = bwd ? cin : cout;
+    const int rpg = bwd ? cin_g : cout_g;   // output rows per group
+    const int kpg = bwd ? cout_g : cin_g;   // contraction channels per group
+    const int BN = bn_override > 0 ? bn_override : choose_bn(rpg);
+    const int n_tiles = (N + BN - 1) / BN;
+    std::vector<int> c0(n_tiles);
+    int cpt = 1;
+    for (int t = 0; t < n_tiles; ++t) {
+        const int n0 = t * BN, n1 = std::min(N, n0 + BN);
+        const int g_lo = n0 / rpg, g_hi = (n1 - 1) / rpg;
+        c0[t] = g_lo * kpg;
+        const int span = (g_hi + 1) * kpg - c0[t];
+        cpt = std::max(cpt, (span + TG_KC - 1) / TG_KC);
+    }
+    const int taps = k * k;
+    const long long ldb = static_cast<long long>(taps) * cpt * TG_KC;
+    const long long rows = static_cast<long long>(n_tiles) * BN;
+    std::vector<uint16_t> hb(static_cast<size_t>(rows * ldb), 0);
+    for (int n = 0; n < N; ++n) {
+        const int g = n / rpg, t = n / BN;
+        for (int tap = 0; tap < taps; ++tap) {
+            for (int kk = 0; kk < kpg; ++kk) {
+                const int c = g * kpg + kk;
+                const int pos = c - c0[t];
+                float v;
+                if (!bwd) {
+                    v = w[(static_cast<long long>(n) * cin_g + kk) * taps + tap];
+                } else {
+                    const int co = g * cout_g + kk, ci_local = n - g * cin_g;
+                    v = w[(static_cast<long long>(co) * cin_g + ci_local) * taps + tap];
+                }
+                hb[static_cast<size_t>(n * ldb + static_cast<long long>(tap) * cpt * TG_KC + pos)] = host_f_to_16(v, bf16);
+            }
+        }
+    }
+    out->release();
+    out->BN = BN;
+    out->n_tiles = n_tiles;
+    out->cpt = cpt;
+    out->n_taps = taps;
+    out->N = N;
+    out->ldb = ldb;
+    out->rows = static_cast<int>(rows);
+    out->in_stride = (mode == 2) ? 2 : 1;
+    for (int ky = 0; ky < k; ++ky)
+        for (int kx = 0; kx < k; ++kx) {
+            const int tap = ky * k + kx;
+            int dy = ky - (k - 1) / 2, dx = kx - (k - 1) / 2;
+            if (mode == 2) { dy = ky; dx = kx; }
+            if (bwd) { dy = -dy; dx = -dx; }
+            out->dx[tap] = dx;
+            out->dy[tap] = dy;
+        }
+    CUDA_CK(cudaMalloc(&out->Bm, hb.size() * 2));
+    CUDA_CK(cudaMemcpy(out->Bm, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice));
+    CUDA_CK(cudaMalloc(&out->a_c0, n_tiles * sizeof(int)));
+    CUDA_CK(cudaMemcpy(out->a_c0, c0.data(), n_tiles * sizeof(int), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int upload_f32(const std::vector<float>& v, float** dev) {
+    if (*dev) cudaFree(*dev);
+    *dev = nullptr;
+    CUDA_CK(cudaMalloc(dev, std::max<size_t>(v.size(), 1) * sizeof(float)));
+    CUDA_CK(cudaMemcpy(*dev, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ plan construction
+static bool pick_box(int W, int H, int* w_box, int* h_box) {
+    for (int wb = 128; wb >= 1; wb >>= 1) {
+        if (W % wb != 0) continue;
+        const int hb = TG_BM / wb;
+        if (H % hb != 0) continue;
+        *w_box = wb;
+        *h_box = hb;
+        return true;
+    }
+    return false;
+}
+
+Decoder::~Decoder() {
+    for (auto& kv : convs) {
+        kv.second.fwd.release();
+        kv.second.bwd.release();
+        if (kv.second.bias) cudaFree(kv.second.bias);
+    }
+    for (auto& kv : vecs)
+        if (kv.second) cudaFree(kv.second);
+}
+
+int Decoder::init(const wfd_decoder_config& c, int h_, int w_, int Bmax, int dtype16) {
+    cfg = c;
+    h = h_;
+    w = w_;
+    B_max = Bmax;
+    bf16 = dtype16 ? 1 : 0;
+    G = c.norm_num_groups;
+    if (c.latent_channels != 4) {
+        set_error("decoder: latent_channels must be 4 (got %d)", c.latent_channels);
+        return -3;
+    }
+    if (c.n_blocks < 1 || c.n_blocks > 8 || Bmax < 1 || h < 1 || w < 1) {
+        set_error("decoder: bad config (n_blocks=%d B_max=%d h=%d w=%d)", c.n_blocks, Bmax, h, w);
+        return -3;
+    }
+    const int nb = c.n_blocks;
+    Cm = c.block_out_channels[nb - 1];
+    // resnet list in execution order: mid.0, [attention], mid.1, then blocks
+    resnets.clear();
+    auto add_res = [&](const std::string& prefix, int cin, int cout, int groups, int hh, int ww) {
+        ResnetDesc r;
+        r.prefix = prefix;
+        r.cin = cin;
+        r.cout = cout;
+        r.groups = groups;
+        r.h = hh;
+        r.w = ww;
+        resnets.push_back(r);
+    };
+    add_res("decoder.mid_block.resnets.0", Cm, Cm, 1, h, w);
+    add_res("decoder.mid_block.resnets.1", Cm, Cm, 1, h, w);
+    int ch = Cm, hh = h, ww = w;
+    down_after.assign(nb, 0);
+    for (int i = 0; i < nb; ++i) {
+        const int cout = c.block_out_channels[nb - 1 - i];
+        const int groups = c.conv_groups[nb - 1 - i];
+        for (int j = 0; j < c.layers_per_block + 1; ++j) {
+            char buf[128];
+            snprintf(buf, sizeof(buf), "decoder.up_blocks.%d.resnets.%d", i, j);
+            add_res(buf, j == 0 ? ch : cout, cout, groups, hh, ww);
+        }
+        ch = cout;
+        if (c.block_down[i]) {
+            down_after[i] = 1;
+            if (hh % 2 || ww % 2) {
+                set_error("decoder: DownDecoderBlock2D needs an even plane (%dx%d)", hh, ww);
+                return -3;
+            }
+            hh /= 2;
+            ww /= 2;
+        }
+    }
+    C_last = ch;
+    H_out = hh;
+    W_out = ww;
+    T_pad = c.out_channels;
+    for (const ResnetDesc& r : resnets) {
+        if (r.cin % 8 || r.cout % 16 || (r.cin / G) % 8 || (r.cout / G) % 8 || r.cin % r.groups || r.cout % r.groups) {
+            set_error("decoder: unsupported channel counts in %s (%d -> %d, groups %d)", r.prefix.c_str(), r.cin, r.cout,
+                      r.groups);
+            return -3;
+        }
+    }
+    if (T_pad % 16 || T_pad % c.conv_init_groups || C_last % c.conv_init_groups) {
+        set_error("decoder: out_channels=%d must be a multiple of 16 and of conv_init_groups", T_pad);
+        return -3;
+    }
+    int wb, hb;
+    if (!pick_box(w, h, &wb, &hb) || !pick_box(W_out, H_out, &wb, &hb) || (static_cast<long long>(h) * w) % 128) {
+        set_error("decoder: plane %dx%d cannot be tiled into 128-pixel patches", h, w);
+        return -3;
+    }
+    layout_workspace();
+    return 0;
+}
+
+// Workspace layout (all offsets 256-byte aligned); sizes for B_max.
+void Decoder::layout_workspace() {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) & ~size_t(255);
+        return o;
+    };
+    const size_t e = 2;  // bytes per 16-bit element
+    const size_t B = static_cast<size_t>(B_max);
+    const size_t hw = static_cast<size_t>(h) * w;
+    int maxC = Cm;
+    for (const ResnetDesc& r : resnets) maxC = std::max(maxC, std::max(r.cin, r.cout));
+    o_x0 = take(B * hw * Cm * e);
+    o_res_h1.clear();
+    o_res_out.clear();
+    for (const ResnetDesc& r : resnets) {
+        const size_t phw = static_cast<size_t>(r.h) * r.w;
+        o_res_h1.push_back(take(B * phw * r.cout * e));
+        o_res_out.push_back(take(B * phw * r.cout * e));
+    }
+    o_down_out.assign(cfg.n_blocks, 0);
+    {
+        int hh = h, ww = w;
+        for (int i = 0; i < cfg.n_blocks; ++i) {
+            if (down_after[i]) {
+                hh /= 2;
+                ww /= 2;
+                o_down_out[i] = take(B * hh * ww * cfg.block_out_channels[cfg.n_blocks - 1 - i] * e);
+            }
+        }
+    }
+    // attention
+    const size_t N = hw;
+    o_attn_out = take(B * N * Cm * e);
+    o_xn = take(B * N * Cm * e);
+    o_qkv = take(B * N * 3 * Cm * e);
+    o_vt = take(B * Cm * N * e);
+    o_S = take(B * N * N * 4);
+    o_P = take(B * N * N * e);
+    o_O = take(B * N * Cm * e);
+    // backward-only attention scratch
+    o_PT = take(B * N * N * e);
+    o_dS = take(B * N * N * e);
+    o_dST = take(B * N * N * e);
+    o_dO = take(B * N * Cm * e);
+    o_dOT = take(B * Cm * N * e);
+    o_KT = take(B * Cm * N * e);
+    o_QT = take(B * Cm * N * e);
+    o_dqkv = take(B * N * 3 * Cm * e);
+    // scratch
+    o_act = take(B * hw * maxC * e);
+    o_act2 = take(B * hw * maxC * e);
+    o_sc = take(B * hw * maxC * e);
+    for (int i = 0; i < 4; ++i) o_g[i] = take(B * hw * maxC * e);
+    const size_t ohw = static_cast<size_t>(H_out) * W_out;
+    o_logits = take(B * ohw * T_pad * e);
+    o_dlogits = take(B * ohw * T_pad * e);
+    n_gn = static_cast<int>(resnets.size()) * 2 + 2;  // + attention group_norm + conv_norm_out
+    o_gn = take(static_cast<size_t>(n_gn) * 2 * B * G * 2 * sizeof(float));  // sums then reds
+    ws_bytes = off;
+}
+
+int Decoder::set_weight(const char* key, const float* data, long long numel) {
+    std::string k(key);
+    if (k.rfind("decoder.", 0) != 0 && k.rfind("post_quant_conv.", 0) != 0) return 1;
+    host[k] = std::vector<float>(data, data + numel);
+    finalized = false;
+    return 0;
+}
+
+int Decoder::need(const std::string& key, long long numel, const std::vector<float>** out) {
+    auto it = host.find(key);
+    if (it == host.end()) {
+        set_error("decoder: missing weight '%s'", key.c_str());
+        return -9;
+    }
+    if (static_cast<long long>(it->second.size()) != numel) {
+        set_error("decoder: weight '%s' has %lld elements, expected %lld", key.c_str(),
+                  static_cast<long long>(it->second.size()), numel);
+        return -9;
+    }
+    *out = &it->second;
+    return 0;
+}
+
+int Decoder::pack_named_conv(const std::string& name, int cout, int cin, int groups, int k, bool want_bwd, int fwd_mode) {
+    const std::vector<float>*wv, *bv;
+    CK(need(name + ".weight", static_cast<long long>(cout) * (cin / groups) * k * k, &wv));
+    CK(need(name + ".bias", cout, &bv));
+    ConvW& cw = convs[name];
+    cw.cin = cin;
+    cw.cout = cout;
+    CK(pack_conv(wv->data(), cout, cin, groups, k, fwd_mode, bf16 != 0, 0, &cw.fwd));
+    if (want_bwd && fwd_mode == 0) CK(pack_conv(wv->data(), cout, cin, groups, k, 1, bf16 != 0, 0, &cw.bwd));
+    CK(upload_f32(*bv, &cw.bias));
+    return 0;
+}
+
+int Decoder::upload_vec(const std::string& key, long long numel) {
+    const std::vector<float>* v;
+    CK(need(key, numel, &v));
+    float*& dev = vecs[key];
+    CK(upload_f32(*v, &dev));
+    return 0;
+}
+
+int Decoder::finalize_weights() {
+    CK(upload_vec("post_quant_conv.weight", 16));
+    CK(upload_vec("post_quant_conv.bias", 4));
+    CK(upload_vec("decoder.conv_in.weight", static_cast<long long>(Cm) * 36));
+    CK(upload_vec("decoder.conv_in.bias", Cm));
+    for (const ResnetDesc& r : resnets) {
+        CK(upload_vec(r.prefix + ".norm1.weight", r.cin));
+        CK(upload_vec(r.prefix + ".norm1.bias", r.cin));
+        CK(upload_vec(r.prefix + ".norm2.weight", r.cout));
+        CK(upload_vec(r.prefix + ".norm2.bias", r.cout));
+        CK(pack_named_conv(r.prefix + ".conv1", r.cout, r.cin, r.groups, 3, true, 0));
+        CK(pack_named_conv(r.prefix + ".conv2", r.cout, r.cout, r.groups, 3, true, 0));
+        if (r.cin != r.cout) CK(pack_named_conv(r.prefix + ".conv_shortcut", r.cout, r.cin, r.groups, 1, true, 0));
+    }
+    for (int i = 0; i < cfg.n_blocks; ++i) {
+        if (!down_after[i]) continue;
+        char buf[128];
+        snprintf(buf, sizeof(buf), "decoder.up_blocks.%d.downsamplers.0.conv", i);
+        const int cch = cfg.block_out_channels[cfg.n_blocks - 1 - i];
+        CK(pack_named_conv(buf, cch, cch, cfg.conv_groups[cfg.n_blocks - 1 - i], 3, false, 2));
+    }
+    // attention: q,k,v merged into one [3C, C] matrix (+ backward form), v alone as an A operand, proj
+    {
+        const std::string a = "decoder.mid_block.attentions.0.";
+        CK(upload_vec(a + "group_norm.weight", Cm));
+        CK(upload_vec(a + "group_norm.bias", Cm));
+        const std::vector<float>*q, *k, *v, *qb, *kb, *vb;
+        const long long cc = static_cast<long long>(Cm) * Cm;
+        CK(need(a + "query.weight", cc, &q));
+        CK(need(a + "key.weight", cc, &k));
+        CK(need(a + "value.weight", cc, &v));
+        CK(need(a + "query.bias", Cm, &qb));
+        CK(need(a + "key.bias", Cm, &kb));
+        CK(need(a + "value.bias", Cm, &vb));
+        std::vector<float> wq(3 * cc), bq(3 * Cm);
+        memcpy(wq.data(), q->data(), cc * 4);
+        memcpy(wq.data() + cc, k->data(), cc * 4);
+        memcpy(wq.data() + 2 * cc, v->data(), cc * 4);
+        memcpy(bq.data(), qb->data(), Cm * 4);
+        memcpy(bq.data() + Cm, kb->data(), Cm * 4);
+        memcpy(bq.data() + 2 * Cm, vb->data(), Cm * 4);
+        ConvW& cq = convs["attn.qkv"];
+        cq.cin = Cm;
+        cq.cout = 3 * Cm;
+        CK(pack_conv(wq.data(), 3 * Cm, Cm, 1, 1, 0, bf16 != 0, 192, &cq.fwd));
+        CK(pack_conv(wq.data(), 3 * Cm, Cm, 1, 1, 1, bf16 != 0, 0, &cq.bwd));
+        CK(upload_f32(bq, &cq.bias));
+        ConvW& cv = convs["attn.v"];
+        cv.cin = Cm;
+        cv.cout = Cm;
+        CK(pack_conv(v->data(), Cm, Cm, 1, 1, 0, bf16 != 0, 0, &cv.fwd));
+        CK(upload_f32(*vb, &cv.bias));
+        CK(pack_named_conv(a + "proj_attn", Cm, Cm, 1, 1, true, 0));
+    }
+    CK(upload_vec("decoder.conv_norm_out.weight", C_last));
+    CK(upload_vec("decoder.conv_norm_out.bias", C_last));
+    CK(pack_named_conv("decoder.conv_out", T_pad, C_last, cfg.conv_init_groups, 3, true, 0));
+    finalized = true;
+    host.clear();
+    if (ws) return prepare_ops();
+    return 0;
+}
+
+int Decoder::bind_workspace(void* p, size_t bytes) {
+    if (bytes < ws_bytes) {
+        set_error("decoder: workspace too small (%zu < %zu)", bytes, ws_bytes);
+        return -3;
+    }
+    if (reinterpret_cast<uintptr_t>(p) & 255) {
+        set_error("decoder: workspace must be 256-byte aligned");
+        return -3;
+    }
+    ws = static_cast<uint8_t*>(p);
+    if (finalized) return prepare_ops();
+    return 0;
+}
+
+int Decoder::prepare_ops() {
+    fwd_ops.clear();
+    bwd_ops.clear();
+    Exec ex;
+    ex.prepare = true;
+    ex.B = B_max;
+    ex.stream = 0;
+    ex.ops = &fwd_ops;
+    CK(forward_impl(ex, nullptr, 0, 1.f));
+    ex.ops = &bwd_ops;
+    ex.cursor = 0;
+    CK(backward_impl(ex, nullptr, nullptr, nullptr));
+    prepared = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ gemm helpers
+int Decoder::run_gemm(Exec& ex, TapGemmOp& tmpl, bool z_is_batch) {
+    if (ex.prepare) {
+        CK(tapgemm_prepare(&tmpl));
+        ex.ops->push_back(tmpl);
+        return 0;
+    }
+    if (ex.cursor >= ex.ops->size()) {
+        set_error("decoder: internal op cursor overrun");
+        return -10;
+    }
+    TapGemmOp op = (*ex.ops)[ex.cursor++];
+    if (z_is_batch) op.p.z_count = ex.B;
+    else op.p.m_tiles = ex.B * op.p.tiles_x * op.p.tiles_y;
+    return g_debug_ref_gemm ? tapgemm_launch_ref(&op, ex.stream) : tapgemm_launch(&op, ex.stream);
+}
+
+// conv-style contraction over a channels-last activation
+int Decoder::conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int Hin, int Win, int Hout, int Wout,
+                       void* out, long long ldc, const float* bias, const void* residual, float* gn_sums, int gn_cpg) {
+    TapGemmOp op;
+    memset(&op, 0, sizeof(op));
+    TapGemmParams& p = op.p;
+    int wb = 0, hb = 0;
+    if (ex.prepare) {
+        if (!pick_box(Wout, Hout, &wb, &hb)) {
+            set_error("decoder: cannot tile %dx%d plane", Hout, Wout);
+            return -3;
+        }
+        p.BN = pk.BN;
+        p.n_tiles = pk.n_tiles;
+        p.z_count = 1;
+        p.w_box = wb;
+        p.h_box = hb;
+        p.tiles_x = Wout / wb;
+        p.tiles_y = Hout / hb;
+        p.m_tiles = B_max * p.tiles_x * p.tiles_y;
+        p.W = Wout;
+        p.H = Hout;
+        p.in_stride = pk.in_stride;
+        p.n_taps = pk.n_taps;
+        p.cpt = pk.cpt;
+        for (int t = 0; t < pk.n_taps; ++t) {
+            p.tap_dx[t] = pk.dx[t];
+            p.tap_dy[t] = pk.dy[t];
+        }
+        p.a_c0 = pk.a_c0;
+        p.N = pk.N;
+        p.out = out;
+        p.out_fp32 = 0;
+        p.out_sx = ldc;
+        p.out_sy = ldc * Wout;
+        p.out_sb = ldc * Wout * Hout;
+        p.bias = bias;
+        p.residual = residual;
+        p.alpha = 1.f;
+        p.gn_sums = fuse_gn ? gn_sums : nullptr;
+        p.gn_cpg = gn_cpg;
+        p.gn_G = G;
+        p.is_bf16 = bf16;
+        p.a_ptr = A;
+        p.a_C = a_C;
+        p.a_W = Win;
+        p.a_H = Hin;
+        p.a_B = B_max;
+        p.a_ld = a_C;
+        p.b_ptr = pk.Bm;
+        p.ldb = pk.ldb;
+        p.b_zstride = 0;
+        p.b_rows = pk.rows;
+        p.b_Z = 1;
+    }
+    return run_gemm(ex, op, false);
+}
+
+// plain batched GEMM: D[rows, N] = alpha * A[rows, K] * Bm[N, K]^T (+bias)(+residual); rows are tokens of sample bb
+struct PlainGemm {
+    const void* A; int K; long long a_ld; int rows_per_sample; int a_B;   // A: [a_B, rows_per_sample, a_ld]
+    bool a_shared;                                                        // A identical for every z (weights as A)
+    const void* Bm; int b_rows; long long ldb, b_zstride; int b_Z;        // Bm: [b_Z][b_rows][ldb]
+    bool b_per_sample;                                                    // Bm slice = sample index
+    int BN, N;
+    void* out; int out_fp32; long long ldc, c_zstride;
+    const float* bias; const void* residual; float alpha;
+    float* gn_sums; int gn_cpg;
+};
+int Decoder::plain_gemm(Exec& ex, const PlainGemm& g) {
+    TapGemmOp op;
+    memset(&op, 0, sizeof(op));
+    if (ex.prepare) {
+        TapGemmParams& p = op.p;
+        if (g.rows_per_sample % TG_BM || g.K % TG_KC) {
+            set_error("decoder: plain gemm needs rows %% 128 == 0 and K %% 64 == 0 (rows=%d K=%d)", g.rows_per_sample, g.K);
+            return -3;
+        }
+        p.BN = g.BN;
+        p.n_tiles = (g.N + g.BN - 1) / g.BN;
+        p.w_box = TG_BM;
+        p.h_box = 1;
+        p.tiles_x = g.rows_per_sample / TG_BM;
+        p.tiles_y = 1;
+        p.W = g.rows_per_sample;
+        p.H = 1;
+        p.in_stride = 1;
+        p.n_taps = 1;
+        p.cpt = g.K / TG_KC;
+        p.tap_dx[0] = p.tap_dy[0] = 0;
+        p.a_c0 = nullptr;
+        if (g.a_shared) {  // z enumerates samples, A is shared
+            p.z_count = B_max;
+            p.m_tiles = p.tiles_x;
+            p.a_zmul = 0;
+            p.b_zmul = 1;
+            p.b_bbmul = 0;
+        } else {
+            p.z_count = 1;
+            p.m_tiles = B_max * p.tiles_x;
+            p.a_zmul = 0;
+            p.b_zmul = 0;
+            p.b_bbmul = g.b_per_sample ? 1 : 0;
+        }
+        p.N = g.N;
+        p.out = g.out;
+        p.out_fp32 = g.out_fp32;
+        p.out_sx = g.ldc;
+        p.out_sy = 0;
+        p.out_sb = g.ldc * g.rows_per_sample;
+        p.c_zstride = g.c_zstride;
+        p.bias = g.bias;
+        p.residual = g.residual;
+        p.alpha = g.alpha;
+        p.gn_sums = fuse_gn ? g.gn_sums : nullptr;
+        p.gn_cpg = g.gn_cpg;
+        p.gn_G = G;
+        p.is_bf16 = bf16;
+        p.a_ptr = g.A;
+        p.a_C = g.K;
+        p.a_W = g.rows_per_sample;
+        p.a_H = 1;
+        p.a_B = g.a_B;
+        p.a_ld = g.a_ld;
+        p.b_ptr = g.Bm;
+        p.ldb = g.ldb;
+        p.b_zstride = g.b_zstride;
+        p.b_rows = g.b_rows;
+        p.b_Z = g.b_Z;
+    }
+    return run_gemm(ex, op, g.a_shared);
+}
+
+float* Decoder::gn_sums_ptr(int idx) const {
+    return reinterpret_cast<float*>(ws + o_gn) + static_cast<size_t>(idx) * B_max * G * 2;
+}
+float* Decoder::gn_red_ptr(int idx) const {
+    return reinterpret_cast<float*>(ws + o_gn) + static_cast<size_t>(n_gn + idx) * B_max * G * 2;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
+    const int B = ex.B;
+    cudaStream_t s = ex.stream;
+    const float eps = 1e-6f;
+    const int hw = h * w;
+    uint8_t* x = ws + o_x0;
+    if (!ex.prepare) {
+        CUDA_CK(cudaMemsetAsync(ws + o_gn, 0, static_cast<size_t>(n_gn) * B_max * G * 2 * sizeof(float), s));
+        CK(latent_in(z, z_f16, in_scale, vecs["post_quant_conv.weight"], vecs["post_quant_conv.bias"],
+                     vecs["decoder.conv_in.weight"], vecs["decoder.conv_in.bias"], x, B, h, w, Cm, bf16, s));
+    }
+    int cur_h = h, cur_w = w;
+    int ri = 0;
+    auto resnet = [&](int idx, uint8_t* xin, bool stats_ready) -> int {
+        const ResnetDesc& r = resnets[idx];
+        const int phw = r.h * r.w;
+        uint8_t* act = ws + o_act;
+        uint8_t* act2 = ws + o_act2;
+        uint8_t* h1 = ws + o_res_h1[idx];
+        uint8_t* xout = ws + o_res_out[idx];
+        const int gi1 = 2 * idx, gi2 = 2 * idx + 1;
+        const bool last = idx + 1 == static_cast<int>(resnets.size());
+        // stats of the resnet output feed the next GroupNorm: the next resnet's norm1, the attention norm after
+        // mid.resnets.0, or conv_norm_out after the last resnet
+        int next_gn = last ? n_gn - 1 : (idx == 0 ? n_gn - 2 : 2 * (idx + 1));
+        int next_cpg = r.cout / G;
+        if (!ex.prepare) {
+            if (!stats_ready || !fuse_gn) CK(gn_stats(xin, gn_sums_ptr(gi1), B, phw, r.cin, G, bf16, s));
+            CK(gn_apply(xin, gn_sums_ptr(gi1), vecs[r.prefix + ".norm1.weight"], vecs[r.prefix + ".norm1.bias"], act, B,
+                        phw, r.cin, G, eps, 1, bf16, s));
+        }
+        const ConvW& c1 = convs[r.prefix + ".conv1"];
+        CK(conv_gemm(ex, c1.fwd, act, r.cin, r.h, r.w, r.h, r.w, h1, r.cout, c1.bias, nullptr, gn_sums_ptr(gi2),
+                     r.cout / G));
+        if (!ex.prepare) {
+            if (!fuse_gn) CK(gn_stats(h1, gn_sums_ptr(gi2), B, phw, r.cout, G, bf16, s));
+            CK(gn_apply(h1, gn_sums_ptr(gi2), vecs[r.prefix + ".norm2.weight"], vecs[r.prefix + ".norm2.bias"], act2, B,
+                        phw, r.cout, G, eps, 1, bf16, s));
+        }
+        const void* residual = xin;
+        if (r.cin != r.cout) {
+            const ConvW& cs = convs[r.prefix + ".conv_shortcut"];
+            CK(conv_gemm(ex, cs.fwd, xin, r.cin, r.h, r.w, r.h, r.w, ws + o_sc, r.cout, cs.bias, nullptr, nullptr, 0));
+            residual = ws + o_sc;
+        }
+        const ConvW& c2 = convs[r.prefix + ".conv2"];
+        // a block that ends in a downsample conv re-computes stats after it, so skip the fused stats there
+        bool feeds_down = false;
+        if (idx >= 2) {
+            const int blk = (idx - 2) / (cfg.layers_per_block + 1), j = (idx - 2) % (cfg.layers_per_block + 1);
+            feeds_down = down_after[blk] && j == cfg.layers_per_block;
+        }
+        CK(conv_gemm(ex, c2.fwd, act2, r.cout, r.h, r.w, r.h, r.w, xout, r.cout, c2.bias, residual,
+                     feeds_down ? nullptr : gn_sums_ptr(next_gn), next_cpg));
+        return 0;
+    };
+
+    // mid block: resnet, attention, resnet (wf_unet_2d_blocks.py:457-464)
+    CK(resnet(0, x, false));  // conv_in is not a tapgemm: its output statistics need the standalone pass
+    x = ws + o_res_out[0];
+    {
+        // AttentionBlock.forward (attention.py:329-380), one head of Cm channels
+        const int N = hw;
+        uint8_t* xn = ws + o_xn;
+        uint8_t* qkv = ws + o_qkv;
+        const std::string a = "decoder.mid_block.attentions.0.";
+        if (!ex.prepare) {
+            if (!fuse_gn) CK(gn_stats(x, gn_sums_ptr(n_gn - 2), B, N, Cm, G, bf16, s));
+            CK(gn_apply(x, gn_sums_ptr(n_gn - 2), vecs[a + "group_norm.weight"], vecs[a + "group_norm.bias"], xn, B, N,
+                        Cm, G, eps, 0, bf16, s));
+        }
+        const ConvW& cq = convs["attn.qkv"];
+        PlainGemm g;
+        memset(&g, 0, sizeof(g));
+        // q | k | v = xn W^T + b
+        g.A = xn; g.K = Cm; g.a_ld = Cm; g.rows_per_sample = N; g.a_B = B_max; g.a_shared = false;
+        g.Bm = cq.fwd.Bm; g.b_rows = cq.fwd.rows; g.ldb = cq.fwd.ldb; g.b_zstride = 0; g.b_Z = 1; g.b_per_sample = false;
+        g.BN = cq.fwd.BN; g.N = 3 * Cm; g.out = qkv; g.out_fp32 = 0; g.ldc = 3 * Cm; g.c_zstride = 0;
+        g.bias = cq.bias; g.residual = nullptr; g.alpha = 1.f;
+        CK(plain_gemm(ex, g));
+        // v^T[b] = Wv xn[b]^T (bias folded into the PV epilogue: softmax rows sum to one)
+        const ConvW& cv = convs["attn.v"];
+        memset(&g, 0, sizeof(g));
+        g.A = cv.fwd.Bm; g.K = Cm; g.a_ld = cv.fwd.ldb; g.rows_per_sample = Cm; g.a_B = 1; g.a_shared = true;
+        g.Bm = xn; g.b_rows = N; g.ldb = Cm; g.b_zstride = static_cast<long long>(N) * Cm; g.b_Z = B_max;
+        g.BN = 256; g.N = N; g.out = ws + o_vt; g.out_fp32 = 0; g.ldc = N; g.c_zstride = static_cast<long long>(Cm) * N;
+        g.alpha = 1.f;
+        CK(plain_gemm(ex, g));
+        // scores = q k^T / sqrt(C) in fp32
+        memset(&g, 0, sizeof(g));
+        g.A = qkv; g.K = Cm; g.a_ld = 3 * Cm; g.rows_per_sample = N; g.a_B = B_max; g.a_shared = false;
+        g.Bm = qkv + static_cast<size_t>(Cm) * 2; g.b_rows = N; g.ldb = 3 * Cm;
+        g.b_zstride = static_cast<long long>(N) * 3 * Cm; g.b_Z = B_max; g.b_per_sample = true;
+        g.BN = 256; g.N = N; g.out = ws + o_S; g.out_fp32 = 1; g.ldc = N; g.alpha = 1.f / sqrtf(static_cast<float>(Cm));
+        CK(plain_gemm(ex, g));
+        if (!ex.prepare) CK(attn_softmax(reinterpret_cast<const float*>(ws + o_S), ws + o_P, static_cast<long long>(B) * N, N, bf16, s));
+        // o = p v + bv
+        memset(&g, 0, sizeof(g));
+        g.A = ws + o_P; g.K = N; g.a_ld = N; g.rows_per_sample = N; g.a_B = B_max; g.a_shared = false;
+        g.Bm = ws + o_vt; g.b_rows = Cm; g.ldb = N; g.b_zstride = static_cast<long long>(Cm) * N; g.b_Z = B_max;
+        g.b_per_sample = true; g.BN = 192; g.N = Cm; g.out = ws + o_O; g.out_fp32 = 0; g.ldc = Cm; g.bias = cv.bias;
+        g.alpha = 1.f;
+        CK(plain_gemm(ex, g));
+        // proj + residual
+        const ConvW& cp = convs[a + "proj_attn"];
+        memset(&g, 0, sizeof(g));
+        g.A = ws + o_O; g.K = Cm; g.a_ld = Cm; g.rows_per_sample = N; g.a_B = B_max; g.a_shared = false;
+        g.Bm = cp.fwd.Bm; g.b_rows = cp.fwd.rows; g.ldb = cp.fwd.ldb; g.b_Z = 1; g.BN = cp.fwd.BN; g.N = Cm;
+        g.out = ws + o_attn_out; g.out_fp32 = 0; g.ldc = Cm; g.bias = cp.bias; g.residual = x; g.alpha = 1.f;
+        g.gn_sums = gn_sums_ptr(2); g.gn_cpg = Cm / G;
+        CK(plain_gemm(ex, g));
+        x = ws + o_attn_out;
+    }
+    CK(resnet(1, x, true));
+    x = ws + o_res_out[1];
+    ri = 2;
+    for (int i = 0; i < cfg.n_blocks; ++i) {
+        for (int j = 0; j < cfg.layers_per_block + 1; ++j) {
+            // the first resnet after a downsample has no fused stats for its input
+            const bool ready = !(j == 0 && i > 0 && down_after[i - 1]);
+            CK(resnet(ri, x, ready));
+            x = ws + o_res_out[ri];
+            ++ri;
+        }
+        if (down_after[i]) {
+            char buf[128];
+            snprintf(buf, sizeof(buf), "decoder.up_blocks.%d.downsamplers.0.conv", i);
+            const ConvW& cd = convs[buf];
+            CK(conv_gemm(ex, cd.fwd, x, cd.cin, cur_h, cur_w, cur_h / 2, cur_w / 2, ws + o_down_out[i], cd.cout,
+                         cd.bias, nullptr, nullptr, 0));
+            x = ws + o_down_out[i];
+            cur_h /= 2;
+            cur_w /= 2;
+        }
+    }
+    x_last = x;
+    // conv_norm_out + SiLU + conv_out (wf_vae.py:228-230)
+    const bool last_down = down_after[cfg.n_blocks - 1] != 0;
+    if (!ex.prepare) {
+        if (!fuse_gn || last_down) CK(gn_stats(x, gn_sums_ptr(n_gn - 1), B, H_out * W_out, C_last, G, bf16, s));
+        CK(gn_apply(x, gn_sums_ptr(n_gn - 1), vecs["decoder.conv_norm_out.weight"], vecs["decoder.conv_norm_out.bias"],
+                    ws + o_act, B, H_out * W_out, C_last, G, eps, 1, bf16, s));
+    }
+    const ConvW& co = convs["decoder.conv_out"];
+    CK(conv_gemm(ex, co.fwd, ws + o_act, C_last, H_out, W_out, H_out, W_out, ws + o_logits, T_pad, co.bias, nullptr,
+                 nullptr, 0));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_b, float* dz) {
+    const int B = ex.B;
+    cudaStream_t s = ex.stream;
+    const float eps = 1e-6f;
+    const int hw = h * w;
+    const void* dlog = dlogits_in ? dlogits_in : ws + o_dlogits;
+    if (!ex.prepare)
+        CUDA_CK(cudaMemsetAsync(gn_red_ptr(0), 0, static_cast<size_t>(n_gn) * B_max * G * 2 * sizeof(float), s));
+    // gradient buffers rotate: `cur` holds d(out) of the layer being differentiated
+    int cur = 0;
+    auto gbuf = [&](int i) { return ws + o_g[i & 3]; };
+    for (int i = 0; i < cfg.n_blocks; ++i)
+        if (down_after[i]) {
+            set_error("decoder: backward through DownDecoderBlock2D is not implemented yet");
+            return -11;
+        }
+    // conv_out^T, then conv_norm_out + SiLU backward
+    const ConvW& co = convs["decoder.conv_out"];
+    CK(conv_gemm(ex, co.bwd, dlog, T_pad, H_out, W_out, H_out, W_out, gbuf(cur), C_last, nullptr, nullptr, nullptr, 0));
+    if (!ex.prepare) {
+        CK(gn_bwd_reduce(gbuf(cur), x_last, gn_sums_ptr(n_gn - 1), vecs["decoder.conv_norm_out.weight"],
+                         vecs["decoder.conv_norm_out.bias"], gn_red_ptr(n_gn - 1), B, H_out * W_out, C_last, G, eps, 1,
+                         bf16, s));
+        CK(gn_bwd_apply(gbuf(cur), x_last, gn_sums_ptr(n_gn - 1), vecs["decoder.conv_norm_out.weight"],
+                        vecs["decoder.conv_norm_out.bias"], gn_red_ptr(n_gn - 1), nullptr, gbuf(cur), B, H_out * W_out,
+                        C_last, G, eps, 1, bf16, s));
+    }
+    auto resnet_bwd = [&](int idx, const uint8_t* xin) -> int {
+        const ResnetDesc& r = resnets[idx];
+        const int phw = r.h * r.w;
+        uint8_t* dout = gbuf(cur);
+        uint8_t* t1 = gbuf(cur + 1);
+        uint8_t* t2 = gbuf(cur + 2);
+        uint8_t* t3 = gbuf(cur + 3);
+        const uint8_t* h1 = ws + o_res_h1[idx];
+        const int gi1 = 2 * idx, gi2 = 2 * idx + 1;
+        const ConvW& c2 = convs[r.prefix + ".conv2"];
+        CK(conv_gemm(ex, c2.bwd, dout, r.cout, r.h, r.w, r.h, r.w, t1, r.cout, nullptr, nullptr, nullptr, 0));
+        if (!ex.prepare) {
+            const float* ga = vecs[r.prefix + ".norm2.weight"];
+            const float* be = vecs[r.prefix + ".norm2.bias"];
+            CK(gn_bwd_reduce(t1, h1, gn_sums_ptr(gi2), ga, be, gn_red_ptr(gi2), B, phw, r.cout, G, eps, 1, bf16, s));
+            CK(gn_bwd_apply(t1, h1, gn_sums_ptr(gi2), ga, be, gn_red_ptr(gi2), nullptr, t1, B, phw, r.cout, G, eps, 1,
+                            bf16, s));
+        }
+        const ConvW& c1 = convs[r.prefix + ".conv1"];
+        CK(conv_gemm(ex, c1.bwd, t1, r.cout, r.h, r.w, r.h, r.w, t2, r.cin, nullptr, nullptr, nullptr, 0));
+        const void* add = dout;
+        if (r.cin != r.cout) {
+            const ConvW& cs = convs[r.prefix + ".conv_shortcut"];
+            CK(conv_gemm(ex, cs.bwd, dout, r.cout, r.h, r.w, r.h, r.w, t3, r.cin, nullptr, nullptr, nullptr, 0));
+            add = t3;
+        }
+        if (!ex.prepare) {
+            const float* ga = vecs[r.prefix + ".norm1.weight"];
+            const float* be = vecs[r.prefix + ".norm1.bias"];
+            CK(gn_bwd_reduce(t2, xin, gn_sums_ptr(gi1), ga, be, gn_red_ptr(gi1), B, phw, r.cin, G, eps, 1, bf16, s));
+            CK(gn_bwd_apply(t2, xin, gn_sums_ptr(gi1), ga, be, gn_red_ptr(gi1), add, t2, B, phw, r.cin, G, eps, 1, bf16,
+                            s));
+        }
+        cur = (cur + 2) & 3;
+        return 0;
+    };
+    // decoder blocks in reverse
+    for (int idx = static_cast<int>(resnets.size()) - 1; idx >= 2; --idx) {
+        const uint8_t* xin = (idx == 2) ? ws + o_res_out[1] : ws + o_res_out[idx - 1];
+        CK(resnet_bwd(idx, xin));
+    }
+    CK(resnet_bwd(1, ws + o_attn_out));
+    {
+        // attention backward
+        const int N = hw;
+        const std::string a = "decoder.mid_block.attentions.0.";
+        uint8_t* dout = gbuf(cur);
+        uint8_t* dxn = gbuf(cur + 1);
+        const uint8_t* xin = ws + o_res_out[0];
+        const uint8_t* qkv = ws + o_qkv;
+        uint8_t* dqkv = ws + o_dqkv;
+        const ConvW& cp = convs[a + "proj_attn"];
+        PlainGemm g;
+        // dO = dout Wp
+        memset(&g, 0, sizeof(g));
+        g.A = dout; g.K = Cm; g.a_ld = Cm; g.rows_per_sample = N; g.a_B = B_max;
+        g.Bm = cp.bwd.Bm; g.b_rows = cp.bwd.rows; g.ldb = cp.bwd.ldb; g.b_Z = 1; g.BN = cp.bwd.BN; g.N = Cm;
+        g.out = ws + o_dO; g.ldc = Cm; g.alpha = 1.f;
+        CK(plain_gemm(ex, g));
+        if (!ex.prepare) {
+            CK(transpose16(ws + o_dO, ws + o_dOT, B, N, Cm, Cm, static_cast<long long>(N) * Cm, s));
+            CK(transpose16(ws + o_P, ws + o_PT, B, N, N, N, static_cast<long long>(N) * N, s));
+            CK(transpose16(qkv, ws + o_QT, B, N, Cm, 3 * Cm, static_cast<long long>(N) * 3 * Cm, s));
+            CK(transpose16(qkv + static_cast<size_t>(Cm) * 2, ws + o_KT, B, N, Cm, 3 * Cm, static_cast<long long>(N) * 3 * Cm, s));
+        }
+        // dV = P^T dO  -> dqkv[:, 2C:3C]
+        memset(&g, 0, sizeof(g));
+        g.A = ws + o_PT; g.K = N; g.a_ld = N; g.rows_per_sample = N; g.a_B = B_max;
+        g.Bm = ws + o_dOT; g.b_rows = Cm; g.ldb = N; g.b_zstride = static_cast<long long>(Cm) * N; g.b_Z = B_max;
+        g.b_per_sample = true; g.BN = 192; g.N = Cm; g.out = dqkv + static_cast<size_t>(2 * Cm) * 2; g.ldc = 3 * Cm; g.alpha = 1.f;
+        CK(plain_gemm(ex, g));
+        // dP = dO V^T (fp32, reuses the score buffer)
+        memset(&g, 0, sizeof(g));
+        g.A = ws + o_dO; g.K = Cm; g.a_ld = Cm; g.rows_per_sample = N; g.a_B = B_max;
+        g.Bm = qkv + static_cast<size_t>(2 * Cm) * 2; g.b_rows = N; g.ldb = 3 * Cm;
+        g.b_zstride = static_cast<long long>(N) * 3 * Cm; g.b_Z = B_max; g.b_per_sample = true;
+        g.BN = 256; g.N = N; g.out = ws + o_S; g.out_fp32 = 1; g.ldc = N; g.alpha = 1.f;
+        CK(plain_gemm(ex, g));
+        if (!ex.prepare) {
+            CK(attn_softmax_bwd(ws + o_P, reinterpret_cast<const float*>(ws + o_S), ws + o_dS, static_cast<long long>(B) * N,
+                                N, 1.f / sqrtf(static_cast<float>(Cm)), bf16, s));
+            CK(transpose16(ws + o_dS, ws + o_dST, B, N, N, N, static_cast<long long>(N) * N, s));
+        }
+        // dQ = dS K -> dqkv[:, 0:C]
+        memset(&g, 0, sizeof(g));
+        g.A = ws + o_dS; g.K = N; g.a_ld = N; g.rows_per_sample = N; g.a_B = B_max;
+        g.Bm = ws + o_KT; g.b_rows = Cm; g.ldb = N; g.b_zstride = static_cast<long long>(Cm) * N; g.b_Z = B_max;
+        g.b_per_sample = true; g.BN = 192; g.N = Cm; g.out = dqkv; g.ldc = 3 * Cm; g.alpha = 1.f;
+        CK(plain_gemm(ex, g));
+        // dK = dS^T Q -> dqkv[:, C:2C]
+        memset(&g, 0, sizeof(g));
+        g.A = ws + o_dST; g.K = N; g.a_ld = N; g.rows_per_sample = N; g.a_B = B_max;
+        g.Bm = ws + o_QT; g.b_rows = Cm; g.ldb = N; g.b_zstride = static_cast<long long>(Cm) * N; g.b_Z = B_max;
+        g.b_per_sample = true; g.BN = 192; g.N = Cm; g.out = dqkv + static_cast<size_t>(Cm) * 2; g.ldc = 3 * Cm; g.alpha = 1.f;
+        CK(plain_gemm(ex, g));
+        // d xn = [dQ | dK | dV] Wqkv
+        const ConvW& cq = convs["attn.qkv"];
+        memset(&g, 0, sizeof(g));
+        g.A = dqkv; g.K = 3 * Cm; g.a_ld = 3 * Cm; g.rows_per_sample = N; g.a_B = B_max;
+        g.Bm = cq.bwd.Bm; g.b_rows = cq.bwd.rows; g.ldb = cq.bwd.ldb; g.b_Z = 1; g.BN = cq.bwd.BN; g.N = Cm;
+        g.out = dxn; g.ldc = Cm; g.alpha = 1.f;
+        CK(plain_gemm(ex, g));
+        if (!ex.prepare) {
+            const float* ga = vecs[a + "group_norm.weight"];
+            const float* be = vecs[a + "group_norm.bias"];
+            CK(gn_bwd_reduce(dxn, xin, gn_sums_ptr(n_gn - 2), ga, be, gn_red_ptr(n_gn - 2), B, N, Cm, G, eps, 0, bf16, s));
+            CK(gn_bwd_apply(dxn, xin, gn_sums_ptr(n_gn - 2), ga, be, gn_red_ptr(n_gn - 2), dout, dxn, B, N, Cm, G, eps, 0,
+                            bf16, s));
+        }
+        cur = (cur + 1) & 3;
+    }
+    CK(resnet_bwd(0, ws + o_x0));
+    if (!ex.prepare)
+        CK(latent_out(gbuf(cur), last_in_scale, scale_b, vecs["post_quant_conv.weight"], vecs["decoder.conv_in.weight"],
+                      dz, B, h, w, Cm, bf16, s));
+    return 0;
+}
+
+int Decoder::forward(const void* z, int z_dtype, int B, float in_scale, cudaStream_t s) {
+    if (!prepared) {
+        set_error("decoder: weights not finalized or workspace not bound");
+        return -12;
+    }
+    if (B < 1 || B > B_max) {
+        set_error("decoder: batch %d outside [1, %d]", B, B_max);
+        return -3;
+    }
+    Exec ex;
+    ex.prepare = false;
+    ex.B = B;
+    ex.stream = s;
+    ex.ops = &fwd_ops;
+    last_in_scale = in_scale;
+    last_B = B;
+    return forward_impl(ex, z, z_dtype, in_scale);
+}
+
+int Decoder::backward(const void* dlogits, int B, const float* scale_b, float* dz, cudaStream_t s) {
+    if (!prepared) {
+        set_error("decoder: weights not finalized or workspace not bound");
+        return -12;
+    }
+    if (B != last_B) {
+        set_error("decoder: backward batch %d does not match the last forward (%d)", B, last_B);
+        return -3;
+    }
+    Exec ex;
+    ex.prepare = false;
+    ex.B = B;
+    ex.stream = s;
+    ex.ops = &bwd_ops;
+    return backward_impl(ex, dlogits, scale_b, dz);
+}
+
+}  // namespace wfd

@@ -1,0 +1,118 @@
+// Decoder plan and WFC handle (internal C++ side of the C ABI in include/wfd_b200.h).
+#pragma once
+#include "../../include/wfd_b200.h"
+#include "tapgemm.cuh"
+#include <map>
+#include <string>
+#include <vector>
+
+namespace wfd {
+
+void debug_set_ref_gemm(int on);
+int debug_ref_gemm();
+
+// A K-major B operand for tapgemm: [rows = n_tiles*BN][ldb = n_taps*cpt*64] 16-bit, zero outside each group's block.
+struct PackedB {
+    uint16_t* Bm = nullptr;
+    int* a_c0 = nullptr;  // first A channel per N tile
+    int BN = 0, n_tiles = 0, cpt = 0, n_taps = 0, N = 0, rows = 0, in_stride = 1;
+    long long ldb = 0;
+    int dx[TG_MAX_TAPS] = {0}, dy[TG_MAX_TAPS] = {0};
+    void release();
+};
+int pack_conv(const float* w, int cout, int cin, int groups, int k, int mode, bool bf16, int bn_override, PackedB* out);
+
+struct ConvW {
+    PackedB fwd, bwd;
+    float* bias = nullptr;
+    int cin = 0, cout = 0;
+};
+
+struct ResnetDesc {
+    std::string prefix;
+    int cin, cout, groups, h, w;
+};
+
+struct Exec {
+    bool prepare = false;
+    int B = 0;
+    cudaStream_t stream = 0;
+    std::vector<TapGemmOp>* ops = nullptr;
+    size_t cursor = 0;
+};
+
+struct PlainGemm;
+
+struct Decoder {
+    wfd_decoder_config cfg;
+    int h = 0, w = 0, B_max = 0, bf16 = 1, G = 8;
+    int Cm = 0, C_last = 0, H_out = 0, W_out = 0, T_pad = 0;
+    int fuse_gn = 1;
+    std::vector<ResnetDesc> resnets;
+    std::vector<int> down_after;
+    std::map<std::string, std::vector<float>> host;
+    std::map<std::string, ConvW> convs;
+    std::map<std::string, float*> vecs;
+    bool finalized = false, prepared = false;
+    // workspace
+    uint8_t* ws = nullptr;
+    size_t ws_bytes = 0;
+    size_t o_x0 = 0, o_attn_out = 0, o_xn = 0, o_qkv = 0, o_vt = 0, o_S = 0, o_P = 0, o_O = 0;
+    size_t o_PT = 0, o_dS = 0, o_dST = 0, o_dO = 0, o_dOT = 0, o_KT = 0, o_QT = 0, o_dqkv = 0;
+    size_t o_act = 0, o_act2 = 0, o_sc = 0, o_g[4] = {0, 0, 0, 0}, o_logits = 0, o_dlogits = 0, o_gn = 0;
+    std::vector<size_t> o_res_h1, o_res_out, o_down_out;
+    int n_gn = 0;
+    uint8_t* x_last = nullptr;
+    float last_in_scale = 1.f;
+    int last_B = 0;
+    std::vector<TapGemmOp> fwd_ops, bwd_ops;
+
+    ~Decoder();
+    int init(const wfd_decoder_config& c, int h, int w, int B_max, int dtype16);
+    void layout_workspace();
+    int set_weight(const char* key, const float* data, long long numel);
+    int finalize_weights();
+    int bind_workspace(void* p, size_t bytes);
+    int forward(const void* z, int z_dtype, int B, float in_scale, cudaStream_t s);
+    int backward(const void* dlogits, int B, const float* scale_b, float* dz, cudaStream_t s);
+
+    // internals
+    int need(const std::string& key, long long numel, const std::vector<float>** out);
+    int pack_named_conv(const std::string& name, int cout, int cin, int groups, int k, bool want_bwd, int fwd_mode);
+    int upload_vec(const std::string& key, long long numel);
+    int prepare_ops();
+    int run_gemm(Exec& ex, TapGemmOp& tmpl, bool z_is_batch);
+    int conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int Hin, int Win, int Hout, int Wout, void* out,
+                  long long ldc, const float* bias, const void* residual, float* gn_sums, int gn_cpg);
+    int plain_gemm(Exec& ex, const PlainGemm& g);
+    float* gn_sums_ptr(int idx) const;
+    float* gn_red_ptr(int idx) const;
+    int forward_impl(Exec& ex, const void* z, int z_f16, float in_scale);
+    int backward_impl(Exec& ex, const void* dlogits, const float* scale_b, float* dz);
+};
+
+// WFC loss handle: packed adjacency operand [T_pad rows][4 * T_pad] = [Ax | Ax^T | Ay | Ay^T] (0/1), see wfc.cu
+struct WfcSavedHeader {  // host-side record of the last forward (what backward needs to know)
+    int B = 0, H = 0, W = 0, is_logits = 0;
+    float coef = 0.f;
+    const void* wave = nullptr;  // the wave operand (inside saved, or the caller's pointer when is_logits == 0)
+};
+
+struct Wfc {
+    int T = 0, T_pad = 0, bf16 = 1;
+    WfcSavedHeader hdr_host;
+    void* hdr_saved = nullptr;
+    uint16_t* Bm = nullptr;
+    // last prepared contraction (tensor maps depend on the buffers of the call)
+    TapGemmOp op;
+    const void* op_wave = nullptr;
+    void* op_a = nullptr;
+    int op_B = 0, op_H = 0, op_W = 0;
+    ~Wfc();
+    int init(const uint8_t* mat_x, const uint8_t* mat_y, int T, int T_pad, int dtype16);
+    size_t saved_bytes(int B, int H, int W) const;
+    int forward(const void* in, int is_logits, int B, int H, int W, float strength, void* saved, float* loss,
+                cudaStream_t s);
+    int backward(void* saved, const float* dloss, void* dout, cudaStream_t s);
+};
+}  // namespace wfd

@@ -1,0 +1,948 @@
+// HBM-bound kernels of the WFC-guidance path. See kernels.cuh for the contract of each entry.
+#include "kernels.cuh"
+#include "tapgemm.cuh"  // set_error, num_sms
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math.h>
+
+namespace wfd {
+
+#define WFD_CHECK_LAUNCH(name)                                          \
+    do {                                                                \
+        cudaError_t e__ = cudaGetLastError();                           \
+        if (e__ != cudaSuccess) {                                       \
+            set_error("%s launch: %s", name, cudaGetErrorString(e__));  \
+            return -7;                                                  \
+        }                                                               \
+        ++g_launch_count;                                               \
+    } while (0)
+
+#define WFD_DISPATCH_BF16(flag, ...)      \
+    do {                                  \
+        if (flag) {                       \
+            constexpr bool BF16 = true;   \
+            __VA_ARGS__;                  \
+        } else {                          \
+            constexpr bool BF16 = false;  \
+            __VA_ARGS__;                  \
+        }                                 \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ 16-bit helpers
+template <bool BF16>
+__device__ __forceinline__ float u16_to_f(uint32_t v) {
+    if (BF16) return __uint_as_float(v << 16);
+    return __half2float(__ushort_as_half(static_cast<unsigned short>(v & 0xFFFF)));
+}
+template <bool BF16>
+__device__ __forceinline__ uint16_t f_to_u16(float f) {
+    if (BF16) {
+        __nv_bfloat16 h = __float2bfloat16_rn(f);
+        return *reinterpret_cast<uint16_t*>(&h);
+    }
+    __half h = __float2half_rn(f);
+    return *reinterpret_cast<uint16_t*>(&h);
+}
+template <bool BF16>
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        f[2 * j] = u16_to_f<BF16>(w[j] & 0xFFFF);
+        f[2 * j + 1] = u16_to_f<BF16>(w[j] >> 16);
+    }
+}
+template <bool BF16>
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        w[j] = static_cast<uint32_t>(f_to_u16<BF16>(f[2 * j])) | (static_cast<uint32_t>(f_to_u16<BF16>(f[2 * j + 1])) << 16);
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm
+constexpr int GN_THREADS = 384;
+constexpr int GN_MAXG = 32;
+
+struct GnMap {  // thread -> (vector column(s), row lane) mapping shared by the four GN kernels
+    int nv, cpt, nvt, R;
+};
+__host__ __device__ inline GnMap gn_map(int C) {
+    GnMap m;
+    m.nv = C / 8;
+    m.cpt = (m.nv + GN_THREADS - 1) / GN_THREADS;
+    m.nvt = (m.nv + m.cpt - 1) / m.cpt;
+    m.R = GN_THREADS / m.nvt;
+    return m;
+}
+__device__ __forceinline__ void gn_finalize(const float* sums, int b, int g, int G, double n, float eps, float& mean,
+                                            float& rstd) {
+    const double s = sums[(b * G + g) * 2], ss = sums[(b * G + g) * 2 + 1];
+    const double m = s / n;
+    double var = ss / n - m * m;
+    if (var < 0) var = 0;
+    mean = static_cast<float>(m);
+    rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_k(const uint4* __restrict__ x, float* __restrict__ sums, int HW,
+                                                          int C, int G, int ppb) {
+    __shared__ float sh[2 * GN_MAXG];
+    const GnMap m = gn_map(C);
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * ppb, p1 = min(HW, p0 + ppb);
+    const int tcol = threadIdx.x % m.nvt, trow = threadIdx.x / m.nvt;
+    const int cpg = C / G;
+    if (threadIdx.x < 2 * G) sh[threadIdx.x] = 0.f;
+    __syncthreads();
+    if (trow < m.R) {
+        for (int k = 0; k < m.cpt; ++k) {
+            const int col = tcol + k * m.nvt;
+            if (col >= m.nv) break;
+            float s = 0.f, ss = 0.f;
+            const uint4* px = x + (static_cast<long long>(b) * HW) * m.nv + col;
+            for (int p = p0 + trow; p < p1; p += m.R) {
+                float f[8];
+                unpack8<BF16>(__ldg(px + static_cast<long long>(p) * m.nv), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    s += f[j];
+                    ss += f[j] * f[j];
+                }
+            }
+            const int g = (col * 8) / cpg;
+            atomicAdd(&sh[2 * g], s);
+            atomicAdd(&sh[2 * g + 1], ss);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * G) atomicAdd(&sums[b * G * 2 + threadIdx.x], sh[threadIdx.x]);
+}
+
+__device__ __forceinline__ float sigmoidf_(float u) { return 1.f / (1.f + __expf(-u)); }
+
+template <bool BF16>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_k(const uint4* __restrict__ x, const float* __restrict__ sums, const float* __restrict__ gamma,
+           const float* __restrict__ beta, uint4* __restrict__ y, int HW, int C, int G, float eps, int silu, int ppb) {
+    const GnMap m = gn_map(C);
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * ppb, p1 = min(HW, p0 + ppb);
+    const int tcol = threadIdx.x % m.nvt, trow = threadIdx.x / m.nvt;
+    const int cpg = C / G;
+    if (trow >= m.R) return;
+    for (int k = 0; k < m.cpt; ++k) {
+        const int col = tcol + k * m.nvt;
+        if (col >= m.nv) break;
+        float mean, rstd;
+        gn_finalize(sums, b, (col * 8) / cpg, G, static_cast<double>(cpg) * HW, eps, mean, rstd);
+        float sc[8], sh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float ga = __ldg(gamma + col * 8 + j);
+            sc[j] = rstd * ga;
+            sh[j] = __ldg(beta + col * 8 + j) - mean * rstd * ga;
+        }
+        const long long base = (static_cast<long long>(b) * HW) * m.nv + col;
+        for (int p = p0 + trow; p < p1; p += m.R) {
+            float f[8];
+            unpack8<BF16>(__ldg(x + base + static_cast<long long>(p) * m.nv), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float u = f[j] * sc[j] + sh[j];
+                f[j] = silu ? u * sigmoidf_(u) : u;
+            }
+            y[base + static_cast<long long>(p) * m.nv] = pack8<BF16>(f);
+        }
+    }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_bwd_reduce_k(const uint4* __restrict__ dy, const uint4* __restrict__ x, const float* __restrict__ sums,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ red, int HW,
+                int C, int G, float eps, int silu, int ppb) {
+    __shared__ float sh[2 * GN_MAXG];
+    const GnMap m = gn_map(C);
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * ppb, p1 = min(HW, p0 + ppb);
+    const int tcol = threadIdx.x % m.nvt, trow = threadIdx.x / m.nvt;
+    const int cpg = C / G;
+    if (threadIdx.x < 2 * G) sh[threadIdx.x] = 0.f;
+    __syncthreads();
+    if (trow < m.R) {
+        for (int k = 0; k < m.cpt; ++k) {
+            const int col = tcol + k * m.nvt;
+            if (col >= m.nv) break;
+            const int g = (col * 8) / cpg;
+            float mean, rstd;
+            gn_finalize(sums, b, g, G, static_cast<double>(cpg) * HW, eps, mean, rstd);
+            float ga[8], be[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                ga[j] = __ldg(gamma + col * 8 + j);
+                be[j] = __ldg(beta + col * 8 + j);
+            }
+            float s1 = 0.f, s2 = 0.f;
+            const long long base = (static_cast<long long>(b) * HW) * m.nv + col;
+            for (int p = p0 + trow; p < p1; p += m.R) {
+                float fx[8], fd[8];
+                unpack8<BF16>(__ldg(x + base + static_cast<long long>(p) * m.nv), fx);
+                unpack8<BF16>(__ldg(dy + base + static_cast<long long>(p) * m.nv), fd);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float xh = (fx[j] - mean) * rstd;
+                    float du = fd[j];
+                    if (silu) {
+                        const float u = xh * ga[j] + be[j];
+                        const float sg = sigmoidf_(u);
+                        du *= sg * (1.f + u * (1.f - sg));
+                    }
+                    const float t = du * ga[j];
+                    s1 += t;
+                    s2 += t * xh;
+                }
+            }
+            atomicAdd(&sh[2 * g], s1);
+            atomicAdd(&sh[2 * g + 1], s2);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * G) atomicAdd(&red[b * G * 2 + threadIdx.x], sh[threadIdx.x]);
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_bwd_apply_k(const uint4* __restrict__ dy, const uint4* __restrict__ x, const float* __restrict__ sums,
+               const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ red,
+               const uint4* __restrict__ add, uint4* __restrict__ dx, int HW, int C, int G, float eps, int silu,
+               int ppb) {
+    const GnMap m = gn_map(C);
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * ppb, p1 = min(HW, p0 + ppb);
+    const int tcol = threadIdx.x % m.nvt, trow = threadIdx.x / m.nvt;
+    const int cpg = C / G;
+    if (trow >= m.R) return;
+    for (int k = 0; k < m.cpt; ++k) {
+        const int col = tcol + k * m.nvt;
+        if (col >= m.nv) break;
+        const int g = (col * 8) / cpg;
+        float mean, rstd;
+        const double n = static_cast<double>(cpg) * HW;
+        gn_finalize(sums, b, g, G, n, eps, mean, rstd);
+        const float inv_n = static_cast<float>(1.0 / n);
+        const float r1 = red[(b * G + g) * 2] * inv_n, r2 = red[(b * G + g) * 2 + 1] * inv_n;
+        float ga[8], be[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            ga[j] = __ldg(gamma + col * 8 + j);
+            be[j] = __ldg(beta + col * 8 + j);
+        }
+        const long long base = (static_cast<long long>(b) * HW) * m.nv + col;
+        for (int p = p0 + trow; p < p1; p += m.R) {
+            const long long idx = base + static_cast<long long>(p) * m.nv;
+            float fx[8], fd[8], fa[8];
+            unpack8<BF16>(__ldg(x + idx), fx);
+            unpack8<BF16>(__ldg(dy + idx), fd);
+            if (add) unpack8<BF16>(__ldg(add + idx), fa);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xh = (fx[j] - mean) * rstd;
+                float du = fd[j];
+                if (silu) {
+                    const float u = xh * ga[j] + be[j];
+                    const float sg = sigmoidf_(u);
+                    du *= sg * (1.f + u * (1.f - sg));
+                }
+                float v = rstd * (du * ga[j] - r1 - xh * r2);
+                if (add) v += fa[j];
+                fd[j] = v;
+            }
+            dx[idx] = pack8<BF16>(fd);
+        }
+    }
+}
+
+static int gn_check(int C, int G) {
+    if (C % 8 != 0 || G <= 0 || G > GN_MAXG || C % G != 0 || (C / G) % 8 != 0) {
+        set_error("GroupNorm kernels need C %% 8 == 0 and (C/G) %% 8 == 0 (C=%d G=%d)", C, G);
+        return -3;
+    }
+    return 0;
+}
+static void gn_grid(int B, int HW, int C, dim3& grid, int& ppb) {
+    const GnMap m = gn_map(C);
+    // aim at ~4 resident blocks per SM in total, each block looping over >= 8 of its row lanes
+    int blocks_x = (num_sms() * 4 + B - 1) / B;
+    int min_ppb = m.R * 8;
+    ppb = (HW + blocks_x - 1) / blocks_x;
+    if (ppb < min_ppb) ppb = min_ppb;
+    if (ppb > HW) ppb = HW;
+    blocks_x = (HW + ppb - 1) / ppb;
+    grid = dim3(blocks_x, B);
+}
+
+int gn_stats(const void* x, float* sums, int B, int HW, int C, int G, int bf16, cudaStream_t s) {
+    if (int r = gn_check(C, G)) return r;
+    dim3 grid;
+    int ppb;
+    gn_grid(B, HW, C, grid, ppb);
+    WFD_DISPATCH_BF16(bf16, (gn_stats_k<BF16><<<grid, GN_THREADS, 0, s>>>(static_cast<const uint4*>(x), sums, HW, C, G, ppb)));
+    WFD_CHECK_LAUNCH("gn_stats");
+    return 0;
+}
+int gn_apply(const void* x, const float* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C,
+             int G, float eps, int silu, int bf16, cudaStream_t s) {
+    if (int r = gn_check(C, G)) return r;
+    dim3 grid;
+    int ppb;
+    gn_grid(B, HW, C, grid, ppb);
+    WFD_DISPATCH_BF16(bf16, (gn_apply_k<BF16><<<grid, GN_THREADS, 0, s>>>(static_cast<const uint4*>(x), sums, gamma, beta,
+                                                                         static_cast<uint4*>(y), HW, C, G, eps, silu, ppb)));
+    WFD_CHECK_LAUNCH("gn_apply");
+    return 0;
+}
+int gn_bwd_reduce(const void* dy, const void* x, const float* sums, const float* gamma, const float* beta, float* red,
+                  int B, int HW, int C, int G, float eps, int silu, int bf16, cudaStream_t s) {
+    if (int r = gn_check(C, G)) return r;
+    dim3 grid;
+    int ppb;
+    gn_grid(B, HW, C, grid, ppb);
+    WFD_DISPATCH_BF16(bf16, (gn_bwd_reduce_k<BF16><<<grid, GN_THREADS, 0, s>>>(
+                                static_cast<const uint4*>(dy), static_cast<const uint4*>(x), sums, gamma, beta, red, HW,
+                                C, G, eps, silu, ppb)));
+    WFD_CHECK_LAUNCH("gn_bwd_reduce");
+    return 0;
+}
+int gn_bwd_apply(const void* dy, const void* x, const float* sums, const float* gamma, const float* beta,
+                 const float* red, const void* add, void* dx, int B, int HW, int C, int G, float eps, int silu,
+                 int bf16, cudaStream_t s) {
+    if (int r = gn_check(C, G)) return r;
+    dim3 grid;
+    int ppb;
+    gn_grid(B, HW, C, grid, ppb);
+    WFD_DISPATCH_BF16(bf16, (gn_bwd_apply_k<BF16><<<grid, GN_THREADS, 0, s>>>(
+                                static_cast<const uint4*>(dy), static_cast<const uint4*>(x), sums, gamma, beta, red,
+                                static_cast<const uint4*>(add), static_cast<uint4*>(dx), HW, C, G, eps, silu, ppb)));
+    WFD_CHECK_LAUNCH("gn_bwd_apply");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ latent side
+// One block per (row segment of LI_PIX pixels, sample). u = pq(z*in_scale) is staged with a one-pixel halo.
+constexpr int LI_PIX = 16;
+template <bool BF16>
+__global__ void __launch_bounds__(128)
+latent_in_k(const void* __restrict__ z, int z_f16, float in_scale, const float* __restrict__ pq_w,
+            const float* __restrict__ pq_b, const float* __restrict__ w, const float* __restrict__ bias,
+            uint16_t* __restrict__ out, int h, int wd, int Cm) {
+    __shared__ float u[3][LI_PIX + 2][4];
+    const int b = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * LI_PIX;
+    for (int i = threadIdx.x; i < 3 * (LI_PIX + 2); i += blockDim.x) {
+        const int r = i / (LI_PIX + 2), c = i % (LI_PIX + 2);
+        const int yy = y + r - 1, xx = x0 + c - 1;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (yy >= 0 && yy < h && xx >= 0 && xx < wd) {
+            float zin[4];
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci) {
+                const long long idx = ((static_cast<long long>(b) * 4 + ci) * h + yy) * wd + xx;
+                zin[ci] = (z_f16 ? __half2float(reinterpret_cast<const __half*>(z)[idx])
+                                 : reinterpret_cast<const float*>(z)[idx]) * in_scale;
+            }
+#pragma unroll
+            for (int co = 0; co < 4; ++co) {
+                float a = pq_b[co];
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) a += pq_w[co * 4 + ci] * zin[ci];
+                v[co] = a;
+            }
+        }
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) u[r][c][ci] = v[ci];
+    }
+    __syncthreads();
+    for (int co = threadIdx.x; co < Cm; co += blockDim.x) {
+        float wr[36];
+#pragma unroll
+        for (int i = 0; i < 36; ++i) wr[i] = __ldg(w + co * 36 + i);  // [ci][ky][kx]
+        const float bs = __ldg(bias + co);
+        for (int px = 0; px < LI_PIX; ++px) {
+            if (x0 + px >= wd) break;
+            float a = bs;
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) a += wr[ci * 9 + ky * 3 + kx] * u[ky][px + kx][ci];
+            out[((static_cast<long long>(b) * h + y) * wd + x0 + px) * Cm + co] = f_to_u16<BF16>(a);
+        }
+    }
+}
+
+int latent_in(const void* z, int z_f16, float in_scale, const float* pq_w, const float* pq_b, const float* w,
+              const float* b, void* out, int B, int h, int wd, int Cm, int bf16, cudaStream_t s) {
+    dim3 grid((wd + LI_PIX - 1) / LI_PIX, h, B);
+    WFD_DISPATCH_BF16(bf16, (latent_in_k<BF16><<<grid, 128, 0, s>>>(z, z_f16, in_scale, pq_w, pq_b, w, b,
+                                                                   static_cast<uint16_t*>(out), h, wd, Cm)));
+    WFD_CHECK_LAUNCH("latent_in");
+    return 0;
+}
+
+// One warp per latent pixel: d_u[ci] = sum_{tap,co} dy[q - off(tap), co] * w[co, ci, tap]; dz = in_scale * pq_w^T d_u.
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+latent_out_k(const uint16_t* __restrict__ dy, float in_scale, const float* __restrict__ scale_b,
+             const float* __restrict__ pq_w, const float* __restrict__ w, float* __restrict__ dz, int B, int h, int wd,
+             int Cm) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int total = B * h * wd;
+    if (warp >= total) return;
+    const int b = warp / (h * wd);
+    const int pr = warp - b * h * wd;
+    const int y = pr / wd, x = pr - y * wd;
+    float du[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ky = 0; ky < 3; ++ky) {
+        const int ys = y - (ky - 1);
+        if (ys < 0 || ys >= h) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+            const int xs = x - (kx - 1);
+            if (xs < 0 || xs >= wd) continue;
+            const uint16_t* row = dy + ((static_cast<long long>(b) * h + ys) * wd + xs) * Cm;
+            for (int co = lane; co < Cm; co += 32) {
+                const float g = u16_to_f<BF16>(row[co]);
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) du[ci] += g * __ldg(w + co * 36 + ci * 9 + ky * 3 + kx);
+            }
+        }
+    }
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) du[ci] = warp_sum(du[ci]);
+    if (lane < 4) {
+        float a = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) a += pq_w[ci * 4 + lane] * du[ci];
+        a *= in_scale;
+        if (scale_b) a *= scale_b[b];
+        dz[((static_cast<long long>(b) * 4 + lane) * h + y) * wd + x] = a;
+    }
+}
+
+int latent_out(const void* dy, float in_scale, const float* scale_b, const float* pq_w, const float* w, float* dz,
+               int B, int h, int wd, int Cm, int bf16, cudaStream_t s) {
+    const long long warps = static_cast<long long>(B) * h * wd;
+    const int threads = 256;
+    const unsigned blocks = static_cast<unsigned>((warps * 32 + threads - 1) / threads);
+    WFD_DISPATCH_BF16(bf16, (latent_out_k<BF16><<<blocks, threads, 0, s>>>(static_cast<const uint16_t*>(dy), in_scale,
+                                                                         scale_b, pq_w, w, dz, B, h, wd, Cm)));
+    WFD_CHECK_LAUNCH("latent_out");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ wave softmax
+constexpr int WS_MAXV = 20;  // vectors of 8 per lane -> rows up to 5120 channels stay in registers
+template <bool BF16, bool SOFTMAX>
+__global__ void __launch_bounds__(256)
+wave_softmax_k(const uint4* __restrict__ logits, uint4* __restrict__ wave, float* __restrict__ rowsum, long long rows,
+               int T_pad, int T) {
+    const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int nv = T_pad / 8;
+    const uint4* src = logits + row * nv;
+    uint4 raw[WS_MAXV];
+#pragma unroll
+    for (int k = 0; k < WS_MAXV; ++k) {
+        const int v = lane + 32 * k;
+        if (v < nv) raw[k] = __ldg(src + v);
+    }
+    float inv = 1.f, mx = 0.f;
+    if (SOFTMAX) {
+        mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < WS_MAXV; ++k) {
+            if (lane + 32 * k < nv) {
+                float f[8];
+                unpack8<BF16>(raw[k], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mx = fmaxf(mx, f[j]);
+            }
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < WS_MAXV; ++k) {
+            if (lane + 32 * k < nv) {
+                float f[8];
+                unpack8<BF16>(raw[k], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sum += __expf(f[j] - mx);
+            }
+        }
+        sum = warp_sum(sum);
+        inv = 1.f / sum;
+    }
+    float st = 0.f;
+#pragma unroll
+    for (int k = 0; k < WS_MAXV; ++k) {
+        const int v = lane + 32 * k;
+        if (v < nv) {
+            float f[8];
+            unpack8<BF16>(raw[k], f);
+            uint4 o = raw[k];
+            if (SOFTMAX) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = __expf(f[j] - mx) * inv;
+                o = pack8<BF16>(f);
+                wave[row * nv + v] = o;
+                unpack8<BF16>(o, f);  // sum the rounded values, the ones the contraction will read
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (v * 8 + j < T) st += f[j];
+        }
+    }
+    st = warp_sum(st);
+    if (lane == 0) rowsum[row] = st;
+}
+
+static int wave_rows_launch(const void* in, void* wave, float* rowsum, long long rows, int T_pad, int T, int bf16,
+                            bool softmax, cudaStream_t s) {
+    if (T_pad % 8 != 0 || T_pad / 8 > 32 * WS_MAXV || T > T_pad) {
+        set_error("wave softmax: T_pad=%d must be a multiple of 8 and <= %d", T_pad, 8 * 32 * WS_MAXV);
+        return -3;
+    }
+    const int threads = 256;
+    const unsigned blocks = static_cast<unsigned>((rows * 32 + threads - 1) / threads);
+    if (softmax)
+        WFD_DISPATCH_BF16(bf16, (wave_softmax_k<BF16, true><<<blocks, threads, 0, s>>>(
+                                    static_cast<const uint4*>(in), static_cast<uint4*>(wave), rowsum, rows, T_pad, T)));
+    else
+        WFD_DISPATCH_BF16(bf16, (wave_softmax_k<BF16, false><<<blocks, threads, 0, s>>>(
+                                    static_cast<const uint4*>(in), static_cast<uint4*>(wave), rowsum, rows, T_pad, T)));
+    WFD_CHECK_LAUNCH("wave_softmax");
+    return 0;
+}
+int wave_softmax(const void* logits, void* wave, float* rowsum, long long rows, int T_pad, int T, int bf16,
+                 cudaStream_t s) {
+    return wave_rows_launch(logits, wave, rowsum, rows, T_pad, T, bf16, true, s);
+}
+int wave_rowsum(const void* wave, float* rowsum, long long rows, int T_pad, int T, int bf16, cudaStream_t s) {
+    return wave_rows_launch(wave, nullptr, rowsum, rows, T_pad, T, bf16, false, s);
+}
+
+// ------------------------------------------------------------------------------------------------ WFC finishing passes
+__device__ __forceinline__ float neighbour_sum(const float* __restrict__ S, int y, int x, int H, int W) {
+    float c = 0.f;
+    if (x + 1 < W) c += S[y * W + x + 1];
+    if (x > 0) c += S[y * W + x - 1];
+    if (y + 1 < H) c += S[(y + 1) * W + x];
+    if (y > 0) c += S[(y - 1) * W + x];
+    return c;
+}
+
+__global__ void __launch_bounds__(1024)
+wfc_loss_finish_k(const float* __restrict__ rowsum, const float* __restrict__ rowdot, float* __restrict__ loss, int H,
+                  int W, float coef) {
+    __shared__ double red[32];
+    const int b = blockIdx.x;
+    const float* S = rowsum + static_cast<long long>(b) * H * W;
+    const float* D = rowdot + static_cast<long long>(b) * H * W;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+        const int y = i / W, x = i - y * W;
+        acc += static_cast<double>(S[i]) * neighbour_sum(S, y, x, H, W) - D[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) loss[b] = static_cast<float>(0.5 * coef * v);
+    }
+}
+int wfc_loss_finish(const float* rowsum, const float* rowdot, float* loss, int B, int H, int W, float coef,
+                    cudaStream_t s) {
+    wfc_loss_finish_k<<<B, 1024, 0, s>>>(rowsum, rowdot, loss, H, W, coef);
+    WFD_CHECK_LAUNCH("wfc_loss_finish");
+    return 0;
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+wfc_grad_finish_k(const uint4* __restrict__ wave, const uint4* __restrict__ a, const float* __restrict__ rowsum,
+                  const float* __restrict__ rowdot, const float* __restrict__ dloss, uint4* __restrict__ dout, int B,
+                  int H, int W, int T_pad, int T, float coef, int through_softmax) {
+    const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long rows = static_cast<long long>(B) * H * W;
+    if (row >= rows) return;
+    const int b = static_cast<int>(row / (H * W));
+    const int pr = static_cast<int>(row - static_cast<long long>(b) * H * W);
+    const int y = pr / W, x = pr - y * W;
+    const float* S = rowsum + static_cast<long long>(b) * H * W;
+    const float c = neighbour_sum(S, y, x, H, W);
+    const float r = S[pr] * c - rowdot[row];
+    const float sc = coef * (dloss ? dloss[b] : 1.f);
+    const int nv = T_pad / 8;
+    for (int v = lane; v < nv; v += 32) {
+        float fa[8], fp[8];
+        unpack8<BF16>(__ldg(a + row * nv + v), fa);
+        if (through_softmax) unpack8<BF16>(__ldg(wave + row * nv + v), fp);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float g = (v * 8 + j < T ? c : 0.f) - fa[j];
+            fa[j] = through_softmax ? sc * fp[j] * (g - r) : sc * g;
+        }
+        dout[row * nv + v] = pack8<BF16>(fa);
+    }
+}
+int wfc_grad_finish(const void* wave, const void* a, const float* rowsum, const float* rowdot, const float* dloss,
+                    void* dout, int B, int H, int W, int T_pad, int T, float coef, int through_softmax, int bf16,
+                    cudaStream_t s) {
+    const long long rows = static_cast<long long>(B) * H * W;
+    const int threads = 256;
+    const unsigned blocks = static_cast<unsigned>((rows * 32 + threads - 1) / threads);
+    WFD_DISPATCH_BF16(bf16, (wfc_grad_finish_k<BF16><<<blocks, threads, 0, s>>>(
+                                static_cast<const uint4*>(wave), static_cast<const uint4*>(a), rowsum, rowdot, dloss,
+                                static_cast<uint4*>(dout), B, H, W, T_pad, T, coef, through_softmax)));
+    WFD_CHECK_LAUNCH("wfc_grad_finish");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ attention helpers
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+attn_softmax_k(const float* __restrict__ scores, uint16_t* __restrict__ probs, int n) {
+    __shared__ float red[2][8];
+    const long long row = blockIdx.x;
+    const float4* src = reinterpret_cast<const float4*>(scores + row * n);
+    const int nv = n / 4;
+    float m = -INFINITY, l = 0.f;
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+        const float4 f = __ldg(src + v);
+        const float vm = fmaxf(fmaxf(f.x, f.y), fmaxf(f.z, f.w));
+        if (vm > m) {
+            l *= __expf(m - vm);
+            m = vm;
+        }
+        l += __expf(f.x - m) + __expf(f.y - m) + __expf(f.z - m) + __expf(f.w - m);
+    }
+    const float wm = warp_max(m);
+    l *= (m == -INFINITY) ? 0.f : __expf(m - wm);
+    l = warp_sum(l);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        red[0][warp] = wm;
+        red[1][warp] = l;
+    }
+    __syncthreads();
+    float M = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) M = fmaxf(M, red[0][i]);
+    float L = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) L += red[1][i] * ((red[0][i] == -INFINITY) ? 0.f : __expf(red[0][i] - M));
+    const float inv = 1.f / L;
+    uint2* dst = reinterpret_cast<uint2*>(probs + row * n);
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+        const float4 f = __ldg(src + v);
+        uint2 o;
+        o.x = static_cast<uint32_t>(f_to_u16<BF16>(__expf(f.x - M) * inv)) |
+              (static_cast<uint32_t>(f_to_u16<BF16>(__expf(f.y - M) * inv)) << 16);
+        o.y = static_cast<uint32_t>(f_to_u16<BF16>(__expf(f.z - M) * inv)) |
+              (static_cast<uint32_t>(f_to_u16<BF16>(__expf(f.w - M) * inv)) << 16);
+        dst[v] = o;
+    }
+}
+int attn_softmax(const float* scores, void* probs, long long rows, int n, int bf16, cudaStream_t s) {
+    if (n % 4 != 0) {
+        set_error("attn_softmax: n=%d must be a multiple of 4", n);
+        return -3;
+    }
+    WFD_DISPATCH_BF16(bf16, (attn_softmax_k<BF16><<<static_cast<unsigned>(rows), 256, 0, s>>>(
+                                scores, static_cast<uint16_t*>(probs), n)));
+    WFD_CHECK_LAUNCH("attn_softmax");
+    return 0;
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+attn_softmax_bwd_k(const uint16_t* __restrict__ probs, const float* __restrict__ dp, uint16_t* __restrict__ ds, int n,
+                   float scale) {
+    __shared__ float red[8];
+    const long long row = blockIdx.x;
+    const float4* dsrc = reinterpret_cast<const float4*>(dp + row * n);
+    const uint2* psrc = reinterpret_cast<const uint2*>(probs + row * n);
+    const int nv = n / 4;
+    float acc = 0.f;
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+        const float4 d = __ldg(dsrc + v);
+        const uint2 p = __ldg(psrc + v);
+        acc += d.x * u16_to_f<BF16>(p.x & 0xFFFF) + d.y * u16_to_f<BF16>(p.x >> 16) +
+               d.z * u16_to_f<BF16>(p.y & 0xFFFF) + d.w * u16_to_f<BF16>(p.y >> 16);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    uint2* dst = reinterpret_cast<uint2*>(ds + row * n);
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+        const float4 d = __ldg(dsrc + v);
+        const uint2 p = __ldg(psrc + v);
+        const float o0 = u16_to_f<BF16>(p.x & 0xFFFF) * (d.x - tot) * scale;
+        const float o1 = u16_to_f<BF16>(p.x >> 16) * (d.y - tot) * scale;
+        const float o2 = u16_to_f<BF16>(p.y & 0xFFFF) * (d.z - tot) * scale;
+        const float o3 = u16_to_f<BF16>(p.y >> 16) * (d.w - tot) * scale;
+        uint2 o;
+        o.x = static_cast<uint32_t>(f_to_u16<BF16>(o0)) | (static_cast<uint32_t>(f_to_u16<BF16>(o1)) << 16);
+        o.y = static_cast<uint32_t>(f_to_u16<BF16>(o2)) | (static_cast<uint32_t>(f_to_u16<BF16>(o3)) << 16);
+        dst[v] = o;
+    }
+}
+int attn_softmax_bwd(const void* probs, const float* dp, void* ds, long long rows, int n, float scale, int bf16,
+                     cudaStream_t s) {
+    if (n % 4 != 0) {
+        set_error("attn_softmax_bwd: n=%d must be a multiple of 4", n);
+        return -3;
+    }
+    WFD_DISPATCH_BF16(bf16, (attn_softmax_bwd_k<BF16><<<static_cast<unsigned>(rows), 256, 0, s>>>(
+                                static_cast<const uint16_t*>(probs), dp, static_cast<uint16_t*>(ds), n, scale)));
+    WFD_CHECK_LAUNCH("attn_softmax_bwd");
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+transpose16_k(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int R, int C, long long ld_in,
+              long long zstride_in) {
+    __shared__ uint16_t tile[64][66];
+    const int z = blockIdx.z;
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    const uint16_t* src = in + z * zstride_in;
+    uint16_t* dst = out + static_cast<long long>(z) * R * C;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+    for (int i = ty; i < 64; i += 4) {
+        const int r = r0 + i, c = c0 + tx;
+        if (r < R && c < C) tile[i][tx] = src[static_cast<long long>(r) * ld_in + c];
+    }
+    __syncthreads();
+    for (int i = ty; i < 64; i += 4) {
+        const int c = c0 + i, r = r0 + tx;
+        if (r < R && c < C) dst[static_cast<long long>(c) * R + r] = tile[tx][i];
+    }
+}
+int transpose16(const void* in, void* out, int Z, int R, int C, long long ld_in, long long zstride_in, cudaStream_t s) {
+    dim3 grid((C + 63) / 64, (R + 63) / 64, Z);
+    transpose16_k<<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), R, C, ld_in,
+                                       zstride_in);
+    WFD_CHECK_LAUNCH("transpose16");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ argmax
+struct Best {
+    float v;
+    int i;
+    bool nan;
+};
+__device__ __forceinline__ void best_take(Best& b, float v, int i) {
+    // scanned in increasing index order: strict '>' keeps the first maximum, the first NaN wins over everything
+    if (b.nan) return;
+    if (v != v) {
+        b.v = v; b.i = i; b.nan = true;
+    } else if (b.i < 0 || v > b.v) {
+        b.v = v; b.i = i;
+    }
+}
+__device__ __forceinline__ bool best_better(const Best& a, const Best& b) {  // is a better than b
+    if (a.i < 0) return false;
+    if (b.i < 0) return true;
+    if (a.nan != b.nan) return a.nan;
+    if (a.nan) return a.i < b.i;
+    if (a.v != b.v) return a.v > b.v;
+    return a.i < b.i;
+}
+template <int DT>
+__global__ void __launch_bounds__(256) argmax_rows_k(const void* __restrict__ x, long long rows, int n,
+                                                     long long* __restrict__ out) {
+    const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    Best b;
+    b.v = 0.f; b.i = -1; b.nan = false;
+    if (DT == 0) {
+        const float* src = reinterpret_cast<const float*>(x) + row * n;
+        const int nv = n / 4;
+        for (int v = lane; v < nv; v += 32) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(src) + v);
+            best_take(b, f.x, v * 4); best_take(b, f.y, v * 4 + 1); best_take(b, f.z, v * 4 + 2); best_take(b, f.w, v * 4 + 3);
+        }
+        for (int i = nv * 4 + lane; i < n; i += 32) best_take(b, src[i], i);
+    } else {
+        const uint16_t* src = reinterpret_cast<const uint16_t*>(x) + row * n;
+        const int nv = n / 8;
+        for (int v = lane; v < nv; v += 32) {
+            float f[8];
+            if (DT == 2) unpack8<true>(__ldg(reinterpret_cast<const uint4*>(src) + v), f);
+            else unpack8<false>(__ldg(reinterpret_cast<const uint4*>(src) + v), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) best_take(b, f[j], v * 8 + j);
+        }
+        for (int i = nv * 8 + lane; i < n; i += 32)
+            best_take(b, DT == 2 ? u16_to_f<true>(src[i]) : u16_to_f<false>(src[i]), i);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Best c;
+        c.v = __shfl_xor_sync(0xffffffffu, b.v, o);
+        c.i = __shfl_xor_sync(0xffffffffu, b.i, o);
+        c.nan = __shfl_xor_sync(0xffffffffu, static_cast<int>(b.nan), o) != 0;
+        if (best_better(c, b)) b = c;
+    }
+    if (lane == 0) out[row] = b.i < 0 ? 0 : b.i;
+}
+int argmax_rows(const void* x, int dtype, long long rows, int n, long long* out, cudaStream_t s) {
+    if ((dtype == 0 && n % 4 != 0) || (dtype != 0 && n % 8 != 0)) {
+        // the vector loads need 16-byte aligned rows
+        set_error("argmax_rows: row length %d not aligned for vector loads", n);
+        return -3;
+    }
+    const int threads = 256;
+    const unsigned blocks = static_cast<unsigned>((rows * 32 + threads - 1) / threads);
+    if (rows == 0) return 0;
+    if (dtype == 0) argmax_rows_k<0><<<blocks, threads, 0, s>>>(x, rows, n, out);
+    else if (dtype == 1) argmax_rows_k<1><<<blocks, threads, 0, s>>>(x, rows, n, out);
+    else if (dtype == 2) argmax_rows_k<2><<<blocks, threads, 0, s>>>(x, rows, n, out);
+    else {
+        set_error("argmax_rows: unknown dtype %d", dtype);
+        return -3;
+    }
+    WFD_CHECK_LAUNCH("argmax_rows");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ layout conversion
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc16_k(const void* __restrict__ in, int in_f16, uint16_t* __restrict__ out, int C, int HW) {
+    __shared__ float tile[64][65];
+    const int b = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    for (int i = ty; i < 64; i += 4) {
+        const int c = c0 + i, p = p0 + tx;
+        if (c < C && p < HW) {
+            const long long idx = (static_cast<long long>(b) * C + c) * HW + p;
+            tile[i][tx] = in_f16 ? __half2float(reinterpret_cast<const __half*>(in)[idx])
+                                 : reinterpret_cast<const float*>(in)[idx];
+        }
+    }
+    __syncthreads();
+    for (int i = ty; i < 64; i += 4) {
+        const int p = p0 + i, c = c0 + tx;
+        if (c < C && p < HW) out[(static_cast<long long>(b) * HW + p) * C + c] = f_to_u16<BF16>(tile[tx][i]);
+    }
+}
+int nchw_to_nhwc16(const void* in, int in_f16, void* out, int B, int C, int HW, int bf16, cudaStream_t s) {
+    dim3 grid((HW + 63) / 64, (C + 63) / 64, B);
+    WFD_DISPATCH_BF16(bf16, (nchw_to_nhwc16_k<BF16><<<grid, 256, 0, s>>>(in, in_f16, static_cast<uint16_t*>(out), C, HW)));
+    WFD_CHECK_LAUNCH("nchw_to_nhwc16");
+    return 0;
+}
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+nhwc16_to_nchw_k(const uint16_t* __restrict__ in, void* __restrict__ out, int out_f16, int C, int HW) {
+    __shared__ float tile[64][65];
+    const int b = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    for (int i = ty; i < 64; i += 4) {
+        const int p = p0 + i, c = c0 + tx;
+        if (c < C && p < HW) tile[i][tx] = u16_to_f<BF16>(in[(static_cast<long long>(b) * HW + p) * C + c]);
+    }
+    __syncthreads();
+    for (int i = ty; i < 64; i += 4) {
+        const int c = c0 + i, p = p0 + tx;
+        if (c < C && p < HW) {
+            const long long idx = (static_cast<long long>(b) * C + c) * HW + p;
+            if (out_f16) reinterpret_cast<__half*>(out)[idx] = __float2half_rn(tile[tx][i]);
+            else reinterpret_cast<float*>(out)[idx] = tile[tx][i];
+        }
+    }
+}
+int nhwc16_to_nchw(const void* in, void* out, int out_f16, int B, int C, int HW, int bf16, cudaStream_t s) {
+    dim3 grid((HW + 63) / 64, (C + 63) / 64, B);
+    WFD_DISPATCH_BF16(bf16, (nhwc16_to_nchw_k<BF16><<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(in), out, out_f16, C, HW)));
+    WFD_CHECK_LAUNCH("nhwc16_to_nchw");
+    return 0;
+}
+
+template <bool BF16>
+__global__ void cvt16_to_f32_k(const uint16_t* __restrict__ in, float* __restrict__ out, long long n) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        out[i] = u16_to_f<BF16>(in[i]);
+}
+template <bool BF16>
+__global__ void cvt_f32_to_16_k(const float* __restrict__ in, uint16_t* __restrict__ out, long long n) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        out[i] = f_to_u16<BF16>(in[i]);
+}
+template <bool BF16>
+__global__ void add16_k(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out, long long nv) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nv;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float fa[8], fb[8];
+        unpack8<BF16>(__ldg(a + i), fa);
+        unpack8<BF16>(__ldg(b + i), fb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) fa[j] += fb[j];
+        out[i] = pack8<BF16>(fa);
+    }
+}
+static unsigned ew_blocks(long long n, int threads) {
+    long long b = (n + threads - 1) / threads;
+    const long long cap = static_cast<long long>(num_sms()) * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return static_cast<unsigned>(b);
+}
+int cvt16_to_f32(const void* in, float* out, long long n, int bf16, cudaStream_t s) {
+    WFD_DISPATCH_BF16(bf16, (cvt16_to_f32_k<BF16><<<ew_blocks(n, 256), 256, 0, s>>>(static_cast<const uint16_t*>(in), out, n)));
+    WFD_CHECK_LAUNCH("cvt16_to_f32");
+    return 0;
+}
+int cvt_f32_to_16(const float* in, void* out, long long n, int bf16, cudaStream_t s) {
+    WFD_DISPATCH_BF16(bf16, (cvt_f32_to_16_k<BF16><<<ew_blocks(n, 256), 256, 0, s>>>(in, static_cast<uint16_t*>(out), n)));
+    WFD_CHECK_LAUNCH("cvt_f32_to_16");
+    return 0;
+}
+int add16(const void* a, const void* b, void* out, long long n, int bf16, cudaStream_t s) {
+    if (n % 8 != 0) {
+        set_error("add16: n must be a multiple of 8");
+        return -3;
+    }
+    WFD_DISPATCH_BF16(bf16, (add16_k<BF16><<<ew_blocks(n / 8, 256), 256, 0, s>>>(
+                                static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<uint4*>(out), n / 8)));
+    WFD_CHECK_LAUNCH("add16");
+    return 0;
+}
+
+}  // namespace wfd

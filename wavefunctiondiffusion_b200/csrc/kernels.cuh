@@ -1,0 +1,66 @@
+// HBM-bound kernels of the WFC-guidance path (everything that is not a tensor-core contraction):
+// GroupNorm(+SiLU) forward/backward, row softmax, WFC finishing passes, argmax, layout conversion, the 4-channel
+// latent-side convs. All tensors are channels-last: [B, H*W, C] with 16-bit elements unless stated otherwise.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wfd {
+
+// ---- GroupNorm (8 groups in the tile VAE; reference resnet.py:407,423, attention.py:278, wf_vae.py:212), eps 1e-6
+// sums: [B, G, 2] fp32 {sum, sumsq}, zeroed by the caller before accumulation.
+int gn_stats(const void* x, float* sums, int B, int HW, int C, int G, int bf16, cudaStream_t s);
+// y = act((x - mean) * rstd * gamma + beta), act = SiLU if silu else identity
+int gn_apply(const void* x, const float* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C,
+             int G, float eps, int silu, int bf16, cudaStream_t s);
+// red: [B, G, 2] fp32 {sum(du*gamma), sum(du*gamma*xhat)}, zeroed by the caller; du = dy * act'(u)
+int gn_bwd_reduce(const void* dy, const void* x, const float* sums, const float* gamma, const float* beta, float* red,
+                  int B, int HW, int C, int G, float eps, int silu, int bf16, cudaStream_t s);
+// dx = rstd * (du*gamma - (red0 + xhat*red1)/n) (+ add)
+int gn_bwd_apply(const void* dy, const void* x, const float* sums, const float* gamma, const float* beta,
+                 const float* red, const void* add, void* dx, int B, int HW, int C, int G, float eps, int silu,
+                 int bf16, cudaStream_t s);
+
+// ---- latent side (reference wf_vae.py:593 post_quant_conv 1x1 4->4, wf_vae.py:218 conv_in 3x3 4->Cm)
+// z: NCHW [B,4,h,w] fp32 (z_f16=0) or fp16 (z_f16=1); out: [B, h*w, Cm] 16-bit. pq_w [4,4], pq_b [4], w [Cm,4,3,3], b [Cm]
+int latent_in(const void* z, int z_f16, float in_scale, const float* pq_w, const float* pq_b, const float* w,
+              const float* b, void* out, int B, int h, int wd, int Cm, int bf16, cudaStream_t s);
+// dz[b,c,y,x] (fp32 NCHW) = in_scale * pq_w^T conv_in^T(dy); dy: [B, h*w, Cm] 16-bit; scale_b: optional per-sample scale
+int latent_out(const void* dy, float in_scale, const float* scale_b, const float* pq_w, const float* w, float* dz,
+               int B, int h, int wd, int Cm, int bf16, cudaStream_t s);
+
+// ---- wave softmax over all T_pad channels (reference pipeline_wfd.py:405); rowsum[n] = sum_{i<T} p~[n,i] of the
+// rounded 16-bit values that feed the contraction.
+int wave_softmax(const void* logits, void* wave, float* rowsum, long long rows, int T_pad, int T, int bf16,
+                 cudaStream_t s);
+// rowsum only (wave given, e.g. WFCLossEinsum(wave) called directly)
+int wave_rowsum(const void* wave, float* rowsum, long long rows, int T_pad, int T, int bf16, cudaStream_t s);
+// loss[b] = coef * 0.5 * sum_n (S_n * c_n - rowdot_a[n]),  c_n = sum of S over the <=4 in-map neighbours
+int wfc_loss_finish(const float* rowsum, const float* rowdot, float* loss, int B, int H, int W, float coef,
+                    cudaStream_t s);
+// grad wrt wave (no softmax): dwave[n,i] = coef*dloss[b] * ([i<T]*c_n - a[n,i]);
+// grad wrt logits (softmax bwd): dlogits[n,i] = coef*dloss[b] * p[n,i] * (([i<T]*c_n - a[n,i]) - (S_n*c_n - rowdot_a[n]))
+int wfc_grad_finish(const void* wave, const void* a, const float* rowsum, const float* rowdot, const float* dloss,
+                    void* dout, int B, int H, int W, int T_pad, int T, float coef, int through_softmax, int bf16,
+                    cudaStream_t s);
+
+// ---- attention helpers (reference attention.py:354-368: scores -> fp32 softmax -> probs)
+int attn_softmax(const float* scores, void* probs, long long rows, int n, int bf16, cudaStream_t s);
+// ds = p * (dp - sum_j dp*p) * scale
+int attn_softmax_bwd(const void* probs, const float* dp, void* ds, long long rows, int n, float scale, int bf16,
+                     cudaStream_t s);
+// batched 16-bit transpose: in [Z, R, C] (row stride ld_in) -> out [Z, C, R]
+int transpose16(const void* in, void* out, int Z, int R, int C, long long ld_in, long long zstride_in, cudaStream_t s);
+
+// ---- argmax over the last axis, numpy semantics (first max wins, NaN is max); dtype: 0 fp32, 1 fp16, 2 bf16
+int argmax_rows(const void* x, int dtype, long long rows, int n, long long* out, cudaStream_t s);
+
+// ---- layout conversion at the API boundary: NCHW (fp32/fp16) <-> channels-last 16-bit
+int nchw_to_nhwc16(const void* in, int in_f16, void* out, int B, int C, int HW, int bf16, cudaStream_t s);
+int nhwc16_to_nchw(const void* in, void* out, int out_f16, int B, int C, int HW, int bf16, cudaStream_t s);
+// 16-bit -> fp32 (same layout) and generic helpers
+int cvt16_to_f32(const void* in, float* out, long long n, int bf16, cudaStream_t s);
+int cvt_f32_to_16(const float* in, void* out, long long n, int bf16, cudaStream_t s);
+int add16(const void* a, const void* b, void* out, long long n, int bf16, cudaStream_t s);
+
+}  // namespace wfd

@@ -1,0 +1,491 @@
+// tapgemm kernel (tcgen05 + TMA + TMEM), its launcher and the CUDA-core checking kernel. See tapgemm.cuh.
+#include "tapgemm.cuh"
+#include "ptx.cuh"
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace wfd {
+
+// ------------------------------------------------------------------------------------------------ error plumbing
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+long long g_launch_count = 0;
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------ device helpers
+template <bool BF16>
+__device__ __forceinline__ float lo16_to_f(uint32_t v) {
+    if (BF16) return __uint_as_float(v << 16);
+    return __half2float(__ushort_as_half(static_cast<unsigned short>(v & 0xFFFF)));
+}
+template <bool BF16>
+__device__ __forceinline__ float hi16_to_f(uint32_t v) {
+    if (BF16) return __uint_as_float(v & 0xFFFF0000u);
+    return __half2float(__ushort_as_half(static_cast<unsigned short>(v >> 16)));
+}
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    if (BF16) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+struct TileCoord {
+    int z, n_tile, bb, ty, tx;
+};
+__device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int t) {
+    TileCoord c;
+    int m_tile = t % p.m_tiles;
+    int rest = t / p.m_tiles;
+    c.n_tile = rest % p.n_tiles;
+    c.z = rest / p.n_tiles;
+    c.tx = m_tile % p.tiles_x;
+    int r2 = m_tile / p.tiles_x;
+    c.ty = r2 % p.tiles_y;
+    c.bb = r2 / p.tiles_y;
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <bool BF16>
+__global__ void __launch_bounds__(TG_THREADS, 1)
+tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ TapGemmParams p, const int stages) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment is required by the 128B swizzle atoms.
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t a_stage_bytes = TG_BM * 128;
+    const uint32_t b_stage_bytes = static_cast<uint32_t>(p.BN) * 128;
+    uint8_t* smA = smem;
+    uint8_t* smB = smem + static_cast<size_t>(stages) * a_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + static_cast<size_t>(stages) * b_stage_bytes);
+    uint64_t* full_bar = bars;                 // [stages]
+    uint64_t* empty_bar = bars + stages;       // [stages]
+    uint64_t* tfull_bar = bars + 2 * stages;   // [2]
+    uint64_t* tempty_bar = bars + 2 * stages + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_tiles = p.m_tiles * p.n_tiles * p.z_count;
+    const int k_iters = p.n_taps * p.cpt;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(p, t);
+                const int c0 = p.a_c0 ? __ldg(p.a_c0 + tc.n_tile) : 0;
+                const int x0 = tc.tx * p.w_box * p.in_stride;
+                const int y0 = tc.ty * p.h_box * p.in_stride;
+                const int ab = tc.bb + tc.z * p.a_zmul;
+                const int bz = tc.z * p.b_zmul + tc.bb * p.b_bbmul;
+                const int n0 = tc.n_tile * p.BN;
+                for (int tap = 0; tap < p.n_taps; ++tap) {
+                    const int xx = x0 + p.tap_dx[tap];
+                    const int yy = y0 + p.tap_dy[tap];
+                    for (int cc = 0; cc < p.cpt; ++cc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&full_bar[stage], a_stage_bytes + b_stage_bytes);
+                        tma_load_4d(smA + static_cast<size_t>(stage) * a_stage_bytes, &tmA, &full_bar[stage],
+                                    c0 + cc * TG_KC, xx, yy, ab);
+                        tma_load_3d(smB + static_cast<size_t>(stage) * b_stage_bytes, &tmB, &full_bar[stage],
+                                    (tap * p.cpt + cc) * TG_KC, n0, bz);
+                        if (++stage == stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer (one thread)
+        const uint32_t idesc = make_idesc_f16(TG_BM, static_cast<uint32_t>(p.BN), BF16 ? 1u : 0u);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
+            for (int kc = 0; kc < k_iters; ++kc) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint64_t adesc =
+                        make_kmajor_desc(smem_u32(smA + static_cast<size_t>(stage) * a_stage_bytes), 128);
+                    const uint64_t bdesc =
+                        make_kmajor_desc(smem_u32(smB + static_cast<size_t>(stage) * b_stage_bytes), 128);
+#pragma unroll
+                    for (int k = 0; k < TG_KC / 16; ++k) {
+                        // advancing 16 elements (32 bytes) along K inside the swizzle atom: +2 in 16-byte units
+                        umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (kc == k_iters - 1) umma_commit(&tfull_bar[acc]);
+                }
+                __syncwarp();
+                if (++stage == stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    } else {
+        // ===================================================== epilogue (4 warps, one TMEM lane quarter each)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const TileCoord tc = decode_tile(p, t);
+            const int yy = row / p.w_box, xx = row - yy * p.w_box;
+            const long long pixel =
+                (static_cast<long long>(tc.bb) * p.H + tc.ty * p.h_box + yy) * p.W + tc.tx * p.w_box + xx;
+            const int n0 = tc.n_tile * p.BN;
+            const long long out_off = tc.z * p.c_zstride + tc.bb * p.out_sb +
+                                      static_cast<long long>(tc.ty * p.h_box + yy) * p.out_sy +
+                                      static_cast<long long>(tc.tx * p.w_box + xx) * p.out_sx;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * 256u + (static_cast<uint32_t>(q * 32) << 16);
+            float dot = 0.f;
+            float gs = 0.f, gss = 0.f;
+            int ggroup = -1;
+            for (int j0 = 0; j0 < p.BN; j0 += 16) {
+                const int n = n0 + j0;
+                if (n >= p.N) break;  // warp-uniform
+                uint32_t r[16];
+                tmem_ld16(taddr + j0, r);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+                if (p.bias) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                    }
+                }
+                if (p.residual) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(
+                        reinterpret_cast<const uint16_t*>(p.residual) + out_off + n);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint4 u = __ldg(rp + h);
+                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            v[h * 8 + 2 * j] += lo16_to_f<BF16>(w[j]);
+                            v[h * 8 + 2 * j + 1] += hi16_to_f<BF16>(w[j]);
+                        }
+                    }
+                }
+                if (p.rowdot) {
+                    const uint4* dp = reinterpret_cast<const uint4*>(
+                        reinterpret_cast<const uint16_t*>(p.dotsrc) + pixel * p.ld_dot + n);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint4 u = __ldg(dp + h);
+                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            dot += v[h * 8 + 2 * j] * lo16_to_f<BF16>(w[j]);
+                            dot += v[h * 8 + 2 * j + 1] * hi16_to_f<BF16>(w[j]);
+                        }
+                    }
+                }
+                if (p.out_fp32) {
+                    float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + n);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                } else {
+                    uint32_t w[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) w[j] = pack2<BF16>(v[2 * j], v[2 * j + 1]);
+                    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + out_off + n);
+                    op[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                    op[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                    if (p.gn_sums) {
+                        const int g = n / p.gn_cpg;
+                        if (g != ggroup) {
+                            if (ggroup >= 0) {
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) {
+                                    gs += __shfl_xor_sync(0xffffffffu, gs, o);
+                                    gss += __shfl_xor_sync(0xffffffffu, gss, o);
+                                }
+                                if (lane == 0) {
+                                    float* dst = p.gn_sums + (static_cast<long long>(tc.bb) * p.gn_G + ggroup) * 2;
+                                    atomicAdd(dst, gs);
+                                    atomicAdd(dst + 1, gss);
+                                }
+                            }
+                            ggroup = g;
+                            gs = 0.f;
+                            gss = 0.f;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float a = lo16_to_f<BF16>(w[j]), b = hi16_to_f<BF16>(w[j]);
+                            gs += a + b;
+                            gss += a * a + b * b;
+                        }
+                    }
+                }
+            }
+            if (p.gn_sums && ggroup >= 0) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    gs += __shfl_xor_sync(0xffffffffu, gs, o);
+                    gss += __shfl_xor_sync(0xffffffffu, gss, o);
+                }
+                if (lane == 0) {
+                    float* dst = p.gn_sums + (static_cast<long long>(tc.bb) * p.gn_G + ggroup) * 2;
+                    atomicAdd(dst, gs);
+                    atomicAdd(dst + 1, gss);
+                }
+            }
+            if (p.rowdot) atomicAdd(p.rowdot + pixel, dot);
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ checking kernel
+// One thread per output element; reads the same A / Bm buffers through raw pointers. Test infrastructure only.
+template <bool BF16>
+__global__ void tapgemm_ref_kernel(const TapGemmParams p) {
+    const long long rows_per_sample = static_cast<long long>(p.H) * p.W;
+    const long long total_rows = static_cast<long long>(p.m_tiles) * TG_BM;
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long per_z = total_rows * p.N;
+    if (idx >= per_z * p.z_count) return;
+    const int z = static_cast<int>(idx / per_z);
+    const long long rem = idx - z * per_z;
+    const long long pixel = rem / p.N;
+    const int n = static_cast<int>(rem - pixel * p.N);
+    const int bb = static_cast<int>(pixel / rows_per_sample);
+    const int pr = static_cast<int>(pixel - bb * rows_per_sample);
+    const int y = pr / p.W, x = pr - y * p.W;
+    const int n_tile = n / p.BN;
+    const int c0 = p.a_c0 ? p.a_c0[n_tile] : 0;
+    const int ab = bb + z * p.a_zmul;
+    const int bz = z * p.b_zmul + bb * p.b_bbmul;
+    const uint16_t* A = reinterpret_cast<const uint16_t*>(p.a_ptr);
+    const uint16_t* Bm = reinterpret_cast<const uint16_t*>(p.b_ptr) + bz * p.b_zstride + static_cast<long long>(n) * p.ldb;
+    float acc = 0.f;
+    for (int tap = 0; tap < p.n_taps; ++tap) {
+        const int xi = x * p.in_stride + p.tap_dx[tap];
+        const int yi = y * p.in_stride + p.tap_dy[tap];
+        if (xi < 0 || xi >= p.a_W || yi < 0 || yi >= p.a_H || ab >= p.a_B) continue;
+        const uint16_t* arow = A + ((static_cast<long long>(ab) * p.a_H + yi) * p.a_W + xi) * p.a_ld;
+        for (int k = 0; k < p.cpt * TG_KC; ++k) {
+            const int c = c0 + k;
+            if (c >= p.a_C) break;
+            const float a = lo16_to_f<BF16>(arow[c]);
+            const float b = lo16_to_f<BF16>(Bm[static_cast<long long>(tap) * p.cpt * TG_KC + k]);
+            acc = fmaf(a, b, acc);
+        }
+    }
+    float v = acc * p.alpha;
+    if (p.bias) v += p.bias[n];
+    const long long off = z * p.c_zstride + bb * p.out_sb + static_cast<long long>(y) * p.out_sy +
+                          static_cast<long long>(x) * p.out_sx + n;
+    if (p.residual) v += lo16_to_f<BF16>(reinterpret_cast<const uint16_t*>(p.residual)[off]);
+    if (p.rowdot) atomicAdd(p.rowdot + pixel, v * lo16_to_f<BF16>(reinterpret_cast<const uint16_t*>(p.dotsrc)[pixel * p.ld_dot + n]));
+    if (p.out_fp32) {
+        reinterpret_cast<float*>(p.out)[off] = v;
+    } else {
+        const uint32_t w = pack2<BF16>(v, 0.f);
+        reinterpret_cast<uint16_t*>(p.out)[off] = static_cast<uint16_t>(w & 0xFFFF);
+        if (p.gn_sums) {
+            const float r = lo16_to_f<BF16>(w);
+            float* dst = p.gn_sums + (static_cast<long long>(bb) * p.gn_G + n / p.gn_cpg) * 2;
+            atomicAdd(dst, r);
+            atomicAdd(dst + 1, r * r);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+int tapgemm_prepare(TapGemmOp* op) {
+    TapGemmParams& p = op->p;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+        return -2;
+    }
+    if (p.BN % 16 != 0 || p.BN < 16 || p.BN > 256 || p.N % 16 != 0 || p.w_box * p.h_box != TG_BM ||
+        p.n_taps < 1 || p.n_taps > TG_MAX_TAPS || p.cpt < 1) {
+        set_error("tapgemm_prepare: bad tiling (BN=%d N=%d box=%dx%d taps=%d cpt=%d)", p.BN, p.N, p.w_box, p.h_box,
+                  p.n_taps, p.cpt);
+        return -3;
+    }
+    const CUtensorMapDataType dt = p.is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)p.a_C, (cuuint64_t)p.a_W, (cuuint64_t)p.a_H, (cuuint64_t)p.a_B};
+        cuuint64_t strides[3] = {(cuuint64_t)p.a_ld * 2, (cuuint64_t)p.a_ld * 2 * p.a_W,
+                                 (cuuint64_t)p.a_ld * 2 * p.a_W * p.a_H};
+        // strided traversal (stride-2 downsample conv): the box spans in_stride * (n - 1) + 1 input elements
+        cuuint32_t box[4] = {TG_KC, (cuuint32_t)((p.w_box - 1) * p.in_stride + 1),
+                             (cuuint32_t)((p.h_box - 1) * p.in_stride + 1), 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)p.in_stride, (cuuint32_t)p.in_stride, 1};
+        CUresult r = enc(&op->tmA, dt, 4, const_cast<void*>(p.a_ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled(A) failed: %d (C=%d W=%d H=%d B=%d ld=%lld box=%ux%u)", (int)r, p.a_C,
+                      p.a_W, p.a_H, p.a_B, p.a_ld, box[1], box[2]);
+            return -4;
+        }
+    }
+    {
+        const long long ktot = static_cast<long long>(p.n_taps) * p.cpt * TG_KC;
+        const int zdim = p.b_Z > 0 ? p.b_Z : 1;
+        cuuint64_t dims[3] = {(cuuint64_t)ktot, (cuuint64_t)p.b_rows, (cuuint64_t)zdim};
+        cuuint64_t strides[2] = {(cuuint64_t)p.ldb * 2, (cuuint64_t)(p.b_zstride > 0 ? p.b_zstride : p.ldb * p.b_rows) * 2};
+        cuuint32_t box[3] = {TG_KC, (cuuint32_t)p.BN, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&op->tmB, dt, 3, const_cast<void*>(p.b_ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled(B) failed: %d (ktot=%lld rows=%d ldb=%lld zstride=%lld BN=%d)", (int)r,
+                      ktot, p.b_rows, p.ldb, p.b_zstride, p.BN);
+            return -5;
+        }
+    }
+    const size_t per_stage = TG_BM * 128 + static_cast<size_t>(p.BN) * 128;
+    int stages = static_cast<int>((220 * 1024) / per_stage);
+    if (stages > 8) stages = 8;
+    if (stages < 2) stages = 2;
+    op->stages = stages;
+    op->smem_bytes = 1024 + stages * per_stage + (2 * stages + 4) * sizeof(uint64_t) + 16;
+    return 0;
+}
+
+int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream) {
+    const TapGemmParams& p = op->p;
+    static bool attr_set[2] = {false, false};
+    const int which = p.is_bf16 ? 1 : 0;
+    if (!attr_set[which]) {
+        cudaError_t e = p.is_bf16 ? cudaFuncSetAttribute(tapgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                                  : cudaFuncSetAttribute(tapgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(tapgemm): %s", cudaGetErrorString(e));
+            return -6;
+        }
+        attr_set[which] = true;
+    }
+    const int total = p.m_tiles * p.n_tiles * p.z_count;
+    if (total <= 0) return 0;
+    const int grid = total < num_sms() ? total : num_sms();
+    if (p.is_bf16)
+        tapgemm_kernel<true><<<grid, TG_THREADS, op->smem_bytes, stream>>>(op->tmA, op->tmB, op->p, op->stages);
+    else
+        tapgemm_kernel<false><<<grid, TG_THREADS, op->smem_bytes, stream>>>(op->tmA, op->tmB, op->p, op->stages);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("tapgemm launch: %s", cudaGetErrorString(e));
+        return -7;
+    }
+    ++g_launch_count;
+    return 0;
+}
+
+int tapgemm_launch_ref(const TapGemmOp* op, cudaStream_t stream) {
+    const TapGemmParams& p = op->p;
+    const long long total = static_cast<long long>(p.m_tiles) * TG_BM * p.N * p.z_count;
+    if (total <= 0) return 0;
+    const int threads = 256;
+    const long long blocks = (total + threads - 1) / threads;
+    if (p.is_bf16)
+        tapgemm_ref_kernel<true><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(op->p);
+    else
+        tapgemm_ref_kernel<false><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(op->p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("tapgemm_ref launch: %s", cudaGetErrorString(e));
+        return -7;
+    }
+    return 0;
+}
+
+}  // namespace wfd

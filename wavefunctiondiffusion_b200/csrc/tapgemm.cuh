@@ -1,0 +1,79 @@
+// tapgemm: the one tensor-core kernel of the WFC-guidance path.
+//
+//   D[m, n] = alpha * sum_{tap} sum_{k} A[pixel(m) + offset(tap), c0(n_tile) + k] * Bm[n, tap*Kt + k]  (+bias[n]) (+res[m,n])
+//
+// A is a channels-last activation tensor (B, H, W, C) read through a 4-D TMA tensor map: a 128-row M tile is a
+// (w_box x h_box) pixel patch of one sample, a tap is a (dx, dy) shift of the TMA start coordinate, and TMA out-of-bounds
+// zero fill provides both the conv padding and the map border of the WFC neighbour contraction. Bm is a K-major matrix
+// (packed conv weights / adjacency matrices / another activation) read through a 3-D TMA map. Accumulation happens in
+// TMEM via tcgen05.mma (kind::f16, fp32 accumulate), double buffered so the epilogue of tile i overlaps the MMAs of
+// tile i+1. The same kernel serves: grouped 3x3 / 1x1 convs forward and backward-data (reference resnet.py:409,425,456),
+// the attention linears and QK^T / PV products (attention.py:339-374), and the WFC wave-by-adjacency contraction
+// (wfdf/losses.py:63-75).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace wfd {
+
+constexpr int TG_BM = 128;      // rows per M tile (UMMA M)
+constexpr int TG_KC = 64;       // K elements per pipeline chunk (128 bytes = one SW128 row)
+constexpr int TG_MAX_TAPS = 9;
+constexpr int TG_THREADS = 192; // warp0 TMA, warp1 MMA, warps2-5 epilogue
+
+struct TapGemmParams {
+    // ---- tiling
+    int m_tiles, n_tiles, z_count;
+    int BN;                 // N tile, multiple of 16, <= 256
+    int tiles_x, tiles_y;   // M tiles per sample along x / y
+    int w_box, h_box;       // w_box * h_box == 128
+    int W, H;               // output plane (pixel index = (bb*H + y)*W + x)
+    int in_stride;          // input coordinate = out coordinate * in_stride + tap offset
+    // ---- K loop
+    int n_taps, cpt;        // taps, 64-wide chunks per tap
+    int tap_dx[TG_MAX_TAPS], tap_dy[TG_MAX_TAPS];
+    const int* a_c0;        // [n_tiles] first input channel of each N tile (nullptr => 0)
+    int a_zmul;             // A dim-3 coordinate = bb + z * a_zmul
+    int b_zmul, b_bbmul;    // B dim-2 coordinate = z * b_zmul + bb * b_bbmul
+    // ---- epilogue
+    int N;                  // valid output columns (multiple of 16)
+    void* out;              // 16-bit (operand dtype) or fp32
+    int out_fp32;
+    long long out_sx, out_sy, out_sb;  // element strides of the output per pixel x / row y / sample (dense: ldc, W*ldc, H*W*ldc)
+    long long c_zstride;
+    const float* bias;      // [N] or nullptr
+    const void* residual;   // same layout/dtype(16-bit) as out, or nullptr
+    float alpha;
+    float* rowdot;          // optional: rowdot[pixel] += sum_n D[m,n] * dotsrc[pixel*ld_dot + n]
+    const void* dotsrc;
+    long long ld_dot;
+    float* gn_sums;         // optional: per (sample, gn_group) {sum, sumsq} of the stored output, fp32 atomics
+    int gn_cpg, gn_G;       // channels per GroupNorm group, number of groups
+    int is_bf16;            // 1: bf16 operands/outputs, 0: fp16
+    // ---- raw views (used only by the CUDA-core checking kernel)
+    const void* a_ptr; int a_C, a_W, a_H, a_B; long long a_ld;
+    const void* b_ptr; long long ldb, b_zstride; int b_rows, b_Z;
+};
+
+struct TapGemmOp {
+    CUtensorMap tmA, tmB;
+    TapGemmParams p;
+    int stages;
+    size_t smem_bytes;
+};
+
+// Encodes the two tensor maps and fills stages/smem. Returns 0 or a negative error (message via set_error).
+int tapgemm_prepare(TapGemmOp* op);
+// Launches on `stream` (persistent grid of min(#tiles, #SMs) CTAs).
+int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream);
+// CUDA-core restatement of the same contraction; test/debug only (WFD_DEBUG_REF_GEMM=1 or the selftest entry).
+int tapgemm_launch_ref(const TapGemmOp* op, cudaStream_t stream);
+
+void set_error(const char* fmt, ...);
+const char* last_error();
+extern long long g_launch_count;
+int num_sms();
+
+}  // namespace wfd

@@ -1,0 +1,190 @@
+// WFC transition-rule loss (reference wfd/wfdf/losses.py:43-75, WFCLossEinsum) and its gradient.
+//
+// loss[b] = strength / P * ( sum_{y,x<W-1} p[y,x]^T (1-Ax) p[y,x+1] + sum_{y<H-1,x} p[y,x]^T (1-Ay) p[y+1,x] ),
+// P = H(W-1) + (H-1)W, p = wave[:T] (the softmax itself runs over all T_pad channels, pipeline_wfd.py:405).
+//
+// With S_n = sum_{i<T} p[n,i] and the complement identity p^T (1-A) q = S_p S_q - p^T A q, the dense tensor-core
+// contraction runs against the adjacency matrices themselves:
+//     a[n,i] = sum_j Ax[i,j] p[right(n),j] + Ax[j,i] p[left(n),j] + Ay[i,j] p[below(n),j] + Ay[j,i] p[above(n),j]
+// (one tapgemm with four taps and K = 4*T_pad), so that g'[n,i] = [i<T] c_n - a[n,i], c_n = sum of S over the in-map
+// neighbours, carries no cancellation through the 16-bit operands. Every adjacent pair is seen from both of its cells:
+//     loss[b] = strength/P * 1/2 * sum_n ( S_n c_n - <p[n], a[n]> ).
+#include "decoder.cuh"
+#include "kernels.cuh"
+#include <string.h>
+#include <vector>
+
+namespace wfd {
+
+#define CK(expr)                      \
+    do {                              \
+        int rc__ = (expr);            \
+        if (rc__ < 0) return rc__;    \
+    } while (0)
+#define CUDA_CK(expr)                                                           \
+    do {                                                                        \
+        cudaError_t e__ = (expr);                                               \
+        if (e__ != cudaSuccess) {                                               \
+            set_error("%s: %s", #expr, cudaGetErrorString(e__));                \
+            return -8;                                                          \
+        }                                                                       \
+    } while (0)
+
+constexpr int WFC_BN = 256;
+
+Wfc::~Wfc() {
+    if (Bm) cudaFree(Bm);
+}
+
+int Wfc::init(const uint8_t* mx, const uint8_t* my, int T_, int T_pad_, int dtype16) {
+    T = T_;
+    T_pad = T_pad_;
+    bf16 = dtype16 ? 1 : 0;
+    if (T < 1 || T_pad < T || T_pad % TG_KC != 0) {
+        set_error("wfc: need 1 <= T <= T_pad and T_pad %% 64 == 0 (T=%d T_pad=%d)", T, T_pad);
+        return -3;
+    }
+    const uint16_t one = bf16 ? 0x3F80 : 0x3C00;
+    const long long rows = static_cast<long long>((T_pad + WFC_BN - 1) / WFC_BN) * WFC_BN;
+    const long long ldb = 4LL * T_pad;
+    std::vector<uint16_t> hb(static_cast<size_t>(rows * ldb), 0);
+    for (int i = 0; i < T; ++i) {
+        uint16_t* row = hb.data() + static_cast<size_t>(i) * ldb;
+        for (int j = 0; j < T; ++j) {
+            if (mx[static_cast<size_t>(i) * T + j]) row[j] = one;                  // right neighbour:  Ax[i,j]
+            if (mx[static_cast<size_t>(j) * T + i]) row[T_pad + j] = one;          // left neighbour:   Ax[j,i]
+            if (my[static_cast<size_t>(i) * T + j]) row[2 * T_pad + j] = one;      // below:            Ay[i,j]
+            if (my[static_cast<size_t>(j) * T + i]) row[3 * T_pad + j] = one;      // above:            Ay[j,i]
+        }
+    }
+    CUDA_CK(cudaMalloc(&Bm, hb.size() * 2));
+    CUDA_CK(cudaMemcpy(Bm, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+size_t Wfc::saved_bytes(int B, int H, int W) const {
+    const size_t rows = static_cast<size_t>(B) * H * W;
+    return 256 + 2 * align256(rows * T_pad * 2) + 2 * align256(rows * 4);
+}
+
+struct SavedView {
+    WfcSavedHeader* hdr;
+    uint8_t* wave;
+    uint8_t* a;
+    float* rowsum;
+    float* rowdot;
+};
+static SavedView view_saved(void* saved, size_t rows, int T_pad) {
+    SavedView v;
+    uint8_t* p = static_cast<uint8_t*>(saved);
+    v.hdr = reinterpret_cast<WfcSavedHeader*>(p);
+    p += 256;
+    v.wave = p;
+    p += align256(rows * T_pad * 2);
+    v.a = p;
+    p += align256(rows * T_pad * 2);
+    v.rowsum = reinterpret_cast<float*>(p);
+    p += align256(rows * 4);
+    v.rowdot = reinterpret_cast<float*>(p);
+    return v;
+}
+
+int Wfc::forward(const void* in, int is_logits, int B, int H, int W, float strength, void* saved, float* loss,
+                 cudaStream_t s) {
+    if (B < 1 || H < 1 || W < 1 || (H == 1 && W == 1)) {
+        set_error("wfc: bad map shape B=%d H=%d W=%d", B, H, W);
+        return -3;
+    }
+    int wb = 0, hb = 0;
+    for (int c = 128; c >= 1; c >>= 1) {
+        if (W % c == 0 && H % (TG_BM / c) == 0) {
+            wb = c;
+            hb = TG_BM / c;
+            break;
+        }
+    }
+    if (!wb) {
+        set_error("wfc: map %dx%d cannot be tiled into 128-cell patches", H, W);
+        return -3;
+    }
+    const size_t rows = static_cast<size_t>(B) * H * W;
+    SavedView v = view_saved(saved, rows, T_pad);
+    const void* wave = is_logits ? v.wave : in;
+    // the header lives in caller memory on the device side of `saved`; keep the host copy in the handle instead
+    hdr_host.B = B;
+    hdr_host.H = H;
+    hdr_host.W = W;
+    hdr_host.is_logits = is_logits;
+    hdr_host.coef = strength / static_cast<float>(H * (W - 1) + (H - 1) * W);
+    hdr_host.wave = wave;
+    hdr_saved = saved;
+    if (is_logits) CK(wave_softmax(in, v.wave, v.rowsum, static_cast<long long>(rows), T_pad, T, bf16, s));
+    else CK(wave_rowsum(in, v.rowsum, static_cast<long long>(rows), T_pad, T, bf16, s));
+    CUDA_CK(cudaMemsetAsync(v.rowdot, 0, rows * sizeof(float), s));
+    if (op_wave != wave || op_a != v.a || op_B != B || op_H != H || op_W != W) {
+        memset(&op, 0, sizeof(op));
+        TapGemmParams& p = op.p;
+        p.BN = WFC_BN;
+        p.n_tiles = (T_pad + WFC_BN - 1) / WFC_BN;
+        p.z_count = 1;
+        p.w_box = wb;
+        p.h_box = hb;
+        p.tiles_x = W / wb;
+        p.tiles_y = H / hb;
+        p.m_tiles = B * p.tiles_x * p.tiles_y;
+        p.W = W;
+        p.H = H;
+        p.in_stride = 1;
+        p.n_taps = 4;
+        p.cpt = T_pad / TG_KC;
+        p.tap_dx[0] = 1;  p.tap_dy[0] = 0;
+        p.tap_dx[1] = -1; p.tap_dy[1] = 0;
+        p.tap_dx[2] = 0;  p.tap_dy[2] = 1;
+        p.tap_dx[3] = 0;  p.tap_dy[3] = -1;
+        p.N = T_pad;
+        p.out = v.a;
+        p.out_fp32 = 0;
+        p.out_sx = T_pad;
+        p.out_sy = static_cast<long long>(T_pad) * W;
+        p.out_sb = static_cast<long long>(T_pad) * W * H;
+        p.alpha = 1.f;
+        p.rowdot = v.rowdot;
+        p.dotsrc = wave;
+        p.ld_dot = T_pad;
+        p.is_bf16 = bf16;
+        p.a_ptr = wave;
+        p.a_C = T_pad;
+        p.a_W = W;
+        p.a_H = H;
+        p.a_B = B;
+        p.a_ld = T_pad;
+        p.b_ptr = Bm;
+        p.ldb = 4LL * T_pad;
+        p.b_rows = p.n_tiles * WFC_BN;
+        p.b_Z = 1;
+        CK(tapgemm_prepare(&op));
+        op_wave = wave;
+        op_a = v.a;
+        op_B = B;
+        op_H = H;
+        op_W = W;
+    }
+    CK(debug_ref_gemm() ? tapgemm_launch_ref(&op, s) : tapgemm_launch(&op, s));
+    CK(wfc_loss_finish(v.rowsum, v.rowdot, loss, B, H, W, hdr_host.coef, s));
+    return 0;
+}
+
+int Wfc::backward(void* saved, const float* dloss, void* dout, cudaStream_t s) {
+    if (saved != hdr_saved || hdr_host.B == 0) {
+        set_error("wfc: backward called with a `saved` block that is not the one of the last forward");
+        return -3;
+    }
+    const size_t rows = static_cast<size_t>(hdr_host.B) * hdr_host.H * hdr_host.W;
+    SavedView v = view_saved(saved, rows, T_pad);
+    return wfc_grad_finish(hdr_host.wave, v.a, v.rowsum, v.rowdot, dloss, dout, hdr_host.B, hdr_host.H, hdr_host.W,
+                           T_pad, T, hdr_host.coef, hdr_host.is_logits, bf16, s);
+}
+
+}  // namespace wfd
