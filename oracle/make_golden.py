@@ -1,0 +1,140 @@
+"""TEST INFRASTRUCTURE ONLY — generates tests/golden/* by running the UNMODIFIED reference modules
+(/root/reference, imported through oracle/reference_loader.py) on seeded inputs. Run in the authoring container:
+
+    python oracle/make_golden.py [--skip-full]
+
+Fixtures (all small; weights are NOT stored — they are re-created from torch.manual_seed(seed) by the product's
+AutoencoderTile, whose initialisation order is checked to be bit-identical to the reference's in this script):
+  wfc_mats/<tileset>.npz   sparse coordinates of the shipped wfc_mats (the adjacency input data of the path) + KATs
+  tiny_step.npz            reference decode+softmax+loss+grad on a small config, fp64 and fp32
+  tiny_down_step.npz       same with a DownDecoderBlock2D (the 32x32-style config)
+  ice_c1_step.npz          BASELINE config 1: ice 64x64, batch 1, tilenet_sc_space_64x64, strength 5
+"""
+import glob
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.reference_loader import REFERENCE_ROOT, load_reference  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+TINY = dict(
+    down_block_types=["EvenEncoderBlock2D"] * 4, up_block_types=["EvenDecoderBlock2D"] * 4,
+    block_out_channels=[512, 256, 128, 64], conv_groups=[8, 4, 2, 1], conv_init_groups=16, layers_per_block=2,
+    act_fn="silu", latent_channels=4, norm_num_groups=8, sample_size=16, in_channels=128, out_channels=128,
+)
+TINY_DOWN = dict(TINY, down_block_types=["EvenEncoderBlock2D", "UpEncoderBlock2D", "EvenEncoderBlock2D", "EvenEncoderBlock2D"],
+                 up_block_types=["EvenDecoderBlock2D", "EvenDecoderBlock2D", "DownDecoderBlock2D", "EvenDecoderBlock2D"])
+
+
+def synthetic_mats(T, density, seed):
+    rng = np.random.RandomState(seed)
+    m = rng.rand(2, T, T) < density
+    m[:, 0, :] = False  # null tile: everything forbidden, like the shipped matrices
+    m[:, :, 0] = False
+    return m
+
+
+def reference_step(vae, losses, cfg, mats, latents, strength, dtype, seed):
+    torch.manual_seed(seed)
+    net = vae.AutoencoderTile(**cfg).eval().to(dtype)
+    lossm = losses.WFCLossEinsum(mats[0], mats[1]).to(dtype)
+    lat = latents.to(dtype).requires_grad_()
+    t0 = time.time()
+    logits = net.decode(1 / 0.18215 * lat).sample      # pipeline_wfd.py:403-404
+    wave = logits.softmax(axis=1)                       # :405
+    loss = lossm(wave) * strength                       # :612
+    (grad,) = torch.autograd.grad(loss.sum(), lat)      # :613 (.sum(): batch > 1 needs a scalar)
+    dt = time.time() - t0
+    return net, logits.detach(), wave.detach(), loss.detach(), grad.detach(), dt
+
+
+def check_seed_parity(vae, cfg, seed):
+    from wavefunctiondiffusion_b200.wf_diffusers.wf_vae import AutoencoderTile
+
+    torch.manual_seed(seed)
+    ref = vae.AutoencoderTile(**cfg)
+    torch.manual_seed(seed)
+    mine = AutoencoderTile(**cfg)
+    a, b = ref.state_dict(), mine.state_dict()
+    assert list(a.keys()) == list(b.keys()), "state_dict keys/order differ from the reference"
+    for k in a:
+        assert torch.equal(a[k], b[k]), "weight %s differs from the reference under the same seed" % k
+
+
+def small_fixture(vae, losses, name, cfg, hw, B, T, seed):
+    check_seed_parity(vae, cfg, seed)
+    mats = synthetic_mats(T, 0.05, seed + 1)
+    g = torch.Generator().manual_seed(seed + 2)
+    lat = torch.randn(B, 4, hw, hw, generator=g)
+    out = {"latents": lat.numpy(), "mats": np.packbits(mats), "T": T, "seed": seed, "strength": 5.0,
+           "cfg_json": json.dumps(cfg)}
+    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        _, logits, wave, loss, grad, _ = reference_step(vae, losses, cfg, mats, lat, 5.0, dtype, seed)
+        out["logits_" + tag] = logits.numpy()
+        out["loss_" + tag] = loss.numpy()
+        out["grad_" + tag] = grad.numpy()
+    np.savez_compressed(os.path.join(GOLD, name), **out)
+    print(name, "loss", out["loss_f64"], "grad norm", np.linalg.norm(out["grad_f64"]))
+
+
+def wfc_mats_fixtures():
+    os.makedirs(os.path.join(GOLD, "wfc_mats"), exist_ok=True)
+    for path in sorted(glob.glob(REFERENCE_ROOT + "/wfd/scmap/tile_data/wfc/*.npz")):
+        name = os.path.basename(path)[:-4]
+        z = np.load(path)
+        m = z["wfc_mats"]
+        T = int(m.shape[1])
+        assert T == int(z["shrink_count"])
+        t_pad = (T + 127) // 128 * 128
+        xs = np.argwhere(m[0]).astype(np.int16)
+        ys = np.argwhere(m[1]).astype(np.int16)
+        kat = (2.0 * T * T - len(xs) - len(ys)) / (2.0 * t_pad * t_pad)
+        np.savez_compressed(os.path.join(GOLD, "wfc_mats", name + ".npz"), T=T, T_pad=t_pad, x=xs, y=ys, uniform_kat=kat)
+        print(name, T, t_pad, len(xs), len(ys), "%.8f" % kat)
+
+
+def full_fixture(vae, losses):
+    cfg = json.load(open(REFERENCE_ROOT + "/configs/tilenet/tilenet_sc_space_64x64.json"))
+    mats = np.load(REFERENCE_ROOT + "/wfd/scmap/tile_data/wfc/ice_64x64.npz")["wfc_mats"]
+    T = mats.shape[1]
+    t_pad = (T + 127) // 128 * 128
+    cfg["in_channels"] = cfg["out_channels"] = t_pad
+    check_seed_parity(vae, cfg, 0)
+    g = torch.Generator().manual_seed(1234)
+    lat = torch.randn(1, 4, 64, 64, generator=g)
+    out = {"latents": lat.numpy(), "seed": 0, "strength": 5.0, "cfg_json": json.dumps(cfg), "tileset": "ice_64x64"}
+    pix = np.array([0, 63, 64 * 31 + 17, 64 * 63, 64 * 64 - 1, 1234, 2048, 3000])
+    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        _, logits, wave, loss, grad, dt = reference_step(vae, losses, cfg, mats, lat, 5.0, dtype, 0)
+        out["loss_" + tag] = loss.numpy()
+        out["grad_" + tag] = grad.numpy().astype(np.float32 if tag == "f32" else np.float64)
+        out["tiles_" + tag] = wave[0].permute(1, 2, 0).numpy().argmax(axis=2).astype(np.int16)
+        out["logits_pix_" + tag] = logits[0].reshape(t_pad, -1)[:, pix].t().numpy().astype(np.float32)
+        lg = logits[0].reshape(t_pad, -1)
+        top2 = torch.topk(lg, 2, dim=0).values
+        out["top2_margin_" + tag] = (top2[0] - top2[1]).numpy().astype(np.float32)
+        out["logits_mean_std_" + tag] = np.array([lg.mean().item(), lg.std().item()])
+        out["seconds_" + tag] = dt
+        print("ice C1", tag, "loss", loss.numpy(), "grad L2", grad.norm().item(), "absmax", grad.abs().max().item(),
+              "%.1fs" % dt)
+    out["pix"] = pix
+    np.savez_compressed(os.path.join(GOLD, "ice_c1_step.npz"), **out)
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    vae, losses = load_reference()
+    wfc_mats_fixtures()
+    small_fixture(vae, losses, "tiny_step.npz", TINY, 16, 2, 100, 7)
+    small_fixture(vae, losses, "tiny_down_step.npz", TINY_DOWN, 16, 2, 100, 11)
+    if "--skip-full" not in sys.argv:
+        full_fixture(vae, losses)

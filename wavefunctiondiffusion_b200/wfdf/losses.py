@@ -1,0 +1,49 @@
+"""WFCLossEinsum — host-side mirror of the reference loss module (wfd/wfdf/losses.py:43-75).
+
+Same constructor, buffers (`cx`, `cy` = 1 - adjacency, shaped (1, T, T, 1, 1)), `count` attribute and call signature
+`loss(t, softmax=False) -> (B,)`; the contraction itself runs in libwfd_b200.so (tcgen05 kernel against the four
+directional adjacency matrices) and is differentiable w.r.t. `t` through a torch.autograd.Function.
+"""
+import torch
+
+from ..wf_diffusers.native_ops import WfcHandle, WfcLossFunction, compute_dtype16
+
+
+class WFCLossEinsum(torch.nn.Module):
+    """
+    Expectation of violating the WFC transition rules on a wave.
+
+    Parameters:
+        wfc_mat_x: (T, T), x[i, j] == 1 means tile j is allowed at the right side of tile i.
+        wfc_mat_y: (T, T), y[i, j] == 1 means tile j is allowed below tile i.
+    """
+
+    def __init__(self, wfc_mat_x, wfc_mat_y):
+        super().__init__()
+        cx = torch.as_tensor(wfc_mat_x, dtype=torch.float32)
+        cy = torch.as_tensor(wfc_mat_y, dtype=torch.float32)
+        assert cx.size(0) == cx.size(1) and cx.size(1) == cy.size(0) and cy.size(0) == cy.size(1), "WFC matrix size mismatch"
+        self.register_buffer("cx", (1 - cx)[None, :, :, None, None])
+        self.register_buffer("cy", (1 - cy)[None, :, :, None, None])
+        self.count = cx.size(0)
+        self._handles = {}
+
+    def _mats(self):
+        ax = (self.cx[0, :, :, 0, 0] < 0.5).to("cpu").numpy()
+        ay = (self.cy[0, :, :, 0, 0] < 0.5).to("cpu").numpy()
+        return ax, ay
+
+    def native_handle(self, t_pad, device):
+        key = (t_pad, compute_dtype16(), str(device))
+        h = self._handles.get(key)
+        if h is None:
+            ax, ay = self._mats()
+            h = WfcHandle(ax, ay, t_pad, key[1], device)
+            self._handles[key] = h
+        return h
+
+    def forward(self, t, softmax=False):
+        if t.dim() != 4 or t.size(1) < self.count:
+            raise ValueError(f"wave must be (B, C>={self.count}, H, W), got {tuple(t.shape)}")
+        handle = self.native_handle(t.size(1), t.device)
+        return WfcLossFunction.apply(t, handle, bool(softmax))
