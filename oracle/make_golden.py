@@ -135,6 +135,6 @@ if __name__ == "__main__":
     vae, losses = load_reference()
     wfc_mats_fixtures()
     small_fixture(vae, losses, "tiny_step.npz", TINY, 16, 2, 100, 7)
-    small_fixture(vae, losses, "tiny_down_step.npz", TINY_DOWN, 16, 2, 100, 11)
+    small_fixture(vae, losses, "tiny_down_step.npz", TINY_DOWN, 32, 2, 100, 11)
     if "--skip-full" not in sys.argv:
         full_fixture(vae, losses)

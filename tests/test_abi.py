@@ -39,7 +39,7 @@ def test_state_dict_keys_and_config():
     net = AutoencoderTile(**cfg)
     keys = set(net.state_dict())
     for k in ["post_quant_conv.weight", "decoder.conv_in.bias", "decoder.mid_block.attentions.0.proj_attn.weight",
-              "decoder.mid_block.resnets.1.conv2.weight", "decoder.up_blocks.1.resnets.0.conv_shortcut.weight",
+              "decoder.mid_block.resnets.1.conv2.weight", "decoder.up_blocks.2.resnets.0.conv_shortcut.weight",
               "decoder.up_blocks.2.downsamplers.0.conv.weight", "decoder.conv_norm_out.weight", "decoder.conv_out.weight",
               "encoder.down_blocks.1.upsamplers.0.conv.weight", "quant_conv.bias"]:
         assert k in keys, k

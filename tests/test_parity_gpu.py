@@ -1,0 +1,227 @@
+"""GPU parity of the CUDA path (through the C ABI, via the host-side mirrors) against the golden vectors of the
+unmodified reference and against the CPU oracle.
+
+Tolerances (bf16 operands, fp32 accumulation; stated against the fp64 reference values):
+  logits  rel-L2 <= 2e-2        loss  rel <= 1e-3        latent gradient  rel-L2 <= 5e-2
+  argmax  bit-exact on identical waves
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import wfd_oracle as orc
+from wavefunctiondiffusion_b200 import _native as nat
+from wavefunctiondiffusion_b200.utils.tilesets import load_wfc_mats, round_up_channels
+from wavefunctiondiffusion_b200.wf_diffusers.native_ops import GuidanceLossFunction, argmax_tiles
+from wavefunctiondiffusion_b200.wf_diffusers.wf_vae import AutoencoderTile
+from wavefunctiondiffusion_b200.wfdf.losses import WFCLossEinsum
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL_LOGITS, TOL_LOSS, TOL_GRAD = 2e-2, 1e-3, 5e-2
+
+
+def _rel(a, b):
+    a = torch.as_tensor(np.asarray(a.detach() if torch.is_tensor(a) else a), dtype=torch.float64)
+    b = torch.as_tensor(np.asarray(b.detach() if torch.is_tensor(b) else b), dtype=torch.float64)
+    return ((a - b).norm() / b.norm()).item()
+
+
+def _load_small(name):
+    z = np.load(os.path.join(GOLD, name))
+    cfg = json.loads(str(z["cfg_json"]))
+    T = int(z["T"])
+    mats = np.unpackbits(z["mats"])[: 2 * T * T].reshape(2, T, T).astype(bool)
+    torch.manual_seed(int(z["seed"]))
+    net = AutoencoderTile(**cfg).eval().cuda()
+    return z, cfg, mats, net
+
+
+@pytest.fixture(autouse=True)
+def _reset_debug():
+    yield
+    nat.lib().wfd_debug_set_ref_gemm(0)
+
+
+@pytest.mark.parametrize("ref_gemm", [1, 0])
+@pytest.mark.parametrize("name", ["tiny_step.npz", "tiny_down_step.npz"])
+def test_decode_logits_small(name, ref_gemm):
+    z, cfg, mats, net = _load_small(name)
+    nat.lib().wfd_debug_set_ref_gemm(ref_gemm)
+    lat = torch.from_numpy(z["latents"]).cuda()
+    with torch.no_grad():
+        logits = net.decode(lat / 0.18215).sample
+    assert logits.shape == z["logits_f64"].shape and logits.dtype == torch.float32
+    assert _rel(logits.cpu(), z["logits_f64"]) < TOL_LOGITS
+
+
+@pytest.mark.parametrize("ref_gemm", [1, 0])
+def test_guidance_block_as_the_reference_pipeline_writes_it(ref_gemm):
+    """decode -> softmax(axis=1) -> WFCLossEinsum -> autograd.grad, i.e. pipeline_wfd.py:609-613 line by line."""
+    z, cfg, mats, net = _load_small("tiny_step.npz")
+    nat.lib().wfd_debug_set_ref_gemm(ref_gemm)
+    wfc_loss = WFCLossEinsum(mats[0], mats[1]).cuda()
+    latents = torch.from_numpy(z["latents"]).cuda()
+    with torch.enable_grad():
+        _latents = latents.detach().requires_grad_()
+        image = net.decode(1 / 0.18215 * _latents).sample
+        wave = image.softmax(axis=1)
+        _loss = wfc_loss(wave) * 5.0
+        (grad,) = torch.autograd.grad(_loss.sum(), _latents)
+    assert _rel(_loss.cpu(), z["loss_f64"]) < TOL_LOSS
+    assert _rel(grad.cpu(), z["grad_f64"]) < TOL_GRAD
+
+
+@pytest.mark.parametrize("ref_gemm", [1, 0])
+def test_fused_guidance_step_small(ref_gemm):
+    z, cfg, mats, net = _load_small("tiny_step.npz")
+    nat.lib().wfd_debug_set_ref_gemm(ref_gemm)
+    wfc_loss = WFCLossEinsum(mats[0], mats[1]).cuda()
+    lat = torch.from_numpy(z["latents"]).cuda().requires_grad_()
+    loss = GuidanceLossFunction.apply(lat, net._native, wfc_loss.native_handle(cfg["out_channels"], lat.device),
+                                      1.0 / 0.18215, 5.0)
+    (grad,) = torch.autograd.grad(loss.sum(), lat)
+    assert _rel(loss.cpu(), z["loss_f64"]) < TOL_LOSS
+    assert _rel(grad.cpu(), z["grad_f64"]) < TOL_GRAD
+    # softmax=True entry of the loss module on the logits gives the same loss
+    with torch.no_grad():
+        logits = net.decode(lat.detach() / 0.18215).sample
+        l2 = wfc_loss(logits, softmax=True) * 5.0
+    assert _rel(l2.cpu(), z["loss_f64"]) < TOL_LOSS
+
+
+def test_ice_config1_against_reference_golden():
+    """BASELINE config 1: ice 64x64, batch 1, tilenet_sc_space_64x64, seed-0 weights, strength 5."""
+    z = np.load(os.path.join(GOLD, "ice_c1_step.npz"))
+    cfg = json.loads(str(z["cfg_json"]))
+    mx, my = load_wfc_mats("ice_64x64")
+    torch.manual_seed(int(z["seed"]))
+    net = AutoencoderTile(**cfg).eval().cuda()
+    wfc_loss = WFCLossEinsum(mx, my).cuda()
+    lat = torch.from_numpy(z["latents"]).cuda().requires_grad_()
+    handle = wfc_loss.native_handle(cfg["out_channels"], lat.device)
+    loss = GuidanceLossFunction.apply(lat, net._native, handle, 1.0 / 0.18215, 5.0)
+    (grad,) = torch.autograd.grad(loss.sum(), lat)
+    print("ice C1: loss", loss.item(), "ref", z["loss_f64"], "grad rel-L2", _rel(grad.cpu(), z["grad_f64"]))
+    assert _rel(loss.cpu(), z["loss_f64"]) < TOL_LOSS
+    assert _rel(grad.cpu(), z["grad_f64"]) < TOL_GRAD
+    # logits at the sampled pixels
+    plan = net._native.plan(1, 64, 64, lat.device)
+    logits = plan.logits_view(1).float()  # (1, T_pad, H, W) view
+    got = logits[0].reshape(cfg["out_channels"], -1)[:, torch.from_numpy(z["pix"]).cuda()].t().cpu()
+    assert _rel(got, z["logits_pix_f64"]) < TOL_LOGITS
+    # argmax: bit-exact on the identical wave; against the reference's own tiles only cells with a clear margin count
+    wave = handle.wave_view(1, 64, 64)
+    tiles = argmax_tiles(wave)
+    assert np.array_equal(tiles.cpu().numpy(), np.argmax(wave.float().cpu().numpy(), axis=-1))
+    clear = z["top2_margin_f64"].reshape(64, 64) > 0.05
+    assert (tiles[0].cpu().numpy()[clear] == z["tiles_f64"][clear]).mean() > 0.99
+
+
+@pytest.mark.parametrize("tileset", ["ice_64x64", "install_64x64"])
+def test_wfc_known_answers_on_device(tileset):
+    mx, my = load_wfc_mats(tileset)
+    T = mx.shape[0]
+    t_pad = round_up_channels(T)
+    wfc_loss = WFCLossEinsum(mx, my).cuda()
+    H, W = 16, 8
+    # uniform wave over t_pad channels: analytic value
+    wave = torch.full((2, t_pad, H, W), 1.0 / t_pad, device="cuda")
+    got = wfc_loss(wave).cpu().numpy()
+    assert np.allclose(got, orc.uniform_wave_loss(mx, my, t_pad), rtol=3e-3)  # 1/t_pad is rounded to bf16
+    # zero logits through the fused softmax give the same number with the exactly representable row sum
+    got = wfc_loss(torch.zeros(2, t_pad, H, W, device="cuda"), softmax=True).cpu().numpy()
+    assert np.allclose(got, orc.uniform_wave_loss(mx, my, t_pad), rtol=3e-3)
+    # one-hot wave of an integer tile map: exactly the fraction of forbidden adjacent pairs
+    rng = np.random.RandomState(0)
+    tiles = rng.randint(0, T, size=(H, W))
+    onehot = torch.zeros(1, t_pad, H, W)
+    onehot[0, torch.from_numpy(tiles), torch.arange(H)[:, None], torch.arange(W)[None, :]] = 1.0
+    got = wfc_loss(onehot.cuda()).item()
+    assert abs(got - orc.forbidden_pair_fraction(tiles, mx, my)) < 1e-6
+    # a map whose pairs are all allowed has loss exactly 0: walk allowed transitions along a single row
+    ax = mx.copy()
+    row = [int(np.argwhere(ax.any(1))[0, 0])]
+    for _ in range(W - 1):
+        nxt = np.argwhere(ax[row[-1]])
+        if len(nxt) == 0:
+            break
+        row.append(int(nxt[0, 0]))
+    if len(row) == W:
+        oh = torch.zeros(1, t_pad, 1, W)
+        oh[0, torch.tensor(row), 0, torch.arange(W)] = 1.0
+        # a 1 x W map cannot be tiled into 128-cell patches: replicate the row only if the vertical pairs are allowed
+        col_ok = all(my[t, t] for t in row)
+        if col_ok:
+            oh = oh.expand(1, t_pad, 16, W).contiguous()
+            assert wfc_loss(oh.cuda()).item() == 0.0
+
+
+def test_wfc_gradient_matches_closed_form():
+    mx, my = load_wfc_mats("install_64x64")
+    T = mx.shape[0]
+    t_pad = round_up_channels(T)
+    wfc_loss = WFCLossEinsum(mx, my).cuda()
+    torch.manual_seed(0)
+    wave = torch.softmax(torch.randn(2, t_pad, 8, 16) * 3, dim=1)
+    wave16 = wave.bfloat16().float()
+    w = wave16.cuda().requires_grad_()
+    loss = wfc_loss(w)
+    (g,) = torch.autograd.grad((loss * torch.tensor([1.0, 2.0], device="cuda")).sum(), w)
+    want_loss = orc.wfc_loss(wave16.double(), mx, my)
+    want_g = orc.wfc_grad_closed_form(wave16.double(), mx, my) * torch.tensor([1.0, 2.0]).view(2, 1, 1, 1)
+    assert _rel(loss.detach().cpu(), want_loss) < 1e-4
+    assert _rel(g.cpu(), want_g) < 5e-3
+    assert g.shape == w.shape and g[:, T:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_argmax_numpy_semantics(dtype):
+    torch.manual_seed(0)
+    x = torch.randn(37, 3200).to(dtype)
+    x[3, 100] = x[3, 2000] = 50.0           # tie: first index wins
+    x[4, 3199] = 60.0                        # last element
+    x[5, 0] = 60.0                           # first element
+    x[6, :] = 1.0                            # all equal -> 0
+    if dtype != torch.float16:
+        x[7, 77] = float("nan")              # NaN is maximal, first NaN wins
+        x[7, 99] = float("nan")
+        x[8, 5] = float("inf")
+    got = argmax_tiles(x.cuda()).cpu().numpy()
+    want = np.argmax(x.float().numpy(), axis=-1)
+    assert got.dtype == np.int64 and np.array_equal(got, want)
+    # ragged row length (not a multiple of the 32-lane vector stride) and an empty batch
+    y = torch.randn(5, 7, 1032).to(dtype)
+    assert np.array_equal(argmax_tiles(y.cuda()).cpu().numpy(), np.argmax(y.float().numpy(), axis=-1))
+    assert argmax_tiles(torch.zeros(0, 128, dtype=dtype, device="cuda")).shape == (0,)
+
+
+def test_batch_properties_full_size():
+    """Size-independent properties at BASELINE config 2's shape (ice 64x64, batch 8): maps are independent, the loss is
+    linear in the strength, and a batch equals its single-map runs."""
+    mx, my = load_wfc_mats("ice_64x64")
+    t_pad = round_up_channels(mx.shape[0])
+    from wavefunctiondiffusion_b200.utils.tilesets import tilenet_config
+
+    torch.manual_seed(0)
+    net = AutoencoderTile(**tilenet_config("64x64", t_pad)).eval().cuda()
+    wfc_loss = WFCLossEinsum(mx, my).cuda()
+    handle = wfc_loss.native_handle(t_pad, torch.device("cuda:0"))
+    g = torch.Generator().manual_seed(5)
+    lat = torch.randn(8, 4, 64, 64, generator=g).cuda()
+    lat[5] = lat[2]
+    z = lat.clone().requires_grad_()
+    loss = GuidanceLossFunction.apply(z, net._native, handle, 1 / 0.18215, 5.0)
+    (grad,) = torch.autograd.grad(loss.sum(), z)
+    assert torch.isfinite(loss).all() and torch.isfinite(grad).all()
+    assert abs(loss[5].item() - loss[2].item()) <= 2e-5 * abs(loss[2].item())
+    assert _rel(grad[5].cpu(), grad[2].cpu()) < 1e-3
+    z1 = lat[:1].clone().requires_grad_()
+    loss1 = GuidanceLossFunction.apply(z1, net._native, handle, 1 / 0.18215, 10.0)
+    (grad1,) = torch.autograd.grad(loss1.sum(), z1)
+    assert abs(loss1.item() - 2 * loss[0].item()) <= 2e-5 * abs(loss1.item())
+    assert _rel(grad1[0].cpu(), 2 * grad[0].cpu()) < 1e-3

@@ -155,9 +155,12 @@ def test_conv3x3_forward_and_backward_data(cin, cout, groups, BN, H, W, use_ref)
     got = out.permute(0, 3, 1, 2).float()
     assert _rel(got, want) < 6e-3
     # fused GroupNorm statistics of the stored (rounded) output
-    g8 = got.reshape(Bn, 8, -1)
-    assert _rel(gn.view(Bn, 8, 2)[..., 0], g8.sum(-1)) < 2e-3 or g8.sum(-1).abs().max() < 50
-    assert _rel(gn.view(Bn, 8, 2)[..., 1], (g8 * g8).sum(-1)) < 2e-3
+    # (the tensor-core epilogue reduces 16-column chunks, so it needs channels-per-group % 16 == 0; the decoder only
+    # fuses in that case and runs the standalone statistics kernel otherwise)
+    if use_ref or (cout // 8) % 16 == 0:
+        g8 = got.reshape(Bn, 8, -1)
+        assert (gn.view(Bn, 8, 2)[..., 0] - g8.sum(-1)).abs().max() < 2e-3 * g8.abs().sum(-1).max()
+        assert _rel(gn.view(Bn, 8, 2)[..., 1], (g8 * g8).sum(-1)) < 2e-3
     # backward data: dX = conv_transpose(dY, w)
     dy = torch.randn(Bn, cout, H, W, device="cuda").bfloat16()
     dy_nhwc = dy.permute(0, 2, 3, 1).contiguous()
@@ -194,4 +197,22 @@ def test_four_tap_neighbour_contraction(use_ref):
     want[:, :, 1:] += torch.einsum("ij,bhwj->bhwi", mats[1].float(), pf[:, :, :-1])
     want[:, :-1] += torch.einsum("ij,bhwj->bhwi", mats[2].float(), pf[:, 1:])
     want[:, 1:] += torch.einsum("ij,bhwj->bhwi", mats[3].float(), pf[:, :-1])
+    assert _rel(out, want) < 6e-3
+
+
+@pytest.mark.parametrize("use_ref", [1, 0])
+def test_persistent_many_tiles_per_cta(use_ref):
+    """More tiles than SMs: every CTA loops over several tiles, exercising the TMEM double buffer and the smem ring
+    across tile boundaries (M = 128 * 450 rows, 3 N tiles -> 1350 tiles on 148 SMs)."""
+    torch.manual_seed(5)
+    M, K, N, BN = 128 * 450, 192, 144, 48
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    Bm = torch.randn(N, K, device="cuda").bfloat16()
+    bias = torch.randn(N, device="cuda")
+    out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    d = _desc(a=A.data_ptr(), a_C=K, a_W=M, a_H=1, a_B=1, a_ld=K, b=Bm.data_ptr(), b_rows=N, ldb=K, b_zstride=0, b_Z=1,
+              n_taps=1, cpt=K // 64, tap_dx=[0], tap_dy=[0], a_c0=None, BN=BN, N=N, W=M, H=1, B=1, w_box=128, h_box=1,
+              in_stride=1, z_count=1, out=out.data_ptr(), out_fp32=0, ldc=N, bias=bias.data_ptr(), alpha=1.0, dtype16=1)
+    _run(d, use_ref)
+    want = A.float() @ Bm.float().t() + bias
     assert _rel(out, want) < 6e-3

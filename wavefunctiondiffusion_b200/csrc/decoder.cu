@@ -68,7 +68,8 @@ void PackedB::release() {
 
 // w: [cout][cin/groups][k][k] fp32 (torch Conv2d / Linear layout). mode 0: forward, pad (k-1)/2; mode 1: backward-data of
 // mode 0; mode 2: forward of the stride-2 downsample conv applied after F.pad(x, (0,1,0,1)) (resnet.py:185-190).
-int pack_conv(const float* w, int cout, int cin, int groups, int k, int mode, bool bf16, int bn_override, PackedB* out) {
+int pack_conv(const float* w, int cout, int cin, int groups, int k, int mode, bool bf16, int bn_override, PackedB* out,
+              const std::vector<TapSel>* tap_sel) {
     const bool bwd = (mode == 1);
     const int cin_g = cin / groups, cout_g = cout / groups;
     const int N = bwd ? cin : cout;
@@ -81,11 +82,12 @@ int pack_conv(const float* w, int cout, int cin, int groups, int k, int mode, bo
     for (int t = 0; t < n_tiles; ++t) {
         const int n0 = t * BN, n1 = std::min(N, n0 + BN);
         const int g_lo = n0 / rpg, g_hi = (n1 - 1) / rpg;
-        c0[t] = g_lo * kpg;
+        c0[t] = (g_lo * kpg) & ~7;  // TMA box start must be 16-byte aligned
         const int span = (g_hi + 1) * kpg - c0[t];
         cpt = std::max(cpt, (span + TG_KC - 1) / TG_KC);
     }
-    const int taps = k * k;
+    const int wtaps = k * k;                                          // taps stored in the weight tensor
+    const int taps = tap_sel ? static_cast<int>(tap_sel->size()) : wtaps;  // taps of this contraction
     const long long ldb = static_cast<long long>(taps) * cpt * TG_KC;
     const long long rows = static_cast<long long>(n_tiles) * BN;
     std::vector<uint16_t> hb(static_cast<size_t>(rows * ldb), 0);
@@ -96,11 +98,12 @@ int pack_conv(const float* w, int cout, int cin, int groups, int k, int mode, bo
                 const int c = g * kpg + kk;
                 const int pos = c - c0[t];
                 float v;
+                const int wt = tap_sel ? (*tap_sel)[tap].w_tap : tap;
                 if (!bwd) {
-                    v = w[(static_cast<long long>(n) * cin_g + kk) * taps + tap];
+                    v = w[(static_cast<long long>(n) * cin_g + kk) * wtaps + wt];
                 } else {
                     const int co = g * cout_g + kk, ci_local = n - g * cin_g;
-                    v = w[(static_cast<long long>(co) * cin_g + ci_local) * taps + tap];
+                    v = w[(static_cast<long long>(co) * cin_g + ci_local) * wtaps + wt];
                 }
                 hb[static_cast<size_t>(n * ldb + static_cast<long long>(tap) * cpt * TG_KC + pos)] = host_f_to_16(v, bf16);
             }
@@ -115,15 +118,22 @@ int pack_conv(const float* w, int cout, int cin, int groups, int k, int mode, bo
     out->ldb = ldb;
     out->rows = static_cast<int>(rows);
     out->in_stride = (mode == 2) ? 2 : 1;
-    for (int ky = 0; ky < k; ++ky)
-        for (int kx = 0; kx < k; ++kx) {
-            const int tap = ky * k + kx;
-            int dy = ky - (k - 1) / 2, dx = kx - (k - 1) / 2;
-            if (mode == 2) { dy = ky; dx = kx; }
-            if (bwd) { dy = -dy; dx = -dx; }
-            out->dx[tap] = dx;
-            out->dy[tap] = dy;
+    if (tap_sel) {
+        for (int t = 0; t < taps; ++t) {
+            out->dx[t] = (*tap_sel)[t].dx;
+            out->dy[t] = (*tap_sel)[t].dy;
         }
+    } else {
+        for (int ky = 0; ky < k; ++ky)
+            for (int kx = 0; kx < k; ++kx) {
+                const int tap = ky * k + kx;
+                int dy = ky - (k - 1) / 2, dx = kx - (k - 1) / 2;
+                if (mode == 2) { dy = ky; dx = kx; }
+                if (bwd) { dy = -dy; dx = -dx; }
+                out->dx[tap] = dx;
+                out->dy[tap] = dy;
+            }
+    }
     CUDA_CK(cudaMalloc(&out->Bm, hb.size() * 2));
     CUDA_CK(cudaMemcpy(out->Bm, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice));
     CUDA_CK(cudaMalloc(&out->a_c0, n_tiles * sizeof(int)));
@@ -331,8 +341,8 @@ int Decoder::pack_named_conv(const std::string& name, int cout, int cin, int gro
     ConvW& cw = convs[name];
     cw.cin = cin;
     cw.cout = cout;
-    CK(pack_conv(wv->data(), cout, cin, groups, k, fwd_mode, bf16 != 0, 0, &cw.fwd));
-    if (want_bwd && fwd_mode == 0) CK(pack_conv(wv->data(), cout, cin, groups, k, 1, bf16 != 0, 0, &cw.bwd));
+    CK(pack_conv(wv->data(), cout, cin, groups, k, fwd_mode, bf16 != 0, 0, &cw.fwd, nullptr));
+    if (want_bwd && fwd_mode == 0) CK(pack_conv(wv->data(), cout, cin, groups, k, 1, bf16 != 0, 0, &cw.bwd, nullptr));
     CK(upload_f32(*bv, &cw.bias));
     return 0;
 }
@@ -364,7 +374,22 @@ int Decoder::finalize_weights() {
         char buf[128];
         snprintf(buf, sizeof(buf), "decoder.up_blocks.%d.downsamplers.0.conv", i);
         const int cch = cfg.block_out_channels[cfg.n_blocks - 1 - i];
-        CK(pack_named_conv(buf, cch, cch, cfg.conv_groups[cfg.n_blocks - 1 - i], 3, false, 2));
+        const int grp = cfg.conv_groups[cfg.n_blocks - 1 - i];
+        CK(pack_named_conv(buf, cch, cch, grp, 3, false, 2));
+        // backward-data of the stride-2 conv: one contraction per output parity (py, px). For row parity 0 the taps
+        // ky = 0 (source row y') and ky = 2 (source row y' - 1) contribute, for parity 1 only ky = 1; same along x.
+        const std::vector<float>* wv;
+        CK(need(std::string(buf) + ".weight", static_cast<long long>(cch) * (cch / grp) * 9, &wv));
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+                std::vector<TapSel> sel;
+                for (int ky = py; ky < 3; ky += 2)
+                    for (int kx = px; kx < 3; kx += 2) sel.push_back(TapSel{ky * 3 + kx, -((kx - px) / 2), -((ky - py) / 2)});
+                ConvW& cw = convs[std::string(buf) + ".bwd" + std::to_string(py * 2 + px)];
+                cw.cin = cch;
+                cw.cout = cch;
+                CK(pack_conv(wv->data(), cch, cch, grp, 3, 1, bf16 != 0, 0, &cw.bwd, &sel));
+            }
     }
     // attention: q,k,v merged into one [3C, C] matrix (+ backward form), v alone as an A operand, proj
     {
@@ -389,14 +414,9 @@ int Decoder::finalize_weights() {
         ConvW& cq = convs["attn.qkv"];
         cq.cin = Cm;
         cq.cout = 3 * Cm;
-        CK(pack_conv(wq.data(), 3 * Cm, Cm, 1, 1, 0, bf16 != 0, 192, &cq.fwd));
-        CK(pack_conv(wq.data(), 3 * Cm, Cm, 1, 1, 1, bf16 != 0, 0, &cq.bwd));
+        CK(pack_conv(wq.data(), 3 * Cm, Cm, 1, 1, 0, bf16 != 0, Cm % 192 == 0 ? 192 : 0, &cq.fwd, nullptr));
+        CK(pack_conv(wq.data(), 3 * Cm, Cm, 1, 1, 1, bf16 != 0, 0, &cq.bwd, nullptr));
         CK(upload_f32(bq, &cq.bias));
-        ConvW& cv = convs["attn.v"];
-        cv.cin = Cm;
-        cv.cout = Cm;
-        CK(pack_conv(v->data(), Cm, Cm, 1, 1, 0, bf16 != 0, 0, &cv.fwd));
-        CK(upload_f32(*vb, &cv.bias));
         CK(pack_named_conv(a + "proj_attn", Cm, Cm, 1, 1, true, 0));
     }
     CK(upload_vec("decoder.conv_norm_out.weight", C_last));
@@ -457,7 +477,8 @@ int Decoder::run_gemm(Exec& ex, TapGemmOp& tmpl, bool z_is_batch) {
 
 // conv-style contraction over a channels-last activation
 int Decoder::conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int Hin, int Win, int Hout, int Wout,
-                       void* out, long long ldc, const float* bias, const void* residual, float* gn_sums, int gn_cpg) {
+                       void* out, long long ldc, const float* bias, const void* residual, float* gn_sums, int gn_cpg,
+                       const OutStrides* os) {
     TapGemmOp op;
     memset(&op, 0, sizeof(op));
     TapGemmParams& p = op.p;
@@ -488,13 +509,13 @@ int Decoder::conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int 
         p.N = pk.N;
         p.out = out;
         p.out_fp32 = 0;
-        p.out_sx = ldc;
-        p.out_sy = ldc * Wout;
-        p.out_sb = ldc * Wout * Hout;
+        p.out_sx = os ? os->sx : ldc;
+        p.out_sy = os ? os->sy : ldc * Wout;
+        p.out_sb = os ? os->sb : ldc * Wout * Hout;
         p.bias = bias;
         p.residual = residual;
         p.alpha = 1.f;
-        p.gn_sums = fuse_gn ? gn_sums : nullptr;
+        p.gn_sums = (fuse_gn && gn_cpg > 0 && gn_cpg % 16 == 0) ? gn_sums : nullptr;
         p.gn_cpg = gn_cpg;
         p.gn_G = G;
         p.is_bf16 = bf16;
@@ -569,7 +590,7 @@ int Decoder::plain_gemm(Exec& ex, const PlainGemm& g) {
         p.bias = g.bias;
         p.residual = g.residual;
         p.alpha = g.alpha;
-        p.gn_sums = fuse_gn ? g.gn_sums : nullptr;
+        p.gn_sums = (fuse_gn && g.gn_cpg > 0 && g.gn_cpg % 16 == 0) ? g.gn_sums : nullptr;
         p.gn_cpg = g.gn_cpg;
         p.gn_G = G;
         p.is_bf16 = bf16;
@@ -609,6 +630,7 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
     }
     int cur_h = h, cur_w = w;
     int ri = 0;
+    auto fused_ok = [&](int C) { return fuse_gn && (C / G) % 16 == 0; };
     auto resnet = [&](int idx, uint8_t* xin, bool stats_ready) -> int {
         const ResnetDesc& r = resnets[idx];
         const int phw = r.h * r.w;
@@ -623,22 +645,22 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
         int next_gn = last ? n_gn - 1 : (idx == 0 ? n_gn - 2 : 2 * (idx + 1));
         int next_cpg = r.cout / G;
         if (!ex.prepare) {
-            if (!stats_ready || !fuse_gn) CK(gn_stats(xin, gn_sums_ptr(gi1), B, phw, r.cin, G, bf16, s));
+            if (!stats_ready || !fused_ok(r.cin)) CK(gn_stats(xin, gn_sums_ptr(gi1), B, phw, r.cin, G, bf16, s));
             CK(gn_apply(xin, gn_sums_ptr(gi1), vecs[r.prefix + ".norm1.weight"], vecs[r.prefix + ".norm1.bias"], act, B,
                         phw, r.cin, G, eps, 1, bf16, s));
         }
         const ConvW& c1 = convs[r.prefix + ".conv1"];
         CK(conv_gemm(ex, c1.fwd, act, r.cin, r.h, r.w, r.h, r.w, h1, r.cout, c1.bias, nullptr, gn_sums_ptr(gi2),
-                     r.cout / G));
+                     r.cout / G, nullptr));
         if (!ex.prepare) {
-            if (!fuse_gn) CK(gn_stats(h1, gn_sums_ptr(gi2), B, phw, r.cout, G, bf16, s));
+            if (!fused_ok(r.cout)) CK(gn_stats(h1, gn_sums_ptr(gi2), B, phw, r.cout, G, bf16, s));
             CK(gn_apply(h1, gn_sums_ptr(gi2), vecs[r.prefix + ".norm2.weight"], vecs[r.prefix + ".norm2.bias"], act2, B,
                         phw, r.cout, G, eps, 1, bf16, s));
         }
         const void* residual = xin;
         if (r.cin != r.cout) {
             const ConvW& cs = convs[r.prefix + ".conv_shortcut"];
-            CK(conv_gemm(ex, cs.fwd, xin, r.cin, r.h, r.w, r.h, r.w, ws + o_sc, r.cout, cs.bias, nullptr, nullptr, 0));
+            CK(conv_gemm(ex, cs.fwd, xin, r.cin, r.h, r.w, r.h, r.w, ws + o_sc, r.cout, cs.bias, nullptr, nullptr, 0, nullptr));
             residual = ws + o_sc;
         }
         const ConvW& c2 = convs[r.prefix + ".conv2"];
@@ -649,7 +671,7 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
             feeds_down = down_after[blk] && j == cfg.layers_per_block;
         }
         CK(conv_gemm(ex, c2.fwd, act2, r.cout, r.h, r.w, r.h, r.w, xout, r.cout, c2.bias, residual,
-                     feeds_down ? nullptr : gn_sums_ptr(next_gn), next_cpg));
+                     feeds_down ? nullptr : gn_sums_ptr(next_gn), next_cpg, nullptr));
         return 0;
     };
 
@@ -663,11 +685,13 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
         uint8_t* qkv = ws + o_qkv;
         const std::string a = "decoder.mid_block.attentions.0.";
         if (!ex.prepare) {
-            if (!fuse_gn) CK(gn_stats(x, gn_sums_ptr(n_gn - 2), B, N, Cm, G, bf16, s));
+            if (!fused_ok(Cm)) CK(gn_stats(x, gn_sums_ptr(n_gn - 2), B, N, Cm, G, bf16, s));
             CK(gn_apply(x, gn_sums_ptr(n_gn - 2), vecs[a + "group_norm.weight"], vecs[a + "group_norm.bias"], xn, B, N,
                         Cm, G, eps, 0, bf16, s));
         }
         const ConvW& cq = convs["attn.qkv"];
+        const int bn_c = Cm % 192 == 0 ? 192 : (Cm % 128 == 0 ? 128 : (Cm % 64 == 0 ? 64 : 16));
+        const int bn_n = N % 256 == 0 ? 256 : 128;
         PlainGemm g;
         memset(&g, 0, sizeof(g));
         // q | k | v = xn W^T + b
@@ -676,27 +700,23 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
         g.BN = cq.fwd.BN; g.N = 3 * Cm; g.out = qkv; g.out_fp32 = 0; g.ldc = 3 * Cm; g.c_zstride = 0;
         g.bias = cq.bias; g.residual = nullptr; g.alpha = 1.f;
         CK(plain_gemm(ex, g));
-        // v^T[b] = Wv xn[b]^T (bias folded into the PV epilogue: softmax rows sum to one)
-        const ConvW& cv = convs["attn.v"];
-        memset(&g, 0, sizeof(g));
-        g.A = cv.fwd.Bm; g.K = Cm; g.a_ld = cv.fwd.ldb; g.rows_per_sample = Cm; g.a_B = 1; g.a_shared = true;
-        g.Bm = xn; g.b_rows = N; g.ldb = Cm; g.b_zstride = static_cast<long long>(N) * Cm; g.b_Z = B_max;
-        g.BN = 256; g.N = N; g.out = ws + o_vt; g.out_fp32 = 0; g.ldc = N; g.c_zstride = static_cast<long long>(Cm) * N;
-        g.alpha = 1.f;
-        CK(plain_gemm(ex, g));
+        // v^T per sample (the B operand of P V must be K-major along the key tokens)
+        if (!ex.prepare)
+            CK(transpose16(qkv + static_cast<size_t>(2 * Cm) * 2, ws + o_vt, B, N, Cm, 3 * Cm,
+                           static_cast<long long>(N) * 3 * Cm, s));
         // scores = q k^T / sqrt(C) in fp32
         memset(&g, 0, sizeof(g));
         g.A = qkv; g.K = Cm; g.a_ld = 3 * Cm; g.rows_per_sample = N; g.a_B = B_max; g.a_shared = false;
         g.Bm = qkv + static_cast<size_t>(Cm) * 2; g.b_rows = N; g.ldb = 3 * Cm;
         g.b_zstride = static_cast<long long>(N) * 3 * Cm; g.b_Z = B_max; g.b_per_sample = true;
-        g.BN = 256; g.N = N; g.out = ws + o_S; g.out_fp32 = 1; g.ldc = N; g.alpha = 1.f / sqrtf(static_cast<float>(Cm));
+        g.BN = bn_n; g.N = N; g.out = ws + o_S; g.out_fp32 = 1; g.ldc = N; g.alpha = 1.f / sqrtf(static_cast<float>(Cm));
         CK(plain_gemm(ex, g));
         if (!ex.prepare) CK(attn_softmax(reinterpret_cast<const float*>(ws + o_S), ws + o_P, static_cast<long long>(B) * N, N, bf16, s));
-        // o = p v + bv
+        // o = p v
         memset(&g, 0, sizeof(g));
         g.A = ws + o_P; g.K = N; g.a_ld = N; g.rows_per_sample = N; g.a_B = B_max; g.a_shared = false;
         g.Bm = ws + o_vt; g.b_rows = Cm; g.ldb = N; g.b_zstride = static_cast<long long>(Cm) * N; g.b_Z = B_max;
-        g.b_per_sample = true; g.BN = 192; g.N = Cm; g.out = ws + o_O; g.out_fp32 = 0; g.ldc = Cm; g.bias = cv.bias;
+        g.b_per_sample = true; g.BN = bn_c; g.N = Cm; g.out = ws + o_O; g.out_fp32 = 0; g.ldc = Cm;
         g.alpha = 1.f;
         CK(plain_gemm(ex, g));
         // proj + residual
@@ -725,7 +745,7 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
             snprintf(buf, sizeof(buf), "decoder.up_blocks.%d.downsamplers.0.conv", i);
             const ConvW& cd = convs[buf];
             CK(conv_gemm(ex, cd.fwd, x, cd.cin, cur_h, cur_w, cur_h / 2, cur_w / 2, ws + o_down_out[i], cd.cout,
-                         cd.bias, nullptr, nullptr, 0));
+                         cd.bias, nullptr, nullptr, 0, nullptr));
             x = ws + o_down_out[i];
             cur_h /= 2;
             cur_w /= 2;
@@ -735,13 +755,13 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
     // conv_norm_out + SiLU + conv_out (wf_vae.py:228-230)
     const bool last_down = down_after[cfg.n_blocks - 1] != 0;
     if (!ex.prepare) {
-        if (!fuse_gn || last_down) CK(gn_stats(x, gn_sums_ptr(n_gn - 1), B, H_out * W_out, C_last, G, bf16, s));
+        if (!fused_ok(C_last) || last_down) CK(gn_stats(x, gn_sums_ptr(n_gn - 1), B, H_out * W_out, C_last, G, bf16, s));
         CK(gn_apply(x, gn_sums_ptr(n_gn - 1), vecs["decoder.conv_norm_out.weight"], vecs["decoder.conv_norm_out.bias"],
                     ws + o_act, B, H_out * W_out, C_last, G, eps, 1, bf16, s));
     }
     const ConvW& co = convs["decoder.conv_out"];
     CK(conv_gemm(ex, co.fwd, ws + o_act, C_last, H_out, W_out, H_out, W_out, ws + o_logits, T_pad, co.bias, nullptr,
-                 nullptr, 0));
+                 nullptr, 0, nullptr));
     return 0;
 }
 
@@ -757,14 +777,9 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
     // gradient buffers rotate: `cur` holds d(out) of the layer being differentiated
     int cur = 0;
     auto gbuf = [&](int i) { return ws + o_g[i & 3]; };
-    for (int i = 0; i < cfg.n_blocks; ++i)
-        if (down_after[i]) {
-            set_error("decoder: backward through DownDecoderBlock2D is not implemented yet");
-            return -11;
-        }
     // conv_out^T, then conv_norm_out + SiLU backward
     const ConvW& co = convs["decoder.conv_out"];
-    CK(conv_gemm(ex, co.bwd, dlog, T_pad, H_out, W_out, H_out, W_out, gbuf(cur), C_last, nullptr, nullptr, nullptr, 0));
+    CK(conv_gemm(ex, co.bwd, dlog, T_pad, H_out, W_out, H_out, W_out, gbuf(cur), C_last, nullptr, nullptr, nullptr, 0, nullptr));
     if (!ex.prepare) {
         CK(gn_bwd_reduce(gbuf(cur), x_last, gn_sums_ptr(n_gn - 1), vecs["decoder.conv_norm_out.weight"],
                          vecs["decoder.conv_norm_out.bias"], gn_red_ptr(n_gn - 1), B, H_out * W_out, C_last, G, eps, 1,
@@ -783,7 +798,7 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         const uint8_t* h1 = ws + o_res_h1[idx];
         const int gi1 = 2 * idx, gi2 = 2 * idx + 1;
         const ConvW& c2 = convs[r.prefix + ".conv2"];
-        CK(conv_gemm(ex, c2.bwd, dout, r.cout, r.h, r.w, r.h, r.w, t1, r.cout, nullptr, nullptr, nullptr, 0));
+        CK(conv_gemm(ex, c2.bwd, dout, r.cout, r.h, r.w, r.h, r.w, t1, r.cout, nullptr, nullptr, nullptr, 0, nullptr));
         if (!ex.prepare) {
             const float* ga = vecs[r.prefix + ".norm2.weight"];
             const float* be = vecs[r.prefix + ".norm2.bias"];
@@ -792,11 +807,11 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
                             bf16, s));
         }
         const ConvW& c1 = convs[r.prefix + ".conv1"];
-        CK(conv_gemm(ex, c1.bwd, t1, r.cout, r.h, r.w, r.h, r.w, t2, r.cin, nullptr, nullptr, nullptr, 0));
+        CK(conv_gemm(ex, c1.bwd, t1, r.cout, r.h, r.w, r.h, r.w, t2, r.cin, nullptr, nullptr, nullptr, 0, nullptr));
         const void* add = dout;
         if (r.cin != r.cout) {
             const ConvW& cs = convs[r.prefix + ".conv_shortcut"];
-            CK(conv_gemm(ex, cs.bwd, dout, r.cout, r.h, r.w, r.h, r.w, t3, r.cin, nullptr, nullptr, nullptr, 0));
+            CK(conv_gemm(ex, cs.bwd, dout, r.cout, r.h, r.w, r.h, r.w, t3, r.cin, nullptr, nullptr, nullptr, 0, nullptr));
             add = t3;
         }
         if (!ex.prepare) {
@@ -809,10 +824,40 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         cur = (cur + 2) & 3;
         return 0;
     };
-    // decoder blocks in reverse
-    for (int idx = static_cast<int>(resnets.size()) - 1; idx >= 2; --idx) {
-        const uint8_t* xin = (idx == 2) ? ws + o_res_out[1] : ws + o_res_out[idx - 1];
-        CK(resnet_bwd(idx, xin));
+    // decoder blocks in reverse; a DownDecoderBlock2D first undoes its stride-2 conv
+    {
+        const int n_res = cfg.layers_per_block + 1;
+        for (int i = cfg.n_blocks - 1; i >= 0; --i) {
+            const int last_idx = 2 + i * n_res + n_res - 1;
+            if (down_after[i]) {
+                const ResnetDesc& r = resnets[last_idx];  // its plane is the conv's input plane
+                char buf[128];
+                uint8_t* dout = gbuf(cur);
+                uint8_t* dxin = gbuf(cur + 1);
+                for (int py = 0; py < 2; ++py)
+                    for (int px = 0; px < 2; ++px) {
+                        snprintf(buf, sizeof(buf), "decoder.up_blocks.%d.downsamplers.0.conv.bwd%d", i, py * 2 + px);
+                        const ConvW& cb = convs[buf];
+                        OutStrides os;
+                        os.sx = 2LL * r.cout;
+                        os.sy = 2LL * r.w * r.cout;
+                        os.sb = static_cast<long long>(r.h) * r.w * r.cout;
+                        uint8_t* base = dxin + (static_cast<size_t>(py) * r.w + px) * r.cout * 2;
+                        CK(conv_gemm(ex, cb.bwd, dout, r.cout, r.h / 2, r.w / 2, r.h / 2, r.w / 2, base, r.cout, nullptr,
+                                     nullptr, nullptr, 0, &os));
+                    }
+                cur = (cur + 1) & 3;
+            }
+            for (int j = n_res - 1; j >= 0; --j) {
+                const int idx = 2 + i * n_res + j;
+                const uint8_t* xin;
+                if (j > 0) xin = ws + o_res_out[idx - 1];
+                else if (i == 0) xin = ws + o_res_out[1];
+                else if (down_after[i - 1]) xin = ws + o_down_out[i - 1];
+                else xin = ws + o_res_out[idx - 1];
+                CK(resnet_bwd(idx, xin));
+            }
+        }
     }
     CK(resnet_bwd(1, ws + o_attn_out));
     {
@@ -825,6 +870,8 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         const uint8_t* qkv = ws + o_qkv;
         uint8_t* dqkv = ws + o_dqkv;
         const ConvW& cp = convs[a + "proj_attn"];
+        const int bn_c = Cm % 192 == 0 ? 192 : (Cm % 128 == 0 ? 128 : (Cm % 64 == 0 ? 64 : 16));
+        const int bn_n = N % 256 == 0 ? 256 : 128;
         PlainGemm g;
         // dO = dout Wp
         memset(&g, 0, sizeof(g));
@@ -842,14 +889,14 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         memset(&g, 0, sizeof(g));
         g.A = ws + o_PT; g.K = N; g.a_ld = N; g.rows_per_sample = N; g.a_B = B_max;
         g.Bm = ws + o_dOT; g.b_rows = Cm; g.ldb = N; g.b_zstride = static_cast<long long>(Cm) * N; g.b_Z = B_max;
-        g.b_per_sample = true; g.BN = 192; g.N = Cm; g.out = dqkv + static_cast<size_t>(2 * Cm) * 2; g.ldc = 3 * Cm; g.alpha = 1.f;
+        g.b_per_sample = true; g.BN = bn_c; g.N = Cm; g.out = dqkv + static_cast<size_t>(2 * Cm) * 2; g.ldc = 3 * Cm; g.alpha = 1.f;
         CK(plain_gemm(ex, g));
         // dP = dO V^T (fp32, reuses the score buffer)
         memset(&g, 0, sizeof(g));
         g.A = ws + o_dO; g.K = Cm; g.a_ld = Cm; g.rows_per_sample = N; g.a_B = B_max;
         g.Bm = qkv + static_cast<size_t>(2 * Cm) * 2; g.b_rows = N; g.ldb = 3 * Cm;
         g.b_zstride = static_cast<long long>(N) * 3 * Cm; g.b_Z = B_max; g.b_per_sample = true;
-        g.BN = 256; g.N = N; g.out = ws + o_S; g.out_fp32 = 1; g.ldc = N; g.alpha = 1.f;
+        g.BN = bn_n; g.N = N; g.out = ws + o_S; g.out_fp32 = 1; g.ldc = N; g.alpha = 1.f;
         CK(plain_gemm(ex, g));
         if (!ex.prepare) {
             CK(attn_softmax_bwd(ws + o_P, reinterpret_cast<const float*>(ws + o_S), ws + o_dS, static_cast<long long>(B) * N,
@@ -860,13 +907,13 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         memset(&g, 0, sizeof(g));
         g.A = ws + o_dS; g.K = N; g.a_ld = N; g.rows_per_sample = N; g.a_B = B_max;
         g.Bm = ws + o_KT; g.b_rows = Cm; g.ldb = N; g.b_zstride = static_cast<long long>(Cm) * N; g.b_Z = B_max;
-        g.b_per_sample = true; g.BN = 192; g.N = Cm; g.out = dqkv; g.ldc = 3 * Cm; g.alpha = 1.f;
+        g.b_per_sample = true; g.BN = bn_c; g.N = Cm; g.out = dqkv; g.ldc = 3 * Cm; g.alpha = 1.f;
         CK(plain_gemm(ex, g));
         // dK = dS^T Q -> dqkv[:, C:2C]
         memset(&g, 0, sizeof(g));
         g.A = ws + o_dST; g.K = N; g.a_ld = N; g.rows_per_sample = N; g.a_B = B_max;
         g.Bm = ws + o_QT; g.b_rows = Cm; g.ldb = N; g.b_zstride = static_cast<long long>(Cm) * N; g.b_Z = B_max;
-        g.b_per_sample = true; g.BN = 192; g.N = Cm; g.out = dqkv + static_cast<size_t>(Cm) * 2; g.ldc = 3 * Cm; g.alpha = 1.f;
+        g.b_per_sample = true; g.BN = bn_c; g.N = Cm; g.out = dqkv + static_cast<size_t>(Cm) * 2; g.ldc = 3 * Cm; g.alpha = 1.f;
         CK(plain_gemm(ex, g));
         // d xn = [dQ | dK | dV] Wqkv
         const ConvW& cq = convs["attn.qkv"];

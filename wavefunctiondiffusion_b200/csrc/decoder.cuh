@@ -20,7 +20,14 @@ struct PackedB {
     int dx[TG_MAX_TAPS] = {0}, dy[TG_MAX_TAPS] = {0};
     void release();
 };
-int pack_conv(const float* w, int cout, int cin, int groups, int k, int mode, bool bf16, int bn_override, PackedB* out);
+struct TapSel {  // one tap of a contraction: which weight tap it reads and where it shifts the input
+    int w_tap, dx, dy;
+};
+struct OutStrides {  // element strides of a strided output plane (downsample backward writes every other pixel)
+    long long sx, sy, sb;
+};
+int pack_conv(const float* w, int cout, int cin, int groups, int k, int mode, bool bf16, int bn_override, PackedB* out,
+              const std::vector<TapSel>* tap_sel);
 
 struct ConvW {
     PackedB fwd, bwd;
@@ -83,7 +90,8 @@ struct Decoder {
     int prepare_ops();
     int run_gemm(Exec& ex, TapGemmOp& tmpl, bool z_is_batch);
     int conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int Hin, int Win, int Hout, int Wout, void* out,
-                  long long ldc, const float* bias, const void* residual, float* gn_sums, int gn_cpg);
+                  long long ldc, const float* bias, const void* residual, float* gn_sums, int gn_cpg,
+                  const OutStrides* os);
     int plain_gemm(Exec& ex, const PlainGemm& g);
     float* gn_sums_ptr(int idx) const;
     float* gn_red_ptr(int idx) const;

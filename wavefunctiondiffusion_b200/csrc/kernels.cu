@@ -15,6 +15,10 @@ namespace wfd {
             return -7;                                                  \
         }                                                               \
         ++g_launch_count;                                               \
+        if (debug_sync_enabled()) {                                     \
+            int rc__ = debug_sync_check(name, s);                       \
+            if (rc__ < 0) return rc__;                                  \
+        }                                                               \
     } while (0)
 
 #define WFD_DISPATCH_BF16(flag, ...)      \

@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace wfd {
 
@@ -17,6 +18,26 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 long long g_launch_count = 0;
+
+// WFD_DEBUG_SYNC=1: synchronise after every launch and report the failing kernel by name (debugging aid only).
+int debug_sync_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("WFD_DEBUG_SYNC");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v;
+}
+int debug_sync_check(const char* what, cudaStream_t stream) {
+    if (!debug_sync_enabled()) return 0;
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+        set_error("%s: device fault: %s", what, cudaGetErrorString(e));
+        fprintf(stderr, "wfd debug: %s: device fault: %s\n", what, cudaGetErrorString(e));
+        return -20;
+    }
+    return 0;
+}
 
 int num_sms() {
     static int n = 0;
@@ -467,6 +488,14 @@ int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream) {
         return -7;
     }
     ++g_launch_count;
+    if (debug_sync_enabled()) {
+        char what[256];
+        snprintf(what, sizeof(what),
+                 "tapgemm(m_tiles=%d n_tiles=%d z=%d BN=%d N=%d taps=%d cpt=%d box=%dx%d stages=%d smem=%zu aC=%d aW=%d aH=%d aB=%d)",
+                 p.m_tiles, p.n_tiles, p.z_count, p.BN, p.N, p.n_taps, p.cpt, p.w_box, p.h_box, op->stages,
+                 op->smem_bytes, p.a_C, p.a_W, p.a_H, p.a_B);
+        return debug_sync_check(what, stream);
+    }
     return 0;
 }
 

@@ -74,6 +74,8 @@ int tapgemm_launch_ref(const TapGemmOp* op, cudaStream_t stream);
 void set_error(const char* fmt, ...);
 const char* last_error();
 extern long long g_launch_count;
+int debug_sync_enabled();
+int debug_sync_check(const char* what, cudaStream_t stream);
 int num_sms();
 
 }  // namespace wfd

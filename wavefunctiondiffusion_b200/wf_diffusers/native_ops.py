@@ -317,8 +317,10 @@ def argmax_tiles(x):
     _require_cuda(x, "argmax_tiles")
     x = x.contiguous()
     n = x.shape[-1]
-    rows = x.numel() // n
+    rows = x.numel() // n if n > 0 else 0
     out = torch.empty(x.shape[:-1], dtype=torch.int64, device=x.device)
+    if rows == 0:
+        return out
     code = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}[x.dtype]
     nat.check(nat.lib().wfd_argmax_tiles(C.c_void_p(x.data_ptr()), code, rows, n, C.c_void_p(out.data_ptr()),
                                          nat.stream_ptr()), "wfd_argmax_tiles")

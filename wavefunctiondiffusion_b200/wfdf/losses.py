@@ -6,7 +6,7 @@ directional adjacency matrices) and is differentiable w.r.t. `t` through a torch
 """
 import torch
 
-from ..wf_diffusers.native_ops import WfcHandle, WfcLossFunction, compute_dtype16
+from ..wf_diffusers.native_ops import WfcHandle, WfcLossFunction, _require_cuda, compute_dtype16
 
 
 class WFCLossEinsum(torch.nn.Module):
@@ -45,5 +45,6 @@ class WFCLossEinsum(torch.nn.Module):
     def forward(self, t, softmax=False):
         if t.dim() != 4 or t.size(1) < self.count:
             raise ValueError(f"wave must be (B, C>={self.count}, H, W), got {tuple(t.shape)}")
+        _require_cuda(t, "WFCLossEinsum")
         handle = self.native_handle(t.size(1), t.device)
         return WfcLossFunction.apply(t, handle, bool(softmax))
