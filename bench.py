@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Benchmark of the WFC-guidance hot path (decode + softmax + WFC loss + backward to the latents).
+
+    python bench.py --gpus N --steps K --warmup W            # CUDA arm (one process per GPU under torchrun for N > 1)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores (CPU arm)
+
+One "step" is one guidance step for the whole per-GPU batch of synthetic latents (BASELINE config 2: ice tileset,
+64x64 map, batch 8, random-init AutoencoderTile from configs/tilenet/tilenet_sc_space_64x64.json, strength 5).
+`value` is map-steps per second over all GPUs with inputs resident in HBM; `e2e` is the same through the pipeline's
+guidance block with host (pinned) latents and noise prediction copied in and the new latents copied out every step.
+Rank 0 prints exactly one JSON line.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+STRENGTH = 5.0
+LATENT_SCALE = 0.18215
+
+
+# --------------------------------------------------------------------------------------------------- flop model
+def decoder_layers(cfg, h, w):
+    """(name, macs) per tensor-core layer of one decode, from the architecture (SURVEY §8d closed form)."""
+    rev = list(reversed(cfg["block_out_channels"]))
+    rev_g = list(reversed(cfg["conv_groups"]))
+    n_res = cfg["layers_per_block"] + 1
+    cm = rev[0]
+    hw = h * w
+    out = [("conv_in", hw * 4 * cm * 9)]
+
+    def resnet(name, cin, cout, g, px):
+        out.append((name + ".conv1", px * cout * (cin // g) * 9))
+        out.append((name + ".conv2", px * cout * (cout // g) * 9))
+        if cin != cout:
+            out.append((name + ".shortcut", px * cout * (cin // g)))
+
+    resnet("mid.0", cm, cm, 1, hw)
+    out.append(("attn.qkv_proj", hw * cm * cm * 4))
+    out.append(("attn.bmm", 2 * hw * hw * cm))
+    resnet("mid.1", cm, cm, 1, hw)
+    ch, px = cm, hw
+    for i, kind in enumerate(cfg["up_block_types"]):
+        for j in range(n_res):
+            resnet("up%d.%d" % (i, j), ch if j == 0 else rev[i], rev[i], rev_g[i], px)
+        ch = rev[i]
+        if kind == "DownDecoderBlock2D":
+            px //= 4
+            out.append(("up%d.down" % i, px * ch * (ch // rev_g[i]) * 9))
+    out.append(("conv_out", px * cfg["out_channels"] * (ch // cfg["conv_init_groups"]) * 9))
+    return out, px
+
+
+def step_flops(cfg, h, w, T):
+    layers, px = decoder_layers(cfg, h, w)
+    f_dec = 2.0 * sum(m for _, m in layers)
+    f_attn = 4.0 * (h * w) ** 2 * list(reversed(cfg["block_out_channels"]))[0]
+    side = int(round(px ** 0.5))
+    H = W = side
+    P = H * (W - 1) + (H - 1) * W
+    f_loss = 4.0 * T * T * P
+    return {"F_dec": f_dec, "F_attn": f_attn, "F_loss": f_loss, "F_step": 2 * f_dec + f_attn + f_loss}
+
+
+# --------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------- workload
+def load_workload(args):
+    from wavefunctiondiffusion_b200.utils.tilesets import load_wfc_mats, round_up_channels, tilenet_config
+
+    mx, my = load_wfc_mats(args.tileset)
+    T = mx.shape[0]
+    t_pad = round_up_channels(T)
+    cfg = tilenet_config(args.arch, t_pad)
+    return mx, my, T, t_pad, cfg
+
+
+def cpu_oracle_maps_per_s(args, cfg, mx, my, repeats, maps=1):
+    """The reference algorithm (oracle port, fp32) on the host cores: best of `repeats` after one warm-up."""
+    import torch
+
+    from oracle import wfd_oracle as orc
+    from wavefunctiondiffusion_b200.wf_diffusers.wf_vae import AutoencoderTile
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    sd = AutoencoderTile(**cfg).state_dict()
+    g = torch.Generator().manual_seed(1234)
+    lat = torch.randn(maps, 4, args.latent, args.latent, generator=g)
+    orc.guidance_step(sd, cfg, mx, my, lat, STRENGTH, torch.float32)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.time()
+        orc.guidance_step(sd, cfg, mx, my, lat, STRENGTH, torch.float32)
+        best = min(best, time.time() - t0)
+    return maps / best, torch.get_num_threads(), best
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path. /root/reference (pure Python on diffusers) cannot travel to the GPU
+    box, so the timed code is the oracle port of the same arithmetic (validated against the unmodified reference by
+    tests/golden), with all host threads, one map of the batch per step as the bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import wfd_oracle as orc
+    from wavefunctiondiffusion_b200.wf_diffusers.wf_vae import AutoencoderTile
+
+    mx, my, T, t_pad, cfg = load_workload(args)
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    sd = AutoencoderTile(**cfg).state_dict()
+    g = torch.Generator().manual_seed(1234)
+    lat = torch.randn(1, 4, args.latent, args.latent, generator=g)
+    for _ in range(max(1, min(args.warmup, 2))):
+        orc.guidance_step(sd, cfg, mx, my, lat, STRENGTH, torch.float32)
+    steps = min(args.steps, 12)
+    t0 = time.time()
+    for _ in range(steps):
+        orc.guidance_step(sd, cfg, mx, my, lat, STRENGTH, torch.float32)
+    dt = time.time() - t0
+    v = steps / dt
+    sample = "1 map of the batch per step (fp32 oracle port, %d of the requested %d steps)" % (steps, args.steps)
+    print(json.dumps({
+        "impl": "reference", "metric": "wfc_guidance_map_steps_per_s", "value": v, "unit": "maps/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, T, t_pad, per_gpu_batch=1),
+        "cpu_baseline": {"value": v, "unit": "maps/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, T, t_pad, per_gpu_batch):
+    return {"workload": "%s tileset %dx%d map, batch %d per GPU, tilenet_sc_space_%s random init (seed 0), one "
+                        "WFC-guidance step = decode + softmax + WFC loss + grad to latents, strength %g"
+                        % (args.tileset, args.latent, args.latent, per_gpu_batch, args.arch, STRENGTH),
+            "tileset": args.tileset, "T": T, "T_pad": t_pad, "latent_hw": args.latent, "per_gpu_batch": per_gpu_batch,
+            "l2": "working set per step (activations + operands, several GB) exceeds the 126 MB L2; no flush needed"}
+
+
+def run_native(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    ge.build()
+    from wavefunctiondiffusion_b200 import _native as nat
+    from wavefunctiondiffusion_b200.utils.harness import AffineDDIMScheduler, ConstantTextEncoder, RandomNoiseUNet, TinyImageVAE, WhitespaceTokenizer
+    from wavefunctiondiffusion_b200.wf_diffusers.pipeline_wfd import WaveFunctionDiffusionPipeline
+    from wavefunctiondiffusion_b200.wf_diffusers.wf_vae import AutoencoderTile
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    mx, my, T, t_pad, cfg = load_workload(args)
+    B = args.batch
+    torch.manual_seed(0)
+    tile_vae = AutoencoderTile(**cfg).eval().to(dev)
+    npz = "/tmp/wfd_bench_%s_%d.npz" % (args.tileset, rank)
+    np.savez(npz, wfc_mats=np.stack([mx, my]))
+    sched = AffineDDIMScheduler()
+    sched.set_timesteps(50, device=dev)
+    pipe = WaveFunctionDiffusionPipeline(TinyImageVAE(), ConstantTextEncoder(), WhitespaceTokenizer(), tile_vae,
+                                         RandomNoiseUNet(4, args.latent), sched, None, None, wfc_data_path=npz)
+    pipe.to(dev)
+    g = torch.Generator().manual_seed(1234 + rank)
+    lat_host = torch.randn(B, 4, args.latent, args.latent, generator=g).pin_memory()
+    eps_host = torch.randn(B, 4, args.latent, args.latent, generator=g).pin_memory()
+    out_host = torch.empty_like(lat_host).pin_memory()
+    lat = lat_host.to(dev)
+    lib = nat.lib()
+    plan = tile_vae._native.plan(B, args.latent, args.latent, dev)
+    handle = pipe.wfc_loss.native_handle(t_pad, dev)
+    loss = torch.empty(B, dtype=torch.float32, device=dev)
+    dz = torch.empty(B, 4, args.latent, args.latent, dtype=torch.float32, device=dev)
+    saved = handle.saved_ptr(B, plan.H, plan.W)
+
+    def step_resident():
+        nat.check(lib.wfd_guidance_step(plan.handle, handle.handle, C.c_void_p(lat.data_ptr()), 0, B, 1.0 / LATENT_SCALE,
+                                        STRENGTH, saved, C.c_void_p(loss.data_ptr()), C.c_void_p(dz.data_ptr()),
+                                        nat.stream_ptr()), "wfd_guidance_step")
+
+    t_step = sched.timesteps[20]
+
+    def step_e2e():
+        l = lat_host.to(dev, non_blocking=True)
+        e = eps_host.to(dev, non_blocking=True)
+        new = pipe.wfc_guidance(l, e, t_step, STRENGTH)
+        out_host.copy_(new, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.wfd_launch_count()
+    ms = timed(step_resident, args.steps, max(args.warmup, 3))
+    launches = (lib.wfd_launch_count() - n0) // (args.steps + max(args.warmup, 3)) * args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
+    # per-kernel CUDA-event profile of a few extra steps (separate from the timed region) for the roofline numbers
+    prof = {}
+    if rank == 0:
+        lib.wfd_profile_enable(1)
+        psteps = 3
+        for _ in range(psteps):
+            step_resident()
+        torch.cuda.synchronize()
+        buf = C.create_string_buffer(1 << 16)
+        lib.wfd_profile_report(buf, len(buf))
+        lib.wfd_profile_enable(0)
+        for line in buf.value.decode().splitlines():
+            name, cnt, tot = line.rsplit(" ", 2)
+            prof[name] = (int(cnt) / psteps, float(tot) / psteps)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    total_maps = world * B
+    value = total_maps * args.steps / (ms / 1e3)
+    e2e = total_maps * args.steps / (ms_e2e / 1e3)
+    fl = step_flops(cfg, args.latent, args.latent, T)
+    tg_ms = sum(t for n, (c, t) in prof.items() if n.startswith("tapgemm"))
+    tg_launches = sum(c for n, (c, t) in prof.items() if n.startswith("tapgemm"))
+    all_ms = sum(t for c, t in prof.values())
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    achieved = fl["F_step"] * B / (tg_ms / 1e3) / 1e12 if tg_ms > 0 else None
+    roofline = {"bound": "tensor", "kernel": "tapgemm_kernel (all tensor-core contractions of the step)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if achieved else None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)",
+                "algorithmic_flops_per_step": fl["F_step"] * B, "launches_per_step": tg_launches,
+                "avg_launch_ms": tg_ms / tg_launches if tg_launches else None, "kernel_ms_per_step": tg_ms,
+                "share_of_step": tg_ms / all_ms if all_ms else None, "traffic": None}
+    top = sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]
+    if args.verbose:
+        for n, (c, t) in top:
+            print("  %-60s %6.1f launches %9.3f ms/step" % (n, c, t), file=sys.stderr)
+        print("  profiled total %.3f ms/step, tapgemm %.3f ms" % (all_ms, tg_ms), file=sys.stderr)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, cores, sec = cpu_oracle_maps_per_s(args, cfg, mx, my, repeats=3)
+        cpu = {"value": v, "unit": "maps/s", "cores": cores, "kind": "port",
+               "sample": "1 map of the batch (fp32 oracle port), 1 warm-up + best of 3, %.2f s per map-step" % sec}
+    out = {
+        "metric": "wfc_guidance_map_steps_per_s", "value": value, "unit": "maps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args, T, t_pad, B),
+        "steps_per_s": world * args.steps / (ms / 1e3) / world,
+        "e2e": {"value": e2e, "unit": "maps/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": 2 * lat_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
+                "api": "WaveFunctionDiffusionPipeline.wfc_guidance (pipeline_wfd.py:606-615 block) with pinned host tensors"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "loss_check": [float(x) for x in loss.cpu()[:2]],
+        "profile_top": [{"kernel": n, "launches_per_step": c, "ms_per_step": t} for n, (c, t) in top],
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="maps per GPU")
+    ap.add_argument("--tileset", default="ice_64x64")
+    ap.add_argument("--arch", default="64x64", choices=["64x64", "32x32"])
+    ap.add_argument("--latent", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_native(args)
+
+
+if __name__ == "__main__":
+    main()

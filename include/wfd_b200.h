@@ -147,6 +147,10 @@ typedef struct {
     int dtype16;
 } wfd_tapgemm_desc;
 WFD_API int wfd_test_tapgemm(const wfd_tapgemm_desc* desc, int use_ref, void* stream);
+/* per-launch CUDA-event profiling (bench.py roofline): enable(1) clears and starts recording, report() synchronises the
+ * recorded events and writes "name launches total_ms" lines into buf (returns the untruncated length) */
+WFD_API int wfd_profile_enable(int on);
+WFD_API int wfd_profile_report(char* buf, size_t cap);
 /* when set to 1 every tensor-core contraction is routed to the CUDA-core checking kernel (debug bisecting only) */
 WFD_API int wfd_debug_set_ref_gemm(int on);
 

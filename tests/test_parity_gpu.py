@@ -76,9 +76,10 @@ def test_guidance_block_as_the_reference_pipeline_writes_it(ref_gemm):
     assert _rel(grad.cpu(), z["grad_f64"]) < TOL_GRAD
 
 
+@pytest.mark.parametrize("name", ["tiny_step.npz", "tiny_down_step.npz"])
 @pytest.mark.parametrize("ref_gemm", [1, 0])
-def test_fused_guidance_step_small(ref_gemm):
-    z, cfg, mats, net = _load_small("tiny_step.npz")
+def test_fused_guidance_step_small(ref_gemm, name):
+    z, cfg, mats, net = _load_small(name)
     nat.lib().wfd_debug_set_ref_gemm(ref_gemm)
     wfc_loss = WFCLossEinsum(mats[0], mats[1]).cuda()
     lat = torch.from_numpy(z["latents"]).cuda().requires_grad_()
@@ -218,10 +219,13 @@ def test_batch_properties_full_size():
     loss = GuidanceLossFunction.apply(z, net._native, handle, 1 / 0.18215, 5.0)
     (grad,) = torch.autograd.grad(loss.sum(), z)
     assert torch.isfinite(loss).all() and torch.isfinite(grad).all()
-    assert abs(loss[5].item() - loss[2].item()) <= 2e-5 * abs(loss[2].item())
-    assert _rel(grad[5].cpu(), grad[2].cpu()) < 1e-3
+    # identical maps agree to the bf16 noise floor only: the GroupNorm statistics are accumulated with fp32 atomics in
+    # nondeterministic order, and 16-bit rounding amplifies a 1e-7 perturbation to the rounding-noise level within a
+    # few layers (same size as the error against the fp64 reference)
+    assert abs(loss[5].item() - loss[2].item()) <= 1e-4 * abs(loss[2].item())
+    assert _rel(grad[5].cpu(), grad[2].cpu()) < TOL_GRAD
     z1 = lat[:1].clone().requires_grad_()
     loss1 = GuidanceLossFunction.apply(z1, net._native, handle, 1 / 0.18215, 10.0)
     (grad1,) = torch.autograd.grad(loss1.sum(), z1)
-    assert abs(loss1.item() - 2 * loss[0].item()) <= 2e-5 * abs(loss1.item())
-    assert _rel(grad1[0].cpu(), 2 * grad[0].cpu()) < 1e-3
+    assert abs(loss1.item() - 2 * loss[0].item()) <= 1e-4 * abs(loss1.item())
+    assert _rel(grad1[0].cpu(), 2 * grad[0].cpu()) < TOL_GRAD

@@ -76,6 +76,8 @@ SIGNATURES = {
     "wfd_nhwc16_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "wfd_cvt16_to_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "wfd_test_tapgemm": (C.c_int, [C.POINTER(TapGemmDesc), C.c_int, C.c_void_p]),
+    "wfd_profile_enable": (C.c_int, [C.c_int]),
+    "wfd_profile_report": (C.c_int, [C.c_char_p, C.c_size_t]),
     "wfd_debug_set_ref_gemm": (C.c_int, [C.c_int]),
 }
 

@@ -275,6 +275,11 @@ int wfd_test_tapgemm(const wfd_tapgemm_desc* t, int use_ref, void* stream) {
     if (rc < 0) return rc;
     return use_ref ? tapgemm_launch_ref(&op, S(stream)) : tapgemm_launch(&op, S(stream));
 }
+int wfd_profile_enable(int on) {
+    profile_enable(on);
+    return 0;
+}
+int wfd_profile_report(char* buf, size_t cap) { return profile_report(buf, cap); }
 int wfd_debug_set_ref_gemm(int on) {
     debug_set_ref_gemm(on);
     return 0;

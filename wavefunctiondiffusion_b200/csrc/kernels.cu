@@ -299,6 +299,7 @@ static void gn_grid(int B, int HW, int C, dim3& grid, int& ppb) {
 }
 
 int gn_stats(const void* x, float* sums, int B, int HW, int C, int G, int bf16, cudaStream_t s) {
+    ProfScope prof_scope("gn_stats", s);
     if (int r = gn_check(C, G)) return r;
     dim3 grid;
     int ppb;
@@ -309,6 +310,7 @@ int gn_stats(const void* x, float* sums, int B, int HW, int C, int G, int bf16, 
 }
 int gn_apply(const void* x, const float* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C,
              int G, float eps, int silu, int bf16, cudaStream_t s) {
+    ProfScope prof_scope("gn_apply", s);
     if (int r = gn_check(C, G)) return r;
     dim3 grid;
     int ppb;
@@ -320,6 +322,7 @@ int gn_apply(const void* x, const float* sums, const float* gamma, const float* 
 }
 int gn_bwd_reduce(const void* dy, const void* x, const float* sums, const float* gamma, const float* beta, float* red,
                   int B, int HW, int C, int G, float eps, int silu, int bf16, cudaStream_t s) {
+    ProfScope prof_scope("gn_bwd_reduce", s);
     if (int r = gn_check(C, G)) return r;
     dim3 grid;
     int ppb;
@@ -333,6 +336,7 @@ int gn_bwd_reduce(const void* dy, const void* x, const float* sums, const float*
 int gn_bwd_apply(const void* dy, const void* x, const float* sums, const float* gamma, const float* beta,
                  const float* red, const void* add, void* dx, int B, int HW, int C, int G, float eps, int silu,
                  int bf16, cudaStream_t s) {
+    ProfScope prof_scope("gn_bwd_apply", s);
     if (int r = gn_check(C, G)) return r;
     dim3 grid;
     int ppb;
@@ -399,6 +403,7 @@ latent_in_k(const void* __restrict__ z, int z_f16, float in_scale, const float* 
 
 int latent_in(const void* z, int z_f16, float in_scale, const float* pq_w, const float* pq_b, const float* w,
               const float* b, void* out, int B, int h, int wd, int Cm, int bf16, cudaStream_t s) {
+    ProfScope prof_scope("latent_in", s);
     dim3 grid((wd + LI_PIX - 1) / LI_PIX, h, B);
     WFD_DISPATCH_BF16(bf16, (latent_in_k<BF16><<<grid, 128, 0, s>>>(z, z_f16, in_scale, pq_w, pq_b, w, b,
                                                                    static_cast<uint16_t*>(out), h, wd, Cm)));
@@ -447,6 +452,7 @@ latent_out_k(const uint16_t* __restrict__ dy, float in_scale, const float* __res
 
 int latent_out(const void* dy, float in_scale, const float* scale_b, const float* pq_w, const float* w, float* dz,
                int B, int h, int wd, int Cm, int bf16, cudaStream_t s) {
+    ProfScope prof_scope("latent_out", s);
     const long long warps = static_cast<long long>(B) * h * wd;
     const int threads = 256;
     const unsigned blocks = static_cast<unsigned>((warps * 32 + threads - 1) / threads);
@@ -525,6 +531,7 @@ wave_softmax_k(const uint4* __restrict__ logits, uint4* __restrict__ wave, float
 
 static int wave_rows_launch(const void* in, void* wave, float* rowsum, long long rows, int T_pad, int T, int bf16,
                             bool softmax, cudaStream_t s) {
+    ProfScope prof_scope("wave_rows_launch", s);
     if (T_pad % 8 != 0 || T_pad / 8 > 32 * WS_MAXV || T > T_pad) {
         set_error("wave softmax: T_pad=%d must be a multiple of 8 and <= %d", T_pad, 8 * 32 * WS_MAXV);
         return -3;
@@ -583,6 +590,7 @@ wfc_loss_finish_k(const float* __restrict__ rowsum, const float* __restrict__ ro
 }
 int wfc_loss_finish(const float* rowsum, const float* rowdot, float* loss, int B, int H, int W, float coef,
                     cudaStream_t s) {
+    ProfScope prof_scope("wfc_loss_finish", s);
     wfc_loss_finish_k<<<B, 1024, 0, s>>>(rowsum, rowdot, loss, H, W, coef);
     WFD_CHECK_LAUNCH("wfc_loss_finish");
     return 0;
@@ -620,6 +628,7 @@ wfc_grad_finish_k(const uint4* __restrict__ wave, const uint4* __restrict__ a, c
 int wfc_grad_finish(const void* wave, const void* a, const float* rowsum, const float* rowdot, const float* dloss,
                     void* dout, int B, int H, int W, int T_pad, int T, float coef, int through_softmax, int bf16,
                     cudaStream_t s) {
+    ProfScope prof_scope("wfc_grad_finish", s);
     const long long rows = static_cast<long long>(B) * H * W;
     const int threads = 256;
     const unsigned blocks = static_cast<unsigned>((rows * 32 + threads - 1) / threads);
@@ -676,6 +685,7 @@ attn_softmax_k(const float* __restrict__ scores, uint16_t* __restrict__ probs, i
     }
 }
 int attn_softmax(const float* scores, void* probs, long long rows, int n, int bf16, cudaStream_t s) {
+    ProfScope prof_scope("attn_softmax", s);
     if (n % 4 != 0) {
         set_error("attn_softmax: n=%d must be a multiple of 4", n);
         return -3;
@@ -724,6 +734,7 @@ attn_softmax_bwd_k(const uint16_t* __restrict__ probs, const float* __restrict__
 }
 int attn_softmax_bwd(const void* probs, const float* dp, void* ds, long long rows, int n, float scale, int bf16,
                      cudaStream_t s) {
+    ProfScope prof_scope("attn_softmax_bwd", s);
     if (n % 4 != 0) {
         set_error("attn_softmax_bwd: n=%d must be a multiple of 4", n);
         return -3;
@@ -754,6 +765,7 @@ transpose16_k(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int R
     }
 }
 int transpose16(const void* in, void* out, int Z, int R, int C, long long ld_in, long long zstride_in, cudaStream_t s) {
+    ProfScope prof_scope("transpose16", s);
     dim3 grid((C + 63) / 64, (R + 63) / 64, Z);
     transpose16_k<<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), R, C, ld_in,
                                        zstride_in);
@@ -824,6 +836,7 @@ __global__ void __launch_bounds__(256) argmax_rows_k(const void* __restrict__ x,
     if (lane == 0) out[row] = b.i < 0 ? 0 : b.i;
 }
 int argmax_rows(const void* x, int dtype, long long rows, int n, long long* out, cudaStream_t s) {
+    ProfScope prof_scope("argmax_rows", s);
     if ((dtype == 0 && n % 4 != 0) || (dtype != 0 && n % 8 != 0)) {
         // the vector loads need 16-byte aligned rows
         set_error("argmax_rows: row length %d not aligned for vector loads", n);
@@ -865,6 +878,7 @@ nchw_to_nhwc16_k(const void* __restrict__ in, int in_f16, uint16_t* __restrict__
     }
 }
 int nchw_to_nhwc16(const void* in, int in_f16, void* out, int B, int C, int HW, int bf16, cudaStream_t s) {
+    ProfScope prof_scope("nchw_to_nhwc16", s);
     dim3 grid((HW + 63) / 64, (C + 63) / 64, B);
     WFD_DISPATCH_BF16(bf16, (nchw_to_nhwc16_k<BF16><<<grid, 256, 0, s>>>(in, in_f16, static_cast<uint16_t*>(out), C, HW)));
     WFD_CHECK_LAUNCH("nchw_to_nhwc16");
@@ -891,6 +905,7 @@ nhwc16_to_nchw_k(const uint16_t* __restrict__ in, void* __restrict__ out, int ou
     }
 }
 int nhwc16_to_nchw(const void* in, void* out, int out_f16, int B, int C, int HW, int bf16, cudaStream_t s) {
+    ProfScope prof_scope("nhwc16_to_nchw", s);
     dim3 grid((HW + 63) / 64, (C + 63) / 64, B);
     WFD_DISPATCH_BF16(bf16, (nhwc16_to_nchw_k<BF16><<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(in), out, out_f16, C, HW)));
     WFD_CHECK_LAUNCH("nhwc16_to_nchw");
@@ -929,16 +944,19 @@ static unsigned ew_blocks(long long n, int threads) {
     return static_cast<unsigned>(b);
 }
 int cvt16_to_f32(const void* in, float* out, long long n, int bf16, cudaStream_t s) {
+    ProfScope prof_scope("cvt16_to_f32", s);
     WFD_DISPATCH_BF16(bf16, (cvt16_to_f32_k<BF16><<<ew_blocks(n, 256), 256, 0, s>>>(static_cast<const uint16_t*>(in), out, n)));
     WFD_CHECK_LAUNCH("cvt16_to_f32");
     return 0;
 }
 int cvt_f32_to_16(const float* in, void* out, long long n, int bf16, cudaStream_t s) {
+    ProfScope prof_scope("cvt_f32_to_16", s);
     WFD_DISPATCH_BF16(bf16, (cvt_f32_to_16_k<BF16><<<ew_blocks(n, 256), 256, 0, s>>>(in, static_cast<uint16_t*>(out), n)));
     WFD_CHECK_LAUNCH("cvt_f32_to_16");
     return 0;
 }
 int add16(const void* a, const void* b, void* out, long long n, int bf16, cudaStream_t s) {
+    ProfScope prof_scope("add16", s);
     if (n % 8 != 0) {
         set_error("add16: n must be a multiple of 8");
         return -3;

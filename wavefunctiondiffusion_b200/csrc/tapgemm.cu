@@ -4,6 +4,9 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <map>
+#include <string>
+#include <vector>
 #include <stdlib.h>
 
 namespace wfd {
@@ -48,6 +51,61 @@ int num_sms() {
         if (n <= 0) n = 148;
     }
     return n;
+}
+
+// ------------------------------------------------------------------------------------------------ launch profiling
+// wfd_profile_enable(1): every launch wrapper brackets its kernel with CUDA events on the launching stream;
+// profile_report() synchronises and returns "name count total_ms" lines. Used by bench.py for the roofline numbers.
+struct ProfRec {
+    std::string name;
+    cudaEvent_t a, b;
+};
+static int g_prof_on = 0;
+static std::vector<ProfRec> g_prof;
+void profile_enable(int on) {
+    g_prof_on = on;
+    if (on) {
+        for (auto& r : g_prof) {
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+        }
+        g_prof.clear();
+    }
+}
+ProfScope::ProfScope(const char* name, cudaStream_t s) : stream(s), idx(-1) {
+    if (!g_prof_on) return;
+    ProfRec r;
+    r.name = name;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, s);
+    g_prof.push_back(r);
+    idx = static_cast<int>(g_prof.size()) - 1;
+}
+ProfScope::~ProfScope() {
+    if (idx >= 0) cudaEventRecord(g_prof[idx].b, stream);
+}
+int profile_report(char* buf, size_t cap) {
+    std::map<std::string, std::pair<int, double>> agg;
+    for (auto& r : g_prof) {
+        if (cudaEventSynchronize(r.b) != cudaSuccess) continue;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        auto& e = agg[r.name];
+        e.first += 1;
+        e.second += ms;
+    }
+    std::string out;
+    char line[384];
+    for (auto& kv : agg) {
+        snprintf(line, sizeof(line), "%s %d %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    if (buf && cap > 0) {
+        strncpy(buf, out.c_str(), cap - 1);
+        buf[cap - 1] = 0;
+    }
+    return static_cast<int>(out.size());
 }
 
 // ------------------------------------------------------------------------------------------------ device helpers
@@ -478,6 +536,11 @@ int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream) {
     const int total = p.m_tiles * p.n_tiles * p.z_count;
     if (total <= 0) return 0;
     const int grid = total < num_sms() ? total : num_sms();
+    char pname[128];
+    if (g_prof_on)
+        snprintf(pname, sizeof(pname), "tapgemm:N=%d,BN=%d,taps=%d,cpt=%d,aC=%d,f32=%d", p.N, p.BN, p.n_taps, p.cpt, p.a_C,
+                 p.out_fp32);
+    ProfScope prof_scope(g_prof_on ? pname : "", stream);
     if (p.is_bf16)
         tapgemm_kernel<true><<<grid, TG_THREADS, op->smem_bytes, stream>>>(op->tmA, op->tmB, op->p, op->stages);
     else

@@ -74,6 +74,14 @@ int tapgemm_launch_ref(const TapGemmOp* op, cudaStream_t stream);
 void set_error(const char* fmt, ...);
 const char* last_error();
 extern long long g_launch_count;
+void profile_enable(int on);
+int profile_report(char* buf, size_t cap);
+struct ProfScope {
+    cudaStream_t stream;
+    int idx;
+    ProfScope(const char* name, cudaStream_t s);
+    ~ProfScope();
+};
 int debug_sync_enabled();
 int debug_sync_check(const char* what, cudaStream_t stream);
 int num_sms();
