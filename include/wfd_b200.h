@@ -145,6 +145,8 @@ typedef struct {
     float* rowdot; const void* dotsrc; long long ld_dot;
     float* gn_sums; int gn_cpg;
     int dtype16;
+    int reuse;        /* 1: row-reuse schedule (3x3 stride-1 taps, b packed in (dx, cc, dy) chunk order) */
+    long long* dbg;   /* optional device int64[8]: cycle counters of CTA 0 per warp role (profiling aid) */
 } wfd_tapgemm_desc;
 WFD_API int wfd_test_tapgemm(const wfd_tapgemm_desc* desc, int use_ref, void* stream);
 /* per-launch CUDA-event profiling (bench.py roofline): enable(1) clears and starts recording, report() synchronises the

@@ -96,8 +96,9 @@ def test_shared_a_z_batch(use_ref):
     assert _rel(out, want) < 6e-3
 
 
-def _pack_conv(w, groups, BN, bwd=False):
-    """Python restatement of the C++ packer for the test: returns (Bm [n_tiles*BN, taps*cpt*64], a_c0, cpt, N)."""
+def _pack_conv(w, groups, BN, bwd=False, reuse=False):
+    """Python restatement of the C++ packer for the test: returns (Bm [n_tiles*BN, taps*cpt*64], a_c0, cpt, N).
+    reuse=True stores the 64-wide chunks in the (dx, cc, dy) order of the row-reuse schedule."""
     cout, cin_g, k, _ = w.shape
     cin = cin_g * groups
     cout_g = cout // groups
@@ -114,22 +115,32 @@ def _pack_conv(w, groups, BN, bwd=False):
     taps = k * k
     Bm = torch.zeros(n_tiles * BN, taps * cpt * 64)
     wf = w.reshape(cout, cin_g, taps)
+    sign = -1 if bwd else 1
+    offs = [(sign * (ky - k // 2), sign * (kx - k // 2)) for ky in range(k) for kx in range(k)]  # (dy, dx) per tap
     for n in range(N):
         g, t = n // rpg, n // BN
         for kk in range(kpg):
             pos = g * kpg + kk - c0[t]
+            cc, within = pos // 64, pos % 64
             if not bwd:
                 vals = wf[n, kk, :]
             else:
                 vals = wf[g * cout_g + kk, n - g * cin_g, :]
-            Bm[n, torch.arange(taps) * cpt * 64 + pos] = vals
+            if reuse:
+                chunk = torch.tensor([((dx + 1) * cpt + cc) * 3 + (dy + 1) for dy, dx in offs])
+            else:
+                chunk = torch.arange(taps) * cpt + cc
+            Bm[n, chunk * 64 + within] = vals
     return Bm, torch.tensor(c0, dtype=torch.int32), cpt, N
 
 
+@pytest.mark.parametrize("reuse", [0, 1])
 @pytest.mark.parametrize("use_ref", [1, 0])
 @pytest.mark.parametrize("cin,cout,groups,BN,H,W", [(64, 64, 1, 64, 16, 16), (192, 96, 4, 48, 8, 64), (96, 192, 2, 96, 32, 32),
                                                    (384, 384, 1, 192, 64, 64)])
-def test_conv3x3_forward_and_backward_data(cin, cout, groups, BN, H, W, use_ref):
+def test_conv3x3_forward_and_backward_data(cin, cout, groups, BN, H, W, use_ref, reuse):
+    if reuse and BN > 96:
+        pytest.skip("row-reuse schedule is used for tiles that leave >= 3 stages")
     torch.manual_seed(3)
     Bn = 2
     x = torch.randn(Bn, cin, H, W, device="cuda").bfloat16()
@@ -139,7 +150,7 @@ def test_conv3x3_forward_and_backward_data(cin, cout, groups, BN, H, W, use_ref)
     w_box = min(W, 128)
     h_box = 128 // w_box
     # forward
-    Bm, c0, cpt, N = _pack_conv(w, groups, BN)
+    Bm, c0, cpt, N = _pack_conv(w, groups, BN, reuse=bool(reuse))
     Bm = Bm.cuda().bfloat16()
     c0 = c0.cuda()
     out = torch.zeros(Bn, H, W, cout, device="cuda", dtype=torch.bfloat16)
@@ -149,7 +160,7 @@ def test_conv3x3_forward_and_backward_data(cin, cout, groups, BN, H, W, use_ref)
               ldb=Bm.shape[1], b_zstride=0, b_Z=1, n_taps=9, cpt=cpt, tap_dx=[t[1] for t in taps],
               tap_dy=[t[0] for t in taps], a_c0=c0.data_ptr(), BN=BN, N=N, W=W, H=H, B=Bn, w_box=w_box, h_box=h_box,
               in_stride=1, z_count=1, out=out.data_ptr(), out_fp32=0, ldc=cout, bias=bias.data_ptr(), alpha=1.0,
-              gn_sums=gn.data_ptr(), gn_cpg=cout // 8, dtype16=1)
+              gn_sums=gn.data_ptr(), gn_cpg=cout // 8, dtype16=1, reuse=reuse)
     _run(d, use_ref)
     want = F.conv2d(x.float(), w.cuda(), bias, padding=1, groups=groups)
     got = out.permute(0, 3, 1, 2).float()
@@ -165,14 +176,14 @@ def test_conv3x3_forward_and_backward_data(cin, cout, groups, BN, H, W, use_ref)
     dy = torch.randn(Bn, cout, H, W, device="cuda").bfloat16()
     dy_nhwc = dy.permute(0, 2, 3, 1).contiguous()
     BNb = BN if (cin // groups) % 16 == 0 and (cin // groups) <= 256 and BN % (cin // groups) == 0 else 64
-    Bm2, c02, cpt2, N2 = _pack_conv(w, groups, BNb, bwd=True)
+    Bm2, c02, cpt2, N2 = _pack_conv(w, groups, BNb, bwd=True, reuse=bool(reuse))
     Bm2 = Bm2.cuda().bfloat16()
     c02 = c02.cuda()
     dx = torch.zeros(Bn, H, W, cin, device="cuda", dtype=torch.bfloat16)
     d = _desc(a=dy_nhwc.data_ptr(), a_C=cout, a_W=W, a_H=H, a_B=Bn, a_ld=cout, b=Bm2.data_ptr(), b_rows=Bm2.shape[0],
               ldb=Bm2.shape[1], b_zstride=0, b_Z=1, n_taps=9, cpt=cpt2, tap_dx=[-t[1] for t in taps],
               tap_dy=[-t[0] for t in taps], a_c0=c02.data_ptr(), BN=BNb, N=N2, W=W, H=H, B=Bn, w_box=w_box, h_box=h_box,
-              in_stride=1, z_count=1, out=dx.data_ptr(), out_fp32=0, ldc=cin, alpha=1.0, dtype16=1)
+              in_stride=1, z_count=1, out=dx.data_ptr(), out_fp32=0, ldc=cin, alpha=1.0, dtype16=1, reuse=reuse)
     _run(d, use_ref)
     want = F.conv_transpose2d(dy.float(), w.cuda(), padding=1, groups=groups)
     assert _rel(dx.permute(0, 3, 1, 2), want) < 6e-3

@@ -240,6 +240,7 @@ int wfd_test_tapgemm(const wfd_tapgemm_desc* t, int use_ref, void* stream) {
         p.tap_dy[i] = t->tap_dy[i];
     }
     p.a_c0 = t->a_c0;
+    p.reuse = t->reuse;
     p.a_zmul = t->a_zmul;
     p.b_zmul = t->b_zmul;
     p.b_bbmul = t->b_bbmul;
@@ -260,6 +261,7 @@ int wfd_test_tapgemm(const wfd_tapgemm_desc* t, int use_ref, void* stream) {
     p.gn_cpg = t->gn_cpg;
     p.gn_G = 8;
     p.is_bf16 = t->dtype16;
+    p.dbg = t->dbg;
     p.a_ptr = t->a;
     p.a_C = t->a_C;
     p.a_W = t->a_W;

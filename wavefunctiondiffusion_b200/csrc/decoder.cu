@@ -69,7 +69,7 @@ void PackedB::release() {
 // w: [cout][cin/groups][k][k] fp32 (torch Conv2d / Linear layout). mode 0: forward, pad (k-1)/2; mode 1: backward-data of
 // mode 0; mode 2: forward of the stride-2 downsample conv applied after F.pad(x, (0,1,0,1)) (resnet.py:185-190).
 int pack_conv(const float* w, int cout, int cin, int groups, int k, int mode, bool bf16, int bn_override, PackedB* out,
-              const std::vector<TapSel>* tap_sel) {
+              const std::vector<TapSel>* tap_sel, bool reuse) {
     const bool bwd = (mode == 1);
     const int cin_g = cin / groups, cout_g = cout / groups;
     const int N = bwd ? cin : cout;
@@ -90,22 +90,48 @@ int pack_conv(const float* w, int cout, int cin, int groups, int k, int mode, bo
     const int taps = tap_sel ? static_cast<int>(tap_sel->size()) : wtaps;  // taps of this contraction
     const long long ldb = static_cast<long long>(taps) * cpt * TG_KC;
     const long long rows = static_cast<long long>(n_tiles) * BN;
+    // tap offsets
+    int tdx[TG_MAX_TAPS] = {0}, tdy[TG_MAX_TAPS] = {0};
+    if (tap_sel) {
+        for (int t = 0; t < taps; ++t) {
+            tdx[t] = (*tap_sel)[t].dx;
+            tdy[t] = (*tap_sel)[t].dy;
+        }
+    } else {
+        for (int ky = 0; ky < k; ++ky)
+            for (int kx = 0; kx < k; ++kx) {
+                const int tap = ky * k + kx;
+                int dy = ky - (k - 1) / 2, dx = kx - (k - 1) / 2;
+                if (mode == 2) { dy = ky; dx = kx; }
+                if (bwd) { dy = -dy; dx = -dx; }
+                tdx[tap] = dx;
+                tdy[tap] = dy;
+            }
+    }
+    if (reuse && (taps != 9 || mode == 2)) {
+        set_error("pack_conv: the row-reuse chunk order needs a 3x3 stride-1 tap set");
+        return -3;
+    }
     std::vector<uint16_t> hb(static_cast<size_t>(rows * ldb), 0);
     for (int n = 0; n < N; ++n) {
         const int g = n / rpg, t = n / BN;
         for (int tap = 0; tap < taps; ++tap) {
+            const int wt = tap_sel ? (*tap_sel)[tap].w_tap : tap;
             for (int kk = 0; kk < kpg; ++kk) {
                 const int c = g * kpg + kk;
                 const int pos = c - c0[t];
+                const int cc = pos / TG_KC, within = pos % TG_KC;
+                // chunk order: plain = (tap, cc); row reuse = (dx, cc, dy), see b_chunk_index() in tapgemm.cu
+                const long long chunk = reuse ? (static_cast<long long>(tdx[tap] + 1) * cpt + cc) * 3 + (tdy[tap] + 1)
+                                              : static_cast<long long>(tap) * cpt + cc;
                 float v;
-                const int wt = tap_sel ? (*tap_sel)[tap].w_tap : tap;
                 if (!bwd) {
                     v = w[(static_cast<long long>(n) * cin_g + kk) * wtaps + wt];
                 } else {
                     const int co = g * cout_g + kk, ci_local = n - g * cin_g;
                     v = w[(static_cast<long long>(co) * cin_g + ci_local) * wtaps + wt];
                 }
-                hb[static_cast<size_t>(n * ldb + static_cast<long long>(tap) * cpt * TG_KC + pos)] = host_f_to_16(v, bf16);
+                hb[static_cast<size_t>(n * ldb + chunk * TG_KC + within)] = host_f_to_16(v, bf16);
             }
         }
     }
@@ -118,21 +144,10 @@ int pack_conv(const float* w, int cout, int cin, int groups, int k, int mode, bo
     out->ldb = ldb;
     out->rows = static_cast<int>(rows);
     out->in_stride = (mode == 2) ? 2 : 1;
-    if (tap_sel) {
-        for (int t = 0; t < taps; ++t) {
-            out->dx[t] = (*tap_sel)[t].dx;
-            out->dy[t] = (*tap_sel)[t].dy;
-        }
-    } else {
-        for (int ky = 0; ky < k; ++ky)
-            for (int kx = 0; kx < k; ++kx) {
-                const int tap = ky * k + kx;
-                int dy = ky - (k - 1) / 2, dx = kx - (k - 1) / 2;
-                if (mode == 2) { dy = ky; dx = kx; }
-                if (bwd) { dy = -dy; dx = -dx; }
-                out->dx[tap] = dx;
-                out->dy[tap] = dy;
-            }
+    out->reuse = reuse ? 1 : 0;
+    for (int t = 0; t < taps; ++t) {
+        out->dx[t] = tdx[t];
+        out->dy[t] = tdy[t];
     }
     CUDA_CK(cudaMalloc(&out->Bm, hb.size() * 2));
     CUDA_CK(cudaMemcpy(out->Bm, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice));
@@ -179,6 +194,12 @@ int Decoder::init(const wfd_decoder_config& c, int h_, int w_, int Bmax, int dty
     B_max = Bmax;
     bf16 = dtype16 ? 1 : 0;
     G = c.norm_num_groups;
+    {
+        const char* e = getenv("WFD_NO_REUSE");
+        use_reuse = (e && e[0] == '1') ? 0 : 1;
+        const char* f = getenv("WFD_NO_FUSE_GN");
+        fuse_gn = (f && f[0] == '1') ? 0 : 1;
+    }
     if (c.latent_channels != 4) {
         set_error("decoder: latent_channels must be 4 (got %d)", c.latent_channels);
         return -3;
@@ -334,15 +355,26 @@ int Decoder::need(const std::string& key, long long numel, const std::vector<flo
     return 0;
 }
 
-int Decoder::pack_named_conv(const std::string& name, int cout, int cin, int groups, int k, bool want_bwd, int fwd_mode) {
+int Decoder::pack_named_conv(const std::string& name, int cout, int cin, int groups, int k, bool want_bwd, int fwd_mode,
+                             int ph, int pw) {
     const std::vector<float>*wv, *bv;
     CK(need(name + ".weight", static_cast<long long>(cout) * (cin / groups) * k * k, &wv));
     CK(need(name + ".bias", cout, &bv));
     ConvW& cw = convs[name];
     cw.cin = cin;
     cw.cout = cout;
-    CK(pack_conv(wv->data(), cout, cin, groups, k, fwd_mode, bf16 != 0, 0, &cw.fwd, nullptr));
-    if (want_bwd && fwd_mode == 0) CK(pack_conv(wv->data(), cout, cin, groups, k, 1, bf16 != 0, 0, &cw.bwd, nullptr));
+    // the row-reuse schedule pays off when a stage (patch with halo rows + three weight boxes) leaves >= 3 stages
+    auto want_reuse = [&](int rows_per_group) {
+        if (k != 3 || fwd_mode != 0 || !use_reuse || ph <= 0) return false;
+        int wb = 0, hb = 0;
+        if (!pick_box(pw, ph, &wb, &hb) || wb < 8) return false;
+        const int BN = choose_bn(rows_per_group);
+        const size_t per_stage = static_cast<size_t>(hb + 2) * wb * 128 + 3 * static_cast<size_t>(BN) * 128;
+        return per_stage * 3 <= 216 * 1024;
+    };
+    CK(pack_conv(wv->data(), cout, cin, groups, k, fwd_mode, bf16 != 0, 0, &cw.fwd, nullptr, want_reuse(cout / groups)));
+    if (want_bwd && fwd_mode == 0)
+        CK(pack_conv(wv->data(), cout, cin, groups, k, 1, bf16 != 0, 0, &cw.bwd, nullptr, want_reuse(cin / groups)));
     CK(upload_f32(*bv, &cw.bias));
     return 0;
 }
@@ -360,14 +392,23 @@ int Decoder::finalize_weights() {
     CK(upload_vec("post_quant_conv.bias", 4));
     CK(upload_vec("decoder.conv_in.weight", static_cast<long long>(Cm) * 36));
     CK(upload_vec("decoder.conv_in.bias", Cm));
+    {   // [co][ci][ky][kx] -> [ky][kx][ci][co] for the coalesced reads of latent_out
+        const std::vector<float>* wv;
+        CK(need("decoder.conv_in.weight", static_cast<long long>(Cm) * 36, &wv));
+        std::vector<float> wt(static_cast<size_t>(Cm) * 36);
+        for (int co = 0; co < Cm; ++co)
+            for (int ci = 0; ci < 4; ++ci)
+                for (int t = 0; t < 9; ++t) wt[(static_cast<size_t>(t) * 4 + ci) * Cm + co] = (*wv)[(co * 4 + ci) * 9 + t];
+        CK(upload_f32(wt, &vecs["decoder.conv_in.weight.T"]));
+    }
     for (const ResnetDesc& r : resnets) {
         CK(upload_vec(r.prefix + ".norm1.weight", r.cin));
         CK(upload_vec(r.prefix + ".norm1.bias", r.cin));
         CK(upload_vec(r.prefix + ".norm2.weight", r.cout));
         CK(upload_vec(r.prefix + ".norm2.bias", r.cout));
-        CK(pack_named_conv(r.prefix + ".conv1", r.cout, r.cin, r.groups, 3, true, 0));
-        CK(pack_named_conv(r.prefix + ".conv2", r.cout, r.cout, r.groups, 3, true, 0));
-        if (r.cin != r.cout) CK(pack_named_conv(r.prefix + ".conv_shortcut", r.cout, r.cin, r.groups, 1, true, 0));
+        CK(pack_named_conv(r.prefix + ".conv1", r.cout, r.cin, r.groups, 3, true, 0, r.h, r.w));
+        CK(pack_named_conv(r.prefix + ".conv2", r.cout, r.cout, r.groups, 3, true, 0, r.h, r.w));
+        if (r.cin != r.cout) CK(pack_named_conv(r.prefix + ".conv_shortcut", r.cout, r.cin, r.groups, 1, true, 0, 0, 0));
     }
     for (int i = 0; i < cfg.n_blocks; ++i) {
         if (!down_after[i]) continue;
@@ -375,7 +416,7 @@ int Decoder::finalize_weights() {
         snprintf(buf, sizeof(buf), "decoder.up_blocks.%d.downsamplers.0.conv", i);
         const int cch = cfg.block_out_channels[cfg.n_blocks - 1 - i];
         const int grp = cfg.conv_groups[cfg.n_blocks - 1 - i];
-        CK(pack_named_conv(buf, cch, cch, grp, 3, false, 2));
+        CK(pack_named_conv(buf, cch, cch, grp, 3, false, 2, 0, 0));
         // backward-data of the stride-2 conv: one contraction per output parity (py, px). For row parity 0 the taps
         // ky = 0 (source row y') and ky = 2 (source row y' - 1) contribute, for parity 1 only ky = 1; same along x.
         const std::vector<float>* wv;
@@ -388,7 +429,7 @@ int Decoder::finalize_weights() {
                 ConvW& cw = convs[std::string(buf) + ".bwd" + std::to_string(py * 2 + px)];
                 cw.cin = cch;
                 cw.cout = cch;
-                CK(pack_conv(wv->data(), cch, cch, grp, 3, 1, bf16 != 0, 0, &cw.bwd, &sel));
+                CK(pack_conv(wv->data(), cch, cch, grp, 3, 1, bf16 != 0, 0, &cw.bwd, &sel, false));
             }
     }
     // attention: q,k,v merged into one [3C, C] matrix (+ backward form), v alone as an A operand, proj
@@ -414,14 +455,14 @@ int Decoder::finalize_weights() {
         ConvW& cq = convs["attn.qkv"];
         cq.cin = Cm;
         cq.cout = 3 * Cm;
-        CK(pack_conv(wq.data(), 3 * Cm, Cm, 1, 1, 0, bf16 != 0, Cm % 192 == 0 ? 192 : 0, &cq.fwd, nullptr));
-        CK(pack_conv(wq.data(), 3 * Cm, Cm, 1, 1, 1, bf16 != 0, 0, &cq.bwd, nullptr));
+        CK(pack_conv(wq.data(), 3 * Cm, Cm, 1, 1, 0, bf16 != 0, Cm % 192 == 0 ? 192 : 0, &cq.fwd, nullptr, false));
+        CK(pack_conv(wq.data(), 3 * Cm, Cm, 1, 1, 1, bf16 != 0, 0, &cq.bwd, nullptr, false));
         CK(upload_f32(bq, &cq.bias));
-        CK(pack_named_conv(a + "proj_attn", Cm, Cm, 1, 1, true, 0));
+        CK(pack_named_conv(a + "proj_attn", Cm, Cm, 1, 1, true, 0, 0, 0));
     }
     CK(upload_vec("decoder.conv_norm_out.weight", C_last));
     CK(upload_vec("decoder.conv_norm_out.bias", C_last));
-    CK(pack_named_conv("decoder.conv_out", T_pad, C_last, cfg.conv_init_groups, 3, true, 0));
+    CK(pack_named_conv("decoder.conv_out", T_pad, C_last, cfg.conv_init_groups, 3, true, 0, H_out, W_out));
     finalized = true;
     host.clear();
     if (ws) return prepare_ops();
@@ -506,6 +547,7 @@ int Decoder::conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int 
             p.tap_dy[t] = pk.dy[t];
         }
         p.a_c0 = pk.a_c0;
+        p.reuse = pk.reuse;
         p.N = pk.N;
         p.out = out;
         p.out_fp32 = 0;
@@ -933,7 +975,7 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
     }
     CK(resnet_bwd(0, ws + o_x0));
     if (!ex.prepare)
-        CK(latent_out(gbuf(cur), last_in_scale, scale_b, vecs["post_quant_conv.weight"], vecs["decoder.conv_in.weight"],
+        CK(latent_out(gbuf(cur), last_in_scale, scale_b, vecs["post_quant_conv.weight"], vecs["decoder.conv_in.weight.T"],
                       dz, B, h, w, Cm, bf16, s));
     return 0;
 }

@@ -15,7 +15,7 @@ int debug_ref_gemm();
 struct PackedB {
     uint16_t* Bm = nullptr;
     int* a_c0 = nullptr;  // first A channel per N tile
-    int BN = 0, n_tiles = 0, cpt = 0, n_taps = 0, N = 0, rows = 0, in_stride = 1;
+    int BN = 0, n_tiles = 0, cpt = 0, n_taps = 0, N = 0, rows = 0, in_stride = 1, reuse = 0;
     long long ldb = 0;
     int dx[TG_MAX_TAPS] = {0}, dy[TG_MAX_TAPS] = {0};
     void release();
@@ -27,7 +27,7 @@ struct OutStrides {  // element strides of a strided output plane (downsample ba
     long long sx, sy, sb;
 };
 int pack_conv(const float* w, int cout, int cin, int groups, int k, int mode, bool bf16, int bn_override, PackedB* out,
-              const std::vector<TapSel>* tap_sel);
+              const std::vector<TapSel>* tap_sel, bool reuse);
 
 struct ConvW {
     PackedB fwd, bwd;
@@ -55,6 +55,7 @@ struct Decoder {
     int h = 0, w = 0, B_max = 0, bf16 = 1, G = 8;
     int Cm = 0, C_last = 0, H_out = 0, W_out = 0, T_pad = 0;
     int fuse_gn = 1;
+    int use_reuse = 1;  // row-reuse schedule for 3x3 convs whose stage fits (WFD_NO_REUSE=1 disables, for A/B runs)
     std::vector<ResnetDesc> resnets;
     std::vector<int> down_after;
     std::map<std::string, std::vector<float>> host;
@@ -85,7 +86,8 @@ struct Decoder {
 
     // internals
     int need(const std::string& key, long long numel, const std::vector<float>** out);
-    int pack_named_conv(const std::string& name, int cout, int cin, int groups, int k, bool want_bwd, int fwd_mode);
+    int pack_named_conv(const std::string& name, int cout, int cin, int groups, int k, bool want_bwd, int fwd_mode, int ph,
+                        int pw);
     int upload_vec(const std::string& key, long long numel);
     int prepare_ops();
     int run_gemm(Exec& ex, TapGemmOp& tmpl, bool z_is_batch);

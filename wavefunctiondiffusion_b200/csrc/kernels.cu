@@ -117,13 +117,22 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_k(const uint4* __restrict
             if (col >= m.nv) break;
             float s = 0.f, ss = 0.f;
             const uint4* px = x + (static_cast<long long>(b) * HW) * m.nv + col;
-            for (int p = p0 + trow; p < p1; p += m.R) {
-                float f[8];
-                unpack8<BF16>(__ldg(px + static_cast<long long>(p) * m.nv), f);
+            constexpr int U = 4;
+            for (int p = p0 + trow; p < p1; p += U * m.R) {
+                uint4 raw[U];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    s += f[j];
-                    ss += f[j] * f[j];
+                for (int u = 0; u < U; ++u)
+                    if (p + u * m.R < p1) raw[u] = __ldg(px + static_cast<long long>(p + u * m.R) * m.nv);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (p + u * m.R >= p1) break;
+                    float f[8];
+                    unpack8<BF16>(raw[u], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        s += f[j];
+                        ss += f[j] * f[j];
+                    }
                 }
             }
             const int g = (col * 8) / cpg;
@@ -160,15 +169,24 @@ gn_apply_k(const uint4* __restrict__ x, const float* __restrict__ sums, const fl
             sh[j] = __ldg(beta + col * 8 + j) - mean * rstd * ga;
         }
         const long long base = (static_cast<long long>(b) * HW) * m.nv + col;
-        for (int p = p0 + trow; p < p1; p += m.R) {
-            float f[8];
-            unpack8<BF16>(__ldg(x + base + static_cast<long long>(p) * m.nv), f);
+        constexpr int U = 4;  // independent 16-byte loads in flight per thread
+        for (int p = p0 + trow; p < p1; p += U * m.R) {
+            uint4 raw[U];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float u = f[j] * sc[j] + sh[j];
-                f[j] = silu ? u * sigmoidf_(u) : u;
+            for (int u = 0; u < U; ++u)
+                if (p + u * m.R < p1) raw[u] = __ldg(x + base + static_cast<long long>(p + u * m.R) * m.nv);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (p + u * m.R >= p1) break;
+                float f[8];
+                unpack8<BF16>(raw[u], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float v = f[j] * sc[j] + sh[j];
+                    f[j] = silu ? v * sigmoidf_(v) : v;
+                }
+                y[base + static_cast<long long>(p + u * m.R) * m.nv] = pack8<BF16>(f);
             }
-            y[base + static_cast<long long>(p) * m.nv] = pack8<BF16>(f);
         }
     }
 }
@@ -201,22 +219,34 @@ gn_bwd_reduce_k(const uint4* __restrict__ dy, const uint4* __restrict__ x, const
             }
             float s1 = 0.f, s2 = 0.f;
             const long long base = (static_cast<long long>(b) * HW) * m.nv + col;
-            for (int p = p0 + trow; p < p1; p += m.R) {
-                float fx[8], fd[8];
-                unpack8<BF16>(__ldg(x + base + static_cast<long long>(p) * m.nv), fx);
-                unpack8<BF16>(__ldg(dy + base + static_cast<long long>(p) * m.nv), fd);
+            constexpr int U = 2;
+            for (int p = p0 + trow; p < p1; p += U * m.R) {
+                uint4 rx[U], rd[U];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float xh = (fx[j] - mean) * rstd;
-                    float du = fd[j];
-                    if (silu) {
-                        const float u = xh * ga[j] + be[j];
-                        const float sg = sigmoidf_(u);
-                        du *= sg * (1.f + u * (1.f - sg));
+                for (int u = 0; u < U; ++u)
+                    if (p + u * m.R < p1) {
+                        rx[u] = __ldg(x + base + static_cast<long long>(p + u * m.R) * m.nv);
+                        rd[u] = __ldg(dy + base + static_cast<long long>(p + u * m.R) * m.nv);
                     }
-                    const float t = du * ga[j];
-                    s1 += t;
-                    s2 += t * xh;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (p + u * m.R >= p1) break;
+                    float fx[8], fd[8];
+                    unpack8<BF16>(rx[u], fx);
+                    unpack8<BF16>(rd[u], fd);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float xh = (fx[j] - mean) * rstd;
+                        float du = fd[j];
+                        if (silu) {
+                            const float v = xh * ga[j] + be[j];
+                            const float sg = sigmoidf_(v);
+                            du *= sg * (1.f + v * (1.f - sg));
+                        }
+                        const float t = du * ga[j];
+                        s1 += t;
+                        s2 += t * xh;
+                    }
                 }
             }
             atomicAdd(&sh[2 * g], s1);
@@ -255,26 +285,40 @@ gn_bwd_apply_k(const uint4* __restrict__ dy, const uint4* __restrict__ x, const 
             be[j] = __ldg(beta + col * 8 + j);
         }
         const long long base = (static_cast<long long>(b) * HW) * m.nv + col;
-        for (int p = p0 + trow; p < p1; p += m.R) {
-            const long long idx = base + static_cast<long long>(p) * m.nv;
-            float fx[8], fd[8], fa[8];
-            unpack8<BF16>(__ldg(x + idx), fx);
-            unpack8<BF16>(__ldg(dy + idx), fd);
-            if (add) unpack8<BF16>(__ldg(add + idx), fa);
+        constexpr int U = 2;
+        for (int p = p0 + trow; p < p1; p += U * m.R) {
+            uint4 rx[U], rd[U], ra[U];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float xh = (fx[j] - mean) * rstd;
-                float du = fd[j];
-                if (silu) {
-                    const float u = xh * ga[j] + be[j];
-                    const float sg = sigmoidf_(u);
-                    du *= sg * (1.f + u * (1.f - sg));
+            for (int u = 0; u < U; ++u)
+                if (p + u * m.R < p1) {
+                    const long long idx = base + static_cast<long long>(p + u * m.R) * m.nv;
+                    rx[u] = __ldg(x + idx);
+                    rd[u] = __ldg(dy + idx);
+                    if (add) ra[u] = __ldg(add + idx);
                 }
-                float v = rstd * (du * ga[j] - r1 - xh * r2);
-                if (add) v += fa[j];
-                fd[j] = v;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (p + u * m.R >= p1) break;
+                const long long idx = base + static_cast<long long>(p + u * m.R) * m.nv;
+                float fx[8], fd[8], fa[8];
+                unpack8<BF16>(rx[u], fx);
+                unpack8<BF16>(rd[u], fd);
+                if (add) unpack8<BF16>(ra[u], fa);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float xh = (fx[j] - mean) * rstd;
+                    float du = fd[j];
+                    if (silu) {
+                        const float v = xh * ga[j] + be[j];
+                        const float sg = sigmoidf_(v);
+                        du *= sg * (1.f + v * (1.f - sg));
+                    }
+                    float v = rstd * (du * ga[j] - r1 - xh * r2);
+                    if (add) v += fa[j];
+                    fd[j] = v;
+                }
+                dx[idx] = pack8<BF16>(fd);
             }
-            dx[idx] = pack8<BF16>(fd);
         }
     }
 }
@@ -415,7 +459,7 @@ int latent_in(const void* z, int z_f16, float in_scale, const float* pq_w, const
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 latent_out_k(const uint16_t* __restrict__ dy, float in_scale, const float* __restrict__ scale_b,
-             const float* __restrict__ pq_w, const float* __restrict__ w, float* __restrict__ dz, int B, int h, int wd,
+             const float* __restrict__ pq_w, const float* __restrict__ wt, float* __restrict__ dz, int B, int h, int wd,
              int Cm) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int total = B * h * wd;
@@ -434,7 +478,7 @@ latent_out_k(const uint16_t* __restrict__ dy, float in_scale, const float* __res
             for (int co = lane; co < Cm; co += 32) {
                 const float g = u16_to_f<BF16>(row[co]);
 #pragma unroll
-                for (int ci = 0; ci < 4; ++ci) du[ci] += g * __ldg(w + co * 36 + ci * 9 + ky * 3 + kx);
+                for (int ci = 0; ci < 4; ++ci) du[ci] += g * __ldg(wt + ((ky * 3 + kx) * 4 + ci) * Cm + co);
             }
         }
     }

@@ -25,7 +25,8 @@ int gn_bwd_apply(const void* dy, const void* x, const float* sums, const float* 
 // z: NCHW [B,4,h,w] fp32 (z_f16=0) or fp16 (z_f16=1); out: [B, h*w, Cm] 16-bit. pq_w [4,4], pq_b [4], w [Cm,4,3,3], b [Cm]
 int latent_in(const void* z, int z_f16, float in_scale, const float* pq_w, const float* pq_b, const float* w,
               const float* b, void* out, int B, int h, int wd, int Cm, int bf16, cudaStream_t s);
-// dz[b,c,y,x] (fp32 NCHW) = in_scale * pq_w^T conv_in^T(dy); dy: [B, h*w, Cm] 16-bit; scale_b: optional per-sample scale
+// dz[b,c,y,x] (fp32 NCHW) = in_scale * pq_w^T conv_in^T(dy); dy: [B, h*w, Cm] 16-bit; scale_b: optional per-sample scale;
+// w must be the conv_in weight re-ordered to [ky][kx][ci][co]
 int latent_out(const void* dy, float in_scale, const float* scale_b, const float* pq_w, const float* w, float* dz,
                int B, int h, int wd, int Cm, int bf16, cudaStream_t s);
 

@@ -145,7 +145,20 @@ __device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int t) 
     return c;
 }
 
+// position (in 64-element chunks) of the (tap, cc) chunk inside a packed Bm row
+__device__ __host__ __forceinline__ int b_chunk_index(const TapGemmParams& p, int tap, int cc) {
+    if (!p.reuse) return tap * p.cpt + cc;
+    // row-reuse order: (dx, cc, dy) so that the three vertical taps of one horizontal shift are adjacent
+    return ((p.tap_dx[tap] + 1) * p.cpt + cc) * 3 + (p.tap_dy[tap] + 1);
+}
+
 // ------------------------------------------------------------------------------------------------ the kernel
+// Two K-loop schedules:
+//   plain      : one pipeline stage = one (tap, 64-channel chunk): A box [128 px][64 ch] + B box [BN][64]; 4 MMAs.
+//   row reuse  : (3x3 stride-1 taps only) one stage = one (horizontal shift dx, chunk): A box [(h_box+2) rows x w_box px]
+//                [64 ch] loaded ONCE and read by the three vertical taps through descriptor row offsets, + the three
+//                matching B boxes fetched by a single 3-D TMA; 12 MMAs. A third of the TMA instructions, two thirds of
+//                the activation bytes.
 template <bool BF16>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -153,8 +166,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle atoms.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t a_stage_bytes = TG_BM * 128;
-    const uint32_t b_stage_bytes = static_cast<uint32_t>(p.BN) * 128;
+    const int a_rows = p.reuse ? (p.h_box + 2) * p.w_box : TG_BM;
+    const uint32_t a_stage_bytes = static_cast<uint32_t>(a_rows) * 128;
+    const uint32_t b_box_bytes = static_cast<uint32_t>(p.BN) * 128;
+    const uint32_t b_stage_bytes = p.reuse ? 3 * b_box_bytes : b_box_bytes;
     uint8_t* smA = smem;
     uint8_t* smB = smem + static_cast<size_t>(stages) * a_stage_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smB + static_cast<size_t>(stages) * b_stage_bytes);
@@ -163,11 +178,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tfull_bar = bars + 2 * stages;   // [2]
     uint64_t* tempty_bar = bars + 2 * stages + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+    float* bias_s = reinterpret_cast<float*>(bars + 2 * stages + 6);  // [2][256]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int total_tiles = p.m_tiles * p.n_tiles * p.z_count;
-    const int k_iters = p.n_taps * p.cpt;
+    const int k_iters = p.reuse ? 3 * p.cpt : p.n_taps * p.cpt;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -189,62 +205,101 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    // shfl from lane 0 marks the value warp-uniform for the compiler: tcgen05/TMA operands then live in uniform
+    // registers instead of going through an ELECT / R2UR.BROADCAST loop per instruction
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
-        // ===================================================== TMA producer
-        if (lane == 0) {
+        // ===================================================== TMA producer (warp-uniform loop, one elected lane issues)
+        {
             int stage = 0;
             uint32_t phase = 0;
+            long long w_empty = 0;
+            const long long t_begin = clock64();
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(p, t);
-                const int c0 = p.a_c0 ? __ldg(p.a_c0 + tc.n_tile) : 0;
+                const int c0 = p.a_c0 ? __shfl_sync(0xffffffffu, __ldg(p.a_c0 + tc.n_tile), 0) : 0;
                 const int x0 = tc.tx * p.w_box * p.in_stride;
                 const int y0 = tc.ty * p.h_box * p.in_stride;
                 const int ab = tc.bb + tc.z * p.a_zmul;
                 const int bz = tc.z * p.b_zmul + tc.bb * p.b_bbmul;
                 const int n0 = tc.n_tile * p.BN;
-                for (int tap = 0; tap < p.n_taps; ++tap) {
-                    const int xx = x0 + p.tap_dx[tap];
-                    const int yy = y0 + p.tap_dy[tap];
-                    for (int cc = 0; cc < p.cpt; ++cc) {
+                for (int it = 0; it < k_iters; ++it) {
+                    int xx, yy, cc, bk;
+                    if (p.reuse) {
+                        const int dxi = it / p.cpt;
+                        cc = it - dxi * p.cpt;
+                        xx = x0 + dxi - 1;
+                        yy = y0 - 1;
+                        bk = it * 3;  // chunk coordinate in the 3-D weight map
+                    } else {
+                        const int tap = it / p.cpt;
+                        cc = it - tap * p.cpt;
+                        xx = x0 + p.tap_dx[tap];
+                        yy = y0 + p.tap_dy[tap];
+                        bk = it * TG_KC;  // element coordinate along K
+                    }
+                    if (p.dbg) {
+                        const long long w0 = clock64();
                         mbar_wait(&empty_bar[stage], phase ^ 1);
+                        w_empty += clock64() - w0;
+                    } else {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                    }
+                    if (elect_one()) {
                         mbar_expect_tx(&full_bar[stage], a_stage_bytes + b_stage_bytes);
                         tma_load_4d(smA + static_cast<size_t>(stage) * a_stage_bytes, &tmA, &full_bar[stage],
                                     c0 + cc * TG_KC, xx, yy, ab);
-                        tma_load_3d(smB + static_cast<size_t>(stage) * b_stage_bytes, &tmB, &full_bar[stage],
-                                    (tap * p.cpt + cc) * TG_KC, n0, bz);
-                        if (++stage == stages) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
+                        if (p.reuse)
+                            tma_load_3d(smB + static_cast<size_t>(stage) * b_stage_bytes, &tmB, &full_bar[stage], 0, n0, bk);
+                        else
+                            tma_load_3d(smB + static_cast<size_t>(stage) * b_stage_bytes, &tmB, &full_bar[stage], bk, n0, bz);
+                    }
+                    __syncwarp();
+                    if (++stage == stages) {
+                        stage = 0;
+                        phase ^= 1;
                     }
                 }
+            }
+            if (p.dbg && blockIdx.x == 0 && lane == 0) {
+                p.dbg[0] = clock64() - t_begin;
+                p.dbg[1] = w_empty;
             }
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer (one thread)
         const uint32_t idesc = make_idesc_f16(TG_BM, static_cast<uint32_t>(p.BN), BF16 ? 1u : 0u);
+        const int n_sub = p.reuse ? 3 : 1;                        // vertical taps served by one stage
+        const uint32_t a_sub_bytes = static_cast<uint32_t>(p.w_box) * 128;  // one image row of the patch
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
+        long long w_tempty = 0, w_full = 0;
+        const long long t_begin = clock64();
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            long long w0 = p.dbg ? clock64() : 0;
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            if (p.dbg) w_tempty += clock64() - w0;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
             for (int kc = 0; kc < k_iters; ++kc) {
+                w0 = p.dbg ? clock64() : 0;
                 mbar_wait(&full_bar[stage], phase);
+                if (p.dbg) w_full += clock64() - w0;
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint64_t adesc =
-                        make_kmajor_desc(smem_u32(smA + static_cast<size_t>(stage) * a_stage_bytes), 128);
-                    const uint64_t bdesc =
-                        make_kmajor_desc(smem_u32(smB + static_cast<size_t>(stage) * b_stage_bytes), 128);
+                if (elect_one()) {
+                    const uint32_t a_base = smem_u32(smA + static_cast<size_t>(stage) * a_stage_bytes);
+                    const uint32_t b_base = smem_u32(smB + static_cast<size_t>(stage) * b_stage_bytes);
+                    for (int sub = 0; sub < n_sub; ++sub) {
+                        const uint64_t adesc = make_kmajor_desc(a_base + sub * a_sub_bytes, 128);
+                        const uint64_t bdesc = make_kmajor_desc(b_base + sub * b_box_bytes, 128);
 #pragma unroll
-                    for (int k = 0; k < TG_KC / 16; ++k) {
-                        // advancing 16 elements (32 bytes) along K inside the swizzle atom: +2 in 16-byte units
-                        umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < TG_KC / 16; ++k) {
+                            // advancing 16 elements (32 bytes) along K inside the swizzle atom: +2 in 16-byte units
+                            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc > 0 || sub > 0 || k > 0) ? 1u : 0u);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);
                     if (kc == k_iters - 1) umma_commit(&tfull_bar[acc]);
@@ -258,12 +313,20 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+        if (p.dbg && blockIdx.x == 0 && lane == 0) {
+            p.dbg[2] = clock64() - t_begin;
+            p.dbg[3] = w_tempty;
+            p.dbg[4] = w_full;
+        }
     } else {
         // ===================================================== epilogue (4 warps, one TMEM lane quarter each)
         const int q = warp & 3;
         const int row = q * 32 + lane;
+        const int etid = threadIdx.x - 64;  // 0..127 among the epilogue threads
         int acc = 0;
         uint32_t acc_phase = 0;
+        long long w_tfull = 0, e_busy = 0;
+        const long long t_begin = clock64();
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const TileCoord tc = decode_tile(p, t);
             const int yy = row / p.w_box, xx = row - yy * p.w_box;
@@ -273,15 +336,44 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const long long out_off = tc.z * p.c_zstride + tc.bb * p.out_sb +
                                       static_cast<long long>(tc.ty * p.h_box + yy) * p.out_sy +
                                       static_cast<long long>(tc.tx * p.w_box + xx) * p.out_sx;
-            mbar_wait(&tfull_bar[acc], acc_phase);
+            // stage this tile's bias in shared memory while the MMAs are still running
+            float* bs = bias_s + acc * 256;
+            if (p.bias) {
+                for (int j = etid; j < p.BN; j += 128) bs[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const uint4* res_ptr = p.residual
+                ? reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.residual) + out_off + n0) : nullptr;
+            const uint4* dot_ptr = p.rowdot
+                ? reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.dotsrc) + pixel * p.ld_dot + n0) : nullptr;
+            const int n_chunks = (min(p.BN, p.N - n0) + 15) / 16;
+            // prefetch the first chunk of the row-wise side inputs before waiting for the accumulator
+            uint4 res_nx[2], dot_nx[2];
+            if (res_ptr) { res_nx[0] = __ldg(res_ptr); res_nx[1] = __ldg(res_ptr + 1); }
+            if (dot_ptr) { dot_nx[0] = __ldg(dot_ptr); dot_nx[1] = __ldg(dot_ptr + 1); }
+            {
+                const long long w0 = p.dbg ? clock64() : 0;
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                if (p.dbg) w_tfull += clock64() - w0;
+            }
             tc_fence_after();
+            const long long e0 = p.dbg ? clock64() : 0;
             const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * 256u + (static_cast<uint32_t>(q * 32) << 16);
             float dot = 0.f;
             float gs = 0.f, gss = 0.f;
             int ggroup = -1;
-            for (int j0 = 0; j0 < p.BN; j0 += 16) {
+            for (int c = 0; c < n_chunks; ++c) {
+                const int j0 = c * 16;
                 const int n = n0 + j0;
-                if (n >= p.N) break;  // warp-uniform
+                uint4 res_cur[2], dot_cur[2];
+                if (res_ptr) {
+                    res_cur[0] = res_nx[0]; res_cur[1] = res_nx[1];
+                    if (c + 1 < n_chunks) { res_nx[0] = __ldg(res_ptr + 2 * (c + 1)); res_nx[1] = __ldg(res_ptr + 2 * (c + 1) + 1); }
+                }
+                if (dot_ptr) {
+                    dot_cur[0] = dot_nx[0]; dot_cur[1] = dot_nx[1];
+                    if (c + 1 < n_chunks) { dot_nx[0] = __ldg(dot_ptr + 2 * (c + 1)); dot_nx[1] = __ldg(dot_ptr + 2 * (c + 1) + 1); }
+                }
                 uint32_t r[16];
                 tmem_ld16(taddr + j0, r);
                 tmem_ld_wait();
@@ -291,17 +383,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (p.bias) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                        const float4 b4 = *reinterpret_cast<const float4*>(bs + j0 + j);
                         v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
                     }
                 }
-                if (p.residual) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(
-                        reinterpret_cast<const uint16_t*>(p.residual) + out_off + n);
+                if (res_ptr) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const uint4 u = __ldg(rp + h);
-                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+                        const uint32_t w[4] = {res_cur[h].x, res_cur[h].y, res_cur[h].z, res_cur[h].w};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             v[h * 8 + 2 * j] += lo16_to_f<BF16>(w[j]);
@@ -309,13 +398,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
-                if (p.rowdot) {
-                    const uint4* dp = reinterpret_cast<const uint4*>(
-                        reinterpret_cast<const uint16_t*>(p.dotsrc) + pixel * p.ld_dot + n);
+                if (dot_ptr) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const uint4 u = __ldg(dp + h);
-                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+                        const uint32_t w[4] = {dot_cur[h].x, dot_cur[h].y, dot_cur[h].z, dot_cur[h].w};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             dot += v[h * 8 + 2 * j] * lo16_to_f<BF16>(w[j]);
@@ -362,6 +448,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             }
+            // the accumulator stage is drained: hand it back to the MMA warp before the remaining bookkeeping
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
             if (p.gn_sums && ggroup >= 0) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
@@ -375,10 +464,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
             if (p.rowdot) atomicAdd(p.rowdot + pixel, dot);
-            tc_fence_before();
-            mbar_arrive(&tempty_bar[acc]);
+            if (p.dbg) e_busy += clock64() - e0;
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
+        }
+        if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) {
+            p.dbg[5] = clock64() - t_begin;
+            p.dbg[6] = w_tfull;
+            p.dbg[7] = e_busy;
         }
     }
 
@@ -418,12 +511,13 @@ __global__ void tapgemm_ref_kernel(const TapGemmParams p) {
         const int yi = y * p.in_stride + p.tap_dy[tap];
         if (xi < 0 || xi >= p.a_W || yi < 0 || yi >= p.a_H || ab >= p.a_B) continue;
         const uint16_t* arow = A + ((static_cast<long long>(ab) * p.a_H + yi) * p.a_W + xi) * p.a_ld;
-        for (int k = 0; k < p.cpt * TG_KC; ++k) {
-            const int c = c0 + k;
-            if (c >= p.a_C) break;
-            const float a = lo16_to_f<BF16>(arow[c]);
-            const float b = lo16_to_f<BF16>(Bm[static_cast<long long>(tap) * p.cpt * TG_KC + k]);
-            acc = fmaf(a, b, acc);
+        for (int cc = 0; cc < p.cpt; ++cc) {
+            const uint16_t* brow = Bm + static_cast<long long>(b_chunk_index(p, tap, cc)) * TG_KC;
+            for (int k = 0; k < TG_KC; ++k) {
+                const int c = c0 + cc * TG_KC + k;
+                if (c >= p.a_C) break;
+                acc = fmaf(lo16_to_f<BF16>(arow[c]), lo16_to_f<BF16>(brow[k]), acc);
+            }
         }
     }
     float v = acc * p.alpha;
@@ -464,6 +558,22 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
+// Row reuse applies to full 3x3 stride-1 tap sets; the caller asks for it with p.reuse = 1 and must have packed Bm in
+// the (dx, cc, dy) chunk order (b_chunk_index). It is dropped here when a stage would not leave room for 3 stages.
+bool tapgemm_reuse_ok(const TapGemmParams& p) {
+    if (p.n_taps != 9 || p.in_stride != 1 || p.w_box < 8 || p.z_count != 1 || p.b_zmul || p.b_bbmul) return false;
+    bool seen[9] = {false};
+    for (int t = 0; t < 9; ++t) {
+        const int dx = p.tap_dx[t], dy = p.tap_dy[t];
+        if (dx < -1 || dx > 1 || dy < -1 || dy > 1) return false;
+        seen[(dy + 1) * 3 + dx + 1] = true;
+    }
+    for (bool b : seen)
+        if (!b) return false;
+    const size_t per_stage = static_cast<size_t>(p.h_box + 2) * p.w_box * 128 + 3 * static_cast<size_t>(p.BN) * 128;
+    return per_stage * 3 <= 216 * 1024;
+}
+
 int tapgemm_prepare(TapGemmOp* op) {
     TapGemmParams& p = op->p;
     EncodeTiledFn enc = get_encode();
@@ -477,6 +587,10 @@ int tapgemm_prepare(TapGemmOp* op) {
                   p.n_taps, p.cpt);
         return -3;
     }
+    if (p.reuse && !tapgemm_reuse_ok(p)) {
+        set_error("tapgemm_prepare: row-reuse schedule requested for an unsupported tap set / tile");
+        return -3;
+    }
     const CUtensorMapDataType dt = p.is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     {
         cuuint64_t dims[4] = {(cuuint64_t)p.a_C, (cuuint64_t)p.a_W, (cuuint64_t)p.a_H, (cuuint64_t)p.a_B};
@@ -485,6 +599,7 @@ int tapgemm_prepare(TapGemmOp* op) {
         // strided traversal (stride-2 downsample conv): the box spans in_stride * (n - 1) + 1 input elements
         cuuint32_t box[4] = {TG_KC, (cuuint32_t)((p.w_box - 1) * p.in_stride + 1),
                              (cuuint32_t)((p.h_box - 1) * p.in_stride + 1), 1};
+        if (p.reuse) box[2] = (cuuint32_t)(p.h_box + 2);
         cuuint32_t estr[4] = {1, (cuuint32_t)p.in_stride, (cuuint32_t)p.in_stride, 1};
         CUresult r = enc(&op->tmA, dt, 4, const_cast<void*>(p.a_ptr), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -495,7 +610,21 @@ int tapgemm_prepare(TapGemmOp* op) {
             return -4;
         }
     }
-    {
+    if (p.reuse) {
+        // weights as (64 elements, rows, chunk): one box fetches the three vertical-tap chunks of a (dx, cc) pair
+        cuuint64_t dims[3] = {(cuuint64_t)TG_KC, (cuuint64_t)p.b_rows, (cuuint64_t)(9 * p.cpt)};
+        cuuint64_t strides[2] = {(cuuint64_t)p.ldb * 2, (cuuint64_t)TG_KC * 2};
+        cuuint32_t box[3] = {TG_KC, (cuuint32_t)p.BN, 3};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&op->tmB, dt, 3, const_cast<void*>(p.b_ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled(B, reuse) failed: %d (rows=%d ldb=%lld BN=%d cpt=%d)", (int)r, p.b_rows,
+                      p.ldb, p.BN, p.cpt);
+            return -5;
+        }
+    } else {
         const long long ktot = static_cast<long long>(p.n_taps) * p.cpt * TG_KC;
         const int zdim = p.b_Z > 0 ? p.b_Z : 1;
         cuuint64_t dims[3] = {(cuuint64_t)ktot, (cuuint64_t)p.b_rows, (cuuint64_t)zdim};
@@ -511,12 +640,14 @@ int tapgemm_prepare(TapGemmOp* op) {
             return -5;
         }
     }
-    const size_t per_stage = TG_BM * 128 + static_cast<size_t>(p.BN) * 128;
-    int stages = static_cast<int>((220 * 1024) / per_stage);
+    const size_t a_stage = p.reuse ? static_cast<size_t>(p.h_box + 2) * p.w_box * 128 : TG_BM * 128;
+    const size_t b_stage = (p.reuse ? 3 : 1) * static_cast<size_t>(p.BN) * 128;
+    const size_t per_stage = a_stage + b_stage;
+    int stages = static_cast<int>((216 * 1024) / per_stage);
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     op->stages = stages;
-    op->smem_bytes = 1024 + stages * per_stage + (2 * stages + 4) * sizeof(uint64_t) + 16;
+    op->smem_bytes = 1024 + stages * per_stage + (2 * stages + 6) * sizeof(uint64_t) + 2 * 256 * sizeof(float) + 16;
     return 0;
 }
 
@@ -538,8 +669,8 @@ int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream) {
     const int grid = total < num_sms() ? total : num_sms();
     char pname[128];
     if (g_prof_on)
-        snprintf(pname, sizeof(pname), "tapgemm:N=%d,BN=%d,taps=%d,cpt=%d,aC=%d,f32=%d", p.N, p.BN, p.n_taps, p.cpt, p.a_C,
-                 p.out_fp32);
+        snprintf(pname, sizeof(pname), "tapgemm:N=%d,BN=%d,taps=%d,cpt=%d,aC=%d,f32=%d,reuse=%d", p.N, p.BN, p.n_taps, p.cpt,
+                 p.a_C, p.out_fp32, p.reuse);
     ProfScope prof_scope(g_prof_on ? pname : "", stream);
     if (p.is_bf16)
         tapgemm_kernel<true><<<grid, TG_THREADS, op->smem_bytes, stream>>>(op->tmA, op->tmB, op->p, op->stages);
@@ -554,9 +685,9 @@ int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream) {
     if (debug_sync_enabled()) {
         char what[256];
         snprintf(what, sizeof(what),
-                 "tapgemm(m_tiles=%d n_tiles=%d z=%d BN=%d N=%d taps=%d cpt=%d box=%dx%d stages=%d smem=%zu aC=%d aW=%d aH=%d aB=%d)",
+                 "tapgemm(m_tiles=%d n_tiles=%d z=%d BN=%d N=%d taps=%d cpt=%d box=%dx%d stages=%d smem=%zu aC=%d aW=%d aH=%d aB=%d reuse=%d)",
                  p.m_tiles, p.n_tiles, p.z_count, p.BN, p.N, p.n_taps, p.cpt, p.w_box, p.h_box, op->stages,
-                 op->smem_bytes, p.a_C, p.a_W, p.a_H, p.a_B);
+                 op->smem_bytes, p.a_C, p.a_W, p.a_H, p.a_B, p.reuse);
         return debug_sync_check(what, stream);
     }
     return 0;

@@ -35,6 +35,7 @@ struct TapGemmParams {
     int n_taps, cpt;        // taps, 64-wide chunks per tap
     int tap_dx[TG_MAX_TAPS], tap_dy[TG_MAX_TAPS];
     const int* a_c0;        // [n_tiles] first input channel of each N tile (nullptr => 0)
+    int reuse;              // 1: row-reuse schedule (3x3 stride-1 taps; Bm chunks in (dx, cc, dy) order)
     int a_zmul;             // A dim-3 coordinate = bb + z * a_zmul
     int b_zmul, b_bbmul;    // B dim-2 coordinate = z * b_zmul + bb * b_bbmul
     // ---- epilogue
@@ -52,6 +53,7 @@ struct TapGemmParams {
     float* gn_sums;         // optional: per (sample, gn_group) {sum, sumsq} of the stored output, fp32 atomics
     int gn_cpg, gn_G;       // channels per GroupNorm group, number of groups
     int is_bf16;            // 1: bf16 operands/outputs, 0: fp16
+    long long* dbg;         // optional [8]: per-role cycle counters of CTA 0 (test hook only)
     // ---- raw views (used only by the CUDA-core checking kernel)
     const void* a_ptr; int a_C, a_W, a_H, a_B; long long a_ld;
     const void* b_ptr; long long ldb, b_zstride; int b_rows, b_Z;
@@ -66,6 +68,8 @@ struct TapGemmOp {
 
 // Encodes the two tensor maps and fills stages/smem. Returns 0 or a negative error (message via set_error).
 int tapgemm_prepare(TapGemmOp* op);
+// whether the row-reuse schedule can serve this contraction (tap set, tile and shared-memory budget)
+bool tapgemm_reuse_ok(const TapGemmParams& p);
 // Launches on `stream` (persistent grid of min(#tiles, #SMs) CTAs).
 int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream);
 // CUDA-core restatement of the same contraction; test/debug only (WFD_DEBUG_REF_GEMM=1 or the selftest entry).
