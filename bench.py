@@ -315,7 +315,7 @@ def run_native(args):
                 "algorithmic_flops_per_step": fl["F_step"] * B, "launches_per_step": tg_launches,
                 "avg_launch_ms": tg_ms / tg_launches if tg_launches else None, "kernel_ms_per_step": tg_ms,
                 "share_of_step": tg_ms / all_ms if all_ms else None, "traffic": None}
-    top = sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]
+    top = sorted(prof.items(), key=lambda kv: -kv[1][1])[:args.top]
     if args.verbose:
         for n, (c, t) in top:
             print("  %-60s %6.1f launches %9.3f ms/step" % (n, c, t), file=sys.stderr)
@@ -358,6 +358,7 @@ def main():
     ap.add_argument("--latent", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--top", type=int, default=12, help="kernels listed in profile_top")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -519,7 +519,7 @@ int Decoder::run_gemm(Exec& ex, TapGemmOp& tmpl, bool z_is_batch) {
 // conv-style contraction over a channels-last activation
 int Decoder::conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int Hin, int Win, int Hout, int Wout,
                        void* out, long long ldc, const float* bias, const void* residual, float* gn_sums, int gn_cpg,
-                       const OutStrides* os) {
+                       const OutStrides* os, const GnBwdFuse* gb) {
     TapGemmOp op;
     memset(&op, 0, sizeof(op));
     TapGemmParams& p = op.p;
@@ -560,6 +560,17 @@ int Decoder::conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int 
         p.gn_sums = (fuse_gn && gn_cpg > 0 && gn_cpg % 16 == 0) ? gn_sums : nullptr;
         p.gn_cpg = gn_cpg;
         p.gn_G = G;
+        if (gb && gb->red) {
+            p.gnb_red = gb->red;
+            p.gnb_x = gb->x;
+            p.gnb_stats = gb->stats;
+            p.gnb_gamma = gb->gamma;
+            p.gnb_beta = gb->beta;
+            p.gnb_cpg = gb->cpg;
+            p.gnb_silu = gb->silu;
+            p.gnb_inv_n = gb->inv_n;
+            p.gnb_eps = gb->eps;
+        }
         p.is_bf16 = bf16;
         p.a_ptr = A;
         p.a_C = a_C;
@@ -586,6 +597,7 @@ struct PlainGemm {
     void* out; int out_fp32; long long ldc, c_zstride;
     const float* bias; const void* residual; float alpha;
     float* gn_sums; int gn_cpg;
+    const GnBwdFuse* gb;
 };
 int Decoder::plain_gemm(Exec& ex, const PlainGemm& g) {
     TapGemmOp op;
@@ -635,6 +647,17 @@ int Decoder::plain_gemm(Exec& ex, const PlainGemm& g) {
         p.gn_sums = (fuse_gn && g.gn_cpg > 0 && g.gn_cpg % 16 == 0) ? g.gn_sums : nullptr;
         p.gn_cpg = g.gn_cpg;
         p.gn_G = G;
+        if (g.gb && g.gb->red) {
+            p.gnb_red = g.gb->red;
+            p.gnb_x = g.gb->x;
+            p.gnb_stats = g.gb->stats;
+            p.gnb_gamma = g.gb->gamma;
+            p.gnb_beta = g.gb->beta;
+            p.gnb_cpg = g.gb->cpg;
+            p.gnb_silu = g.gb->silu;
+            p.gnb_inv_n = g.gb->inv_n;
+            p.gnb_eps = g.gb->eps;
+        }
         p.is_bf16 = bf16;
         p.a_ptr = g.A;
         p.a_C = g.K;
@@ -693,7 +716,7 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
         }
         const ConvW& c1 = convs[r.prefix + ".conv1"];
         CK(conv_gemm(ex, c1.fwd, act, r.cin, r.h, r.w, r.h, r.w, h1, r.cout, c1.bias, nullptr, gn_sums_ptr(gi2),
-                     r.cout / G, nullptr));
+                     r.cout / G, nullptr, nullptr));
         if (!ex.prepare) {
             if (!fused_ok(r.cout)) CK(gn_stats(h1, gn_sums_ptr(gi2), B, phw, r.cout, G, bf16, s));
             CK(gn_apply(h1, gn_sums_ptr(gi2), vecs[r.prefix + ".norm2.weight"], vecs[r.prefix + ".norm2.bias"], act2, B,
@@ -702,7 +725,7 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
         const void* residual = xin;
         if (r.cin != r.cout) {
             const ConvW& cs = convs[r.prefix + ".conv_shortcut"];
-            CK(conv_gemm(ex, cs.fwd, xin, r.cin, r.h, r.w, r.h, r.w, ws + o_sc, r.cout, cs.bias, nullptr, nullptr, 0, nullptr));
+            CK(conv_gemm(ex, cs.fwd, xin, r.cin, r.h, r.w, r.h, r.w, ws + o_sc, r.cout, cs.bias, nullptr, nullptr, 0, nullptr, nullptr));
             residual = ws + o_sc;
         }
         const ConvW& c2 = convs[r.prefix + ".conv2"];
@@ -713,7 +736,7 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
             feeds_down = down_after[blk] && j == cfg.layers_per_block;
         }
         CK(conv_gemm(ex, c2.fwd, act2, r.cout, r.h, r.w, r.h, r.w, xout, r.cout, c2.bias, residual,
-                     feeds_down ? nullptr : gn_sums_ptr(next_gn), next_cpg, nullptr));
+                     feeds_down ? nullptr : gn_sums_ptr(next_gn), next_cpg, nullptr, nullptr));
         return 0;
     };
 
@@ -787,7 +810,7 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
             snprintf(buf, sizeof(buf), "decoder.up_blocks.%d.downsamplers.0.conv", i);
             const ConvW& cd = convs[buf];
             CK(conv_gemm(ex, cd.fwd, x, cd.cin, cur_h, cur_w, cur_h / 2, cur_w / 2, ws + o_down_out[i], cd.cout,
-                         cd.bias, nullptr, nullptr, 0, nullptr));
+                         cd.bias, nullptr, nullptr, 0, nullptr, nullptr));
             x = ws + o_down_out[i];
             cur_h /= 2;
             cur_w /= 2;
@@ -803,7 +826,7 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
     }
     const ConvW& co = convs["decoder.conv_out"];
     CK(conv_gemm(ex, co.fwd, ws + o_act, C_last, H_out, W_out, H_out, W_out, ws + o_logits, T_pad, co.bias, nullptr,
-                 nullptr, 0, nullptr));
+                 nullptr, 0, nullptr, nullptr));
     return 0;
 }
 
@@ -816,13 +839,38 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
     const void* dlog = dlogits_in ? dlogits_in : ws + o_dlogits;
     if (!ex.prepare)
         CUDA_CK(cudaMemsetAsync(gn_red_ptr(0), 0, static_cast<size_t>(n_gn) * B_max * G * 2 * sizeof(float), s));
+    // GroupNorm-backward reduction fused into the epilogue of the contraction that produces dy (when the channel
+    // groups are 16-column aligned); otherwise the standalone gn_bwd_reduce pass runs
+    // (measured on B200: the fused form wins for the <= 768-channel layers whose tiles carry enough MMA work to hide the
+    // extra epilogue math; for the 1536/3072-channel grouped layers the standalone pass is cheaper)
+    auto fuse_ok = [&](int C) { return fuse_gn && (C / G) % 16 == 0 && C <= 768; };
+    auto make_gb = [&](int gn_idx, const void* xsaved, const std::string& norm, int C, int px, int silu) {
+        GnBwdFuse gb;
+        memset(&gb, 0, sizeof(gb));
+        if (!fuse_ok(C)) return gb;
+        gb.red = gn_red_ptr(gn_idx);
+        gb.x = xsaved;
+        gb.stats = gn_sums_ptr(gn_idx);
+        gb.gamma = vecs[norm + ".weight"];
+        gb.beta = vecs[norm + ".bias"];
+        gb.cpg = C / G;
+        gb.silu = silu;
+        gb.inv_n = 1.f / (static_cast<float>(C / G) * static_cast<float>(px));
+        gb.eps = eps;
+        return gb;
+    };
     // gradient buffers rotate: `cur` holds d(out) of the layer being differentiated
     int cur = 0;
     auto gbuf = [&](int i) { return ws + o_g[i & 3]; };
     // conv_out^T, then conv_norm_out + SiLU backward
     const ConvW& co = convs["decoder.conv_out"];
-    CK(conv_gemm(ex, co.bwd, dlog, T_pad, H_out, W_out, H_out, W_out, gbuf(cur), C_last, nullptr, nullptr, nullptr, 0, nullptr));
+    {
+        const GnBwdFuse gb = make_gb(n_gn - 1, x_last, "decoder.conv_norm_out", C_last, H_out * W_out, 1);
+        CK(conv_gemm(ex, co.bwd, dlog, T_pad, H_out, W_out, H_out, W_out, gbuf(cur), C_last, nullptr, nullptr, nullptr, 0,
+                     nullptr, &gb));
+    }
     if (!ex.prepare) {
+        if (!fuse_ok(C_last))
         CK(gn_bwd_reduce(gbuf(cur), x_last, gn_sums_ptr(n_gn - 1), vecs["decoder.conv_norm_out.weight"],
                          vecs["decoder.conv_norm_out.bias"], gn_red_ptr(n_gn - 1), B, H_out * W_out, C_last, G, eps, 1,
                          bf16, s));
@@ -840,25 +888,33 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         const uint8_t* h1 = ws + o_res_h1[idx];
         const int gi1 = 2 * idx, gi2 = 2 * idx + 1;
         const ConvW& c2 = convs[r.prefix + ".conv2"];
-        CK(conv_gemm(ex, c2.bwd, dout, r.cout, r.h, r.w, r.h, r.w, t1, r.cout, nullptr, nullptr, nullptr, 0, nullptr));
+        {
+            const GnBwdFuse gb = make_gb(gi2, h1, r.prefix + ".norm2", r.cout, phw, 1);
+            CK(conv_gemm(ex, c2.bwd, dout, r.cout, r.h, r.w, r.h, r.w, t1, r.cout, nullptr, nullptr, nullptr, 0, nullptr, &gb));
+        }
         if (!ex.prepare) {
             const float* ga = vecs[r.prefix + ".norm2.weight"];
             const float* be = vecs[r.prefix + ".norm2.bias"];
+            if (!fuse_ok(r.cout))
             CK(gn_bwd_reduce(t1, h1, gn_sums_ptr(gi2), ga, be, gn_red_ptr(gi2), B, phw, r.cout, G, eps, 1, bf16, s));
             CK(gn_bwd_apply(t1, h1, gn_sums_ptr(gi2), ga, be, gn_red_ptr(gi2), nullptr, t1, B, phw, r.cout, G, eps, 1,
                             bf16, s));
         }
         const ConvW& c1 = convs[r.prefix + ".conv1"];
-        CK(conv_gemm(ex, c1.bwd, t1, r.cout, r.h, r.w, r.h, r.w, t2, r.cin, nullptr, nullptr, nullptr, 0, nullptr));
+        {
+            const GnBwdFuse gb = make_gb(gi1, xin, r.prefix + ".norm1", r.cin, phw, 1);
+            CK(conv_gemm(ex, c1.bwd, t1, r.cout, r.h, r.w, r.h, r.w, t2, r.cin, nullptr, nullptr, nullptr, 0, nullptr, &gb));
+        }
         const void* add = dout;
         if (r.cin != r.cout) {
             const ConvW& cs = convs[r.prefix + ".conv_shortcut"];
-            CK(conv_gemm(ex, cs.bwd, dout, r.cout, r.h, r.w, r.h, r.w, t3, r.cin, nullptr, nullptr, nullptr, 0, nullptr));
+            CK(conv_gemm(ex, cs.bwd, dout, r.cout, r.h, r.w, r.h, r.w, t3, r.cin, nullptr, nullptr, nullptr, 0, nullptr, nullptr));
             add = t3;
         }
         if (!ex.prepare) {
             const float* ga = vecs[r.prefix + ".norm1.weight"];
             const float* be = vecs[r.prefix + ".norm1.bias"];
+            if (!fuse_ok(r.cin))
             CK(gn_bwd_reduce(t2, xin, gn_sums_ptr(gi1), ga, be, gn_red_ptr(gi1), B, phw, r.cin, G, eps, 1, bf16, s));
             CK(gn_bwd_apply(t2, xin, gn_sums_ptr(gi1), ga, be, gn_red_ptr(gi1), add, t2, B, phw, r.cin, G, eps, 1, bf16,
                             s));
@@ -886,7 +942,7 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
                         os.sb = static_cast<long long>(r.h) * r.w * r.cout;
                         uint8_t* base = dxin + (static_cast<size_t>(py) * r.w + px) * r.cout * 2;
                         CK(conv_gemm(ex, cb.bwd, dout, r.cout, r.h / 2, r.w / 2, r.h / 2, r.w / 2, base, r.cout, nullptr,
-                                     nullptr, nullptr, 0, &os));
+                                     nullptr, nullptr, 0, &os, nullptr));
                     }
                 cur = (cur + 1) & 3;
             }
@@ -963,10 +1019,13 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         g.A = dqkv; g.K = 3 * Cm; g.a_ld = 3 * Cm; g.rows_per_sample = N; g.a_B = B_max;
         g.Bm = cq.bwd.Bm; g.b_rows = cq.bwd.rows; g.ldb = cq.bwd.ldb; g.b_Z = 1; g.BN = cq.bwd.BN; g.N = Cm;
         g.out = dxn; g.ldc = Cm; g.alpha = 1.f;
+        const GnBwdFuse gba = make_gb(n_gn - 2, xin, a + "group_norm", Cm, N, 0);
+        g.gb = &gba;
         CK(plain_gemm(ex, g));
         if (!ex.prepare) {
             const float* ga = vecs[a + "group_norm.weight"];
             const float* be = vecs[a + "group_norm.bias"];
+            if (!fuse_ok(Cm))
             CK(gn_bwd_reduce(dxn, xin, gn_sums_ptr(n_gn - 2), ga, be, gn_red_ptr(n_gn - 2), B, N, Cm, G, eps, 0, bf16, s));
             CK(gn_bwd_apply(dxn, xin, gn_sums_ptr(n_gn - 2), ga, be, gn_red_ptr(n_gn - 2), dout, dxn, B, N, Cm, G, eps, 0,
                             bf16, s));

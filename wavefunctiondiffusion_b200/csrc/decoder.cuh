@@ -23,6 +23,15 @@ struct PackedB {
 struct TapSel {  // one tap of a contraction: which weight tap it reads and where it shifts the input
     int w_tap, dx, dy;
 };
+struct GnBwdFuse {  // GroupNorm(+SiLU) backward reduction fused into the producing contraction's epilogue
+    float* red;
+    const void* x;
+    const float* stats;
+    const float* gamma;
+    const float* beta;
+    int cpg, silu;
+    float inv_n, eps;
+};
 struct OutStrides {  // element strides of a strided output plane (downsample backward writes every other pixel)
     long long sx, sy, sb;
 };
@@ -93,7 +102,7 @@ struct Decoder {
     int run_gemm(Exec& ex, TapGemmOp& tmpl, bool z_is_batch);
     int conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int Hin, int Win, int Hout, int Wout, void* out,
                   long long ldc, const float* bias, const void* residual, float* gn_sums, int gn_cpg,
-                  const OutStrides* os);
+                  const OutStrides* os, const GnBwdFuse* gb);
     int plain_gemm(Exec& ex, const PlainGemm& g);
     float* gn_sums_ptr(int idx) const;
     float* gn_red_ptr(int idx) const;

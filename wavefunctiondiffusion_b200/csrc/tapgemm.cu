@@ -129,6 +129,12 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+__device__ __forceinline__ float fast_sigmoid(float u) {  // 0.5 * tanh(0.5 u) + 0.5 on the hardware tanh
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * u));
+    return fmaf(0.5f, t, 0.5f);
+}
+
 struct TileCoord {
     int z, n_tile, bb, ty, tx;
 };
@@ -179,6 +185,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tempty_bar = bars + 2 * stages + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
     float* bias_s = reinterpret_cast<float*>(bars + 2 * stages + 6);  // [2][256]
+    float* gam_s = bias_s + 512;                                      // [2][256] GroupNorm-backward gamma
+    float* bet_s = gam_s + 512;                                       // [2][256] GroupNorm-backward beta
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -194,7 +202,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], 128);
+            mbar_init(&tempty_bar[a], TG_EPI_THREADS);
         }
         fence_barrier_init();
     }
@@ -319,10 +327,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             p.dbg[4] = w_full;
         }
     } else {
-        // ===================================================== epilogue (4 warps, one TMEM lane quarter each)
+        // ===================================================== epilogue (8 warps: a TMEM lane quarter is shared by two
+        // warps that take the even / odd 16-column chunks of the tile)
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        const int etid = threadIdx.x - 64;  // 0..127 among the epilogue threads
+        const int etid = threadIdx.x - 64;   // 0..255 among the epilogue threads
+        const int half = (warp - 2) >> 2;    // 0: even chunks, 1: odd chunks
         int acc = 0;
         uint32_t acc_phase = 0;
         long long w_tfull = 0, e_busy = 0;
@@ -339,18 +349,35 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // stage this tile's bias in shared memory while the MMAs are still running
             float* bs = bias_s + acc * 256;
             if (p.bias) {
-                for (int j = etid; j < p.BN; j += 128) bs[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+                for (int j = etid; j < p.BN; j += TG_EPI_THREADS) bs[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            const uint4* res_ptr = p.residual
-                ? reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.residual) + out_off + n0) : nullptr;
-            const uint4* dot_ptr = p.rowdot
-                ? reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.dotsrc) + pixel * p.ld_dot + n0) : nullptr;
+            float* gms = gam_s + acc * 256;
+            float* bts = bet_s + acc * 256;
+            if (p.gnb_red) {
+                for (int j = etid; j < p.BN; j += TG_EPI_THREADS) {
+                    gms[j] = (n0 + j < p.N) ? __ldg(p.gnb_gamma + n0 + j) : 0.f;
+                    bts[j] = (n0 + j < p.N) ? __ldg(p.gnb_beta + n0 + j) : 0.f;
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(TG_EPI_THREADS) : "memory");
+            // one row-wise side input per launch: residual (forward), dot operand (WFC) or saved activation (GroupNorm
+            // backward). Its 32-byte pieces are prefetched three chunks deep, the first three before the accumulator wait,
+            // so that DRAM latency overlaps the MMAs instead of serialising the column loop.
+            const int side_kind = p.residual ? 1 : (p.rowdot ? 2 : (p.gnb_red ? 3 : 0));
+            const uint4* side_ptr = nullptr;
+            if (side_kind == 1)
+                side_ptr = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.residual) + out_off + n0);
+            else if (side_kind == 2)
+                side_ptr = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.dotsrc) + pixel * p.ld_dot + n0);
+            else if (side_kind == 3)
+                side_ptr = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.gnb_x) + out_off + n0);
             const int n_chunks = (min(p.BN, p.N - n0) + 15) / 16;
-            // prefetch the first chunk of the row-wise side inputs before waiting for the accumulator
-            uint4 res_nx[2], dot_nx[2];
-            if (res_ptr) { res_nx[0] = __ldg(res_ptr); res_nx[1] = __ldg(res_ptr + 1); }
-            if (dot_ptr) { dot_nx[0] = __ldg(dot_ptr); dot_nx[1] = __ldg(dot_ptr + 1); }
+            uint4 sb0[2], sb1[2], sb2[2];
+            if (side_ptr) {
+                if (half < n_chunks) { sb0[0] = __ldg(side_ptr + 2 * half); sb0[1] = __ldg(side_ptr + 2 * half + 1); }
+                if (half + 2 < n_chunks) { sb1[0] = __ldg(side_ptr + 2 * (half + 2)); sb1[1] = __ldg(side_ptr + 2 * (half + 2) + 1); }
+                if (half + 4 < n_chunks) { sb2[0] = __ldg(side_ptr + 2 * (half + 4)); sb2[1] = __ldg(side_ptr + 2 * (half + 4) + 1); }
+            }
             {
                 const long long w0 = p.dbg ? clock64() : 0;
                 mbar_wait(&tfull_bar[acc], acc_phase);
@@ -362,17 +389,17 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float dot = 0.f;
             float gs = 0.f, gss = 0.f;
             int ggroup = -1;
-            for (int c = 0; c < n_chunks; ++c) {
+            float b1 = 0.f, b2 = 0.f, bmean = 0.f, brstd = 0.f;
+            int bgroup = -1;
+            for (int c = half; c < n_chunks; c += 2) {
                 const int j0 = c * 16;
                 const int n = n0 + j0;
-                uint4 res_cur[2], dot_cur[2];
-                if (res_ptr) {
-                    res_cur[0] = res_nx[0]; res_cur[1] = res_nx[1];
-                    if (c + 1 < n_chunks) { res_nx[0] = __ldg(res_ptr + 2 * (c + 1)); res_nx[1] = __ldg(res_ptr + 2 * (c + 1) + 1); }
-                }
-                if (dot_ptr) {
-                    dot_cur[0] = dot_nx[0]; dot_cur[1] = dot_nx[1];
-                    if (c + 1 < n_chunks) { dot_nx[0] = __ldg(dot_ptr + 2 * (c + 1)); dot_nx[1] = __ldg(dot_ptr + 2 * (c + 1) + 1); }
+                uint4 side_cur[2];
+                if (side_ptr) {
+                    side_cur[0] = sb0[0]; side_cur[1] = sb0[1];
+                    sb0[0] = sb1[0]; sb0[1] = sb1[1];
+                    sb1[0] = sb2[0]; sb1[1] = sb2[1];
+                    if (c + 6 < n_chunks) { sb2[0] = __ldg(side_ptr + 2 * (c + 6)); sb2[1] = __ldg(side_ptr + 2 * (c + 6) + 1); }
                 }
                 uint32_t r[16];
                 tmem_ld16(taddr + j0, r);
@@ -387,10 +414,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
                     }
                 }
-                if (res_ptr) {
+                if (side_kind == 1) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const uint32_t w[4] = {res_cur[h].x, res_cur[h].y, res_cur[h].z, res_cur[h].w};
+                        const uint32_t w[4] = {side_cur[h].x, side_cur[h].y, side_cur[h].z, side_cur[h].w};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             v[h * 8 + 2 * j] += lo16_to_f<BF16>(w[j]);
@@ -398,10 +425,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
-                if (dot_ptr) {
+                if (side_kind == 2) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const uint32_t w[4] = {dot_cur[h].x, dot_cur[h].y, dot_cur[h].z, dot_cur[h].w};
+                        const uint32_t w[4] = {side_cur[h].x, side_cur[h].y, side_cur[h].z, side_cur[h].w};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             dot += v[h * 8 + 2 * j] * lo16_to_f<BF16>(w[j]);
@@ -446,6 +473,57 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             gss += a * a + b * b;
                         }
                     }
+                    if (side_kind == 3) {
+                        // fused GroupNorm(+SiLU) backward reduction over the just-stored gradient dy and the saved
+                        // forward activation x: sum(du*gamma), sum(du*gamma*xhat), du = dy * act'(xhat*gamma+beta)
+                        const int g = n / p.gnb_cpg;
+                        if (g != bgroup) {
+                            if (bgroup >= 0) {
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) {
+                                    b1 += __shfl_xor_sync(0xffffffffu, b1, o);
+                                    b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+                                }
+                                if (lane == 0) {
+                                    float* dst = p.gnb_red + (static_cast<long long>(tc.bb) * p.gn_G + bgroup) * 2;
+                                    atomicAdd(dst, b1);
+                                    atomicAdd(dst + 1, b2);
+                                }
+                            }
+                            bgroup = g;
+                            b1 = 0.f;
+                            b2 = 0.f;
+                            const float* st = p.gnb_stats + (static_cast<long long>(tc.bb) * p.gn_G + g) * 2;
+                            const float m = __ldg(st) * p.gnb_inv_n;
+                            const float var = fmaxf(__ldg(st + 1) * p.gnb_inv_n - m * m, 0.f);
+                            bmean = m;
+                            brstd = rsqrtf(var + p.gnb_eps);
+                        }
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint32_t xw[4] = {side_cur[h].x, side_cur[h].y, side_cur[h].z, side_cur[h].w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    const int col = h * 8 + 2 * j + e;
+                                    const float dyv = e ? hi16_to_f<BF16>(w[h * 4 + j]) : lo16_to_f<BF16>(w[h * 4 + j]);
+                                    const float xv = e ? hi16_to_f<BF16>(xw[j]) : lo16_to_f<BF16>(xw[j]);
+                                    const float xh = (xv - bmean) * brstd;
+                                    const float ga = gms[j0 + col];
+                                    float du = dyv;
+                                    if (p.gnb_silu) {
+                                        const float u = fmaf(xh, ga, bts[j0 + col]);
+                                        const float sg = fast_sigmoid(u);
+                                        du *= sg * fmaf(u, 1.f - sg, 1.f);
+                                    }
+                                    const float tt = du * ga;
+                                    b1 += tt;
+                                    b2 = fmaf(tt, xh, b2);
+                                }
+                            }
+                        }
+                    }
                 }
             }
             // the accumulator stage is drained: hand it back to the MMA warp before the remaining bookkeeping
@@ -461,6 +539,18 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     float* dst = p.gn_sums + (static_cast<long long>(tc.bb) * p.gn_G + ggroup) * 2;
                     atomicAdd(dst, gs);
                     atomicAdd(dst + 1, gss);
+                }
+            }
+            if (p.gnb_red && bgroup >= 0) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    b1 += __shfl_xor_sync(0xffffffffu, b1, o);
+                    b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+                }
+                if (lane == 0) {
+                    float* dst = p.gnb_red + (static_cast<long long>(tc.bb) * p.gn_G + bgroup) * 2;
+                    atomicAdd(dst, b1);
+                    atomicAdd(dst + 1, b2);
                 }
             }
             if (p.rowdot) atomicAdd(p.rowdot + pixel, dot);
@@ -537,6 +627,24 @@ __global__ void tapgemm_ref_kernel(const TapGemmParams p) {
             atomicAdd(dst, r);
             atomicAdd(dst + 1, r * r);
         }
+        if (p.gnb_red) {
+            const int g = n / p.gnb_cpg;
+            const float* st = p.gnb_stats + (static_cast<long long>(bb) * p.gn_G + g) * 2;
+            const float m = st[0] * p.gnb_inv_n;
+            const float var = fmaxf(st[1] * p.gnb_inv_n - m * m, 0.f);
+            const float rstd = rsqrtf(var + p.gnb_eps);
+            const float xh = (lo16_to_f<BF16>(reinterpret_cast<const uint16_t*>(p.gnb_x)[off]) - m) * rstd;
+            const float ga = p.gnb_gamma[n];
+            float du = lo16_to_f<BF16>(w);
+            if (p.gnb_silu) {
+                const float u = fmaf(xh, ga, p.gnb_beta[n]);
+                const float sg = fast_sigmoid(u);
+                du *= sg * fmaf(u, 1.f - sg, 1.f);
+            }
+            float* dst = p.gnb_red + (static_cast<long long>(bb) * p.gn_G + g) * 2;
+            atomicAdd(dst, du * ga);
+            atomicAdd(dst + 1, du * ga * xh);
+        }
     }
 }
 
@@ -585,6 +693,10 @@ int tapgemm_prepare(TapGemmOp* op) {
         p.n_taps < 1 || p.n_taps > TG_MAX_TAPS || p.cpt < 1) {
         set_error("tapgemm_prepare: bad tiling (BN=%d N=%d box=%dx%d taps=%d cpt=%d)", p.BN, p.N, p.w_box, p.h_box,
                   p.n_taps, p.cpt);
+        return -3;
+    }
+    if ((p.residual ? 1 : 0) + (p.rowdot ? 1 : 0) + (p.gnb_red ? 1 : 0) > 1) {
+        set_error("tapgemm_prepare: residual, row-dot and GroupNorm-backward epilogues are mutually exclusive");
         return -3;
     }
     if (p.reuse && !tapgemm_reuse_ok(p)) {
@@ -643,11 +755,11 @@ int tapgemm_prepare(TapGemmOp* op) {
     const size_t a_stage = p.reuse ? static_cast<size_t>(p.h_box + 2) * p.w_box * 128 : TG_BM * 128;
     const size_t b_stage = (p.reuse ? 3 : 1) * static_cast<size_t>(p.BN) * 128;
     const size_t per_stage = a_stage + b_stage;
-    int stages = static_cast<int>((216 * 1024) / per_stage);
+    int stages = static_cast<int>((212 * 1024) / per_stage);
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     op->stages = stages;
-    op->smem_bytes = 1024 + stages * per_stage + (2 * stages + 6) * sizeof(uint64_t) + 2 * 256 * sizeof(float) + 16;
+    op->smem_bytes = 1024 + stages * per_stage + (2 * stages + 6) * sizeof(uint64_t) + 6 * 256 * sizeof(float) + 16;
     return 0;
 }
 
@@ -669,8 +781,9 @@ int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream) {
     const int grid = total < num_sms() ? total : num_sms();
     char pname[128];
     if (g_prof_on)
-        snprintf(pname, sizeof(pname), "tapgemm:N=%d,BN=%d,taps=%d,cpt=%d,aC=%d,f32=%d,reuse=%d", p.N, p.BN, p.n_taps, p.cpt,
-                 p.a_C, p.out_fp32, p.reuse);
+        snprintf(pname, sizeof(pname), "tapgemm:N=%d,BN=%d,taps=%d,cpt=%d,aC=%d,f32=%d,reuse=%d,side=%d,gns=%d", p.N, p.BN,
+                 p.n_taps, p.cpt, p.a_C, p.out_fp32, p.reuse, p.residual ? 1 : (p.rowdot ? 2 : (p.gnb_red ? 3 : 0)),
+                 p.gn_sums ? 1 : 0);
     ProfScope prof_scope(g_prof_on ? pname : "", stream);
     if (p.is_bf16)
         tapgemm_kernel<true><<<grid, TG_THREADS, op->smem_bytes, stream>>>(op->tmA, op->tmB, op->p, op->stages);

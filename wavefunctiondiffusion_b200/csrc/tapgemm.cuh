@@ -21,7 +21,8 @@ namespace wfd {
 constexpr int TG_BM = 128;      // rows per M tile (UMMA M)
 constexpr int TG_KC = 64;       // K elements per pipeline chunk (128 bytes = one SW128 row)
 constexpr int TG_MAX_TAPS = 9;
-constexpr int TG_THREADS = 192; // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int TG_EPI_THREADS = 256;                 // warps 2-9: epilogue (two warps per TMEM lane quarter)
+constexpr int TG_THREADS = 64 + TG_EPI_THREADS;     // warp 0 TMA, warp 1 MMA
 
 struct TapGemmParams {
     // ---- tiling
@@ -52,6 +53,15 @@ struct TapGemmParams {
     long long ld_dot;
     float* gn_sums;         // optional: per (sample, gn_group) {sum, sumsq} of the stored output, fp32 atomics
     int gn_cpg, gn_G;       // channels per GroupNorm group, number of groups
+    // optional fused GroupNorm(+SiLU) backward reduction over (stored output dy, saved activation x with the output's
+    // layout): red[b, g] += {sum(du*gamma), sum(du*gamma*xhat)}; needs gnb_cpg % 16 == 0
+    float* gnb_red;
+    const void* gnb_x;
+    const float* gnb_stats;   // forward {sum, sumsq} per (sample, group)
+    const float* gnb_gamma;
+    const float* gnb_beta;
+    int gnb_cpg, gnb_silu;
+    float gnb_inv_n, gnb_eps;
     int is_bf16;            // 1: bf16 operands/outputs, 0: fp16
     long long* dbg;         // optional [8]: per-role cycle counters of CTA 0 (test hook only)
     // ---- raw views (used only by the CUDA-core checking kernel)
