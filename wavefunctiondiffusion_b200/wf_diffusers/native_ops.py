@@ -284,6 +284,12 @@ class WfcLossFunction(torch.autograd.Function):
         return from_nhwc16(dout, ctx.like, h.dtype16), None, None
 
 
+def max_micro_batch():
+    """Largest batch one library call carries (activation workspace ~0.6 GB per 64x64 map); larger batches are run
+    as consecutive micro-batches (maps are independent). Override with WFD_MAX_BATCH."""
+    return max(1, int(os.environ.get("WFD_MAX_BATCH", "64")))
+
+
 class GuidanceLossFunction(torch.autograd.Function):
     """Fused guidance loss: loss[b] = strength * WFCLossEinsum(softmax(decode(latents * in_scale)))[b]
     (reference pipeline_wfd.py:612 with decode_latents_tile :402-408). One library call computes loss and d loss / d
@@ -293,14 +299,19 @@ class GuidanceLossFunction(torch.autograd.Function):
     def forward(ctx, latents, native, handle, in_scale, strength):
         _require_cuda(latents, "guidance loss")
         B, _, h, w = latents.shape
-        plan = native.plan(B, h, w, latents.device)
+        mb = min(B, max_micro_batch())
+        plan = native.plan(mb, h, w, latents.device)
         z = latents.contiguous()
         loss = torch.empty(B, dtype=torch.float32, device=z.device)
         dz = torch.empty((B, 4, h, w), dtype=torch.float32, device=z.device)
-        nat.check(nat.lib().wfd_guidance_step(plan.handle, handle.handle, C.c_void_p(z.data_ptr()), _z_dtype_code(z), B,
-                                              float(in_scale), float(strength), handle.saved_ptr(B, plan.H, plan.W),
-                                              C.c_void_p(loss.data_ptr()), C.c_void_p(dz.data_ptr()), nat.stream_ptr()),
-                  "wfd_guidance_step")
+        esz = z.element_size() * 4 * h * w
+        for lo in range(0, B, mb):
+            n = min(mb, B - lo)
+            nat.check(nat.lib().wfd_guidance_step(plan.handle, handle.handle, C.c_void_p(z.data_ptr() + lo * esz),
+                                                  _z_dtype_code(z), n, float(in_scale), float(strength),
+                                                  handle.saved_ptr(n, plan.H, plan.W), C.c_void_p(loss.data_ptr() + 4 * lo),
+                                                  C.c_void_p(dz.data_ptr() + 16 * h * w * lo), nat.stream_ptr()),
+                      "wfd_guidance_step")
         ctx.save_for_backward(dz)
         ctx.zdtype = latents.dtype
         return loss
