@@ -38,12 +38,9 @@ def run(cin, cout, groups, BN, Bn=8, H=64, W=64, taps9=True, reuse=0):
     tiles = (Bn * H * W // 128) * n_tiles
     per_cta = tiles / 148
     flops = 2.0 * Bn * H * W * cout * cin_g * ntap
-    print("cin %d cout %d g %d BN %d cpt %d taps %d: %.3f ms  %.0f TF/s | tiles/CTA %.1f | producer total %d wait_empty %d | mma total %d wait_tempty %d wait_full %d | epi total %d wait_tfull %d busy %d reuse %d (cycles; per tile: total %.0f)"
-          % (cin, cout, groups, BN, cpt, ntap, ms, flops / ms / 1e9, per_cta, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], reuse, v[2] / per_cta))
+    print("cin %d cout %d g %d BN %d cpt %d taps %d: %.3f ms  %.0f TF/s | tiles/CTA %.1f | producer total %d wait_empty %d | mma total %d wait_tempty %d wait_full %d | epi total %d wait_tfull %d busy %d reuse %d | Bprod total %d wait %d | issueA %d issueB %d (cycles; per tile: total %.0f)"
+          % (cin, cout, groups, BN, cpt, ntap, ms, flops / ms / 1e9, per_cta, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], reuse, v[8], v[9], v[10], v[11], v[2] / per_cta))
 
-for reuse in (0, 1):
-    run(3072, 3072, 64, 48, reuse=reuse)
-    run(1536, 1536, 16, 96, reuse=reuse)
-run(1536, 3072, 64, 48, taps9=False)
-run(768, 768, 4, 192)
+run(3072, 3072, 64, 48, reuse=0)
+run(3072, 3072, 64, 48, reuse=1)
 run(384, 384, 1, 192)

@@ -212,7 +212,8 @@ def test_four_tap_neighbour_contraction(use_ref):
 
 
 @pytest.mark.parametrize("use_ref", [1, 0])
-def test_persistent_many_tiles_per_cta(use_ref):
+@pytest.mark.parametrize("n_group", [0, 4])
+def test_persistent_many_tiles_per_cta(use_ref, n_group):
     """More tiles than SMs: every CTA loops over several tiles, exercising the TMEM double buffer and the smem ring
     across tile boundaries (M = 128 * 450 rows, 3 N tiles -> 1350 tiles on 148 SMs)."""
     torch.manual_seed(5)
@@ -223,7 +224,8 @@ def test_persistent_many_tiles_per_cta(use_ref):
     out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
     d = _desc(a=A.data_ptr(), a_C=K, a_W=M, a_H=1, a_B=1, a_ld=K, b=Bm.data_ptr(), b_rows=N, ldb=K, b_zstride=0, b_Z=1,
               n_taps=1, cpt=K // 64, tap_dx=[0], tap_dy=[0], a_c0=None, BN=BN, N=N, W=M, H=1, B=1, w_box=128, h_box=1,
-              in_stride=1, z_count=1, out=out.data_ptr(), out_fp32=0, ldc=N, bias=bias.data_ptr(), alpha=1.0, dtype16=1)
+              in_stride=1, z_count=1, out=out.data_ptr(), out_fp32=0, ldc=N, bias=bias.data_ptr(), alpha=1.0, dtype16=1,
+              n_group=n_group)
     _run(d, use_ref)
     want = A.float() @ Bm.float().t() + bias
     assert _rel(out, want) < 6e-3

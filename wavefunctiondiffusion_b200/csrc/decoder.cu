@@ -78,14 +78,17 @@ int pack_conv(const float* w, int cout, int cin, int groups, int k, int mode, bo
     const int BN = bn_override > 0 ? bn_override : choose_bn(rpg);
     const int n_tiles = (N + BN - 1) / BN;
     std::vector<int> c0(n_tiles);
-    int cpt = 1;
+    int cpt = 1, span_max = 1;
     for (int t = 0; t < n_tiles; ++t) {
         const int n0 = t * BN, n1 = std::min(N, n0 + BN);
         const int g_lo = n0 / rpg, g_hi = (n1 - 1) / rpg;
         c0[t] = (g_lo * kpg) & ~7;  // TMA box start must be 16-byte aligned
         const int span = (g_hi + 1) * kpg - c0[t];
+        span_max = std::max(span_max, span);
         cpt = std::max(cpt, (span + TG_KC - 1) / TG_KC);
     }
+    // useful 16-channel steps in the last chunk of a tap: the rest only meets zero-padded weights
+    const int kk_last = (span_max - (cpt - 1) * TG_KC + 15) / 16;
     const int wtaps = k * k;                                          // taps stored in the weight tensor
     const int taps = tap_sel ? static_cast<int>(tap_sel->size()) : wtaps;  // taps of this contraction
     const long long ldb = static_cast<long long>(taps) * cpt * TG_KC;
@@ -145,6 +148,7 @@ int pack_conv(const float* w, int cout, int cin, int groups, int k, int mode, bo
     out->rows = static_cast<int>(rows);
     out->in_stride = (mode == 2) ? 2 : 1;
     out->reuse = reuse ? 1 : 0;
+    out->kk_last = kk_last;
     for (int t = 0; t < taps; ++t) {
         out->dx[t] = tdx[t];
         out->dy[t] = tdy[t];
@@ -548,6 +552,7 @@ int Decoder::conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int 
         }
         p.a_c0 = pk.a_c0;
         p.reuse = pk.reuse;
+        p.kk_last = pk.kk_last;
         p.N = pk.N;
         p.out = out;
         p.out_fp32 = 0;

@@ -15,7 +15,7 @@ int debug_ref_gemm();
 struct PackedB {
     uint16_t* Bm = nullptr;
     int* a_c0 = nullptr;  // first A channel per N tile
-    int BN = 0, n_tiles = 0, cpt = 0, n_taps = 0, N = 0, rows = 0, in_stride = 1, reuse = 0;
+    int BN = 0, n_tiles = 0, cpt = 0, n_taps = 0, N = 0, rows = 0, in_stride = 1, reuse = 0, kk_last = 0;
     long long ldb = 0;
     int dx[TG_MAX_TAPS] = {0}, dy[TG_MAX_TAPS] = {0};
     void release();

@@ -140,10 +140,26 @@ struct TileCoord {
 };
 __device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int t) {
     TileCoord c;
-    int m_tile = t % p.m_tiles;
-    int rest = t / p.m_tiles;
-    c.n_tile = rest % p.n_tiles;
-    c.z = rest / p.n_tiles;
+    int m_tile, rest;
+    if (p.n_group > 1) {
+        // L2-friendly rasterisation: consecutive tile ids (= the CTAs of one wave) cover a patch of
+        // (#SMs / n_group) M tiles x n_group N tiles, so each A tile is fetched from HBM once per band of N tiles
+        const int per_z = p.m_tiles * p.n_tiles;
+        c.z = t / per_z;
+        const int r0 = t - c.z * per_z;
+        const int per_band = p.m_tiles * p.n_group;
+        const int band = r0 / per_band;
+        const int r = r0 - band * per_band;
+        const int nb = min(p.n_group, p.n_tiles - band * p.n_group);
+        m_tile = r / nb;
+        c.n_tile = band * p.n_group + (r - m_tile * nb);
+        rest = 0;
+    } else {
+        m_tile = t % p.m_tiles;
+        rest = t / p.m_tiles;
+        c.n_tile = rest % p.n_tiles;
+        c.z = rest / p.n_tiles;
+    }
     c.tx = m_tile % p.tiles_x;
     int r2 = m_tile / p.tiles_x;
     c.ty = r2 % p.tiles_y;
@@ -197,7 +213,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < stages; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], 2);
             mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -217,68 +233,85 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // registers instead of going through an ELECT / R2UR.BROADCAST loop per instruction
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-    if (warp == 0) {
-        // ===================================================== TMA producer (warp-uniform loop, one elected lane issues)
+    if (warp == 0 || warp == TG_THREADS / 32 - 1) {
+        // ===================================================== TMA producers (warp-uniform loops, one elected lane issues):
+        // warp 0 streams the activation boxes, the last warp the weight boxes; both arrive on the stage's full barrier
+        const bool load_a = (warp == 0);
         {
             int stage = 0;
             uint32_t phase = 0;
-            long long w_empty = 0;
+            long long w_empty = 0, w_issue = 0;
             const long long t_begin = clock64();
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const TileCoord tc = decode_tile(p, t);
-                const int c0 = p.a_c0 ? __shfl_sync(0xffffffffu, __ldg(p.a_c0 + tc.n_tile), 0) : 0;
-                const int x0 = tc.tx * p.w_box * p.in_stride;
-                const int y0 = tc.ty * p.h_box * p.in_stride;
-                const int ab = tc.bb + tc.z * p.a_zmul;
-                const int bz = tc.z * p.b_zmul + tc.bb * p.b_bbmul;
-                const int n0 = tc.n_tile * p.BN;
-                for (int it = 0; it < k_iters; ++it) {
-                    int xx, yy, cc, bk;
-                    if (p.reuse) {
-                        const int dxi = it / p.cpt;
-                        cc = it - dxi * p.cpt;
-                        xx = x0 + dxi - 1;
-                        yy = y0 - 1;
-                        bk = it * 3;  // chunk coordinate in the 3-D weight map
-                    } else {
-                        const int tap = it / p.cpt;
-                        cc = it - tap * p.cpt;
-                        xx = x0 + p.tap_dx[tap];
-                        yy = y0 + p.tap_dy[tap];
-                        bk = it * TG_KC;  // element coordinate along K
-                    }
-                    if (p.dbg) {
-                        const long long w0 = clock64();
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        w_empty += clock64() - w0;
-                    } else {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                    }
-                    if (elect_one()) {
-                        mbar_expect_tx(&full_bar[stage], a_stage_bytes + b_stage_bytes);
-                        tma_load_4d(smA + static_cast<size_t>(stage) * a_stage_bytes, &tmA, &full_bar[stage],
-                                    c0 + cc * TG_KC, xx, yy, ab);
-                        if (p.reuse)
-                            tma_load_3d(smB + static_cast<size_t>(stage) * b_stage_bytes, &tmB, &full_bar[stage], 0, n0, bk);
-                        else
-                            tma_load_3d(smB + static_cast<size_t>(stage) * b_stage_bytes, &tmB, &full_bar[stage], bk, n0, bz);
-                    }
-                    __syncwarp();
-                    if (++stage == stages) {
-                        stage = 0;
-                        phase ^= 1;
+            // Tile coordinates cost several integer divisions and one global load (a_c0): each lane decodes a different
+            // upcoming tile, the warp then walks through them with shuffles (32 tiles per batch).
+            for (int base = blockIdx.x; base < total_tiles; base += 32 * gridDim.x) {
+                const int my_t = base + lane * gridDim.x;
+                TileCoord mine = decode_tile(p, my_t < total_tiles ? my_t : base);
+                int my_c0 = 0;
+                if (p.a_c0 && my_t < total_tiles) my_c0 = __ldg(p.a_c0 + mine.n_tile);
+                const int batch = min(32, (total_tiles - base + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x));
+                for (int l = 0; l < batch; ++l) {
+                    TileCoord tc;
+                    tc.z = __shfl_sync(0xffffffffu, mine.z, l);
+                    tc.n_tile = __shfl_sync(0xffffffffu, mine.n_tile, l);
+                    tc.bb = __shfl_sync(0xffffffffu, mine.bb, l);
+                    tc.ty = __shfl_sync(0xffffffffu, mine.ty, l);
+                    tc.tx = __shfl_sync(0xffffffffu, mine.tx, l);
+                    const int c0 = __shfl_sync(0xffffffffu, my_c0, l);
+                    const int x0 = tc.tx * p.w_box * p.in_stride;
+                    const int y0 = tc.ty * p.h_box * p.in_stride;
+                    const int ab = tc.bb + tc.z * p.a_zmul;
+                    const int bz = tc.z * p.b_zmul + tc.bb * p.b_bbmul;
+                    const int n0 = tc.n_tile * p.BN;
+                    const int n_outer = p.reuse ? 3 : p.n_taps;
+                    int it = 0;
+                    for (int o = 0; o < n_outer; ++o) {
+                        const int xx = p.reuse ? x0 + o - 1 : x0 + p.tap_dx[o];
+                        const int yy = p.reuse ? y0 - 1 : y0 + p.tap_dy[o];
+                        for (int cc = 0; cc < p.cpt; ++cc, ++it) {
+                            const int bk = p.reuse ? it * 3 : it * TG_KC;  // chunk / element coordinate of the weights
+                            if (p.dbg) {
+                                const long long w0 = clock64();
+                                mbar_wait(&empty_bar[stage], phase ^ 1);
+                                w_empty += clock64() - w0;
+                            } else {
+                                mbar_wait(&empty_bar[stage], phase ^ 1);
+                            }
+                            const long long i0 = p.dbg ? clock64() : 0;
+                            if (elect_one()) {
+                                if (load_a) {
+                                    mbar_expect_tx(&full_bar[stage], a_stage_bytes);
+                                    tma_load_4d(smA + static_cast<size_t>(stage) * a_stage_bytes, &tmA, &full_bar[stage],
+                                                c0 + cc * TG_KC, xx, yy, ab);
+                                } else {
+                                    mbar_expect_tx(&full_bar[stage], b_stage_bytes);
+                                    if (p.reuse)
+                                        tma_load_3d(smB + static_cast<size_t>(stage) * b_stage_bytes, &tmB, &full_bar[stage], 0, n0, bk);
+                                    else
+                                        tma_load_3d(smB + static_cast<size_t>(stage) * b_stage_bytes, &tmB, &full_bar[stage], bk, n0, bz);
+                                }
+                            }
+                            __syncwarp();
+                            if (p.dbg) w_issue += clock64() - i0;
+                            if (++stage == stages) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
                     }
                 }
             }
             if (p.dbg && blockIdx.x == 0 && lane == 0) {
-                p.dbg[0] = clock64() - t_begin;
-                p.dbg[1] = w_empty;
+                p.dbg[load_a ? 10 : 11] = w_issue;
+                p.dbg[load_a ? 0 : 8] = clock64() - t_begin;
+                p.dbg[load_a ? 1 : 9] = w_empty;
             }
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer (one thread)
         const uint32_t idesc = make_idesc_f16(TG_BM, static_cast<uint32_t>(p.BN), BF16 ? 1u : 0u);
         const int n_sub = p.reuse ? 3 : 1;                        // vertical taps served by one stage
+        const int kk_last = (p.kk_last > 0 && p.kk_last < TG_KC / 16) ? p.kk_last : TG_KC / 16;
         const uint32_t a_sub_bytes = static_cast<uint32_t>(p.w_box) * 128;  // one image row of the patch
         int stage = 0;
         uint32_t phase = 0;
@@ -292,7 +325,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.dbg) w_tempty += clock64() - w0;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
+            int cc = 0;  // chunk index within the tap (the last chunk of a tap may hold fewer than 64 useful channels)
             for (int kc = 0; kc < k_iters; ++kc) {
+                const int n_k = (cc == p.cpt - 1) ? kk_last : TG_KC / 16;
+                if (++cc == p.cpt) cc = 0;
                 w0 = p.dbg ? clock64() : 0;
                 mbar_wait(&full_bar[stage], phase);
                 if (p.dbg) w_full += clock64() - w0;
@@ -305,8 +341,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint64_t bdesc = make_kmajor_desc(b_base + sub * b_box_bytes, 128);
 #pragma unroll
                         for (int k = 0; k < TG_KC / 16; ++k) {
-                            // advancing 16 elements (32 bytes) along K inside the swizzle atom: +2 in 16-byte units
-                            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc > 0 || sub > 0 || k > 0) ? 1u : 0u);
+                            // advancing 16 elements (32 bytes) along K inside the swizzle atom: +2 in 16-byte units;
+                            // 16-channel steps that only meet zero-padded weights are skipped
+                            if (k < n_k)
+                                umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc > 0 || sub > 0 || k > 0) ? 1u : 0u);
                         }
                     }
                     umma_commit(&empty_bar[stage]);
@@ -337,9 +375,18 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t acc_phase = 0;
         long long w_tfull = 0, e_busy = 0;
         const long long t_begin = clock64();
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const TileCoord tc = decode_tile(p, t);
-            const int yy = row / p.w_box, xx = row - yy * p.w_box;
+        const int yy = row / p.w_box, xx = row - yy * p.w_box;
+        for (int base = blockIdx.x; base < total_tiles; base += 32 * gridDim.x) {
+          const int my_t = base + lane * gridDim.x;
+          const TileCoord mine = decode_tile(p, my_t < total_tiles ? my_t : base);
+          const int batch = min(32, (total_tiles - base + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x));
+          for (int l = 0; l < batch; ++l) {
+            TileCoord tc;
+            tc.z = __shfl_sync(0xffffffffu, mine.z, l);
+            tc.n_tile = __shfl_sync(0xffffffffu, mine.n_tile, l);
+            tc.bb = __shfl_sync(0xffffffffu, mine.bb, l);
+            tc.ty = __shfl_sync(0xffffffffu, mine.ty, l);
+            tc.tx = __shfl_sync(0xffffffffu, mine.tx, l);
             const long long pixel =
                 (static_cast<long long>(tc.bb) * p.H + tc.ty * p.h_box + yy) * p.W + tc.tx * p.w_box + xx;
             const int n0 = tc.n_tile * p.BN;
@@ -557,6 +604,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.dbg) e_busy += clock64() - e0;
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
+          }
         }
         if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) {
             p.dbg[5] = clock64() - t_begin;
@@ -757,6 +805,14 @@ int tapgemm_prepare(TapGemmOp* op) {
     const size_t per_stage = a_stage + b_stage;
     int stages = static_cast<int>((212 * 1024) / per_stage);
     if (stages > 8) stages = 8;
+    {
+        static int cap = -1;  // WFD_MAX_STAGES: experiment knob
+        if (cap < 0) {
+            const char* e = getenv("WFD_MAX_STAGES");
+            cap = e ? atoi(e) : 0;
+        }
+        if (cap > 0 && stages > cap) stages = cap;
+    }
     if (stages < 2) stages = 2;
     op->stages = stages;
     op->smem_bytes = 1024 + stages * per_stage + (2 * stages + 6) * sizeof(uint64_t) + 6 * 256 * sizeof(float) + 16;
@@ -778,7 +834,15 @@ int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream) {
     }
     const int total = p.m_tiles * p.n_tiles * p.z_count;
     if (total <= 0) return 0;
-    const int grid = total < num_sms() ? total : num_sms();
+    int grid = total < num_sms() ? total : num_sms();
+    {
+        static int limit = -1;  // WFD_GRID_LIMIT: experiment knob (fewer resident CTAs), not used in production
+        if (limit < 0) {
+            const char* e = getenv("WFD_GRID_LIMIT");
+            limit = e ? atoi(e) : 0;
+        }
+        if (limit > 0 && grid > limit) grid = limit;
+    }
     char pname[128];
     if (g_prof_on)
         snprintf(pname, sizeof(pname), "tapgemm:N=%d,BN=%d,taps=%d,cpt=%d,aC=%d,f32=%d,reuse=%d,side=%d,gns=%d", p.N, p.BN,

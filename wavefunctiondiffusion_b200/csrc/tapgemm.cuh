@@ -22,11 +22,12 @@ constexpr int TG_BM = 128;      // rows per M tile (UMMA M)
 constexpr int TG_KC = 64;       // K elements per pipeline chunk (128 bytes = one SW128 row)
 constexpr int TG_MAX_TAPS = 9;
 constexpr int TG_EPI_THREADS = 256;                 // warps 2-9: epilogue (two warps per TMEM lane quarter)
-constexpr int TG_THREADS = 64 + TG_EPI_THREADS;     // warp 0 TMA, warp 1 MMA
+constexpr int TG_THREADS = 64 + TG_EPI_THREADS + 32; // warp 0 TMA (activations), warp 1 MMA, last warp TMA (weights)
 
 struct TapGemmParams {
     // ---- tiling
     int m_tiles, n_tiles, z_count;
+    int n_group;            // >1: tile ids sweep bands of n_group N tiles (L2 reuse of A for large-K GEMMs); 0/1: M fastest
     int BN;                 // N tile, multiple of 16, <= 256
     int tiles_x, tiles_y;   // M tiles per sample along x / y
     int w_box, h_box;       // w_box * h_box == 128
@@ -34,6 +35,7 @@ struct TapGemmParams {
     int in_stride;          // input coordinate = out coordinate * in_stride + tap offset
     // ---- K loop
     int n_taps, cpt;        // taps, 64-wide chunks per tap
+    int kk_last;            // 16-channel MMA steps needed in the last chunk of a tap (0 = all four)
     int tap_dx[TG_MAX_TAPS], tap_dy[TG_MAX_TAPS];
     const int* a_c0;        // [n_tiles] first input channel of each N tile (nullptr => 0)
     int reuse;              // 1: row-reuse schedule (3x3 stride-1 taps; Bm chunks in (dx, cc, dy) order)

@@ -129,6 +129,7 @@ int Wfc::forward(const void* in, int is_logits, int B, int H, int W, float stren
         p.BN = WFC_BN;
         p.n_tiles = (T_pad + WFC_BN - 1) / WFC_BN;
         p.z_count = 1;
+        p.n_group = 4;
         p.w_box = wb;
         p.h_box = hb;
         p.tiles_x = W / wb;
