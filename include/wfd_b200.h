@@ -145,6 +145,7 @@ typedef struct {
     float* rowdot; const void* dotsrc; long long ld_dot;
     float* gn_sums; int gn_cpg;
     int dtype16;
+    int cg;           /* 0: library chooses, 1: single CTA, 2: CTA pair (cta_group::2) */
     int n_group;      /* >1: tile rasterisation in bands of n_group N tiles */
     int reuse;        /* 1: row-reuse schedule (3x3 stride-1 taps, b packed in (dx, cc, dy) chunk order) */
     long long* dbg;   /* optional device int64[8]: cycle counters of CTA 0 per warp role (profiling aid) */

@@ -6,7 +6,7 @@ import torch
 from wavefunctiondiffusion_b200 import _native as nat
 from test_tapgemm_gpu import _desc
 
-def run(cin, cout, groups, BN, Bn=8, H=64, W=64, taps9=True, reuse=0):
+def run(cin, cout, groups, BN, Bn=8, H=64, W=64, taps9=True, reuse=0, cg=0):
     cin_g, cout_g = cin // groups, cout // groups
     n_tiles = cout // BN
     gpt = max(1, BN // cout_g)                      # groups per N tile
@@ -23,7 +23,7 @@ def run(cin, cout, groups, BN, Bn=8, H=64, W=64, taps9=True, reuse=0):
               ldb=Bm.shape[1], b_zstride=0, b_Z=1, n_taps=ntap, cpt=cpt, tap_dx=[t[1] for t in taps],
               tap_dy=[t[0] for t in taps], a_c0=c0.data_ptr(), BN=BN, N=cout, W=W, H=H, B=Bn, w_box=64, h_box=2,
               in_stride=1, z_count=1, out=out.data_ptr(), out_fp32=0, ldc=cout, bias=bias.data_ptr(), alpha=1.0,
-              dtype16=1, dbg=dbg.data_ptr(), reuse=reuse)
+              dtype16=1, dbg=dbg.data_ptr(), reuse=reuse, cg=cg)
     lib = nat.lib()
     for _ in range(2):
         nat.check(lib.wfd_test_tapgemm(C.byref(d), 0, nat.stream_ptr()))
@@ -38,9 +38,10 @@ def run(cin, cout, groups, BN, Bn=8, H=64, W=64, taps9=True, reuse=0):
     tiles = (Bn * H * W // 128) * n_tiles
     per_cta = tiles / 148
     flops = 2.0 * Bn * H * W * cout * cin_g * ntap
-    print("cin %d cout %d g %d BN %d cpt %d taps %d: %.3f ms  %.0f TF/s | tiles/CTA %.1f | producer total %d wait_empty %d | mma total %d wait_tempty %d wait_full %d | epi total %d wait_tfull %d busy %d reuse %d | Bprod total %d wait %d | issueA %d issueB %d (cycles; per tile: total %.0f)"
+    print("cg %d " % cg + "cin %d cout %d g %d BN %d cpt %d taps %d: %.3f ms  %.0f TF/s | tiles/CTA %.1f | producer total %d wait_empty %d | mma total %d wait_tempty %d wait_full %d | epi total %d wait_tfull %d busy %d reuse %d | Bprod total %d wait %d | issueA %d issueB %d (cycles; per tile: total %.0f)"
           % (cin, cout, groups, BN, cpt, ntap, ms, flops / ms / 1e9, per_cta, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], reuse, v[8], v[9], v[10], v[11], v[2] / per_cta))
 
-run(3072, 3072, 64, 48, reuse=0)
-run(3072, 3072, 64, 48, reuse=1)
-run(384, 384, 1, 192)
+for cg in (1, 2):
+    run(384, 384, 1, 192, cg=cg)
+    run(768, 768, 4, 192, cg=cg)
+    run(384, 384, 1, 128, cg=cg)

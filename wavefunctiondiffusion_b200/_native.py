@@ -41,6 +41,7 @@ class TapGemmDesc(C.Structure):
         ("rowdot", C.c_void_p), ("dotsrc", C.c_void_p), ("ld_dot", C.c_longlong),
         ("gn_sums", C.c_void_p), ("gn_cpg", C.c_int),
         ("dtype16", C.c_int),
+        ("cg", C.c_int),
         ("n_group", C.c_int),
         ("reuse", C.c_int),
         ("dbg", C.c_void_p),

@@ -241,6 +241,7 @@ int wfd_test_tapgemm(const wfd_tapgemm_desc* t, int use_ref, void* stream) {
     }
     p.a_c0 = t->a_c0;
     p.reuse = t->reuse;
+    p.cg = t->cg;
     p.n_group = t->n_group;
     p.a_zmul = t->a_zmul;
     p.b_zmul = t->b_zmul;

@@ -138,16 +138,18 @@ __device__ __forceinline__ float fast_sigmoid(float u) {  // 0.5 * tanh(0.5 u) +
 struct TileCoord {
     int z, n_tile, bb, ty, tx;
 };
-__device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int t) {
+__device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int t, int cg, int rank) {
+    // with cta_group::2 a tile id names a PAIR of adjacent M tiles; `rank` picks this CTA's half
     TileCoord c;
+    const int m_count = p.m_tiles / cg;
     int m_tile, rest;
     if (p.n_group > 1) {
         // L2-friendly rasterisation: consecutive tile ids (= the CTAs of one wave) cover a patch of
         // (#SMs / n_group) M tiles x n_group N tiles, so each A tile is fetched from HBM once per band of N tiles
-        const int per_z = p.m_tiles * p.n_tiles;
+        const int per_z = m_count * p.n_tiles;
         c.z = t / per_z;
         const int r0 = t - c.z * per_z;
-        const int per_band = p.m_tiles * p.n_group;
+        const int per_band = m_count * p.n_group;
         const int band = r0 / per_band;
         const int r = r0 - band * per_band;
         const int nb = min(p.n_group, p.n_tiles - band * p.n_group);
@@ -155,11 +157,12 @@ __device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int t) 
         c.n_tile = band * p.n_group + (r - m_tile * nb);
         rest = 0;
     } else {
-        m_tile = t % p.m_tiles;
-        rest = t / p.m_tiles;
+        m_tile = t % m_count;
+        rest = t / m_count;
         c.n_tile = rest % p.n_tiles;
         c.z = rest / p.n_tiles;
     }
+    m_tile = m_tile * cg + rank;
     c.tx = m_tile % p.tiles_x;
     int r2 = m_tile / p.tiles_x;
     c.ty = r2 % p.tiles_y;
@@ -181,7 +184,7 @@ __device__ __host__ __forceinline__ int b_chunk_index(const TapGemmParams& p, in
 //                [64 ch] loaded ONCE and read by the three vertical taps through descriptor row offsets, + the three
 //                matching B boxes fetched by a single 3-D TMA; 12 MMAs. A third of the TMA instructions, two thirds of
 //                the activation bytes.
-template <bool BF16>
+template <bool BF16, int CG>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ TapGemmParams p, const int stages) {
@@ -190,7 +193,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int a_rows = p.reuse ? (p.h_box + 2) * p.w_box : TG_BM;
     const uint32_t a_stage_bytes = static_cast<uint32_t>(a_rows) * 128;
-    const uint32_t b_box_bytes = static_cast<uint32_t>(p.BN) * 128;
+    const uint32_t b_box_bytes = static_cast<uint32_t>(p.BN / CG) * 128;  // with CG == 2 each CTA holds half of the B rows
     const uint32_t b_stage_bytes = p.reuse ? 3 * b_box_bytes : b_box_bytes;
     uint8_t* smA = smem;
     uint8_t* smB = smem + static_cast<size_t>(stages) * a_stage_bytes;
@@ -206,8 +209,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int total_tiles = p.m_tiles * p.n_tiles * p.z_count;
+    const int total_tiles = (p.m_tiles / CG) * p.n_tiles * p.z_count;  // pair tiles when CG == 2
     const int k_iters = p.reuse ? 3 * p.cpt : p.n_taps * p.cpt;
+    const int rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+    const int first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -218,16 +223,22 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], TG_EPI_THREADS);
+            mbar_init(&tempty_bar[a], TG_EPI_THREADS * CG);
         }
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, 512);
-        tmem_relinquish();
+        if (CG == 2) {
+            tmem_alloc_2sm(tmem_slot, 512);
+            tmem_relinquish_2sm();
+        } else {
+            tmem_alloc(tmem_slot, 512);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
     tc_fence_after();
     // shfl from lane 0 marks the value warp-uniform for the compiler: tcgen05/TMA operands then live in uniform
     // registers instead of going through an ELECT / R2UR.BROADCAST loop per instruction
@@ -244,12 +255,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const long long t_begin = clock64();
             // Tile coordinates cost several integer divisions and one global load (a_c0): each lane decodes a different
             // upcoming tile, the warp then walks through them with shuffles (32 tiles per batch).
-            for (int base = blockIdx.x; base < total_tiles; base += 32 * gridDim.x) {
-                const int my_t = base + lane * gridDim.x;
-                TileCoord mine = decode_tile(p, my_t < total_tiles ? my_t : base);
+            for (int base = first_tile; base < total_tiles; base += 32 * tile_step) {
+                const int my_t = base + lane * tile_step;
+                TileCoord mine = decode_tile(p, my_t < total_tiles ? my_t : base, CG, rank);
                 int my_c0 = 0;
                 if (p.a_c0 && my_t < total_tiles) my_c0 = __ldg(p.a_c0 + mine.n_tile);
-                const int batch = min(32, (total_tiles - base + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x));
+                const int batch = min(32, (total_tiles - base + tile_step - 1) / tile_step);
                 for (int l = 0; l < batch; ++l) {
                     TileCoord tc;
                     tc.z = __shfl_sync(0xffffffffu, mine.z, l);
@@ -262,7 +273,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int y0 = tc.ty * p.h_box * p.in_stride;
                     const int ab = tc.bb + tc.z * p.a_zmul;
                     const int bz = tc.z * p.b_zmul + tc.bb * p.b_bbmul;
-                    const int n0 = tc.n_tile * p.BN;
+                    const int n0 = tc.n_tile * p.BN + rank * (p.BN / CG);  // this CTA's rows of the B tile
                     const int n_outer = p.reuse ? 3 : p.n_taps;
                     int it = 0;
                     for (int o = 0; o < n_outer; ++o) {
@@ -279,7 +290,18 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                             const long long i0 = p.dbg ? clock64() : 0;
                             if (elect_one()) {
-                                if (load_a) {
+                                if (CG == 2) {
+                                    // both CTAs load into their own shared memory; the leader's barrier counts all bytes
+                                    if (load_a) {
+                                        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * a_stage_bytes);
+                                        tma_load_4d_2sm(smA + static_cast<size_t>(stage) * a_stage_bytes, &tmA,
+                                                        &full_bar[stage], c0 + cc * TG_KC, xx, yy, ab);
+                                    } else {
+                                        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * b_stage_bytes);
+                                        tma_load_3d_2sm(smB + static_cast<size_t>(stage) * b_stage_bytes, &tmB,
+                                                        &full_bar[stage], bk, n0, bz);
+                                    }
+                                } else if (load_a) {
                                     mbar_expect_tx(&full_bar[stage], a_stage_bytes);
                                     tma_load_4d(smA + static_cast<size_t>(stage) * a_stage_bytes, &tmA, &full_bar[stage],
                                                 c0 + cc * TG_KC, xx, yy, ab);
@@ -308,8 +330,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer (one thread)
-        const uint32_t idesc = make_idesc_f16(TG_BM, static_cast<uint32_t>(p.BN), BF16 ? 1u : 0u);
+      // ===================================================== MMA issuer (one thread; with CG == 2 only in the leader CTA)
+      if (rank == 0) {
+        const uint32_t idesc = make_idesc_f16(TG_BM * CG, static_cast<uint32_t>(p.BN), BF16 ? 1u : 0u);
         const int n_sub = p.reuse ? 3 : 1;                        // vertical taps served by one stage
         const int kk_last = (p.kk_last > 0 && p.kk_last < TG_KC / 16) ? p.kk_last : TG_KC / 16;
         const uint32_t a_sub_bytes = static_cast<uint32_t>(p.w_box) * 128;  // one image row of the patch
@@ -319,7 +342,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t acc_phase = 0;
         long long w_tempty = 0, w_full = 0;
         const long long t_begin = clock64();
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int t = first_tile; t < total_tiles; t += tile_step) {
             long long w0 = p.dbg ? clock64() : 0;
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             if (p.dbg) w_tempty += clock64() - w0;
@@ -343,12 +366,21 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int k = 0; k < TG_KC / 16; ++k) {
                             // advancing 16 elements (32 bytes) along K inside the swizzle atom: +2 in 16-byte units;
                             // 16-channel steps that only meet zero-padded weights are skipped
-                            if (k < n_k)
-                                umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc > 0 || sub > 0 || k > 0) ? 1u : 0u);
+                            if (k < n_k) {
+                                if (CG == 2)
+                                    umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc > 0 || sub > 0 || k > 0) ? 1u : 0u);
+                                else
+                                    umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc > 0 || sub > 0 || k > 0) ? 1u : 0u);
+                            }
                         }
                     }
-                    umma_commit(&empty_bar[stage]);
-                    if (kc == k_iters - 1) umma_commit(&tfull_bar[acc]);
+                    if (CG == 2) {  // release the stage / publish the accumulator in both CTAs of the pair
+                        umma_commit_2sm(&empty_bar[stage]);
+                        if (kc == k_iters - 1) umma_commit_2sm(&tfull_bar[acc]);
+                    } else {
+                        umma_commit(&empty_bar[stage]);
+                        if (kc == k_iters - 1) umma_commit(&tfull_bar[acc]);
+                    }
                 }
                 __syncwarp();
                 if (++stage == stages) {
@@ -364,6 +396,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             p.dbg[3] = w_tempty;
             p.dbg[4] = w_full;
         }
+      }
     } else {
         // ===================================================== epilogue (8 warps: a TMEM lane quarter is shared by two
         // warps that take the even / odd 16-column chunks of the tile)
@@ -376,10 +409,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         long long w_tfull = 0, e_busy = 0;
         const long long t_begin = clock64();
         const int yy = row / p.w_box, xx = row - yy * p.w_box;
-        for (int base = blockIdx.x; base < total_tiles; base += 32 * gridDim.x) {
-          const int my_t = base + lane * gridDim.x;
-          const TileCoord mine = decode_tile(p, my_t < total_tiles ? my_t : base);
-          const int batch = min(32, (total_tiles - base + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x));
+        for (int base = first_tile; base < total_tiles; base += 32 * tile_step) {
+          const int my_t = base + lane * tile_step;
+          const TileCoord mine = decode_tile(p, my_t < total_tiles ? my_t : base, CG, rank);
+          const int batch = min(32, (total_tiles - base + tile_step - 1) / tile_step);
           for (int l = 0; l < batch; ++l) {
             TileCoord tc;
             tc.z = __shfl_sync(0xffffffffu, mine.z, l);
@@ -575,7 +608,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             // the accumulator stage is drained: hand it back to the MMA warp before the remaining bookkeeping
             tc_fence_before();
-            mbar_arrive(&tempty_bar[acc]);
+            if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]);  // the MMA thread lives in the leader CTA
+            else mbar_arrive(&tempty_bar[acc]);
             if (p.gn_sums && ggroup >= 0) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
@@ -615,9 +649,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();  // neither CTA may free TMEM / exit while the pair still works on its memory
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (CG == 2) tmem_dealloc_2sm(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -751,6 +787,17 @@ int tapgemm_prepare(TapGemmOp* op) {
         set_error("tapgemm_prepare: row-reuse schedule requested for an unsupported tap set / tile");
         return -3;
     }
+    // CTA pairs (cta_group::2, one 256 x BN tile per pair, each CTA holding half of the B rows) halve the shared-memory
+    // traffic per MMA; used for the wide-N plain-schedule contractions whenever M tiles come in pairs
+    {
+        static int no2 = -1;
+        if (no2 < 0) {
+            const char* e = getenv("WFD_NO_2CTA");
+            no2 = (e && e[0] == '1') ? 1 : 0;
+        }
+        const bool pairs_ok = ((p.tiles_x * p.tiles_y) % 2 == 0) && !p.a_zmul;
+        p.cg = (!no2 && p.cg != 1 && !p.reuse && p.BN >= 128 && p.BN % 32 == 0 && pairs_ok) ? 2 : 1;
+    }
     const CUtensorMapDataType dt = p.is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     {
         cuuint64_t dims[4] = {(cuuint64_t)p.a_C, (cuuint64_t)p.a_W, (cuuint64_t)p.a_H, (cuuint64_t)p.a_B};
@@ -789,7 +836,7 @@ int tapgemm_prepare(TapGemmOp* op) {
         const int zdim = p.b_Z > 0 ? p.b_Z : 1;
         cuuint64_t dims[3] = {(cuuint64_t)ktot, (cuuint64_t)p.b_rows, (cuuint64_t)zdim};
         cuuint64_t strides[2] = {(cuuint64_t)p.ldb * 2, (cuuint64_t)(p.b_zstride > 0 ? p.b_zstride : p.ldb * p.b_rows) * 2};
-        cuuint32_t box[3] = {TG_KC, (cuuint32_t)p.BN, 1};
+        cuuint32_t box[3] = {TG_KC, (cuuint32_t)(p.BN / p.cg), 1};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(&op->tmB, dt, 3, const_cast<void*>(p.b_ptr), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -801,7 +848,7 @@ int tapgemm_prepare(TapGemmOp* op) {
         }
     }
     const size_t a_stage = p.reuse ? static_cast<size_t>(p.h_box + 2) * p.w_box * 128 : TG_BM * 128;
-    const size_t b_stage = (p.reuse ? 3 : 1) * static_cast<size_t>(p.BN) * 128;
+    const size_t b_stage = (p.reuse ? 3 : 1) * static_cast<size_t>(p.BN / p.cg) * 128;
     const size_t per_stage = a_stage + b_stage;
     int stages = static_cast<int>((212 * 1024) / per_stage);
     if (stages > 8) stages = 8;
@@ -819,41 +866,59 @@ int tapgemm_prepare(TapGemmOp* op) {
     return 0;
 }
 
+template <bool BF16, int CG>
+static cudaError_t launch_variant(const TapGemmOp* op, int grid, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BF16, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(TG_THREADS);
+    cfg.dynamicSmemBytes = op->smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, tapgemm_kernel<BF16, CG>, op->tmA, op->tmB, op->p, op->stages);
+}
+
 int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream) {
     const TapGemmParams& p = op->p;
-    static bool attr_set[2] = {false, false};
-    const int which = p.is_bf16 ? 1 : 0;
-    if (!attr_set[which]) {
-        cudaError_t e = p.is_bf16 ? cudaFuncSetAttribute(tapgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-                                  : cudaFuncSetAttribute(tapgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) {
-            set_error("cudaFuncSetAttribute(tapgemm): %s", cudaGetErrorString(e));
-            return -6;
-        }
-        attr_set[which] = true;
+    const int cg = p.cg == 2 ? 2 : 1;
+    if (cg == 2 && (p.m_tiles % 2)) {
+        set_error("tapgemm launch: CTA-pair schedule needs an even number of M tiles (got %d)", p.m_tiles);
+        return -3;
     }
-    const int total = p.m_tiles * p.n_tiles * p.z_count;
+    const int total = (p.m_tiles / cg) * p.n_tiles * p.z_count;  // (pair) tiles
     if (total <= 0) return 0;
-    int grid = total < num_sms() ? total : num_sms();
+    int sms = num_sms();
     {
         static int limit = -1;  // WFD_GRID_LIMIT: experiment knob (fewer resident CTAs), not used in production
         if (limit < 0) {
             const char* e = getenv("WFD_GRID_LIMIT");
             limit = e ? atoi(e) : 0;
         }
-        if (limit > 0 && grid > limit) grid = limit;
+        if (limit > 0 && sms > limit) sms = limit;
     }
-    char pname[128];
+    int grid = total * cg < sms ? total * cg : (sms / cg) * cg;
+    char pname[160];
     if (g_prof_on)
-        snprintf(pname, sizeof(pname), "tapgemm:N=%d,BN=%d,taps=%d,cpt=%d,aC=%d,f32=%d,reuse=%d,side=%d,gns=%d", p.N, p.BN,
+        snprintf(pname, sizeof(pname), "tapgemm:N=%d,BN=%d,taps=%d,cpt=%d,aC=%d,f32=%d,reuse=%d,side=%d,gns=%d,cg=%d", p.N, p.BN,
                  p.n_taps, p.cpt, p.a_C, p.out_fp32, p.reuse, p.residual ? 1 : (p.rowdot ? 2 : (p.gnb_red ? 3 : 0)),
-                 p.gn_sums ? 1 : 0);
+                 p.gn_sums ? 1 : 0, cg);
     ProfScope prof_scope(g_prof_on ? pname : "", stream);
-    if (p.is_bf16)
-        tapgemm_kernel<true><<<grid, TG_THREADS, op->smem_bytes, stream>>>(op->tmA, op->tmB, op->p, op->stages);
-    else
-        tapgemm_kernel<false><<<grid, TG_THREADS, op->smem_bytes, stream>>>(op->tmA, op->tmB, op->p, op->stages);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e;
+    if (p.is_bf16) e = (cg == 2) ? launch_variant<true, 2>(op, grid, stream) : launch_variant<true, 1>(op, grid, stream);
+    else e = (cg == 2) ? launch_variant<false, 2>(op, grid, stream) : launch_variant<false, 1>(op, grid, stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("tapgemm launch: %s", cudaGetErrorString(e));
         return -7;
@@ -862,9 +927,9 @@ int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream) {
     if (debug_sync_enabled()) {
         char what[256];
         snprintf(what, sizeof(what),
-                 "tapgemm(m_tiles=%d n_tiles=%d z=%d BN=%d N=%d taps=%d cpt=%d box=%dx%d stages=%d smem=%zu aC=%d aW=%d aH=%d aB=%d reuse=%d)",
+                 "tapgemm(m_tiles=%d n_tiles=%d z=%d BN=%d N=%d taps=%d cpt=%d box=%dx%d stages=%d smem=%zu aC=%d aW=%d aH=%d aB=%d reuse=%d cg=%d)",
                  p.m_tiles, p.n_tiles, p.z_count, p.BN, p.N, p.n_taps, p.cpt, p.w_box, p.h_box, op->stages,
-                 op->smem_bytes, p.a_C, p.a_W, p.a_H, p.a_B, p.reuse);
+                 op->smem_bytes, p.a_C, p.a_W, p.a_H, p.a_B, p.reuse, cg);
         return debug_sync_check(what, stream);
     }
     return 0;

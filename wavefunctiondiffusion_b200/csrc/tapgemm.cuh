@@ -38,6 +38,7 @@ struct TapGemmParams {
     int kk_last;            // 16-channel MMA steps needed in the last chunk of a tap (0 = all four)
     int tap_dx[TG_MAX_TAPS], tap_dy[TG_MAX_TAPS];
     const int* a_c0;        // [n_tiles] first input channel of each N tile (nullptr => 0)
+    int cg;                 // CTA group: 0 = let tapgemm_prepare choose, 1 = single CTA, 2 = CTA pair (cta_group::2)
     int reuse;              // 1: row-reuse schedule (3x3 stride-1 taps; Bm chunks in (dx, cc, dy) order)
     int a_zmul;             // A dim-3 coordinate = bb + z * a_zmul
     int b_zmul, b_bbmul;    // B dim-2 coordinate = z * b_zmul + bb * b_bbmul
