@@ -875,13 +875,9 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
                      nullptr, &gb));
     }
     if (!ex.prepare) {
-        if (!fuse_ok(C_last))
-        CK(gn_bwd_reduce(gbuf(cur), x_last, gn_sums_ptr(n_gn - 1), vecs["decoder.conv_norm_out.weight"],
-                         vecs["decoder.conv_norm_out.bias"], gn_red_ptr(n_gn - 1), B, H_out * W_out, C_last, G, eps, 1,
-                         bf16, s));
-        CK(gn_bwd_apply(gbuf(cur), x_last, gn_sums_ptr(n_gn - 1), vecs["decoder.conv_norm_out.weight"],
-                        vecs["decoder.conv_norm_out.bias"], gn_red_ptr(n_gn - 1), nullptr, gbuf(cur), B, H_out * W_out,
-                        C_last, G, eps, 1, bf16, s));
+        CK(gn_bwd(gbuf(cur), x_last, gn_sums_ptr(n_gn - 1), vecs["decoder.conv_norm_out.weight"],
+                  vecs["decoder.conv_norm_out.bias"], gn_red_ptr(n_gn - 1), nullptr, gbuf(cur), B, H_out * W_out, C_last, G,
+                  eps, 1, bf16, fuse_ok(C_last) ? 0 : 1, s));
     }
     auto resnet_bwd = [&](int idx, const uint8_t* xin) -> int {
         const ResnetDesc& r = resnets[idx];
@@ -900,10 +896,8 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         if (!ex.prepare) {
             const float* ga = vecs[r.prefix + ".norm2.weight"];
             const float* be = vecs[r.prefix + ".norm2.bias"];
-            if (!fuse_ok(r.cout))
-            CK(gn_bwd_reduce(t1, h1, gn_sums_ptr(gi2), ga, be, gn_red_ptr(gi2), B, phw, r.cout, G, eps, 1, bf16, s));
-            CK(gn_bwd_apply(t1, h1, gn_sums_ptr(gi2), ga, be, gn_red_ptr(gi2), nullptr, t1, B, phw, r.cout, G, eps, 1,
-                            bf16, s));
+            CK(gn_bwd(t1, h1, gn_sums_ptr(gi2), ga, be, gn_red_ptr(gi2), nullptr, t1, B, phw, r.cout, G, eps, 1, bf16,
+                      fuse_ok(r.cout) ? 0 : 1, s));
         }
         const ConvW& c1 = convs[r.prefix + ".conv1"];
         {
@@ -919,10 +913,8 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         if (!ex.prepare) {
             const float* ga = vecs[r.prefix + ".norm1.weight"];
             const float* be = vecs[r.prefix + ".norm1.bias"];
-            if (!fuse_ok(r.cin))
-            CK(gn_bwd_reduce(t2, xin, gn_sums_ptr(gi1), ga, be, gn_red_ptr(gi1), B, phw, r.cin, G, eps, 1, bf16, s));
-            CK(gn_bwd_apply(t2, xin, gn_sums_ptr(gi1), ga, be, gn_red_ptr(gi1), add, t2, B, phw, r.cin, G, eps, 1, bf16,
-                            s));
+            CK(gn_bwd(t2, xin, gn_sums_ptr(gi1), ga, be, gn_red_ptr(gi1), add, t2, B, phw, r.cin, G, eps, 1, bf16,
+                      fuse_ok(r.cin) ? 0 : 1, s));
         }
         cur = (cur + 2) & 3;
         return 0;
@@ -1030,10 +1022,8 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         if (!ex.prepare) {
             const float* ga = vecs[a + "group_norm.weight"];
             const float* be = vecs[a + "group_norm.bias"];
-            if (!fuse_ok(Cm))
-            CK(gn_bwd_reduce(dxn, xin, gn_sums_ptr(n_gn - 2), ga, be, gn_red_ptr(n_gn - 2), B, N, Cm, G, eps, 0, bf16, s));
-            CK(gn_bwd_apply(dxn, xin, gn_sums_ptr(n_gn - 2), ga, be, gn_red_ptr(n_gn - 2), dout, dxn, B, N, Cm, G, eps, 0,
-                            bf16, s));
+            CK(gn_bwd(dxn, xin, gn_sums_ptr(n_gn - 2), ga, be, gn_red_ptr(n_gn - 2), dout, dxn, B, N, Cm, G, eps, 0, bf16,
+                      fuse_ok(Cm) ? 0 : 1, s));
         }
         cur = (cur + 1) & 3;
     }

@@ -21,6 +21,11 @@ int gn_bwd_apply(const void* dy, const void* x, const float* sums, const float* 
                  const float* red, const void* add, void* dx, int B, int HW, int C, int G, float eps, int silu,
                  int bf16, cudaStream_t s);
 
+// reduce (optional: skipped when the producing contraction fused it) + apply, in L2-sized blocks of samples
+int gn_bwd(const void* dy, const void* x, const float* sums, const float* gamma, const float* beta, float* red,
+           const void* add, void* dx, int B, int HW, int C, int G, float eps, int silu, int bf16, int do_reduce,
+           cudaStream_t s);
+
 // ---- latent side (reference wf_vae.py:593 post_quant_conv 1x1 4->4, wf_vae.py:218 conv_in 3x3 4->Cm)
 // z: NCHW [B,4,h,w] fp32 (z_f16=0) or fp16 (z_f16=1); out: [B, h*w, Cm] 16-bit. pq_w [4,4], pq_b [4], w [Cm,4,3,3], b [Cm]
 int latent_in(const void* z, int z_f16, float in_scale, const float* pq_w, const float* pq_b, const float* w,
