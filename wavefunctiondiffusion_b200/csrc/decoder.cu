@@ -203,6 +203,10 @@ int Decoder::init(const wfd_decoder_config& c, int h_, int w_, int Bmax, int dty
         use_reuse = (e && e[0] == '1') ? 0 : 1;
         const char* f = getenv("WFD_NO_FUSE_GN");
         fuse_gn = (f && f[0] == '1') ? 0 : 1;
+        const char* ng = getenv("WFD_CONV_NGROUP");
+        conv_n_group = ng ? atoi(ng) : 0;
+        const char* m = getenv("WFD_FUSE_BWD_MAX_C");
+        fuse_bwd_max_c = m ? atoi(m) : 768;
     }
     if (c.latent_channels != 4) {
         set_error("decoder: latent_channels must be 4 (got %d)", c.latent_channels);
@@ -536,6 +540,9 @@ int Decoder::conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int 
         p.BN = pk.BN;
         p.n_tiles = pk.n_tiles;
         p.z_count = 1;
+        // N fastest: the CTAs of a wave work on the same pixels across channel groups, so activations are read and
+        // written as whole channels-last pixel rows (DRAM page locality) and dense layers fetch each A tile once
+        p.n_group = conv_n_group > 1 ? std::min(conv_n_group, pk.n_tiles) : 0;  // default: M fastest (measured best)
         p.w_box = wb;
         p.h_box = hb;
         p.tiles_x = Wout / wb;
@@ -848,7 +855,7 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
     // groups are 16-column aligned); otherwise the standalone gn_bwd_reduce pass runs
     // (measured on B200: the fused form wins for the <= 768-channel layers whose tiles carry enough MMA work to hide the
     // extra epilogue math; for the 1536/3072-channel grouped layers the standalone pass is cheaper)
-    auto fuse_ok = [&](int C) { return fuse_gn && (C / G) % 16 == 0 && C <= 768; };
+    auto fuse_ok = [&](int C) { return fuse_gn && (C / G) % 16 == 0 && C <= fuse_bwd_max_c; };
     auto make_gb = [&](int gn_idx, const void* xsaved, const std::string& norm, int C, int px, int silu) {
         GnBwdFuse gb;
         memset(&gb, 0, sizeof(gb));

@@ -64,6 +64,8 @@ struct Decoder {
     int h = 0, w = 0, B_max = 0, bf16 = 1, G = 8;
     int Cm = 0, C_last = 0, H_out = 0, W_out = 0, T_pad = 0;
     int fuse_gn = 1;
+    int conv_n_group = 0;  // tile rasterisation of the convs: 0/1 = M fastest (default), k = bands of k N tiles (WFD_CONV_NGROUP)
+    int fuse_bwd_max_c = 768;  // largest channel count whose GroupNorm-backward reduction is fused into the conv epilogue
     int use_reuse = 1;  // row-reuse schedule for 3x3 convs whose stage fits (WFD_NO_REUSE=1 disables, for A/B runs)
     std::vector<ResnetDesc> resnets;
     std::vector<int> down_after;

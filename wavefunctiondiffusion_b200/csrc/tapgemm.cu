@@ -194,18 +194,27 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int a_rows = p.reuse ? (p.h_box + 2) * p.w_box : TG_BM;
     const uint32_t a_stage_bytes = static_cast<uint32_t>(a_rows) * 128;
     const uint32_t b_box_bytes = static_cast<uint32_t>(p.BN / CG) * 128;  // with CG == 2 each CTA holds half of the B rows
-    const uint32_t b_stage_bytes = p.reuse ? 3 * b_box_bytes : b_box_bytes;
+    // resident weights (row-reuse schedule with a small weight set): all 9*cpt chunks of the current N tile stay in
+    // shared memory and only the activation boxes stream through the stage ring
+    const bool b_res = (CG == 1) && p.b_resident;
+    const uint32_t b_stage_bytes = b_res ? 0u : (p.reuse ? 3 * b_box_bytes : b_box_bytes);
+    const uint32_t b_res_bytes = b_res ? 9u * p.cpt * b_box_bytes : 0u;
     uint8_t* smA = smem;
     uint8_t* smB = smem + static_cast<size_t>(stages) * a_stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + static_cast<size_t>(stages) * b_stage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + static_cast<size_t>(stages) * b_stage_bytes + b_res_bytes);
     uint64_t* full_bar = bars;                 // [stages]
     uint64_t* empty_bar = bars + stages;       // [stages]
     uint64_t* tfull_bar = bars + 2 * stages;   // [2]
     uint64_t* tempty_bar = bars + 2 * stages + 2;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
-    float* bias_s = reinterpret_cast<float*>(bars + 2 * stages + 6);  // [2][256]
+    uint64_t* bres_full = bars + 2 * stages + 4;   // resident weights landed
+    uint64_t* tdone_bar = bars + 2 * stages + 5;   // all MMAs of a tile completed (resident weights may be replaced)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 6);
+    float* bias_s = reinterpret_cast<float*>(bars + 2 * stages + 8);  // [2][256]
     float* gam_s = bias_s + 512;                                      // [2][256] GroupNorm-backward gamma
     float* bet_s = gam_s + 512;                                       // [2][256] GroupNorm-backward beta
+    // per-CTA partial sums of the fused GroupNorm statistics / backward reductions, flushed once at kernel end: thousands
+    // of tiles would otherwise hammer the same few global addresses with atomics
+    float* stat_s = bet_s + 512;                                      // [2][TG_STAT_SLOTS]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -218,15 +227,18 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < stages; ++s) {
-            mbar_init(&full_bar[s], 2);
+            mbar_init(&full_bar[s], b_res ? 1 : 2);
             mbar_init(&empty_bar[s], 1);
         }
+        mbar_init(bres_full, 1);
+        mbar_init(tdone_bar, 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], TG_EPI_THREADS * CG);
         }
         fence_barrier_init();
     }
+    for (int i = threadIdx.x; i < 2 * TG_STAT_SLOTS; i += TG_THREADS) stat_s[i] = 0.f;
     if (warp == 1) {
         if (CG == 2) {
             tmem_alloc_2sm(tmem_slot, 512);
@@ -252,6 +264,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             long long w_empty = 0, w_issue = 0;
+            int tiles_seen = 0, res_n_tile = -1;
             const long long t_begin = clock64();
             // Tile coordinates cost several integer divisions and one global load (a_c0): each lane decodes a different
             // upcoming tile, the warp then walks through them with shuffles (32 tiles per batch).
@@ -269,6 +282,23 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tc.ty = __shfl_sync(0xffffffffu, mine.ty, l);
                     tc.tx = __shfl_sync(0xffffffffu, mine.tx, l);
                     const int c0 = __shfl_sync(0xffffffffu, my_c0, l);
+                    if (b_res && !load_a) {
+                        // weight warp, resident mode: reload only when the N tile changes, after every MMA that reads the
+                        // old weights has completed (tdone is waited tile by tile, so its parity never aliases)
+                        if (tiles_seen > 0) mbar_wait(tdone_bar, (tiles_seen - 1) & 1);
+                        if (tc.n_tile != res_n_tile) {
+                            res_n_tile = tc.n_tile;
+                            if (elect_one()) {
+                                mbar_expect_tx(bres_full, b_res_bytes);
+                                for (int it = 0; it < 3 * p.cpt; ++it)
+                                    tma_load_3d(smB + static_cast<size_t>(it) * 3 * b_box_bytes, &tmB, bres_full, 0,
+                                                tc.n_tile * p.BN, it * 3);
+                            }
+                            __syncwarp();
+                        }
+                        ++tiles_seen;
+                        continue;
+                    }
                     const int x0 = tc.tx * p.w_box * p.in_stride;
                     const int y0 = tc.ty * p.h_box * p.in_stride;
                     const int ab = tc.bb + tc.z * p.a_zmul;
@@ -342,7 +372,18 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t acc_phase = 0;
         long long w_tempty = 0, w_full = 0;
         const long long t_begin = clock64();
+        int res_n_tile = -1;
+        uint32_t res_phase = 0;
         for (int t = first_tile; t < total_tiles; t += tile_step) {
+            if (b_res) {
+                const int nt = decode_tile(p, t, CG, rank).n_tile;
+                if (nt != res_n_tile) {
+                    res_n_tile = nt;
+                    mbar_wait(bres_full, res_phase);
+                    res_phase ^= 1;
+                    tc_fence_after();
+                }
+            }
             long long w0 = p.dbg ? clock64() : 0;
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             if (p.dbg) w_tempty += clock64() - w0;
@@ -358,7 +399,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t a_base = smem_u32(smA + static_cast<size_t>(stage) * a_stage_bytes);
-                    const uint32_t b_base = smem_u32(smB + static_cast<size_t>(stage) * b_stage_bytes);
+                    const uint32_t b_base = b_res ? smem_u32(smB) + static_cast<uint32_t>(kc) * 3u * b_box_bytes
+                                                  : smem_u32(smB + static_cast<size_t>(stage) * b_stage_bytes);
                     for (int sub = 0; sub < n_sub; ++sub) {
                         const uint64_t adesc = make_kmajor_desc(a_base + sub * a_sub_bytes, 128);
                         const uint64_t bdesc = make_kmajor_desc(b_base + sub * b_box_bytes, 128);
@@ -379,7 +421,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (kc == k_iters - 1) umma_commit_2sm(&tfull_bar[acc]);
                     } else {
                         umma_commit(&empty_bar[stage]);
-                        if (kc == k_iters - 1) umma_commit(&tfull_bar[acc]);
+                        if (kc == k_iters - 1) {
+                            umma_commit(&tfull_bar[acc]);
+                            if (b_res) umma_commit(tdone_bar);
+                        }
                     }
                 }
                 __syncwarp();
@@ -537,9 +582,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     gss += __shfl_xor_sync(0xffffffffu, gss, o);
                                 }
                                 if (lane == 0) {
-                                    float* dst = p.gn_sums + (static_cast<long long>(tc.bb) * p.gn_G + ggroup) * 2;
-                                    atomicAdd(dst, gs);
-                                    atomicAdd(dst + 1, gss);
+                                    const int slot = (tc.bb * p.gn_G + ggroup) * 2;
+                                    if (slot + 1 < TG_STAT_SLOTS) {
+                                        atomicAdd(stat_s + slot, gs);
+                                        atomicAdd(stat_s + slot + 1, gss);
+                                    } else {
+                                        atomicAdd(p.gn_sums + slot, gs);
+                                        atomicAdd(p.gn_sums + slot + 1, gss);
+                                    }
                                 }
                             }
                             ggroup = g;
@@ -565,9 +615,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     b2 += __shfl_xor_sync(0xffffffffu, b2, o);
                                 }
                                 if (lane == 0) {
-                                    float* dst = p.gnb_red + (static_cast<long long>(tc.bb) * p.gn_G + bgroup) * 2;
-                                    atomicAdd(dst, b1);
-                                    atomicAdd(dst + 1, b2);
+                                    const int slot = (tc.bb * p.gn_G + bgroup) * 2;
+                                    if (slot + 1 < TG_STAT_SLOTS) {
+                                        atomicAdd(stat_s + TG_STAT_SLOTS + slot, b1);
+                                        atomicAdd(stat_s + TG_STAT_SLOTS + slot + 1, b2);
+                                    } else {
+                                        atomicAdd(p.gnb_red + slot, b1);
+                                        atomicAdd(p.gnb_red + slot + 1, b2);
+                                    }
                                 }
                             }
                             bgroup = g;
@@ -617,9 +672,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     gss += __shfl_xor_sync(0xffffffffu, gss, o);
                 }
                 if (lane == 0) {
-                    float* dst = p.gn_sums + (static_cast<long long>(tc.bb) * p.gn_G + ggroup) * 2;
-                    atomicAdd(dst, gs);
-                    atomicAdd(dst + 1, gss);
+                    const int slot = (tc.bb * p.gn_G + ggroup) * 2;
+                    if (slot + 1 < TG_STAT_SLOTS) {
+                        atomicAdd(stat_s + slot, gs);
+                        atomicAdd(stat_s + slot + 1, gss);
+                    } else {
+                        atomicAdd(p.gn_sums + slot, gs);
+                        atomicAdd(p.gn_sums + slot + 1, gss);
+                    }
                 }
             }
             if (p.gnb_red && bgroup >= 0) {
@@ -629,9 +689,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     b2 += __shfl_xor_sync(0xffffffffu, b2, o);
                 }
                 if (lane == 0) {
-                    float* dst = p.gnb_red + (static_cast<long long>(tc.bb) * p.gn_G + bgroup) * 2;
-                    atomicAdd(dst, b1);
-                    atomicAdd(dst + 1, b2);
+                    const int slot = (tc.bb * p.gn_G + bgroup) * 2;
+                    if (slot + 1 < TG_STAT_SLOTS) {
+                        atomicAdd(stat_s + TG_STAT_SLOTS + slot, b1);
+                        atomicAdd(stat_s + TG_STAT_SLOTS + slot + 1, b2);
+                    } else {
+                        atomicAdd(p.gnb_red + slot, b1);
+                        atomicAdd(p.gnb_red + slot + 1, b2);
+                    }
                 }
             }
             if (p.rowdot) atomicAdd(p.rowdot + pixel, dot);
@@ -649,6 +714,18 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
+    if (p.gn_sums || p.gnb_red) {
+        for (int i = threadIdx.x; i < TG_STAT_SLOTS; i += TG_THREADS) {
+            if (p.gn_sums) {
+                const float v = stat_s[i];
+                if (v != 0.f) atomicAdd(p.gn_sums + i, v);
+            }
+            if (p.gnb_red) {
+                const float v = stat_s[TG_STAT_SLOTS + i];
+                if (v != 0.f) atomicAdd(p.gnb_red + i, v);
+            }
+        }
+    }
     if (CG == 2) cluster_sync_all();  // neither CTA may free TMEM / exit while the pair still works on its memory
     if (warp == 1) {
         tc_fence_after();
@@ -848,9 +925,21 @@ int tapgemm_prepare(TapGemmOp* op) {
         }
     }
     const size_t a_stage = p.reuse ? static_cast<size_t>(p.h_box + 2) * p.w_box * 128 : TG_BM * 128;
-    const size_t b_stage = (p.reuse ? 3 : 1) * static_cast<size_t>(p.BN / p.cg) * 128;
+    // weights of one N tile resident in shared memory when they are small (grouped layers with few channels per group)
+    const size_t b_res_bytes = 9 * static_cast<size_t>(p.cpt) * p.BN * 128;
+    {
+        // measured on B200 (round 1): 0.27 ms vs 0.21 ms per 3072-channel groups=64 conv with / without resident weights,
+        // so the mode is opt-in (WFD_RESIDENT_B=1) until the stall is understood
+        static int res = -1;
+        if (res < 0) {
+            const char* e = getenv("WFD_RESIDENT_B");
+            res = (e && e[0] == '1') ? 1 : 0;
+        }
+        p.b_resident = (res && p.reuse && p.cg == 1 && b_res_bytes <= 64 * 1024) ? 1 : 0;
+    }
+    const size_t b_stage = p.b_resident ? 0 : (p.reuse ? 3 : 1) * static_cast<size_t>(p.BN / p.cg) * 128;
     const size_t per_stage = a_stage + b_stage;
-    int stages = static_cast<int>((212 * 1024) / per_stage);
+    int stages = static_cast<int>((204 * 1024 - (p.b_resident ? b_res_bytes : 0)) / per_stage);
     if (stages > 8) stages = 8;
     {
         static int cap = -1;  // WFD_MAX_STAGES: experiment knob
@@ -862,7 +951,8 @@ int tapgemm_prepare(TapGemmOp* op) {
     }
     if (stages < 2) stages = 2;
     op->stages = stages;
-    op->smem_bytes = 1024 + stages * per_stage + (2 * stages + 6) * sizeof(uint64_t) + 6 * 256 * sizeof(float) + 16;
+    op->smem_bytes = 1024 + stages * per_stage + (p.b_resident ? b_res_bytes : 0) + (2 * stages + 8) * sizeof(uint64_t) +
+                     (6 * 256 + 2 * TG_STAT_SLOTS) * sizeof(float) + 16;
     return 0;
 }
 

@@ -21,6 +21,7 @@ namespace wfd {
 constexpr int TG_BM = 128;      // rows per M tile (UMMA M)
 constexpr int TG_KC = 64;       // K elements per pipeline chunk (128 bytes = one SW128 row)
 constexpr int TG_MAX_TAPS = 9;
+constexpr int TG_STAT_SLOTS = 1024;  // per-CTA shared-memory slots for fused GroupNorm partial sums ((sample, group) x 2)
 constexpr int TG_EPI_THREADS = 256;                 // warps 2-9: epilogue (two warps per TMEM lane quarter)
 constexpr int TG_THREADS = 64 + TG_EPI_THREADS + 32; // warp 0 TMA (activations), warp 1 MMA, last warp TMA (weights)
 
@@ -39,6 +40,7 @@ struct TapGemmParams {
     int tap_dx[TG_MAX_TAPS], tap_dy[TG_MAX_TAPS];
     const int* a_c0;        // [n_tiles] first input channel of each N tile (nullptr => 0)
     int cg;                 // CTA group: 0 = let tapgemm_prepare choose, 1 = single CTA, 2 = CTA pair (cta_group::2)
+    int b_resident;         // set by tapgemm_prepare: weights of the current N tile stay resident in shared memory
     int reuse;              // 1: row-reuse schedule (3x3 stride-1 taps; Bm chunks in (dx, cc, dy) order)
     int a_zmul;             // A dim-3 coordinate = bb + z * a_zmul
     int b_zmul, b_bbmul;    // B dim-2 coordinate = z * b_zmul + bb * b_bbmul
