@@ -241,6 +241,21 @@ def run_native(args):
                                         STRENGTH, saved, C.c_void_p(loss.data_ptr()), C.c_void_p(dz.data_ptr()),
                                         nat.stream_ptr()), "wfd_guidance_step")
 
+    # the resident step is a fixed launch sequence: replay it from a CUDA graph (as the pipeline path does)
+    launches_per_step = None
+    if not args.no_graph:
+        n0 = lib.wfd_launch_count()
+        step_resident()
+        launches_per_step = lib.wfd_launch_count() - n0
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step_resident()
+        step_plain = step_resident
+
+        def step_resident():  # noqa: F811
+            graph.replay()
+
     t_step = sched.timesteps[20]
 
     def step_e2e():
@@ -275,6 +290,8 @@ def run_native(args):
     n0 = lib.wfd_launch_count()
     ms = timed(step_resident, args.steps, max(args.warmup, 3))
     launches = (lib.wfd_launch_count() - n0) // (args.steps + max(args.warmup, 3)) * args.steps
+    if launches_per_step is not None:
+        launches = launches_per_step * args.steps  # kernels inside the replayed graph
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
     # per-kernel CUDA-event profile of a few extra steps (separate from the timed region) for the roofline numbers
@@ -283,7 +300,7 @@ def run_native(args):
         lib.wfd_profile_enable(1)
         psteps = 3
         for _ in range(psteps):
-            step_resident()
+            (step_plain if not args.no_graph else step_resident)()
         torch.cuda.synchronize()
         buf = C.create_string_buffer(1 << 16)
         lib.wfd_profile_report(buf, len(buf))
@@ -330,7 +347,7 @@ def run_native(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": workload_config(args, T, t_pad, B),
-        "steps_per_s": world * args.steps / (ms / 1e3) / world,
+        "steps_per_s": args.steps / (ms / 1e3), "cuda_graph": not args.no_graph,
         "e2e": {"value": e2e, "unit": "maps/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": 2 * lat_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
                 "api": "WaveFunctionDiffusionPipeline.wfc_guidance (pipeline_wfd.py:606-615 block) with pinned host tensors"},
@@ -357,6 +374,7 @@ def main():
     ap.add_argument("--arch", default="64x64", choices=["64x64", "32x32"])
     ap.add_argument("--latent", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--top", type=int, default=12, help="kernels listed in profile_top")
     args = ap.parse_args()

@@ -290,6 +290,54 @@ def max_micro_batch():
     return max(1, int(os.environ.get("WFD_MAX_BATCH", "64")))
 
 
+def cuda_graphs_enabled():
+    """The guidance step is a fixed launch sequence (no host sync, no allocation), so it is replayed from a CUDA graph
+    once its shapes are known; WFD_CUDA_GRAPH=0 falls back to plain launches."""
+    return os.environ.get("WFD_CUDA_GRAPH", "1") != "0"
+
+
+class GraphedGuidanceStep:
+    """One captured wfd_guidance_step for fixed (plan, handle, batch, dtype, scales): static input/output buffers."""
+
+    def __init__(self, plan, handle, B, h, w, zdtype, in_scale, strength, device):
+        self.z = torch.zeros((B, 4, h, w), dtype=zdtype, device=device)
+        self.loss = torch.empty(B, dtype=torch.float32, device=device)
+        self.dz = torch.empty((B, 4, h, w), dtype=torch.float32, device=device)
+        self.plan, self.handle = plan, handle
+        saved = handle.saved_ptr(B, plan.H, plan.W)
+        zcode = _z_dtype_code(self.z)
+
+        def run():
+            nat.check(nat.lib().wfd_guidance_step(plan.handle, handle.handle, C.c_void_p(self.z.data_ptr()), zcode, B,
+                                                  float(in_scale), float(strength), saved,
+                                                  C.c_void_p(self.loss.data_ptr()), C.c_void_p(self.dz.data_ptr()),
+                                                  nat.stream_ptr()), "wfd_guidance_step")
+
+        cur = torch.cuda.current_stream(device)
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            run()  # warm-up outside capture: function attributes, tensor maps
+        cur.wait_stream(side)
+        torch.cuda.synchronize(device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            run()
+        self.saved_owner = handle._saved  # keep the saved block alive / detect reallocation
+
+    def valid(self):
+        return self.saved_owner is self.handle._saved
+
+    def __call__(self, z):
+        self.z.copy_(z)
+        self.plan.generation += 1
+        self.graph.replay()
+        return self.loss, self.dz
+
+
+_GRAPH_CACHE = {}
+
+
 class GuidanceLossFunction(torch.autograd.Function):
     """Fused guidance loss: loss[b] = strength * WFCLossEinsum(softmax(decode(latents * in_scale)))[b]
     (reference pipeline_wfd.py:612 with decode_latents_tile :402-408). One library call computes loss and d loss / d
@@ -302,6 +350,18 @@ class GuidanceLossFunction(torch.autograd.Function):
         mb = min(B, max_micro_batch())
         plan = native.plan(mb, h, w, latents.device)
         z = latents.contiguous()
+        if cuda_graphs_enabled() and B <= mb and not torch.cuda.is_current_stream_capturing():
+            key = (id(plan), id(handle), B, z.dtype, float(in_scale), float(strength), torch.cuda.current_stream().cuda_stream)
+            g = _GRAPH_CACHE.get(key)
+            if g is None or not g.valid() or g.plan is not plan:
+                if len(_GRAPH_CACHE) > 16:
+                    _GRAPH_CACHE.clear()
+                g = GraphedGuidanceStep(plan, handle, B, h, w, z.dtype, in_scale, strength, z.device)
+                _GRAPH_CACHE[key] = g
+            loss_s, dz_s = g(z)
+            ctx.save_for_backward(dz_s.clone())
+            ctx.zdtype = latents.dtype
+            return loss_s.clone()
         loss = torch.empty(B, dtype=torch.float32, device=z.device)
         dz = torch.empty((B, 4, h, w), dtype=torch.float32, device=z.device)
         esz = z.element_size() * 4 * h * w
