@@ -101,9 +101,11 @@ def test_micro_batching_matches_one_call(tmp_path, monkeypatch):
     assert _rel(l2.cpu(), l1.cpu()) < 1e-4 and _rel(g2.cpu(), g1.cpu()) < 5e-2
 
 
-@pytest.mark.parametrize("arch,tileset,latent", [("32x32", "platform_32x32", 64), ("64x64", "install_64x64", 128)])
+@pytest.mark.parametrize("arch,tileset,latent", [("32x32", "platform_32x32", 64), ("64x64", "install_64x64", 128),
+                                                 ("64x64", "twilight_64x64", 64), ("64x64", "ashworld_64x64", 64)])
 def test_other_configs_against_the_oracle(arch, tileset, latent):
-    """BASELINE config 5's architecture (DownDecoderBlock2D, 32x32 map from 64x64 latents) and a 128x128 map."""
+    """BASELINE config 5's architecture (DownDecoderBlock2D, 32x32 map from 64x64 latents), a 128x128 map, and the
+    largest / smallest-but-one tilesets of config 3 (T_pad 4352 and 1536)."""
     mx, my = load_wfc_mats(tileset)
     t_pad = round_up_channels(mx.shape[0])
     cfg = tilenet_config(arch, t_pad)
@@ -134,3 +136,30 @@ def test_large_map_256_runs():
     (grad,) = torch.autograd.grad(loss.sum(), z)
     assert torch.isfinite(loss).all() and torch.isfinite(grad).all() and grad.abs().max() > 0
     assert 0.5 * 5 < loss.item() < 5.0
+
+
+def test_img2img_from_a_tile_map(tmp_path):
+    """img2img twin started from an integer tile map (image_is_wave=True): tile-VAE encode -> noised latents -> the same
+    guided loop (reference pipeline_wfd_img2img.py:478-486, 667-700)."""
+    from wavefunctiondiffusion_b200.wf_diffusers.pipeline_wfd_img2img import WaveFunctionDiffusionImg2ImgPipeline, preprocess_wave
+
+    z = np.load(os.path.join(GOLD, "tiny_step.npz"))
+    cfg = json.loads(str(z["cfg_json"]))
+    T = int(z["T"])
+    mats = np.unpackbits(z["mats"])[: 2 * T * T].reshape(2, T, T).astype(bool)
+    torch.manual_seed(int(z["seed"]))
+    net = AutoencoderTile(**cfg).eval()
+    npz = str(tmp_path / "wfc.npz")
+    np.savez(npz, wfc_mats=mats)
+    pipe = WaveFunctionDiffusionImg2ImgPipeline(TinyImageVAE(), ConstantTextEncoder(), WhitespaceTokenizer(), net,
+                                                RandomNoiseUNet(4, 16), AffineDDIMScheduler(), None, None, wfc_data_path=npz)
+    pipe.set_progress_bar_config(disable=True)
+    pipe.to("cuda")
+    tiles = np.random.RandomState(0).randint(0, T, size=(16, 16))
+    assert preprocess_wave(tiles, cfg["in_channels"]).shape == (1, cfg["in_channels"], 16, 16)
+    out = pipe("a map", image=tiles, image_is_wave=True, strength=0.5, num_inference_steps=6, wfc_guidance_start_step=1,
+               wfc_guidance_strength=5, wfc_guidance_final_steps=1, wfc_guidance_final_strength=10, output_type="np",
+               generator=torch.Generator("cuda").manual_seed(0))
+    assert out.waves.shape == (1, 16, 16, cfg["out_channels"]) and np.isfinite(out.waves).all()
+    with pytest.raises(ValueError):
+        pipe("x", image=tiles, image_is_wave=True, strength=1.5)

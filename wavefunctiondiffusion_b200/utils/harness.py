@@ -37,6 +37,12 @@ class AffineDDIMScheduler:
         ap = self.alphas_cumprod[prev_t] if prev_t >= 0 else 1.0
         return math.sqrt(ap / at), math.sqrt(1 - ap) - math.sqrt(ap * (1 - at) / at)
 
+    def add_noise(self, original, noise, timesteps):
+        acp = torch.as_tensor(self.alphas_cumprod, dtype=torch.float32, device=original.device)[timesteps.long()]
+        a = acp.sqrt().view(-1, 1, 1, 1).to(original.dtype)
+        b = (1 - acp).sqrt().view(-1, 1, 1, 1).to(original.dtype)
+        return a * original + b * noise
+
     def step(self, model_output, timestep, sample, **kwargs):
         a, b = self.coefficients(timestep)
         return SimpleNamespace(prev_sample=a * sample + b * model_output)

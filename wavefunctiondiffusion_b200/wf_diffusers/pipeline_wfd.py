@@ -258,6 +258,15 @@ class WaveFunctionDiffusionPipeline:
         latents = self.prepare_latents(batch_size * num_images_per_prompt, self.unet.in_channels, height, width,
                                        text_embeddings.dtype, device, generator, latents)
         extra_step_kwargs = self.prepare_extra_step_kwargs(generator, eta)
+        latents = self._denoise(latents, timesteps, num_inference_steps, text_embeddings, do_cfg, guidance_scale,
+                                extra_step_kwargs, callback, callback_steps, wfc_guidance_start_step,
+                                wfc_guidance_strength, wfc_guidance_final_steps, wfc_guidance_final_strength)
+        return self._finish(latents, device, text_embeddings.dtype, output_type, return_dict)
+
+    def _denoise(self, latents, timesteps, num_inference_steps, text_embeddings, do_cfg, guidance_scale, extra_step_kwargs,
+                 callback, callback_steps, wfc_guidance_start_step, wfc_guidance_strength, wfc_guidance_final_steps,
+                 wfc_guidance_final_strength):
+        """The denoising loop with WFC guidance (reference :590-639), shared by txt2img and img2img."""
         order = getattr(self.scheduler, "order", 1)
         num_warmup_steps = len(timesteps) - num_inference_steps * order
         noise_pred, t = None, None
@@ -282,10 +291,12 @@ class WaveFunctionDiffusionPipeline:
                 for _ in range(wfc_guidance_final_steps):
                     latents = self.wfc_guidance(latents, noise_pred, t, wfc_guidance_final_strength)
                     bar.update()
+        return latents
 
+    def _finish(self, latents, device, dtype, output_type, return_dict):
         image = self.decode_latents(latents)
         wave = self.decode_latents_tile(latents, numpy=True)
-        image, has_nsfw_concept = self.run_safety_checker(image, device, text_embeddings.dtype)
+        image, has_nsfw_concept = self.run_safety_checker(image, device, dtype)
         if output_type == "pil":
             image = self.numpy_to_pil(image)
         if not return_dict:
