@@ -142,8 +142,8 @@ typedef struct {
     int z_count, a_zmul, b_zmul, b_bbmul;
     void* out; int out_fp32; long long ldc, c_zstride;
     const float* bias; const void* residual; float alpha;
-    float* rowdot; const void* dotsrc; long long ld_dot;
-    float* gn_sums; int gn_cpg;
+    void* rowdot; const void* dotsrc; long long ld_dot;   /* int64 fixed point (2^40) per output row */
+    void* gn_sums; int gn_cpg;                              /* int64 fixed point (2^20) {sum, sumsq} per (sample, group) */
     int dtype16;
     int cg;           /* 0: library chooses, 1: single CTA, 2: CTA pair (cta_group::2) */
     int n_group;      /* >1: tile rasterisation in bands of n_group N tiles */

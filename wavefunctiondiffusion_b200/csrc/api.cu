@@ -256,10 +256,10 @@ int wfd_test_tapgemm(const wfd_tapgemm_desc* t, int use_ref, void* stream) {
     p.bias = t->bias;
     p.residual = t->residual;
     p.alpha = t->alpha;
-    p.rowdot = t->rowdot;
+    p.rowdot = static_cast<acc_t*>(t->rowdot);
     p.dotsrc = t->dotsrc;
     p.ld_dot = t->ld_dot;
-    p.gn_sums = t->gn_sums;
+    p.gn_sums = static_cast<acc_t*>(t->gn_sums);
     p.gn_cpg = t->gn_cpg;
     p.gn_G = 8;
     p.is_bf16 = t->dtype16;

@@ -336,7 +336,7 @@ void Decoder::layout_workspace() {
     o_logits = take(B * ohw * T_pad * e);
     o_dlogits = take(B * ohw * T_pad * e);
     n_gn = static_cast<int>(resnets.size()) * 2 + 2;  // + attention group_norm + conv_norm_out
-    o_gn = take(static_cast<size_t>(n_gn) * 2 * B * G * 2 * sizeof(float));  // sums then reds
+    o_gn = take(static_cast<size_t>(n_gn) * 2 * B * G * 2 * sizeof(acc_t));  // sums then reds (fixed point)
     ws_bytes = off;
 }
 
@@ -526,7 +526,7 @@ int Decoder::run_gemm(Exec& ex, TapGemmOp& tmpl, bool z_is_batch) {
 
 // conv-style contraction over a channels-last activation
 int Decoder::conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int Hin, int Win, int Hout, int Wout,
-                       void* out, long long ldc, const float* bias, const void* residual, float* gn_sums, int gn_cpg,
+                       void* out, long long ldc, const float* bias, const void* residual, acc_t* gn_sums, int gn_cpg,
                        const OutStrides* os, const GnBwdFuse* gb) {
     TapGemmOp op;
     memset(&op, 0, sizeof(op));
@@ -608,7 +608,7 @@ struct PlainGemm {
     int BN, N;
     void* out; int out_fp32; long long ldc, c_zstride;
     const float* bias; const void* residual; float alpha;
-    float* gn_sums; int gn_cpg;
+    acc_t* gn_sums; int gn_cpg;
     const GnBwdFuse* gb;
 };
 int Decoder::plain_gemm(Exec& ex, const PlainGemm& g) {
@@ -686,11 +686,11 @@ int Decoder::plain_gemm(Exec& ex, const PlainGemm& g) {
     return run_gemm(ex, op, g.a_shared);
 }
 
-float* Decoder::gn_sums_ptr(int idx) const {
-    return reinterpret_cast<float*>(ws + o_gn) + static_cast<size_t>(idx) * B_max * G * 2;
+acc_t* Decoder::gn_sums_ptr(int idx) const {
+    return reinterpret_cast<acc_t*>(ws + o_gn) + static_cast<size_t>(idx) * B_max * G * 2;
 }
-float* Decoder::gn_red_ptr(int idx) const {
-    return reinterpret_cast<float*>(ws + o_gn) + static_cast<size_t>(n_gn + idx) * B_max * G * 2;
+acc_t* Decoder::gn_red_ptr(int idx) const {
+    return reinterpret_cast<acc_t*>(ws + o_gn) + static_cast<size_t>(n_gn + idx) * B_max * G * 2;
 }
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -701,7 +701,7 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
     const int hw = h * w;
     uint8_t* x = ws + o_x0;
     if (!ex.prepare) {
-        CUDA_CK(cudaMemsetAsync(ws + o_gn, 0, static_cast<size_t>(n_gn) * B_max * G * 2 * sizeof(float), s));
+        CUDA_CK(cudaMemsetAsync(ws + o_gn, 0, static_cast<size_t>(n_gn) * B_max * G * 2 * sizeof(acc_t), s));
         CK(latent_in(z, z_f16, in_scale, vecs["post_quant_conv.weight"], vecs["post_quant_conv.bias"],
                      vecs["decoder.conv_in.weight"], vecs["decoder.conv_in.bias"], x, B, h, w, Cm, bf16, s));
     }
@@ -850,7 +850,7 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
     const int hw = h * w;
     const void* dlog = dlogits_in ? dlogits_in : ws + o_dlogits;
     if (!ex.prepare)
-        CUDA_CK(cudaMemsetAsync(gn_red_ptr(0), 0, static_cast<size_t>(n_gn) * B_max * G * 2 * sizeof(float), s));
+        CUDA_CK(cudaMemsetAsync(gn_red_ptr(0), 0, static_cast<size_t>(n_gn) * B_max * G * 2 * sizeof(acc_t), s));
     // GroupNorm-backward reduction fused into the epilogue of the contraction that produces dy (when the channel
     // groups are 16-column aligned); otherwise the standalone gn_bwd_reduce pass runs
     // (measured on B200: the fused form wins for the <= 768-channel layers whose tiles carry enough MMA work to hide the

@@ -24,9 +24,9 @@ struct TapSel {  // one tap of a contraction: which weight tap it reads and wher
     int w_tap, dx, dy;
 };
 struct GnBwdFuse {  // GroupNorm(+SiLU) backward reduction fused into the producing contraction's epilogue
-    float* red;
+    acc_t* red;
     const void* x;
-    const float* stats;
+    const acc_t* stats;
     const float* gamma;
     const float* beta;
     int cpg, silu;
@@ -103,11 +103,11 @@ struct Decoder {
     int prepare_ops();
     int run_gemm(Exec& ex, TapGemmOp& tmpl, bool z_is_batch);
     int conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int Hin, int Win, int Hout, int Wout, void* out,
-                  long long ldc, const float* bias, const void* residual, float* gn_sums, int gn_cpg,
+                  long long ldc, const float* bias, const void* residual, acc_t* gn_sums, int gn_cpg,
                   const OutStrides* os, const GnBwdFuse* gb);
     int plain_gemm(Exec& ex, const PlainGemm& g);
-    float* gn_sums_ptr(int idx) const;
-    float* gn_red_ptr(int idx) const;
+    acc_t* gn_sums_ptr(int idx) const;
+    acc_t* gn_red_ptr(int idx) const;
     int forward_impl(Exec& ex, const void* z, int z_f16, float in_scale);
     int backward_impl(Exec& ex, const void* dlogits, const float* scale_b, float* dz);
 };

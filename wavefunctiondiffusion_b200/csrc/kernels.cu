@@ -104,9 +104,13 @@ __host__ __device__ inline GnMap gn_map(int C) {
     m.R = GN_THREADS / m.nvt;
     return m;
 }
-__device__ __forceinline__ void gn_finalize(const float* sums, int b, int g, int G, double n, float eps, float& mean,
+__device__ __forceinline__ unsigned long long to_fx(float v, float scale) {
+    return static_cast<unsigned long long>(__float2ll_rn(v * scale));
+}
+__device__ __forceinline__ void gn_finalize(const acc_t* sums, int b, int g, int G, double n, float eps, float& mean,
                                             float& rstd) {
-    const double s = sums[(b * G + g) * 2], ss = sums[(b * G + g) * 2 + 1];
+    const double s = static_cast<double>(sums[(b * G + g) * 2]) * (1.0 / WFD_FX_STATS);
+    const double ss = static_cast<double>(sums[(b * G + g) * 2 + 1]) * (1.0 / WFD_FX_STATS);
     const double m = s / n;
     double var = ss / n - m * m;
     if (var < 0) var = 0;
@@ -115,15 +119,15 @@ __device__ __forceinline__ void gn_finalize(const float* sums, int b, int g, int
 }
 
 template <bool BF16>
-__global__ void __launch_bounds__(GN_THREADS) gn_stats_k(const uint4* __restrict__ x, float* __restrict__ sums, int HW,
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_k(const uint4* __restrict__ x, acc_t* __restrict__ sums, int HW,
                                                           int C, int G, int ppb) {
-    __shared__ float sh[2 * GN_MAXG];
+    __shared__ unsigned long long sh[2 * GN_MAXG];
     const GnMap m = gn_map(C);
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * ppb, p1 = min(HW, p0 + ppb);
     const int tcol = threadIdx.x % m.nvt, trow = threadIdx.x / m.nvt;
     const int cpg = C / G;
-    if (threadIdx.x < 2 * G) sh[threadIdx.x] = 0.f;
+    if (threadIdx.x < 2 * G) sh[threadIdx.x] = 0ull;
     __syncthreads();
     if (trow < m.R) {
         for (int k = 0; k < m.cpt; ++k) {
@@ -150,12 +154,13 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_k(const uint4* __restrict
                 }
             }
             const int g = (col * 8) / cpg;
-            atomicAdd(&sh[2 * g], s);
-            atomicAdd(&sh[2 * g + 1], ss);
+            atomicAdd(&sh[2 * g], to_fx(s, WFD_FX_STATS));
+            atomicAdd(&sh[2 * g + 1], to_fx(ss, WFD_FX_STATS));
         }
     }
     __syncthreads();
-    if (threadIdx.x < 2 * G) atomicAdd(&sums[b * G * 2 + threadIdx.x], sh[threadIdx.x]);
+    if (threadIdx.x < 2 * G)
+        atomicAdd(reinterpret_cast<unsigned long long*>(sums) + b * G * 2 + threadIdx.x, sh[threadIdx.x]);
 }
 
 // sigmoid through the hardware tanh (one MUFU): 0.5 * tanh(0.5 u) + 0.5, abs error ~2.5e-4 — below the 16-bit output
@@ -168,7 +173,7 @@ __device__ __forceinline__ float sigmoidf_(float u) {
 
 template <bool BF16>
 __global__ void __launch_bounds__(GN_THREADS, 3)
-gn_apply_k(const uint4* __restrict__ x, const float* __restrict__ sums, const float* __restrict__ gamma,
+gn_apply_k(const uint4* __restrict__ x, const acc_t* __restrict__ sums, const float* __restrict__ gamma,
            const float* __restrict__ beta, uint4* __restrict__ y, int HW, int C, int G, float eps, int silu, int ppb) {
     const GnMap m = gn_map(C);
     const int b = blockIdx.y;
@@ -213,16 +218,16 @@ gn_apply_k(const uint4* __restrict__ x, const float* __restrict__ sums, const fl
 
 template <bool BF16>
 __global__ void __launch_bounds__(GN_THREADS, 3)
-gn_bwd_reduce_k(const uint4* __restrict__ dy, const uint4* __restrict__ x, const float* __restrict__ sums,
-                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ red, int HW,
+gn_bwd_reduce_k(const uint4* __restrict__ dy, const uint4* __restrict__ x, const acc_t* __restrict__ sums,
+                const float* __restrict__ gamma, const float* __restrict__ beta, acc_t* __restrict__ red, int HW,
                 int C, int G, float eps, int silu, int ppb) {
-    __shared__ float sh[2 * GN_MAXG];
+    __shared__ unsigned long long sh[2 * GN_MAXG];
     const GnMap m = gn_map(C);
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * ppb, p1 = min(HW, p0 + ppb);
     const int tcol = threadIdx.x % m.nvt, trow = threadIdx.x / m.nvt;
     const int cpg = C / G;
-    if (threadIdx.x < 2 * G) sh[threadIdx.x] = 0.f;
+    if (threadIdx.x < 2 * G) sh[threadIdx.x] = 0ull;
     __syncthreads();
     if (trow < m.R) {
         for (int k = 0; k < m.cpt; ++k) {
@@ -269,18 +274,19 @@ gn_bwd_reduce_k(const uint4* __restrict__ dy, const uint4* __restrict__ x, const
                     }
                 }
             }
-            atomicAdd(&sh[2 * g], s1);
-            atomicAdd(&sh[2 * g + 1], s2);
+            atomicAdd(&sh[2 * g], to_fx(s1, WFD_FX_GRAD));
+            atomicAdd(&sh[2 * g + 1], to_fx(s2, WFD_FX_GRAD));
         }
     }
     __syncthreads();
-    if (threadIdx.x < 2 * G) atomicAdd(&red[b * G * 2 + threadIdx.x], sh[threadIdx.x]);
+    if (threadIdx.x < 2 * G)
+        atomicAdd(reinterpret_cast<unsigned long long*>(red) + b * G * 2 + threadIdx.x, sh[threadIdx.x]);
 }
 
 template <bool BF16>
 __global__ void __launch_bounds__(GN_THREADS, 2)
-gn_bwd_apply_k(const uint4* __restrict__ dy, const uint4* __restrict__ x, const float* __restrict__ sums,
-               const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ red,
+gn_bwd_apply_k(const uint4* __restrict__ dy, const uint4* __restrict__ x, const acc_t* __restrict__ sums,
+               const float* __restrict__ gamma, const float* __restrict__ beta, const acc_t* __restrict__ red,
                const uint4* __restrict__ add, uint4* __restrict__ dx, int HW, int C, int G, float eps, int silu,
                int ppb) {
     const GnMap m = gn_map(C);
@@ -297,7 +303,8 @@ gn_bwd_apply_k(const uint4* __restrict__ dy, const uint4* __restrict__ x, const 
         const double n = static_cast<double>(cpg) * HW;
         gn_finalize(sums, b, g, G, n, eps, mean, rstd);
         const float inv_n = static_cast<float>(1.0 / n);
-        const float r1 = red[(b * G + g) * 2] * inv_n, r2 = red[(b * G + g) * 2 + 1] * inv_n;
+        const float r1 = static_cast<float>(static_cast<double>(red[(b * G + g) * 2]) * (1.0 / WFD_FX_GRAD) / n);
+        const float r2 = static_cast<float>(static_cast<double>(red[(b * G + g) * 2 + 1]) * (1.0 / WFD_FX_GRAD) / n);
         float ga[8], be[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -362,7 +369,7 @@ static void gn_grid(int B, int HW, int C, dim3& grid, int& ppb) {
     grid = dim3(blocks_x, B);
 }
 
-int gn_stats(const void* x, float* sums, int B, int HW, int C, int G, int bf16, cudaStream_t s) {
+int gn_stats(const void* x, acc_t* sums, int B, int HW, int C, int G, int bf16, cudaStream_t s) {
     ProfScope prof_scope("gn_stats", s);
     if (int r = gn_check(C, G)) return r;
     dim3 grid;
@@ -372,7 +379,7 @@ int gn_stats(const void* x, float* sums, int B, int HW, int C, int G, int bf16, 
     WFD_CHECK_LAUNCH("gn_stats");
     return 0;
 }
-int gn_apply(const void* x, const float* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C,
+int gn_apply(const void* x, const acc_t* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C,
              int G, float eps, int silu, int bf16, cudaStream_t s) {
     ProfScope prof_scope("gn_apply", s);
     if (int r = gn_check(C, G)) return r;
@@ -384,7 +391,7 @@ int gn_apply(const void* x, const float* sums, const float* gamma, const float* 
     WFD_CHECK_LAUNCH("gn_apply");
     return 0;
 }
-int gn_bwd_reduce(const void* dy, const void* x, const float* sums, const float* gamma, const float* beta, float* red,
+int gn_bwd_reduce(const void* dy, const void* x, const acc_t* sums, const float* gamma, const float* beta, acc_t* red,
                   int B, int HW, int C, int G, float eps, int silu, int bf16, cudaStream_t s) {
     ProfScope prof_scope("gn_bwd_reduce", s);
     if (int r = gn_check(C, G)) return r;
@@ -397,8 +404,8 @@ int gn_bwd_reduce(const void* dy, const void* x, const float* sums, const float*
     WFD_CHECK_LAUNCH("gn_bwd_reduce");
     return 0;
 }
-int gn_bwd_apply(const void* dy, const void* x, const float* sums, const float* gamma, const float* beta,
-                 const float* red, const void* add, void* dx, int B, int HW, int C, int G, float eps, int silu,
+int gn_bwd_apply(const void* dy, const void* x, const acc_t* sums, const float* gamma, const float* beta,
+                 const acc_t* red, const void* add, void* dx, int B, int HW, int C, int G, float eps, int silu,
                  int bf16, cudaStream_t s) {
     ProfScope prof_scope("gn_bwd_apply", s);
     if (int r = gn_check(C, G)) return r;
@@ -416,7 +423,7 @@ int gn_bwd_apply(const void* dy, const void* x, const float* sums, const float* 
 // sample, so the batch can be walked in L2-sized blocks of samples (WFD_GN_L2_BLOCK_MB > 0) to make the second read of
 // (dy, x) hit L2; measured on B200 the extra small launches cost more than the saved HBM reads (17.8 vs 16.5 ms per
 // step at batch 8), so the default is one block.
-int gn_bwd(const void* dy, const void* x, const float* sums, const float* gamma, const float* beta, float* red,
+int gn_bwd(const void* dy, const void* x, const acc_t* sums, const float* gamma, const float* beta, acc_t* red,
            const void* add, void* dx, int B, int HW, int C, int G, float eps, int silu, int bf16, int do_reduce,
            cudaStream_t s) {
     const size_t per_sample = static_cast<size_t>(HW) * C * 2;
@@ -438,8 +445,8 @@ int gn_bwd(const void* dy, const void* x, const float* sums, const float* gamma,
         const uint8_t* xb = static_cast<const uint8_t*>(x) + off;
         const uint8_t* addb = add ? static_cast<const uint8_t*>(add) + off : nullptr;
         uint8_t* dxb = static_cast<uint8_t*>(dx) + off;
-        const float* sb = sums + static_cast<size_t>(b0) * G * 2;
-        float* rb = red + static_cast<size_t>(b0) * G * 2;
+        const acc_t* sb = sums + static_cast<size_t>(b0) * G * 2;
+        acc_t* rb = red + static_cast<size_t>(b0) * G * 2;
         if (do_reduce) {
             int rc = gn_bwd_reduce(dyb, xb, sb, gamma, beta, rb, n, HW, C, G, eps, silu, bf16, s);
             if (rc < 0) return rc;
@@ -668,16 +675,16 @@ __device__ __forceinline__ float neighbour_sum(const float* __restrict__ S, int 
 }
 
 __global__ void __launch_bounds__(1024)
-wfc_loss_finish_k(const float* __restrict__ rowsum, const float* __restrict__ rowdot, float* __restrict__ loss, int H,
+wfc_loss_finish_k(const float* __restrict__ rowsum, const acc_t* __restrict__ rowdot, float* __restrict__ loss, int H,
                   int W, float coef) {
     __shared__ double red[32];
     const int b = blockIdx.x;
     const float* S = rowsum + static_cast<long long>(b) * H * W;
-    const float* D = rowdot + static_cast<long long>(b) * H * W;
+    const acc_t* D = rowdot + static_cast<long long>(b) * H * W;
     double acc = 0.0;
     for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
         const int y = i / W, x = i - y * W;
-        acc += static_cast<double>(S[i]) * neighbour_sum(S, y, x, H, W) - D[i];
+        acc += static_cast<double>(S[i]) * neighbour_sum(S, y, x, H, W) - static_cast<double>(D[i]) * (1.0 / WFD_FX_GRAD);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -690,7 +697,7 @@ wfc_loss_finish_k(const float* __restrict__ rowsum, const float* __restrict__ ro
         if (threadIdx.x == 0) loss[b] = static_cast<float>(0.5 * coef * v);
     }
 }
-int wfc_loss_finish(const float* rowsum, const float* rowdot, float* loss, int B, int H, int W, float coef,
+int wfc_loss_finish(const float* rowsum, const acc_t* rowdot, float* loss, int B, int H, int W, float coef,
                     cudaStream_t s) {
     ProfScope prof_scope("wfc_loss_finish", s);
     wfc_loss_finish_k<<<B, 1024, 0, s>>>(rowsum, rowdot, loss, H, W, coef);
@@ -701,7 +708,7 @@ int wfc_loss_finish(const float* rowsum, const float* rowdot, float* loss, int B
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 wfc_grad_finish_k(const uint4* __restrict__ wave, const uint4* __restrict__ a, const float* __restrict__ rowsum,
-                  const float* __restrict__ rowdot, const float* __restrict__ dloss, uint4* __restrict__ dout, int B,
+                  const acc_t* __restrict__ rowdot, const float* __restrict__ dloss, uint4* __restrict__ dout, int B,
                   int H, int W, int T_pad, int T, float coef, int through_softmax) {
     const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -712,7 +719,7 @@ wfc_grad_finish_k(const uint4* __restrict__ wave, const uint4* __restrict__ a, c
     const int y = pr / W, x = pr - y * W;
     const float* S = rowsum + static_cast<long long>(b) * H * W;
     const float c = neighbour_sum(S, y, x, H, W);
-    const float r = S[pr] * c - rowdot[row];
+    const float r = S[pr] * c - static_cast<float>(static_cast<double>(rowdot[row]) * (1.0 / WFD_FX_GRAD));
     const float sc = coef * (dloss ? dloss[b] : 1.f);
     const int nv = T_pad / 8;
     for (int v = lane; v < nv; v += 32) {
@@ -727,7 +734,7 @@ wfc_grad_finish_k(const uint4* __restrict__ wave, const uint4* __restrict__ a, c
         dout[row * nv + v] = pack8<BF16>(fa);
     }
 }
-int wfc_grad_finish(const void* wave, const void* a, const float* rowsum, const float* rowdot, const float* dloss,
+int wfc_grad_finish(const void* wave, const void* a, const float* rowsum, const acc_t* rowdot, const float* dloss,
                     void* dout, int B, int H, int W, int T_pad, int T, float coef, int through_softmax, int bf16,
                     cudaStream_t s) {
     ProfScope prof_scope("wfc_grad_finish", s);

@@ -4,25 +4,26 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "tapgemm.cuh"  // acc_t, fixed-point scales
 
 namespace wfd {
 
 // ---- GroupNorm (8 groups in the tile VAE; reference resnet.py:407,423, attention.py:278, wf_vae.py:212), eps 1e-6
-// sums: [B, G, 2] fp32 {sum, sumsq}, zeroed by the caller before accumulation.
-int gn_stats(const void* x, float* sums, int B, int HW, int C, int G, int bf16, cudaStream_t s);
+// sums: [B, G, 2] fixed-point (2^20) {sum, sumsq}, zeroed by the caller before accumulation.
+int gn_stats(const void* x, acc_t* sums, int B, int HW, int C, int G, int bf16, cudaStream_t s);
 // y = act((x - mean) * rstd * gamma + beta), act = SiLU if silu else identity
-int gn_apply(const void* x, const float* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C,
+int gn_apply(const void* x, const acc_t* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C,
              int G, float eps, int silu, int bf16, cudaStream_t s);
-// red: [B, G, 2] fp32 {sum(du*gamma), sum(du*gamma*xhat)}, zeroed by the caller; du = dy * act'(u)
-int gn_bwd_reduce(const void* dy, const void* x, const float* sums, const float* gamma, const float* beta, float* red,
+// red: [B, G, 2] fixed-point (2^40) {sum(du*gamma), sum(du*gamma*xhat)}, zeroed by the caller; du = dy * act'(u)
+int gn_bwd_reduce(const void* dy, const void* x, const acc_t* sums, const float* gamma, const float* beta, acc_t* red,
                   int B, int HW, int C, int G, float eps, int silu, int bf16, cudaStream_t s);
 // dx = rstd * (du*gamma - (red0 + xhat*red1)/n) (+ add)
-int gn_bwd_apply(const void* dy, const void* x, const float* sums, const float* gamma, const float* beta,
-                 const float* red, const void* add, void* dx, int B, int HW, int C, int G, float eps, int silu,
+int gn_bwd_apply(const void* dy, const void* x, const acc_t* sums, const float* gamma, const float* beta,
+                 const acc_t* red, const void* add, void* dx, int B, int HW, int C, int G, float eps, int silu,
                  int bf16, cudaStream_t s);
 
 // reduce (optional: skipped when the producing contraction fused it) + apply, in L2-sized blocks of samples
-int gn_bwd(const void* dy, const void* x, const float* sums, const float* gamma, const float* beta, float* red,
+int gn_bwd(const void* dy, const void* x, const acc_t* sums, const float* gamma, const float* beta, acc_t* red,
            const void* add, void* dx, int B, int HW, int C, int G, float eps, int silu, int bf16, int do_reduce,
            cudaStream_t s);
 
@@ -42,11 +43,11 @@ int wave_softmax(const void* logits, void* wave, float* rowsum, long long rows, 
 // rowsum only (wave given, e.g. WFCLossEinsum(wave) called directly)
 int wave_rowsum(const void* wave, float* rowsum, long long rows, int T_pad, int T, int bf16, cudaStream_t s);
 // loss[b] = coef * 0.5 * sum_n (S_n * c_n - rowdot_a[n]),  c_n = sum of S over the <=4 in-map neighbours
-int wfc_loss_finish(const float* rowsum, const float* rowdot, float* loss, int B, int H, int W, float coef,
+int wfc_loss_finish(const float* rowsum, const acc_t* rowdot, float* loss, int B, int H, int W, float coef,
                     cudaStream_t s);
 // grad wrt wave (no softmax): dwave[n,i] = coef*dloss[b] * ([i<T]*c_n - a[n,i]);
 // grad wrt logits (softmax bwd): dlogits[n,i] = coef*dloss[b] * p[n,i] * (([i<T]*c_n - a[n,i]) - (S_n*c_n - rowdot_a[n]))
-int wfc_grad_finish(const void* wave, const void* a, const float* rowsum, const float* rowdot, const float* dloss,
+int wfc_grad_finish(const void* wave, const void* a, const float* rowsum, const acc_t* rowdot, const float* dloss,
                     void* dout, int B, int H, int W, int T_pad, int T, float coef, int through_softmax, int bf16,
                     cudaStream_t s);
 

@@ -214,7 +214,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* bet_s = gam_s + 512;                                       // [2][256] GroupNorm-backward beta
     // per-CTA partial sums of the fused GroupNorm statistics / backward reductions, flushed once at kernel end: thousands
     // of tiles would otherwise hammer the same few global addresses with atomics
-    float* stat_s = bet_s + 512;                                      // [2][TG_STAT_SLOTS]
+    unsigned long long* stat_s = reinterpret_cast<unsigned long long*>(bet_s + 512);  // [2][TG_STAT_SLOTS] fixed point
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -238,7 +238,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         fence_barrier_init();
     }
-    for (int i = threadIdx.x; i < 2 * TG_STAT_SLOTS; i += TG_THREADS) stat_s[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * TG_STAT_SLOTS; i += TG_THREADS) stat_s[i] = 0ull;
     if (warp == 1) {
         if (CG == 2) {
             tmem_alloc_2sm(tmem_slot, 512);
@@ -584,11 +584,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 if (lane == 0) {
                                     const int slot = (tc.bb * p.gn_G + ggroup) * 2;
                                     if (slot + 1 < TG_STAT_SLOTS) {
-                                        atomicAdd(stat_s + slot, gs);
-                                        atomicAdd(stat_s + slot + 1, gss);
+                                        atomicAdd(stat_s + slot, static_cast<unsigned long long>(__float2ll_rn((gs) * WFD_FX_STATS)));
+                                        atomicAdd(stat_s + slot + 1, static_cast<unsigned long long>(__float2ll_rn((gss) * WFD_FX_STATS)));
                                     } else {
-                                        atomicAdd(p.gn_sums + slot, gs);
-                                        atomicAdd(p.gn_sums + slot + 1, gss);
+                                        atomicAdd(reinterpret_cast<unsigned long long*>(p.gn_sums) + slot, static_cast<unsigned long long>(__float2ll_rn((gs) * WFD_FX_STATS)));
+                                        atomicAdd(reinterpret_cast<unsigned long long*>(p.gn_sums) + slot + 1, static_cast<unsigned long long>(__float2ll_rn((gss) * WFD_FX_STATS)));
                                     }
                                 }
                             }
@@ -617,20 +617,22 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 if (lane == 0) {
                                     const int slot = (tc.bb * p.gn_G + bgroup) * 2;
                                     if (slot + 1 < TG_STAT_SLOTS) {
-                                        atomicAdd(stat_s + TG_STAT_SLOTS + slot, b1);
-                                        atomicAdd(stat_s + TG_STAT_SLOTS + slot + 1, b2);
+                                        atomicAdd(stat_s + TG_STAT_SLOTS + slot, static_cast<unsigned long long>(__float2ll_rn((b1) * WFD_FX_GRAD)));
+                                        atomicAdd(stat_s + TG_STAT_SLOTS + slot + 1, static_cast<unsigned long long>(__float2ll_rn((b2) * WFD_FX_GRAD)));
                                     } else {
-                                        atomicAdd(p.gnb_red + slot, b1);
-                                        atomicAdd(p.gnb_red + slot + 1, b2);
+                                        atomicAdd(reinterpret_cast<unsigned long long*>(p.gnb_red) + slot, static_cast<unsigned long long>(__float2ll_rn((b1) * WFD_FX_GRAD)));
+                                        atomicAdd(reinterpret_cast<unsigned long long*>(p.gnb_red) + slot + 1, static_cast<unsigned long long>(__float2ll_rn((b2) * WFD_FX_GRAD)));
                                     }
                                 }
                             }
                             bgroup = g;
                             b1 = 0.f;
                             b2 = 0.f;
-                            const float* st = p.gnb_stats + (static_cast<long long>(tc.bb) * p.gn_G + g) * 2;
-                            const float m = __ldg(st) * p.gnb_inv_n;
-                            const float var = fmaxf(__ldg(st + 1) * p.gnb_inv_n - m * m, 0.f);
+                            const acc_t* st = p.gnb_stats + (static_cast<long long>(tc.bb) * p.gn_G + g) * 2;
+                            const double dm = static_cast<double>(__ldg(st)) * (1.0 / WFD_FX_STATS) * p.gnb_inv_n;
+                            const double dv = static_cast<double>(__ldg(st + 1)) * (1.0 / WFD_FX_STATS) * p.gnb_inv_n - dm * dm;
+                            const float m = static_cast<float>(dm);
+                            const float var = fmaxf(static_cast<float>(dv), 0.f);
                             bmean = m;
                             brstd = rsqrtf(var + p.gnb_eps);
                         }
@@ -674,11 +676,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (lane == 0) {
                     const int slot = (tc.bb * p.gn_G + ggroup) * 2;
                     if (slot + 1 < TG_STAT_SLOTS) {
-                        atomicAdd(stat_s + slot, gs);
-                        atomicAdd(stat_s + slot + 1, gss);
+                        atomicAdd(stat_s + slot, static_cast<unsigned long long>(__float2ll_rn((gs) * WFD_FX_STATS)));
+                        atomicAdd(stat_s + slot + 1, static_cast<unsigned long long>(__float2ll_rn((gss) * WFD_FX_STATS)));
                     } else {
-                        atomicAdd(p.gn_sums + slot, gs);
-                        atomicAdd(p.gn_sums + slot + 1, gss);
+                        atomicAdd(reinterpret_cast<unsigned long long*>(p.gn_sums) + slot, static_cast<unsigned long long>(__float2ll_rn((gs) * WFD_FX_STATS)));
+                        atomicAdd(reinterpret_cast<unsigned long long*>(p.gn_sums) + slot + 1, static_cast<unsigned long long>(__float2ll_rn((gss) * WFD_FX_STATS)));
                     }
                 }
             }
@@ -691,15 +693,16 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (lane == 0) {
                     const int slot = (tc.bb * p.gn_G + bgroup) * 2;
                     if (slot + 1 < TG_STAT_SLOTS) {
-                        atomicAdd(stat_s + TG_STAT_SLOTS + slot, b1);
-                        atomicAdd(stat_s + TG_STAT_SLOTS + slot + 1, b2);
+                        atomicAdd(stat_s + TG_STAT_SLOTS + slot, static_cast<unsigned long long>(__float2ll_rn((b1) * WFD_FX_GRAD)));
+                        atomicAdd(stat_s + TG_STAT_SLOTS + slot + 1, static_cast<unsigned long long>(__float2ll_rn((b2) * WFD_FX_GRAD)));
                     } else {
-                        atomicAdd(p.gnb_red + slot, b1);
-                        atomicAdd(p.gnb_red + slot + 1, b2);
+                        atomicAdd(reinterpret_cast<unsigned long long*>(p.gnb_red) + slot, static_cast<unsigned long long>(__float2ll_rn((b1) * WFD_FX_GRAD)));
+                        atomicAdd(reinterpret_cast<unsigned long long*>(p.gnb_red) + slot + 1, static_cast<unsigned long long>(__float2ll_rn((b2) * WFD_FX_GRAD)));
                     }
                 }
             }
-            if (p.rowdot) atomicAdd(p.rowdot + pixel, dot);
+            if (p.rowdot)
+                atomicAdd(reinterpret_cast<unsigned long long*>(p.rowdot) + pixel, static_cast<unsigned long long>(__float2ll_rn((dot) * WFD_FX_GRAD)));
             if (p.dbg) e_busy += clock64() - e0;
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
@@ -717,12 +720,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.gn_sums || p.gnb_red) {
         for (int i = threadIdx.x; i < TG_STAT_SLOTS; i += TG_THREADS) {
             if (p.gn_sums) {
-                const float v = stat_s[i];
-                if (v != 0.f) atomicAdd(p.gn_sums + i, v);
+                const unsigned long long v = stat_s[i];
+                if (v != 0ull) atomicAdd(reinterpret_cast<unsigned long long*>(p.gn_sums) + i, v);
             }
             if (p.gnb_red) {
-                const float v = stat_s[TG_STAT_SLOTS + i];
-                if (v != 0.f) atomicAdd(p.gnb_red + i, v);
+                const unsigned long long v = stat_s[TG_STAT_SLOTS + i];
+                if (v != 0ull) atomicAdd(reinterpret_cast<unsigned long long*>(p.gnb_red) + i, v);
             }
         }
     }
@@ -776,7 +779,9 @@ __global__ void tapgemm_ref_kernel(const TapGemmParams p) {
     const long long off = z * p.c_zstride + bb * p.out_sb + static_cast<long long>(y) * p.out_sy +
                           static_cast<long long>(x) * p.out_sx + n;
     if (p.residual) v += lo16_to_f<BF16>(reinterpret_cast<const uint16_t*>(p.residual)[off]);
-    if (p.rowdot) atomicAdd(p.rowdot + pixel, v * lo16_to_f<BF16>(reinterpret_cast<const uint16_t*>(p.dotsrc)[pixel * p.ld_dot + n]));
+    if (p.rowdot)
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.rowdot) + pixel,
+                  static_cast<unsigned long long>(__float2ll_rn((v * lo16_to_f<BF16>(reinterpret_cast<const uint16_t*>(p.dotsrc)[pixel * p.ld_dot + n])) * WFD_FX_GRAD)));
     if (p.out_fp32) {
         reinterpret_cast<float*>(p.out)[off] = v;
     } else {
@@ -784,15 +789,16 @@ __global__ void tapgemm_ref_kernel(const TapGemmParams p) {
         reinterpret_cast<uint16_t*>(p.out)[off] = static_cast<uint16_t>(w & 0xFFFF);
         if (p.gn_sums) {
             const float r = lo16_to_f<BF16>(w);
-            float* dst = p.gn_sums + (static_cast<long long>(bb) * p.gn_G + n / p.gn_cpg) * 2;
-            atomicAdd(dst, r);
-            atomicAdd(dst + 1, r * r);
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.gn_sums) + (static_cast<long long>(bb) * p.gn_G + n / p.gn_cpg) * 2;
+            atomicAdd(dst, static_cast<unsigned long long>(__float2ll_rn((r) * WFD_FX_STATS)));
+            atomicAdd(dst + 1, static_cast<unsigned long long>(__float2ll_rn((r * r) * WFD_FX_STATS)));
         }
         if (p.gnb_red) {
             const int g = n / p.gnb_cpg;
-            const float* st = p.gnb_stats + (static_cast<long long>(bb) * p.gn_G + g) * 2;
-            const float m = st[0] * p.gnb_inv_n;
-            const float var = fmaxf(st[1] * p.gnb_inv_n - m * m, 0.f);
+            const acc_t* st = p.gnb_stats + (static_cast<long long>(bb) * p.gn_G + g) * 2;
+            const double dm = static_cast<double>(st[0]) * (1.0 / WFD_FX_STATS) * p.gnb_inv_n;
+            const float m = static_cast<float>(dm);
+            const float var = fmaxf(static_cast<float>(static_cast<double>(st[1]) * (1.0 / WFD_FX_STATS) * p.gnb_inv_n - dm * dm), 0.f);
             const float rstd = rsqrtf(var + p.gnb_eps);
             const float xh = (lo16_to_f<BF16>(reinterpret_cast<const uint16_t*>(p.gnb_x)[off]) - m) * rstd;
             const float ga = p.gnb_gamma[n];
@@ -802,9 +808,9 @@ __global__ void tapgemm_ref_kernel(const TapGemmParams p) {
                 const float sg = fast_sigmoid(u);
                 du *= sg * fmaf(u, 1.f - sg, 1.f);
             }
-            float* dst = p.gnb_red + (static_cast<long long>(bb) * p.gn_G + g) * 2;
-            atomicAdd(dst, du * ga);
-            atomicAdd(dst + 1, du * ga * xh);
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.gnb_red) + (static_cast<long long>(bb) * p.gn_G + g) * 2;
+            atomicAdd(dst, static_cast<unsigned long long>(__float2ll_rn((du * ga) * WFD_FX_GRAD)));
+            atomicAdd(dst + 1, static_cast<unsigned long long>(__float2ll_rn((du * ga * xh) * WFD_FX_GRAD)));
         }
     }
 }
@@ -939,7 +945,7 @@ int tapgemm_prepare(TapGemmOp* op) {
     }
     const size_t b_stage = p.b_resident ? 0 : (p.reuse ? 3 : 1) * static_cast<size_t>(p.BN / p.cg) * 128;
     const size_t per_stage = a_stage + b_stage;
-    int stages = static_cast<int>((204 * 1024 - (p.b_resident ? b_res_bytes : 0)) / per_stage);
+    int stages = static_cast<int>((196 * 1024 - (p.b_resident ? b_res_bytes : 0)) / per_stage);
     if (stages > 8) stages = 8;
     {
         static int cap = -1;  // WFD_MAX_STAGES: experiment knob
@@ -952,7 +958,7 @@ int tapgemm_prepare(TapGemmOp* op) {
     if (stages < 2) stages = 2;
     op->stages = stages;
     op->smem_bytes = 1024 + stages * per_stage + (p.b_resident ? b_res_bytes : 0) + (2 * stages + 8) * sizeof(uint64_t) +
-                     (6 * 256 + 2 * TG_STAT_SLOTS) * sizeof(float) + 16;
+                     6 * 256 * sizeof(float) + 2 * TG_STAT_SLOTS * sizeof(unsigned long long) + 16;
     return 0;
 }
 

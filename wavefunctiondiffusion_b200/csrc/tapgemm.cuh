@@ -21,6 +21,11 @@ namespace wfd {
 constexpr int TG_BM = 128;      // rows per M tile (UMMA M)
 constexpr int TG_KC = 64;       // K elements per pipeline chunk (128 bytes = one SW128 row)
 constexpr int TG_MAX_TAPS = 9;
+// Cross-CTA reductions (GroupNorm sums, backward reductions, WFC row dots) are accumulated as 64-bit FIXED-POINT integers:
+// integer atomics are order independent, so results are bitwise reproducible run to run and independent of the batch slot.
+typedef long long acc_t;
+constexpr float WFD_FX_STATS = 1048576.f;          // 2^20: forward statistics (sum x, sum x^2)
+constexpr float WFD_FX_GRAD = 1099511627776.f;     // 2^40: backward reductions and row dots (small magnitudes)
 constexpr int TG_STAT_SLOTS = 1024;  // per-CTA shared-memory slots for fused GroupNorm partial sums ((sample, group) x 2)
 constexpr int TG_EPI_THREADS = 256;                 // warps 2-9: epilogue (two warps per TMEM lane quarter)
 constexpr int TG_THREADS = 64 + TG_EPI_THREADS + 32; // warp 0 TMA (activations), warp 1 MMA, last warp TMA (weights)
@@ -53,16 +58,16 @@ struct TapGemmParams {
     const float* bias;      // [N] or nullptr
     const void* residual;   // same layout/dtype(16-bit) as out, or nullptr
     float alpha;
-    float* rowdot;          // optional: rowdot[pixel] += sum_n D[m,n] * dotsrc[pixel*ld_dot + n]
+    acc_t* rowdot;          // optional: rowdot[pixel] += sum_n D[m,n] * dotsrc[pixel*ld_dot + n] (fixed point 2^40)
     const void* dotsrc;
     long long ld_dot;
-    float* gn_sums;         // optional: per (sample, gn_group) {sum, sumsq} of the stored output, fp32 atomics
+    acc_t* gn_sums;         // optional: per (sample, gn_group) {sum, sumsq} of the stored output (fixed point 2^20)
     int gn_cpg, gn_G;       // channels per GroupNorm group, number of groups
     // optional fused GroupNorm(+SiLU) backward reduction over (stored output dy, saved activation x with the output's
     // layout): red[b, g] += {sum(du*gamma), sum(du*gamma*xhat)}; needs gnb_cpg % 16 == 0
-    float* gnb_red;
+    acc_t* gnb_red;           // fixed point 2^40
     const void* gnb_x;
-    const float* gnb_stats;   // forward {sum, sumsq} per (sample, group)
+    const acc_t* gnb_stats;   // forward {sum, sumsq} per (sample, group), fixed point 2^20
     const float* gnb_gamma;
     const float* gnb_beta;
     int gnb_cpg, gnb_silu;

@@ -66,7 +66,7 @@ static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 size_t Wfc::saved_bytes(int B, int H, int W) const {
     const size_t rows = static_cast<size_t>(B) * H * W;
-    return 256 + 2 * align256(rows * T_pad * 2) + 2 * align256(rows * 4);
+    return 256 + 2 * align256(rows * T_pad * 2) + align256(rows * 4) + align256(rows * sizeof(acc_t));
 }
 
 struct SavedView {
@@ -74,7 +74,7 @@ struct SavedView {
     uint8_t* wave;
     uint8_t* a;
     float* rowsum;
-    float* rowdot;
+    acc_t* rowdot;  // fixed point 2^40
 };
 static SavedView view_saved(void* saved, size_t rows, int T_pad) {
     SavedView v;
@@ -87,7 +87,7 @@ static SavedView view_saved(void* saved, size_t rows, int T_pad) {
     p += align256(rows * T_pad * 2);
     v.rowsum = reinterpret_cast<float*>(p);
     p += align256(rows * 4);
-    v.rowdot = reinterpret_cast<float*>(p);
+    v.rowdot = reinterpret_cast<acc_t*>(p);
     return v;
 }
 
@@ -122,7 +122,7 @@ int Wfc::forward(const void* in, int is_logits, int B, int H, int W, float stren
     hdr_saved = saved;
     if (is_logits) CK(wave_softmax(in, v.wave, v.rowsum, static_cast<long long>(rows), T_pad, T, bf16, s));
     else CK(wave_rowsum(in, v.rowsum, static_cast<long long>(rows), T_pad, T, bf16, s));
-    CUDA_CK(cudaMemsetAsync(v.rowdot, 0, rows * sizeof(float), s));
+    CUDA_CK(cudaMemsetAsync(v.rowdot, 0, rows * sizeof(acc_t), s));
     if (op_wave != wave || op_a != v.a || op_B != B || op_H != H || op_W != W) {
         memset(&op, 0, sizeof(op));
         TapGemmParams& p = op.p;
