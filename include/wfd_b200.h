@@ -119,6 +119,36 @@ WFD_API int wfd_guidance_step(wfd_decoder* d, wfd_wfc* h, const void* z, int z_d
                       void* wfc_saved, float* loss, float* dz, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Row bands: ONE large map (BASELINE config 4, 256x256) split along y over R GPUs, one band of h/R rows per rank.
+ * The reference runs such a map on one device (pipeline_wfd.py:283-290 only widens width/height); cutting the plane
+ * turns its single-device ops into exchanges between neighbouring bands: a one-row halo for every 3x3 conv
+ * (resnet.py:416,432, wf_vae.py:218,232) and for the vertical WFC pairs (losses.py:60-66), an all-reduce of the
+ * GroupNorm sums (resnet.py:407,423) and of the loss (losses.py:69-75), an all-gather of the mid-block keys/values and
+ * a reduce-scatter of their gradients (attention.py:329-380).
+ *
+ * wfd_comm: the exchange transport. NCCL (one process per GPU; `libnccl_path` names the libnccl the process already
+ * uses, e.g. torch's bundled one; the 128-byte id comes from rank 0 via wfd_comm_unique_id and travels to the other
+ * ranks by whatever channel the host has) or an in-process loopback group (R bands on one GPU, one host thread per
+ * band; for tests).
+ * A band decoder takes the WHOLE latent plane z [1,4,h,w] in wfd_decoder_forward / wfd_guidance_step and produces the
+ * logits / dz of its own rows only: logits [h/R * w, T_pad], dz fp32 [1,4,h/R,w]. The loss is the map's on every rank.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct wfd_comm wfd_comm;
+typedef struct wfd_loop_group wfd_loop_group;
+WFD_API int wfd_comm_unique_id(const char* libnccl_path, void* id128);
+WFD_API int wfd_comm_create_nccl(const char* libnccl_path, const void* id128, int rank, int nranks, wfd_comm** out);
+WFD_API wfd_loop_group* wfd_loop_group_create(int nranks);
+WFD_API void wfd_loop_group_destroy(wfd_loop_group* g);
+WFD_API int wfd_comm_create_loopback(wfd_loop_group* g, int rank, wfd_comm** out);
+WFD_API void wfd_comm_destroy(wfd_comm* c);
+/* h is the height of the whole latent plane; batch is 1 */
+WFD_API int wfd_decoder_create_band(const wfd_decoder_config* cfg, int h, int w, int rank, int nranks, int dtype16,
+                                    wfd_decoder** out);
+WFD_API int wfd_decoder_attach_comm(wfd_decoder* d, wfd_comm* c);
+/* after this, wfd_wfc_forward takes the band's logits (B = 1, H = H_total / nranks) */
+WFD_API int wfd_wfc_attach_comm(wfd_wfc* h, wfd_comm* c, int H_total);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Wave argmax into tiles: numpy.argmax(wave, axis=-1) (wfd/webui/ui.py:228, README.md:90-91)
  * x: [rows, n] contiguous, dtype 0 = fp32, 1 = fp16, 2 = bf16; out: int64 [rows]. First maximum wins, NaN is maximal.
  * ---------------------------------------------------------------------------------------------------------------- */

@@ -205,6 +205,9 @@ def test_argmax_numpy_semantics(dtype):
     y = torch.randn(5, 7, 1032).to(dtype)
     assert np.array_equal(argmax_tiles(y.cuda()).cpu().numpy(), np.argmax(y.float().numpy(), axis=-1))
     assert argmax_tiles(torch.zeros(0, 128, dtype=dtype, device="cuda")).shape == (0,)
+    # rows that do not start 16-byte aligned (the ice tileset's 3074 real tiles cut out of the 3200 padded channels)
+    w = torch.randn(9, 3074).to(dtype)
+    assert np.array_equal(argmax_tiles(w.cuda()).cpu().numpy(), np.argmax(w.float().numpy(), axis=-1))
 
 
 def test_batch_properties_full_size():

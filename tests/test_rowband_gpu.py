@@ -1,0 +1,110 @@
+"""Row-band plans (one map split along y) against the single-plan path and the reference's golden vectors.
+
+The bands run on ONE GPU here, each on its own host thread and CUDA stream, exchanging through the library's in-process
+loopback transport; `scripts/band_nccl_check.py` repeats the comparison over NCCL with one process per GPU.
+
+What must hold: cutting the plane changes no arithmetic in the forward pass (GroupNorm sums are fixed-point integers,
+every conv / attention row accumulates in the same order), so the band logits are BIT-EXACT against the single plan;
+backward differs only in the fp32 summation order of the key/value gradients over the bands.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from wavefunctiondiffusion_b200 import _native as nat
+from wavefunctiondiffusion_b200.utils.tilesets import load_wfc_mats
+from wavefunctiondiffusion_b200.wf_diffusers.native_ops import GuidanceLossFunction, argmax_tiles
+from wavefunctiondiffusion_b200.wf_diffusers.rowband import BandGuidance, run_loopback
+from wavefunctiondiffusion_b200.wf_diffusers.wf_vae import AutoencoderTile
+from wavefunctiondiffusion_b200.wfdf.losses import WFCLossEinsum
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _rel(a, b):
+    a = torch.as_tensor(np.asarray(a), dtype=torch.float64)
+    b = torch.as_tensor(np.asarray(b), dtype=torch.float64)
+    return ((a - b).norm() / b.norm()).item()
+
+
+def _single(net, mats, lat, in_scale, strength, t_pad):
+    wfc_loss = WFCLossEinsum(mats[0], mats[1]).cuda()
+    handle = wfc_loss.native_handle(t_pad, lat.device)
+    x = lat.clone().requires_grad_()
+    loss = GuidanceLossFunction.apply(x, net._native, handle, in_scale, strength)
+    (grad,) = torch.autograd.grad(loss.sum(), x)
+    plan = net._native.plan(1, lat.shape[2], lat.shape[3], lat.device)
+    logits = plan.logits_view(1).float().clone()
+    tiles = argmax_tiles(handle.wave_view(1, plan.H, plan.W)[..., : mats[0].shape[0]].float().contiguous())
+    torch.cuda.synchronize()
+    return loss.cpu(), grad.cpu(), logits.cpu(), tiles.cpu()
+
+
+def _banded(net, mats, lat, in_scale, strength, R):
+    h, w = lat.shape[2], lat.shape[3]
+    T = mats[0].shape[0]
+    torch.cuda.synchronize()
+
+    def fn(rank, comm):
+        bg = BandGuidance(net, mats[0], mats[1], h, w, comm, lat.device)
+        loss, dz = bg.step(lat, in_scale, strength)
+        logits = bg.plan.logits_view(1).float().clone()
+        tiles = argmax_tiles(bg.wave()[..., :T].float().contiguous())
+        torch.cuda.current_stream().synchronize()
+        return loss.cpu(), dz.cpu(), logits.cpu(), tiles.cpu()
+
+    outs = run_loopback(R, fn)
+    losses = [o[0] for o in outs]
+    for l in losses[1:]:
+        assert torch.equal(l, losses[0]), "every band must hold the same (all-reduced) loss"
+    return (losses[0], torch.cat([o[1] for o in outs], dim=2), torch.cat([o[2] for o in outs], dim=2),
+            torch.cat([o[3] for o in outs], dim=1))
+
+
+@pytest.mark.parametrize("R", [1, 2, 4])
+def test_band_plan_matches_single_plan_tiny_arch(R):
+    z = np.load(os.path.join(GOLD, "tiny_step.npz"))
+    cfg = json.loads(str(z["cfg_json"]))
+    T = int(z["T"])
+    mats = np.unpackbits(z["mats"])[: 2 * T * T].reshape(2, T, T).astype(bool)
+    torch.manual_seed(int(z["seed"]))
+    net = AutoencoderTile(**cfg).eval().cuda()
+    g = torch.Generator().manual_seed(11)
+    lat = (torch.randn(1, 4, 32, 32, generator=g) * 0.8).cuda()
+    ref = _single(net, mats, lat, 1.0 / 0.18215, 5.0, cfg["out_channels"])
+    got = _banded(net, mats, lat, 1.0 / 0.18215, 5.0, R)
+    assert torch.equal(got[2], ref[2]), "band logits must be bit-exact (rel %.3e)" % _rel(got[2], ref[2])
+    assert torch.equal(got[3], ref[3])
+    assert abs(got[0].item() - ref[0].item()) <= 1e-6 * abs(ref[0].item())
+    assert _rel(got[1], ref[1]) < 2e-3
+
+
+@pytest.mark.parametrize("R", [2, 4])
+def test_band_plan_ice_config1_against_reference_golden(R):
+    """BASELINE config 1 weights and latents cut into R bands: same tolerances as the single-plan parity test."""
+    z = np.load(os.path.join(GOLD, "ice_c1_step.npz"))
+    cfg = json.loads(str(z["cfg_json"]))
+    mats = load_wfc_mats("ice_64x64")
+    torch.manual_seed(int(z["seed"]))
+    net = AutoencoderTile(**cfg).eval().cuda()
+    lat = torch.from_numpy(z["latents"]).cuda()
+    loss, grad, _, _ = _banded(net, mats, lat, 1.0 / 0.18215, 5.0, R)
+    assert abs(loss.item() - float(np.asarray(z["loss_f64"]).reshape(-1)[0])) <= 1e-3 * abs(float(np.asarray(z["loss_f64"]).reshape(-1)[0]))
+    assert _rel(grad, z["grad_f64"]) < 5e-2
+
+
+def test_band_shape_errors():
+    z = np.load(os.path.join(GOLD, "tiny_step.npz"))
+    cfg = json.loads(str(z["cfg_json"]))
+    torch.manual_seed(0)
+    net = AutoencoderTile(**cfg).eval().cuda()
+    from wavefunctiondiffusion_b200.wf_diffusers.native_ops import DecoderPlan
+
+    with pytest.raises(nat.WfdError):
+        DecoderPlan(net, 30, 32, 1, 1, torch.device("cuda"), band=(0, 4))  # 30 rows do not split into 4 bands
+    with pytest.raises(nat.WfdError):
+        DecoderPlan(net, 32, 32, 2, 1, torch.device("cuda"), band=(0, 2))  # one map per band plan

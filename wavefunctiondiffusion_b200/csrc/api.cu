@@ -12,6 +12,13 @@ struct wfd_decoder {
 struct wfd_wfc {
     Wfc w;
 };
+struct wfd_comm {
+    Comm* c = nullptr;
+    ~wfd_comm() { delete c; }
+};
+struct wfd_loop_group {
+    LoopGroup* g = nullptr;
+};
 
 #define API_CUDA_CK(expr)                                                       \
     do {                                                                        \
@@ -175,8 +182,96 @@ int wfd_wfc_backward(wfd_wfc* h, void* saved, const float* dloss, void* dout, vo
     return h->w.backward(saved, dloss, dout, S(stream));
 }
 void* wfd_wfc_saved_wave(const wfd_wfc* h, void* saved, int B, int H, int W) {
-    (void)h; (void)B; (void)H; (void)W;
-    return saved ? static_cast<uint8_t*>(saved) + 256 : nullptr;
+    (void)B; (void)H;
+    if (!saved) return nullptr;
+    size_t halo = 0;
+    if (h && h->w.band) halo = (static_cast<size_t>(W) * h->w.T_pad * 2 + 255) & ~size_t(255);
+    return static_cast<uint8_t*>(saved) + 256 + halo;
+}
+
+int wfd_comm_unique_id(const char* libnccl_path, void* id128) {
+    if (!id128) return -1;
+    return nccl_unique_id(libnccl_path, id128);
+}
+int wfd_comm_create_nccl(const char* libnccl_path, const void* id128, int rank, int nranks, wfd_comm** out) {
+    if (!id128 || !out) {
+        set_error("wfd_comm_create_nccl: null argument");
+        return -1;
+    }
+    Comm* c = nullptr;
+    int rc = nccl_comm_create(libnccl_path, id128, rank, nranks, &c);
+    if (rc < 0) return rc;
+    *out = new wfd_comm();
+    (*out)->c = c;
+    return 0;
+}
+wfd_loop_group* wfd_loop_group_create(int nranks) {
+    LoopGroup* g = loop_group_create(nranks);
+    if (!g) return nullptr;
+    wfd_loop_group* p = new wfd_loop_group();
+    p->g = g;
+    return p;
+}
+void wfd_loop_group_destroy(wfd_loop_group* g) {
+    if (!g) return;
+    loop_group_destroy(g->g);
+    delete g;
+}
+int wfd_comm_create_loopback(wfd_loop_group* g, int rank, wfd_comm** out) {
+    if (!g || !out) {
+        set_error("wfd_comm_create_loopback: null argument");
+        return -1;
+    }
+    Comm* c = nullptr;
+    int rc = loop_comm_create(g->g, rank, &c);
+    if (rc < 0) return rc;
+    *out = new wfd_comm();
+    (*out)->c = c;
+    return 0;
+}
+void wfd_comm_destroy(wfd_comm* c) { delete c; }
+
+int wfd_decoder_create_band(const wfd_decoder_config* cfg, int h, int w, int rank, int nranks, int dtype16,
+                            wfd_decoder** out) {
+    if (!cfg || !out) {
+        set_error("wfd_decoder_create_band: null argument");
+        return -1;
+    }
+    if (rank < 0) {
+        set_error("wfd_decoder_create_band: negative rank");
+        return -3;
+    }
+    wfd_decoder* p = new (std::nothrow) wfd_decoder();
+    if (!p) {
+        set_error("wfd_decoder_create_band: out of host memory");
+        return -1;
+    }
+    int rc = p->d.init(*cfg, h, w, 1, dtype16, rank, nranks);
+    if (rc < 0) {
+        delete p;
+        return rc;
+    }
+    *out = p;
+    return 0;
+}
+int wfd_decoder_attach_comm(wfd_decoder* d, wfd_comm* c) {
+    if (!d || !c || !c->c) {
+        set_error("wfd_decoder_attach_comm: null argument");
+        return -1;
+    }
+    if (!d->d.band || c->c->nranks != d->d.band_R || c->c->rank != d->d.band_r) {
+        set_error("wfd_decoder_attach_comm: communicator rank/size does not match the band plan");
+        return -3;
+    }
+    d->d.comm = c->c;
+    return 0;
+}
+int wfd_wfc_attach_comm(wfd_wfc* h, wfd_comm* c, int H_total) {
+    if (!h || !c || !c->c) {
+        set_error("wfd_wfc_attach_comm: null argument");
+        return -1;
+    }
+    return h->w.set_band(c->c, H_total);
 }
 
 int wfd_guidance_step(wfd_decoder* d, wfd_wfc* h, const void* z, int z_dtype, int B, float in_scale, float strength,

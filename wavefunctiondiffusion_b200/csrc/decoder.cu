@@ -191,10 +191,30 @@ Decoder::~Decoder() {
         if (kv.second) cudaFree(kv.second);
 }
 
-int Decoder::init(const wfd_decoder_config& c, int h_, int w_, int Bmax, int dtype16) {
+int Decoder::init(const wfd_decoder_config& c, int h_, int w_, int Bmax, int dtype16, int band_rank, int band_nranks) {
     cfg = c;
     h = h_;
     w = w_;
+    if (band_rank >= 0) {
+        // row-band plan: this handle decodes rows [band_rank * h/R, (band_rank + 1) * h/R) of one h x w latent plane
+        if (band_nranks < 1 || band_rank >= band_nranks || h_ % band_nranks != 0 || Bmax != 1) {
+            set_error("decoder: row bands need batch 1 and a plane height (%d) divisible by the rank count (%d)", h_,
+                      band_nranks);
+            return -3;
+        }
+        for (int i = 0; i < c.n_blocks; ++i)
+            if (c.block_down[i]) {
+                set_error("decoder: row bands do not support DownDecoderBlock2D configs");
+                return -3;
+            }
+        band = true;
+        band_R = band_nranks;
+        band_r = band_rank;
+        h_total = h_;
+        h = h_ / band_nranks;
+    } else {
+        h_total = h_;
+    }
     B_max = Bmax;
     bf16 = dtype16 ? 1 : 0;
     G = c.norm_num_groups;
@@ -282,7 +302,7 @@ void Decoder::layout_workspace() {
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t o = off;
-        off += (bytes + 255) & ~size_t(255);
+        off += ((bytes + 255) & ~size_t(255)) + halo_pad;
         return o;
     };
     const size_t e = 2;  // bytes per 16-bit element
@@ -290,6 +310,11 @@ void Decoder::layout_workspace() {
     const size_t hw = static_cast<size_t>(h) * w;
     int maxC = Cm;
     for (const ResnetDesc& r : resnets) maxC = std::max(maxC, std::max(r.cin, r.cout));
+    if (band) {
+        // every buffer keeps one row of its widest tenant free on both sides: the halo rows of the 3x3 contractions
+        halo_pad = (static_cast<size_t>(w) * std::max(std::max(maxC, T_pad), 3 * Cm) * e + 255) & ~size_t(255);
+        off = halo_pad;
+    }
     o_x0 = take(B * hw * Cm * e);
     o_res_h1.clear();
     o_res_out.clear();
@@ -310,23 +335,25 @@ void Decoder::layout_workspace() {
         }
     }
     // attention
-    const size_t N = hw;
+    // N queries (this band's pixels) attend over Nk keys (the whole plane)
+    const size_t N = hw, Nk = hw * band_R;
     o_attn_out = take(B * N * Cm * e);
     o_xn = take(B * N * Cm * e);
-    o_qkv = take(B * N * 3 * Cm * e);
-    o_vt = take(B * Cm * N * e);
-    o_S = take(B * N * N * 4);
-    o_P = take(B * N * N * e);
+    o_qkv = take(B * Nk * 3 * Cm * e);
+    o_vt = take(B * Cm * Nk * e);
+    o_S = take(B * N * Nk * 4);
+    o_P = take(B * N * Nk * e);
     o_O = take(B * N * Cm * e);
     // backward-only attention scratch
-    o_PT = take(B * N * N * e);
-    o_dS = take(B * N * N * e);
-    o_dST = take(B * N * N * e);
+    o_PT = take(B * N * Nk * e);
+    o_dS = take(B * N * Nk * e);
+    o_dST = take(B * N * Nk * e);
     o_dO = take(B * N * Cm * e);
     o_dOT = take(B * Cm * N * e);
-    o_KT = take(B * Cm * N * e);
+    o_KT = take(B * Cm * Nk * e);
     o_QT = take(B * Cm * N * e);
     o_dqkv = take(B * N * 3 * Cm * e);
+    o_dkv = band_R > 1 ? take(Nk * 2 * Cm * 4) : 0;
     // scratch
     o_act = take(B * hw * maxC * e);
     o_act2 = take(B * hw * maxC * e);
@@ -532,6 +559,9 @@ int Decoder::conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int 
     memset(&op, 0, sizeof(op));
     TapGemmParams& p = op.p;
     int wb = 0, hb = 0;
+    bool vertical = false;  // any tap that leaves the output row: its input needs the neighbour bands' edge rows
+    for (int t = 0; t < pk.n_taps; ++t) vertical |= pk.dy[t] != 0;
+    if (band && vertical) CK(halo_rows(ex, const_cast<void*>(A), Hin, Win, a_C));
     if (ex.prepare) {
         if (!pick_box(Wout, Hout, &wb, &hb)) {
             set_error("decoder: cannot tile %dx%d plane", Hout, Wout);
@@ -588,6 +618,11 @@ int Decoder::conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int 
         p.a_C = a_C;
         p.a_W = Win;
         p.a_H = Hin;
+        if (band && vertical) {  // the view starts at the top halo row
+            p.a_ptr = static_cast<const uint8_t*>(A) - static_cast<size_t>(Win) * a_C * 2;
+            p.a_H = Hin + 2;
+            p.a_y_off = 1;
+        }
         p.a_B = B_max;
         p.a_ld = a_C;
         p.b_ptr = pk.Bm;
@@ -686,6 +721,48 @@ int Decoder::plain_gemm(Exec& ex, const PlainGemm& g) {
     return run_gemm(ex, op, g.a_shared);
 }
 
+// ---- row-band exchanges (no-ops outside band plans)
+int Decoder::sync_sums(Exec& ex, acc_t* slot) {
+    if (!band || ex.prepare || band_R == 1) return 0;
+    if (!comm) {
+        set_error("decoder: row-band plan without an attached communicator");
+        return -12;
+    }
+    return comm->allreduce_i64(slot, static_cast<size_t>(G) * 2, ex.stream);
+}
+int Decoder::halo_rows(Exec& ex, void* buf, int rows, int W, int C) {
+    if (!band || ex.prepare) return 0;
+    const size_t rb = static_cast<size_t>(W) * C * 2;
+    uint8_t* b = static_cast<uint8_t*>(buf);
+    uint8_t* top = b - rb;
+    uint8_t* bottom = b + static_cast<size_t>(rows) * rb;
+    if (band_R == 1) {
+        CUDA_CK(cudaMemsetAsync(top, 0, rb, ex.stream));
+        CUDA_CK(cudaMemsetAsync(bottom, 0, rb, ex.stream));
+        return 0;
+    }
+    if (!comm) {
+        set_error("decoder: row-band plan without an attached communicator");
+        return -12;
+    }
+    return comm->halo(top, b, b + static_cast<size_t>(rows - 1) * rb, bottom, rb, ex.stream);
+}
+// GroupNorm(+SiLU) backward; in a band plan the two reduction sums are completed over the bands before the apply pass
+int Decoder::gn_backward(Exec& ex, const void* dy, const void* x, int gn_idx, const float* gamma, const float* beta,
+                         const void* add, void* dx, int HW, int C, int silu, int do_reduce) {
+    const float eps = 1e-6f;
+    if (!band)
+        return gn_bwd(dy, x, gn_sums_ptr(gn_idx), gamma, beta, gn_red_ptr(gn_idx), add, dx, ex.B, HW, C, G, eps, silu, bf16,
+                      do_reduce, ex.stream);
+    const int HW_stat = HW * band_R;
+    if (do_reduce)
+        CK(gn_bwd_reduce(dy, x, gn_sums_ptr(gn_idx), gamma, beta, gn_red_ptr(gn_idx), ex.B, HW, C, G, eps, silu, bf16,
+                         ex.stream, HW_stat));
+    CK(sync_sums(ex, gn_red_ptr(gn_idx)));
+    return gn_bwd_apply(dy, x, gn_sums_ptr(gn_idx), gamma, beta, gn_red_ptr(gn_idx), add, dx, ex.B, HW, C, G, eps, silu, bf16,
+                        ex.stream, HW_stat);
+}
+
 acc_t* Decoder::gn_sums_ptr(int idx) const {
     return reinterpret_cast<acc_t*>(ws + o_gn) + static_cast<size_t>(idx) * B_max * G * 2;
 }
@@ -703,7 +780,8 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
     if (!ex.prepare) {
         CUDA_CK(cudaMemsetAsync(ws + o_gn, 0, static_cast<size_t>(n_gn) * B_max * G * 2 * sizeof(acc_t), s));
         CK(latent_in(z, z_f16, in_scale, vecs["post_quant_conv.weight"], vecs["post_quant_conv.bias"],
-                     vecs["decoder.conv_in.weight"], vecs["decoder.conv_in.bias"], x, B, h, w, Cm, bf16, s));
+                     vecs["decoder.conv_in.weight"], vecs["decoder.conv_in.bias"], x, B, h, w, Cm, bf16, s, band_r * h,
+                     h_total));
     }
     int cur_h = h, cur_w = w;
     int ri = 0;
@@ -723,16 +801,18 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
         int next_cpg = r.cout / G;
         if (!ex.prepare) {
             if (!stats_ready || !fused_ok(r.cin)) CK(gn_stats(xin, gn_sums_ptr(gi1), B, phw, r.cin, G, bf16, s));
+            CK(sync_sums(ex, gn_sums_ptr(gi1)));
             CK(gn_apply(xin, gn_sums_ptr(gi1), vecs[r.prefix + ".norm1.weight"], vecs[r.prefix + ".norm1.bias"], act, B,
-                        phw, r.cin, G, eps, 1, bf16, s));
+                        phw, r.cin, G, eps, 1, bf16, s, phw * band_R));
         }
         const ConvW& c1 = convs[r.prefix + ".conv1"];
         CK(conv_gemm(ex, c1.fwd, act, r.cin, r.h, r.w, r.h, r.w, h1, r.cout, c1.bias, nullptr, gn_sums_ptr(gi2),
                      r.cout / G, nullptr, nullptr));
         if (!ex.prepare) {
             if (!fused_ok(r.cout)) CK(gn_stats(h1, gn_sums_ptr(gi2), B, phw, r.cout, G, bf16, s));
+            CK(sync_sums(ex, gn_sums_ptr(gi2)));
             CK(gn_apply(h1, gn_sums_ptr(gi2), vecs[r.prefix + ".norm2.weight"], vecs[r.prefix + ".norm2.bias"], act2, B,
-                        phw, r.cout, G, eps, 1, bf16, s));
+                        phw, r.cout, G, eps, 1, bf16, s, phw * band_R));
         }
         const void* residual = xin;
         if (r.cin != r.cout) {
@@ -756,19 +836,22 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
     CK(resnet(0, x, false));  // conv_in is not a tapgemm: its output statistics need the standalone pass
     x = ws + o_res_out[0];
     {
-        // AttentionBlock.forward (attention.py:329-380), one head of Cm channels
-        const int N = hw;
+        // AttentionBlock.forward (attention.py:329-380), one head of Cm channels. N queries (this band's pixels)
+        // attend over Nk keys; in a band plan the q|k|v rows of all bands are gathered into one [Nk, 3*Cm] block
+        const int N = hw, Nk = hw * band_R;
         uint8_t* xn = ws + o_xn;
-        uint8_t* qkv = ws + o_qkv;
+        uint8_t* qkv_all = ws + o_qkv;
+        uint8_t* qkv = qkv_all + static_cast<size_t>(band_r) * N * 3 * Cm * 2;  // this band's rows
         const std::string a = "decoder.mid_block.attentions.0.";
         if (!ex.prepare) {
             if (!fused_ok(Cm)) CK(gn_stats(x, gn_sums_ptr(n_gn - 2), B, N, Cm, G, bf16, s));
+            CK(sync_sums(ex, gn_sums_ptr(n_gn - 2)));
             CK(gn_apply(x, gn_sums_ptr(n_gn - 2), vecs[a + "group_norm.weight"], vecs[a + "group_norm.bias"], xn, B, N,
-                        Cm, G, eps, 0, bf16, s));
+                        Cm, G, eps, 0, bf16, s, N * band_R));
         }
         const ConvW& cq = convs["attn.qkv"];
         const int bn_c = Cm % 192 == 0 ? 192 : (Cm % 128 == 0 ? 128 : (Cm % 64 == 0 ? 64 : 16));
-        const int bn_n = N % 256 == 0 ? 256 : 128;
+        const int bn_n = Nk % 256 == 0 ? 256 : 128;
         PlainGemm g;
         memset(&g, 0, sizeof(g));
         // q | k | v = xn W^T + b
@@ -777,22 +860,23 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
         g.BN = cq.fwd.BN; g.N = 3 * Cm; g.out = qkv; g.out_fp32 = 0; g.ldc = 3 * Cm; g.c_zstride = 0;
         g.bias = cq.bias; g.residual = nullptr; g.alpha = 1.f;
         CK(plain_gemm(ex, g));
+        if (!ex.prepare && band_R > 1) CK(comm->allgather(qkv_all, static_cast<size_t>(N) * 3 * Cm * 2, s));
         // v^T per sample (the B operand of P V must be K-major along the key tokens)
         if (!ex.prepare)
-            CK(transpose16(qkv + static_cast<size_t>(2 * Cm) * 2, ws + o_vt, B, N, Cm, 3 * Cm,
-                           static_cast<long long>(N) * 3 * Cm, s));
+            CK(transpose16(qkv_all + static_cast<size_t>(2 * Cm) * 2, ws + o_vt, B, Nk, Cm, 3 * Cm,
+                           static_cast<long long>(Nk) * 3 * Cm, s));
         // scores = q k^T / sqrt(C) in fp32
         memset(&g, 0, sizeof(g));
         g.A = qkv; g.K = Cm; g.a_ld = 3 * Cm; g.rows_per_sample = N; g.a_B = B_max; g.a_shared = false;
-        g.Bm = qkv + static_cast<size_t>(Cm) * 2; g.b_rows = N; g.ldb = 3 * Cm;
-        g.b_zstride = static_cast<long long>(N) * 3 * Cm; g.b_Z = B_max; g.b_per_sample = true;
-        g.BN = bn_n; g.N = N; g.out = ws + o_S; g.out_fp32 = 1; g.ldc = N; g.alpha = 1.f / sqrtf(static_cast<float>(Cm));
+        g.Bm = qkv_all + static_cast<size_t>(Cm) * 2; g.b_rows = Nk; g.ldb = 3 * Cm;
+        g.b_zstride = static_cast<long long>(Nk) * 3 * Cm; g.b_Z = B_max; g.b_per_sample = true;
+        g.BN = bn_n; g.N = Nk; g.out = ws + o_S; g.out_fp32 = 1; g.ldc = Nk; g.alpha = 1.f / sqrtf(static_cast<float>(Cm));
         CK(plain_gemm(ex, g));
-        if (!ex.prepare) CK(attn_softmax(reinterpret_cast<const float*>(ws + o_S), ws + o_P, static_cast<long long>(B) * N, N, bf16, s));
+        if (!ex.prepare) CK(attn_softmax(reinterpret_cast<const float*>(ws + o_S), ws + o_P, static_cast<long long>(B) * N, Nk, bf16, s));
         // o = p v
         memset(&g, 0, sizeof(g));
-        g.A = ws + o_P; g.K = N; g.a_ld = N; g.rows_per_sample = N; g.a_B = B_max; g.a_shared = false;
-        g.Bm = ws + o_vt; g.b_rows = Cm; g.ldb = N; g.b_zstride = static_cast<long long>(Cm) * N; g.b_Z = B_max;
+        g.A = ws + o_P; g.K = Nk; g.a_ld = Nk; g.rows_per_sample = N; g.a_B = B_max; g.a_shared = false;
+        g.Bm = ws + o_vt; g.b_rows = Cm; g.ldb = Nk; g.b_zstride = static_cast<long long>(Cm) * Nk; g.b_Z = B_max;
         g.b_per_sample = true; g.BN = bn_c; g.N = Cm; g.out = ws + o_O; g.out_fp32 = 0; g.ldc = Cm;
         g.alpha = 1.f;
         CK(plain_gemm(ex, g));
@@ -833,8 +917,9 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
     const bool last_down = down_after[cfg.n_blocks - 1] != 0;
     if (!ex.prepare) {
         if (!fused_ok(C_last) || last_down) CK(gn_stats(x, gn_sums_ptr(n_gn - 1), B, H_out * W_out, C_last, G, bf16, s));
+        CK(sync_sums(ex, gn_sums_ptr(n_gn - 1)));
         CK(gn_apply(x, gn_sums_ptr(n_gn - 1), vecs["decoder.conv_norm_out.weight"], vecs["decoder.conv_norm_out.bias"],
-                    ws + o_act, B, H_out * W_out, C_last, G, eps, 1, bf16, s));
+                    ws + o_act, B, H_out * W_out, C_last, G, eps, 1, bf16, s, H_out * W_out * band_R));
     }
     const ConvW& co = convs["decoder.conv_out"];
     CK(conv_gemm(ex, co.fwd, ws + o_act, C_last, H_out, W_out, H_out, W_out, ws + o_logits, T_pad, co.bias, nullptr,
@@ -867,7 +952,7 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         gb.beta = vecs[norm + ".bias"];
         gb.cpg = C / G;
         gb.silu = silu;
-        gb.inv_n = 1.f / (static_cast<float>(C / G) * static_cast<float>(px));
+        gb.inv_n = 1.f / (static_cast<float>(C / G) * static_cast<float>(px) * static_cast<float>(band_R));
         gb.eps = eps;
         return gb;
     };
@@ -882,9 +967,9 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
                      nullptr, &gb));
     }
     if (!ex.prepare) {
-        CK(gn_bwd(gbuf(cur), x_last, gn_sums_ptr(n_gn - 1), vecs["decoder.conv_norm_out.weight"],
-                  vecs["decoder.conv_norm_out.bias"], gn_red_ptr(n_gn - 1), nullptr, gbuf(cur), B, H_out * W_out, C_last, G,
-                  eps, 1, bf16, fuse_ok(C_last) ? 0 : 1, s));
+        CK(gn_backward(ex, gbuf(cur), x_last, n_gn - 1, vecs["decoder.conv_norm_out.weight"],
+                       vecs["decoder.conv_norm_out.bias"], nullptr, gbuf(cur), H_out * W_out, C_last, 1,
+                       fuse_ok(C_last) ? 0 : 1));
     }
     auto resnet_bwd = [&](int idx, const uint8_t* xin) -> int {
         const ResnetDesc& r = resnets[idx];
@@ -903,8 +988,7 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         if (!ex.prepare) {
             const float* ga = vecs[r.prefix + ".norm2.weight"];
             const float* be = vecs[r.prefix + ".norm2.bias"];
-            CK(gn_bwd(t1, h1, gn_sums_ptr(gi2), ga, be, gn_red_ptr(gi2), nullptr, t1, B, phw, r.cout, G, eps, 1, bf16,
-                      fuse_ok(r.cout) ? 0 : 1, s));
+            CK(gn_backward(ex, t1, h1, gi2, ga, be, nullptr, t1, phw, r.cout, 1, fuse_ok(r.cout) ? 0 : 1));
         }
         const ConvW& c1 = convs[r.prefix + ".conv1"];
         {
@@ -920,8 +1004,7 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         if (!ex.prepare) {
             const float* ga = vecs[r.prefix + ".norm1.weight"];
             const float* be = vecs[r.prefix + ".norm1.bias"];
-            CK(gn_bwd(t2, xin, gn_sums_ptr(gi1), ga, be, gn_red_ptr(gi1), add, t2, B, phw, r.cin, G, eps, 1, bf16,
-                      fuse_ok(r.cin) ? 0 : 1, s));
+            CK(gn_backward(ex, t2, xin, gi1, ga, be, add, t2, phw, r.cin, 1, fuse_ok(r.cin) ? 0 : 1));
         }
         cur = (cur + 2) & 3;
         return 0;
@@ -963,17 +1046,21 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
     }
     CK(resnet_bwd(1, ws + o_attn_out));
     {
-        // attention backward
-        const int N = hw;
+        // attention backward. In a band plan (N local queries, Nk keys) dQ is complete locally, while dK and dV collect a
+        // term from every band's queries: the fp32 partials [Nk, dK | dV] are reduce-scattered over the bands.
+        const int N = hw, Nk = hw * band_R;
+        const bool split = band_R > 1;
         const std::string a = "decoder.mid_block.attentions.0.";
         uint8_t* dout = gbuf(cur);
         uint8_t* dxn = gbuf(cur + 1);
         const uint8_t* xin = ws + o_res_out[0];
-        const uint8_t* qkv = ws + o_qkv;
+        const uint8_t* qkv_all = ws + o_qkv;
+        const uint8_t* qkv = qkv_all + static_cast<size_t>(band_r) * N * 3 * Cm * 2;
         uint8_t* dqkv = ws + o_dqkv;
+        uint8_t* dkv = ws + o_dkv;
         const ConvW& cp = convs[a + "proj_attn"];
         const int bn_c = Cm % 192 == 0 ? 192 : (Cm % 128 == 0 ? 128 : (Cm % 64 == 0 ? 64 : 16));
-        const int bn_n = N % 256 == 0 ? 256 : 128;
+        const int bn_n = Nk % 256 == 0 ? 256 : 128;
         PlainGemm g;
         // dO = dout Wp
         memset(&g, 0, sizeof(g));
@@ -983,40 +1070,52 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         CK(plain_gemm(ex, g));
         if (!ex.prepare) {
             CK(transpose16(ws + o_dO, ws + o_dOT, B, N, Cm, Cm, static_cast<long long>(N) * Cm, s));
-            CK(transpose16(ws + o_P, ws + o_PT, B, N, N, N, static_cast<long long>(N) * N, s));
+            CK(transpose16(ws + o_P, ws + o_PT, B, N, Nk, Nk, static_cast<long long>(N) * Nk, s));
             CK(transpose16(qkv, ws + o_QT, B, N, Cm, 3 * Cm, static_cast<long long>(N) * 3 * Cm, s));
-            CK(transpose16(qkv + static_cast<size_t>(Cm) * 2, ws + o_KT, B, N, Cm, 3 * Cm, static_cast<long long>(N) * 3 * Cm, s));
+            CK(transpose16(qkv_all + static_cast<size_t>(Cm) * 2, ws + o_KT, B, Nk, Cm, 3 * Cm,
+                           static_cast<long long>(Nk) * 3 * Cm, s));
         }
-        // dV = P^T dO  -> dqkv[:, 2C:3C]
+        // dV = P^T dO  -> dqkv[:, 2C:3C] (band plan: partial over this band's queries, fp32)
         memset(&g, 0, sizeof(g));
-        g.A = ws + o_PT; g.K = N; g.a_ld = N; g.rows_per_sample = N; g.a_B = B_max;
+        g.A = ws + o_PT; g.K = N; g.a_ld = N; g.rows_per_sample = Nk; g.a_B = B_max;
         g.Bm = ws + o_dOT; g.b_rows = Cm; g.ldb = N; g.b_zstride = static_cast<long long>(Cm) * N; g.b_Z = B_max;
-        g.b_per_sample = true; g.BN = bn_c; g.N = Cm; g.out = dqkv + static_cast<size_t>(2 * Cm) * 2; g.ldc = 3 * Cm; g.alpha = 1.f;
+        g.b_per_sample = true; g.BN = bn_c; g.N = Cm; g.alpha = 1.f;
+        if (split) { g.out = dkv + static_cast<size_t>(Cm) * 4; g.out_fp32 = 1; g.ldc = 2 * Cm; }
+        else { g.out = dqkv + static_cast<size_t>(2 * Cm) * 2; g.ldc = 3 * Cm; }
         CK(plain_gemm(ex, g));
         // dP = dO V^T (fp32, reuses the score buffer)
         memset(&g, 0, sizeof(g));
         g.A = ws + o_dO; g.K = Cm; g.a_ld = Cm; g.rows_per_sample = N; g.a_B = B_max;
-        g.Bm = qkv + static_cast<size_t>(2 * Cm) * 2; g.b_rows = N; g.ldb = 3 * Cm;
-        g.b_zstride = static_cast<long long>(N) * 3 * Cm; g.b_Z = B_max; g.b_per_sample = true;
-        g.BN = bn_n; g.N = N; g.out = ws + o_S; g.out_fp32 = 1; g.ldc = N; g.alpha = 1.f;
+        g.Bm = qkv_all + static_cast<size_t>(2 * Cm) * 2; g.b_rows = Nk; g.ldb = 3 * Cm;
+        g.b_zstride = static_cast<long long>(Nk) * 3 * Cm; g.b_Z = B_max; g.b_per_sample = true;
+        g.BN = bn_n; g.N = Nk; g.out = ws + o_S; g.out_fp32 = 1; g.ldc = Nk; g.alpha = 1.f;
         CK(plain_gemm(ex, g));
         if (!ex.prepare) {
             CK(attn_softmax_bwd(ws + o_P, reinterpret_cast<const float*>(ws + o_S), ws + o_dS, static_cast<long long>(B) * N,
-                                N, 1.f / sqrtf(static_cast<float>(Cm)), bf16, s));
-            CK(transpose16(ws + o_dS, ws + o_dST, B, N, N, N, static_cast<long long>(N) * N, s));
+                                Nk, 1.f / sqrtf(static_cast<float>(Cm)), bf16, s));
+            CK(transpose16(ws + o_dS, ws + o_dST, B, N, Nk, Nk, static_cast<long long>(N) * Nk, s));
         }
         // dQ = dS K -> dqkv[:, 0:C]
         memset(&g, 0, sizeof(g));
-        g.A = ws + o_dS; g.K = N; g.a_ld = N; g.rows_per_sample = N; g.a_B = B_max;
-        g.Bm = ws + o_KT; g.b_rows = Cm; g.ldb = N; g.b_zstride = static_cast<long long>(Cm) * N; g.b_Z = B_max;
+        g.A = ws + o_dS; g.K = Nk; g.a_ld = Nk; g.rows_per_sample = N; g.a_B = B_max;
+        g.Bm = ws + o_KT; g.b_rows = Cm; g.ldb = Nk; g.b_zstride = static_cast<long long>(Cm) * Nk; g.b_Z = B_max;
         g.b_per_sample = true; g.BN = bn_c; g.N = Cm; g.out = dqkv; g.ldc = 3 * Cm; g.alpha = 1.f;
         CK(plain_gemm(ex, g));
         // dK = dS^T Q -> dqkv[:, C:2C]
         memset(&g, 0, sizeof(g));
-        g.A = ws + o_dST; g.K = N; g.a_ld = N; g.rows_per_sample = N; g.a_B = B_max;
+        g.A = ws + o_dST; g.K = N; g.a_ld = N; g.rows_per_sample = Nk; g.a_B = B_max;
         g.Bm = ws + o_QT; g.b_rows = Cm; g.ldb = N; g.b_zstride = static_cast<long long>(Cm) * N; g.b_Z = B_max;
-        g.b_per_sample = true; g.BN = bn_c; g.N = Cm; g.out = dqkv + static_cast<size_t>(Cm) * 2; g.ldc = 3 * Cm; g.alpha = 1.f;
+        g.b_per_sample = true; g.BN = bn_c; g.N = Cm; g.alpha = 1.f;
+        if (split) { g.out = dkv; g.out_fp32 = 1; g.ldc = 2 * Cm; }
+        else { g.out = dqkv + static_cast<size_t>(Cm) * 2; g.ldc = 3 * Cm; }
         CK(plain_gemm(ex, g));
+        if (!ex.prepare && split) {
+            float* part = reinterpret_cast<float*>(dkv);
+            const size_t per_rank = static_cast<size_t>(N) * 2 * Cm;
+            CK(comm->reduce_scatter_f32(part, per_rank, s));
+            CK(cvt_f32_to_16_2d(part + static_cast<size_t>(band_r) * per_rank, 2 * Cm, dqkv + static_cast<size_t>(Cm) * 2,
+                                3 * Cm, N, 2 * Cm, bf16, s));
+        }
         // d xn = [dQ | dK | dV] Wqkv
         const ConvW& cq = convs["attn.qkv"];
         memset(&g, 0, sizeof(g));
@@ -1029,15 +1128,17 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         if (!ex.prepare) {
             const float* ga = vecs[a + "group_norm.weight"];
             const float* be = vecs[a + "group_norm.bias"];
-            CK(gn_bwd(dxn, xin, gn_sums_ptr(n_gn - 2), ga, be, gn_red_ptr(n_gn - 2), dout, dxn, B, N, Cm, G, eps, 0, bf16,
-                      fuse_ok(Cm) ? 0 : 1, s));
+            CK(gn_backward(ex, dxn, xin, n_gn - 2, ga, be, dout, dxn, N, Cm, 0, fuse_ok(Cm) ? 0 : 1));
         }
         cur = (cur + 1) & 3;
     }
     CK(resnet_bwd(0, ws + o_x0));
     if (!ex.prepare)
+    {
+        if (band) CK(halo_rows(ex, gbuf(cur), h, w, Cm));  // conv_in^T reads the neighbour bands' edge rows
         CK(latent_out(gbuf(cur), last_in_scale, scale_b, vecs["post_quant_conv.weight"], vecs["decoder.conv_in.weight.T"],
-                      dz, B, h, w, Cm, bf16, s));
+                      dz, B, h, w, Cm, bf16, s, band_r * h, h_total));
+    }
     return 0;
 }
 

@@ -1,6 +1,7 @@
 // Decoder plan and WFC handle (internal C++ side of the C ABI in include/wfd_b200.h).
 #pragma once
 #include "../../include/wfd_b200.h"
+#include "comm.cuh"
 #include "tapgemm.cuh"
 #include <map>
 #include <string>
@@ -67,6 +68,12 @@ struct Decoder {
     int conv_n_group = 0;  // tile rasterisation of the convs: 0/1 = M fastest (default), k = bands of k N tiles (WFD_CONV_NGROUP)
     int fuse_bwd_max_c = 768;  // largest channel count whose GroupNorm-backward reduction is fused into the conv epilogue
     int use_reuse = 1;  // row-reuse schedule for 3x3 convs whose stage fits (WFD_NO_REUSE=1 disables, for A/B runs)
+    // row bands (one map split along y over band_R ranks): h is the local band height, h_total the map's
+    bool band = false;
+    int band_R = 1, band_r = 0, h_total = 0;
+    Comm* comm = nullptr;   // not owned
+    size_t halo_pad = 0;    // bytes kept free before and after every workspace buffer for the halo rows
+    size_t o_dkv = 0;       // fp32 [Nk, 2*Cm] partial dK | dV of this band's queries (reduce-scattered over the bands)
     std::vector<ResnetDesc> resnets;
     std::vector<int> down_after;
     std::map<std::string, std::vector<float>> host;
@@ -87,7 +94,7 @@ struct Decoder {
     std::vector<TapGemmOp> fwd_ops, bwd_ops;
 
     ~Decoder();
-    int init(const wfd_decoder_config& c, int h, int w, int B_max, int dtype16);
+    int init(const wfd_decoder_config& c, int h, int w, int B_max, int dtype16, int band_rank = -1, int band_nranks = 1);
     void layout_workspace();
     int set_weight(const char* key, const float* data, long long numel);
     int finalize_weights();
@@ -108,6 +115,10 @@ struct Decoder {
     int plain_gemm(Exec& ex, const PlainGemm& g);
     acc_t* gn_sums_ptr(int idx) const;
     acc_t* gn_red_ptr(int idx) const;
+    int sync_sums(Exec& ex, acc_t* slot);
+    int halo_rows(Exec& ex, void* buf, int rows, int W, int C);
+    int gn_backward(Exec& ex, const void* dy, const void* x, int gn_idx, const float* gamma, const float* beta,
+                    const void* add, void* dx, int HW, int C, int silu, int do_reduce);
     int forward_impl(Exec& ex, const void* z, int z_f16, float in_scale);
     int backward_impl(Exec& ex, const void* dlogits, const float* scale_b, float* dz);
 };
@@ -129,6 +140,11 @@ struct Wfc {
     const void* op_wave = nullptr;
     void* op_a = nullptr;
     int op_B = 0, op_H = 0, op_W = 0;
+    // row bands: this handle scores rows [band_r * H, (band_r + 1) * H) of a map of H_total rows
+    bool band = false;
+    int band_R = 1, band_r = 0, H_total = 0;
+    Comm* comm = nullptr;
+    int set_band(Comm* c, int H_total);
     ~Wfc();
     int init(const uint8_t* mat_x, const uint8_t* mat_y, int T, int T_pad, int dtype16);
     size_t saved_bytes(int B, int H, int W) const;

@@ -133,7 +133,9 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_k(const uint4* __restrict
         for (int k = 0; k < m.cpt; ++k) {
             const int col = tcol + k * m.nvt;
             if (col >= m.nv) break;
-            float s = 0.f, ss = 0.f;
+            // every 8-channel vector goes to fixed point on its own, so the sums do not depend on how pixels are split
+            // over threads, blocks or row bands (integer addition is associative)
+            unsigned long long is = 0ull, iss = 0ull;
             const uint4* px = x + (static_cast<long long>(b) * HW) * m.nv + col;
             constexpr int U = 4;
             for (int p = p0 + trow; p < p1; p += U * m.R) {
@@ -146,16 +148,19 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_k(const uint4* __restrict
                     if (p + u * m.R >= p1) break;
                     float f[8];
                     unpack8<BF16>(raw[u], f);
+                    float s = 0.f, ss = 0.f;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         s += f[j];
                         ss += f[j] * f[j];
                     }
+                    is += to_fx(s, WFD_FX_STATS);
+                    iss += to_fx(ss, WFD_FX_STATS);
                 }
             }
             const int g = (col * 8) / cpg;
-            atomicAdd(&sh[2 * g], to_fx(s, WFD_FX_STATS));
-            atomicAdd(&sh[2 * g + 1], to_fx(ss, WFD_FX_STATS));
+            atomicAdd(&sh[2 * g], is);
+            atomicAdd(&sh[2 * g + 1], iss);
         }
     }
     __syncthreads();
@@ -174,7 +179,8 @@ __device__ __forceinline__ float sigmoidf_(float u) {
 template <bool BF16>
 __global__ void __launch_bounds__(GN_THREADS, 3)
 gn_apply_k(const uint4* __restrict__ x, const acc_t* __restrict__ sums, const float* __restrict__ gamma,
-           const float* __restrict__ beta, uint4* __restrict__ y, int HW, int C, int G, float eps, int silu, int ppb) {
+           const float* __restrict__ beta, uint4* __restrict__ y, int HW, int HW_stat, int C, int G, float eps, int silu,
+           int ppb) {
     const GnMap m = gn_map(C);
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * ppb, p1 = min(HW, p0 + ppb);
@@ -185,7 +191,7 @@ gn_apply_k(const uint4* __restrict__ x, const acc_t* __restrict__ sums, const fl
         const int col = tcol + k * m.nvt;
         if (col >= m.nv) break;
         float mean, rstd;
-        gn_finalize(sums, b, (col * 8) / cpg, G, static_cast<double>(cpg) * HW, eps, mean, rstd);
+        gn_finalize(sums, b, (col * 8) / cpg, G, static_cast<double>(cpg) * HW_stat, eps, mean, rstd);
         float sc[8], sh[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -220,7 +226,7 @@ template <bool BF16>
 __global__ void __launch_bounds__(GN_THREADS, 3)
 gn_bwd_reduce_k(const uint4* __restrict__ dy, const uint4* __restrict__ x, const acc_t* __restrict__ sums,
                 const float* __restrict__ gamma, const float* __restrict__ beta, acc_t* __restrict__ red, int HW,
-                int C, int G, float eps, int silu, int ppb) {
+                int HW_stat, int C, int G, float eps, int silu, int ppb) {
     __shared__ unsigned long long sh[2 * GN_MAXG];
     const GnMap m = gn_map(C);
     const int b = blockIdx.y;
@@ -235,7 +241,7 @@ gn_bwd_reduce_k(const uint4* __restrict__ dy, const uint4* __restrict__ x, const
             if (col >= m.nv) break;
             const int g = (col * 8) / cpg;
             float mean, rstd;
-            gn_finalize(sums, b, g, G, static_cast<double>(cpg) * HW, eps, mean, rstd);
+            gn_finalize(sums, b, g, G, static_cast<double>(cpg) * HW_stat, eps, mean, rstd);
             float ga[8], be[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -287,8 +293,8 @@ template <bool BF16>
 __global__ void __launch_bounds__(GN_THREADS, 2)
 gn_bwd_apply_k(const uint4* __restrict__ dy, const uint4* __restrict__ x, const acc_t* __restrict__ sums,
                const float* __restrict__ gamma, const float* __restrict__ beta, const acc_t* __restrict__ red,
-               const uint4* __restrict__ add, uint4* __restrict__ dx, int HW, int C, int G, float eps, int silu,
-               int ppb) {
+               const uint4* __restrict__ add, uint4* __restrict__ dx, int HW, int HW_stat, int C, int G, float eps,
+               int silu, int ppb) {
     const GnMap m = gn_map(C);
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * ppb, p1 = min(HW, p0 + ppb);
@@ -300,7 +306,7 @@ gn_bwd_apply_k(const uint4* __restrict__ dy, const uint4* __restrict__ x, const 
         if (col >= m.nv) break;
         const int g = (col * 8) / cpg;
         float mean, rstd;
-        const double n = static_cast<double>(cpg) * HW;
+        const double n = static_cast<double>(cpg) * HW_stat;
         gn_finalize(sums, b, g, G, n, eps, mean, rstd);
         const float inv_n = static_cast<float>(1.0 / n);
         const float r1 = static_cast<float>(static_cast<double>(red[(b * G + g) * 2]) * (1.0 / WFD_FX_GRAD) / n);
@@ -380,19 +386,19 @@ int gn_stats(const void* x, acc_t* sums, int B, int HW, int C, int G, int bf16, 
     return 0;
 }
 int gn_apply(const void* x, const acc_t* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C,
-             int G, float eps, int silu, int bf16, cudaStream_t s) {
+             int G, float eps, int silu, int bf16, cudaStream_t s, int HW_stat) {
     ProfScope prof_scope("gn_apply", s);
     if (int r = gn_check(C, G)) return r;
     dim3 grid;
     int ppb;
     gn_grid(B, HW, C, grid, ppb);
     WFD_DISPATCH_BF16(bf16, (gn_apply_k<BF16><<<grid, GN_THREADS, 0, s>>>(static_cast<const uint4*>(x), sums, gamma, beta,
-                                                                         static_cast<uint4*>(y), HW, C, G, eps, silu, ppb)));
+                                                                         static_cast<uint4*>(y), HW, HW_stat > 0 ? HW_stat : HW, C, G, eps, silu, ppb)));
     WFD_CHECK_LAUNCH("gn_apply");
     return 0;
 }
 int gn_bwd_reduce(const void* dy, const void* x, const acc_t* sums, const float* gamma, const float* beta, acc_t* red,
-                  int B, int HW, int C, int G, float eps, int silu, int bf16, cudaStream_t s) {
+                  int B, int HW, int C, int G, float eps, int silu, int bf16, cudaStream_t s, int HW_stat) {
     ProfScope prof_scope("gn_bwd_reduce", s);
     if (int r = gn_check(C, G)) return r;
     dim3 grid;
@@ -400,13 +406,13 @@ int gn_bwd_reduce(const void* dy, const void* x, const acc_t* sums, const float*
     gn_grid(B, HW, C, grid, ppb);
     WFD_DISPATCH_BF16(bf16, (gn_bwd_reduce_k<BF16><<<grid, GN_THREADS, 0, s>>>(
                                 static_cast<const uint4*>(dy), static_cast<const uint4*>(x), sums, gamma, beta, red, HW,
-                                C, G, eps, silu, ppb)));
+                                HW_stat > 0 ? HW_stat : HW, C, G, eps, silu, ppb)));
     WFD_CHECK_LAUNCH("gn_bwd_reduce");
     return 0;
 }
 int gn_bwd_apply(const void* dy, const void* x, const acc_t* sums, const float* gamma, const float* beta,
                  const acc_t* red, const void* add, void* dx, int B, int HW, int C, int G, float eps, int silu,
-                 int bf16, cudaStream_t s) {
+                 int bf16, cudaStream_t s, int HW_stat) {
     ProfScope prof_scope("gn_bwd_apply", s);
     if (int r = gn_check(C, G)) return r;
     dim3 grid;
@@ -414,7 +420,8 @@ int gn_bwd_apply(const void* dy, const void* x, const acc_t* sums, const float* 
     gn_grid(B, HW, C, grid, ppb);
     WFD_DISPATCH_BF16(bf16, (gn_bwd_apply_k<BF16><<<grid, GN_THREADS, 0, s>>>(
                                 static_cast<const uint4*>(dy), static_cast<const uint4*>(x), sums, gamma, beta, red,
-                                static_cast<const uint4*>(add), static_cast<uint4*>(dx), HW, C, G, eps, silu, ppb)));
+                                static_cast<const uint4*>(add), static_cast<uint4*>(dx), HW, HW_stat > 0 ? HW_stat : HW,
+                                C, G, eps, silu, ppb)));
     WFD_CHECK_LAUNCH("gn_bwd_apply");
     return 0;
 }
@@ -464,18 +471,19 @@ template <bool BF16>
 __global__ void __launch_bounds__(128)
 latent_in_k(const void* __restrict__ z, int z_f16, float in_scale, const float* __restrict__ pq_w,
             const float* __restrict__ pq_b, const float* __restrict__ w, const float* __restrict__ bias,
-            uint16_t* __restrict__ out, int h, int wd, int Cm) {
+            uint16_t* __restrict__ out, int h, int wd, int Cm, int y_off, int h_total) {
+    // rows [y_off, y_off + h) of a z plane of h_total rows are produced (row bands); out is the local band
     __shared__ float u[3][LI_PIX + 2][4];
     const int b = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * LI_PIX;
     for (int i = threadIdx.x; i < 3 * (LI_PIX + 2); i += blockDim.x) {
         const int r = i / (LI_PIX + 2), c = i % (LI_PIX + 2);
-        const int yy = y + r - 1, xx = x0 + c - 1;
+        const int yy = y + y_off + r - 1, xx = x0 + c - 1;
         float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (yy >= 0 && yy < h && xx >= 0 && xx < wd) {
+        if (yy >= 0 && yy < h_total && xx >= 0 && xx < wd) {
             float zin[4];
 #pragma unroll
             for (int ci = 0; ci < 4; ++ci) {
-                const long long idx = ((static_cast<long long>(b) * 4 + ci) * h + yy) * wd + xx;
+                const long long idx = ((static_cast<long long>(b) * 4 + ci) * h_total + yy) * wd + xx;
                 zin[ci] = (z_f16 ? __half2float(reinterpret_cast<const __half*>(z)[idx])
                                  : reinterpret_cast<const float*>(z)[idx]) * in_scale;
             }
@@ -511,11 +519,13 @@ latent_in_k(const void* __restrict__ z, int z_f16, float in_scale, const float* 
 }
 
 int latent_in(const void* z, int z_f16, float in_scale, const float* pq_w, const float* pq_b, const float* w,
-              const float* b, void* out, int B, int h, int wd, int Cm, int bf16, cudaStream_t s) {
+              const float* b, void* out, int B, int h, int wd, int Cm, int bf16, cudaStream_t s, int y_off,
+              int h_total) {
     ProfScope prof_scope("latent_in", s);
+    if (h_total <= 0) h_total = h;
     dim3 grid((wd + LI_PIX - 1) / LI_PIX, h, B);
     WFD_DISPATCH_BF16(bf16, (latent_in_k<BF16><<<grid, 128, 0, s>>>(z, z_f16, in_scale, pq_w, pq_b, w, b,
-                                                                   static_cast<uint16_t*>(out), h, wd, Cm)));
+                                                                   static_cast<uint16_t*>(out), h, wd, Cm, y_off, h_total)));
     WFD_CHECK_LAUNCH("latent_in");
     return 0;
 }
@@ -525,7 +535,8 @@ template <bool BF16>
 __global__ void __launch_bounds__(256)
 latent_out_k(const uint16_t* __restrict__ dy, float in_scale, const float* __restrict__ scale_b,
              const float* __restrict__ pq_w, const float* __restrict__ wt, float* __restrict__ dz, int B, int h, int wd,
-             int Cm) {
+             int Cm, int y_off, int h_total) {
+    // row bands: dy has valid halo rows -1 and h wherever those rows are inside the h_total-row plane
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int total = B * h * wd;
     if (warp >= total) return;
@@ -535,7 +546,7 @@ latent_out_k(const uint16_t* __restrict__ dy, float in_scale, const float* __res
     float du[4] = {0.f, 0.f, 0.f, 0.f};
     for (int ky = 0; ky < 3; ++ky) {
         const int ys = y - (ky - 1);
-        if (ys < 0 || ys >= h) continue;
+        if (ys + y_off < 0 || ys + y_off >= h_total) continue;
         for (int kx = 0; kx < 3; ++kx) {
             const int xs = x - (kx - 1);
             if (xs < 0 || xs >= wd) continue;
@@ -560,13 +571,14 @@ latent_out_k(const uint16_t* __restrict__ dy, float in_scale, const float* __res
 }
 
 int latent_out(const void* dy, float in_scale, const float* scale_b, const float* pq_w, const float* w, float* dz,
-               int B, int h, int wd, int Cm, int bf16, cudaStream_t s) {
+               int B, int h, int wd, int Cm, int bf16, cudaStream_t s, int y_off, int h_total) {
     ProfScope prof_scope("latent_out", s);
+    if (h_total <= 0) h_total = h;
     const long long warps = static_cast<long long>(B) * h * wd;
     const int threads = 256;
     const unsigned blocks = static_cast<unsigned>((warps * 32 + threads - 1) / threads);
     WFD_DISPATCH_BF16(bf16, (latent_out_k<BF16><<<blocks, threads, 0, s>>>(static_cast<const uint16_t*>(dy), in_scale,
-                                                                         scale_b, pq_w, w, dz, B, h, wd, Cm)));
+                                                                         scale_b, pq_w, w, dz, B, h, wd, Cm, y_off, h_total)));
     WFD_CHECK_LAUNCH("latent_out");
     return 0;
 }
@@ -665,18 +677,20 @@ int wave_rowsum(const void* wave, float* rowsum, long long rows, int T_pad, int 
 }
 
 // ------------------------------------------------------------------------------------------------ WFC finishing passes
-__device__ __forceinline__ float neighbour_sum(const float* __restrict__ S, int y, int x, int H, int W) {
+// row bands: S points at the band's first row and has valid halo rows -1 and H_loc wherever they are inside the map
+__device__ __forceinline__ float neighbour_sum(const float* __restrict__ S, int y, int x, int W, int y_off,
+                                               int H_total) {
     float c = 0.f;
     if (x + 1 < W) c += S[y * W + x + 1];
     if (x > 0) c += S[y * W + x - 1];
-    if (y + 1 < H) c += S[(y + 1) * W + x];
-    if (y > 0) c += S[(y - 1) * W + x];
+    if (y + y_off + 1 < H_total) c += S[(y + 1) * W + x];
+    if (y + y_off > 0) c += S[(y - 1) * W + x];
     return c;
 }
 
 __global__ void __launch_bounds__(1024)
 wfc_loss_finish_k(const float* __restrict__ rowsum, const acc_t* __restrict__ rowdot, float* __restrict__ loss, int H,
-                  int W, float coef) {
+                  int W, float coef, int y_off, int H_total) {
     __shared__ double red[32];
     const int b = blockIdx.x;
     const float* S = rowsum + static_cast<long long>(b) * H * W;
@@ -684,7 +698,8 @@ wfc_loss_finish_k(const float* __restrict__ rowsum, const acc_t* __restrict__ ro
     double acc = 0.0;
     for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
         const int y = i / W, x = i - y * W;
-        acc += static_cast<double>(S[i]) * neighbour_sum(S, y, x, H, W) - static_cast<double>(D[i]) * (1.0 / WFD_FX_GRAD);
+        acc += static_cast<double>(S[i]) * neighbour_sum(S, y, x, W, y_off, H_total) -
+               static_cast<double>(D[i]) * (1.0 / WFD_FX_GRAD);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -698,9 +713,10 @@ wfc_loss_finish_k(const float* __restrict__ rowsum, const acc_t* __restrict__ ro
     }
 }
 int wfc_loss_finish(const float* rowsum, const acc_t* rowdot, float* loss, int B, int H, int W, float coef,
-                    cudaStream_t s) {
+                    cudaStream_t s, int y_off, int H_total) {
     ProfScope prof_scope("wfc_loss_finish", s);
-    wfc_loss_finish_k<<<B, 1024, 0, s>>>(rowsum, rowdot, loss, H, W, coef);
+    if (H_total <= 0) H_total = H;
+    wfc_loss_finish_k<<<B, 1024, 0, s>>>(rowsum, rowdot, loss, H, W, coef, y_off, H_total);
     WFD_CHECK_LAUNCH("wfc_loss_finish");
     return 0;
 }
@@ -709,7 +725,7 @@ template <bool BF16>
 __global__ void __launch_bounds__(256)
 wfc_grad_finish_k(const uint4* __restrict__ wave, const uint4* __restrict__ a, const float* __restrict__ rowsum,
                   const acc_t* __restrict__ rowdot, const float* __restrict__ dloss, uint4* __restrict__ dout, int B,
-                  int H, int W, int T_pad, int T, float coef, int through_softmax) {
+                  int H, int W, int T_pad, int T, float coef, int through_softmax, int y_off, int H_total) {
     const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const long long rows = static_cast<long long>(B) * H * W;
@@ -718,7 +734,7 @@ wfc_grad_finish_k(const uint4* __restrict__ wave, const uint4* __restrict__ a, c
     const int pr = static_cast<int>(row - static_cast<long long>(b) * H * W);
     const int y = pr / W, x = pr - y * W;
     const float* S = rowsum + static_cast<long long>(b) * H * W;
-    const float c = neighbour_sum(S, y, x, H, W);
+    const float c = neighbour_sum(S, y, x, W, y_off, H_total);
     const float r = S[pr] * c - static_cast<float>(static_cast<double>(rowdot[row]) * (1.0 / WFD_FX_GRAD));
     const float sc = coef * (dloss ? dloss[b] : 1.f);
     const int nv = T_pad / 8;
@@ -736,14 +752,15 @@ wfc_grad_finish_k(const uint4* __restrict__ wave, const uint4* __restrict__ a, c
 }
 int wfc_grad_finish(const void* wave, const void* a, const float* rowsum, const acc_t* rowdot, const float* dloss,
                     void* dout, int B, int H, int W, int T_pad, int T, float coef, int through_softmax, int bf16,
-                    cudaStream_t s) {
+                    cudaStream_t s, int y_off, int H_total) {
     ProfScope prof_scope("wfc_grad_finish", s);
+    if (H_total <= 0) H_total = H;
     const long long rows = static_cast<long long>(B) * H * W;
     const int threads = 256;
     const unsigned blocks = static_cast<unsigned>((rows * 32 + threads - 1) / threads);
     WFD_DISPATCH_BF16(bf16, (wfc_grad_finish_k<BF16><<<blocks, threads, 0, s>>>(
                                 static_cast<const uint4*>(wave), static_cast<const uint4*>(a), rowsum, rowdot, dloss,
-                                static_cast<uint4*>(dout), B, H, W, T_pad, T, coef, through_softmax)));
+                                static_cast<uint4*>(dout), B, H, W, T_pad, T, coef, through_softmax, y_off, H_total)));
     WFD_CHECK_LAUNCH("wfc_grad_finish");
     return 0;
 }
@@ -945,9 +962,10 @@ __global__ void __launch_bounds__(256) argmax_rows_k(const void* __restrict__ x,
     if (row >= rows) return;
     Best b;
     b.v = 0.f; b.i = -1; b.nan = false;
+    const bool vec_ok = (n % (DT == 0 ? 4 : 8) == 0) && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     if (DT == 0) {
         const float* src = reinterpret_cast<const float*>(x) + row * n;
-        const int nv = n / 4;
+        const int nv = vec_ok ? n / 4 : 0;  // rows that do not start 16-byte aligned take the scalar loop
         for (int v = lane; v < nv; v += 32) {
             const float4 f = __ldg(reinterpret_cast<const float4*>(src) + v);
             best_take(b, f.x, v * 4); best_take(b, f.y, v * 4 + 1); best_take(b, f.z, v * 4 + 2); best_take(b, f.w, v * 4 + 3);
@@ -955,7 +973,7 @@ __global__ void __launch_bounds__(256) argmax_rows_k(const void* __restrict__ x,
         for (int i = nv * 4 + lane; i < n; i += 32) best_take(b, src[i], i);
     } else {
         const uint16_t* src = reinterpret_cast<const uint16_t*>(x) + row * n;
-        const int nv = n / 8;
+        const int nv = vec_ok ? n / 8 : 0;
         for (int v = lane; v < nv; v += 32) {
             float f[8];
             if (DT == 2) unpack8<true>(__ldg(reinterpret_cast<const uint4*>(src) + v), f);
@@ -978,11 +996,6 @@ __global__ void __launch_bounds__(256) argmax_rows_k(const void* __restrict__ x,
 }
 int argmax_rows(const void* x, int dtype, long long rows, int n, long long* out, cudaStream_t s) {
     ProfScope prof_scope("argmax_rows", s);
-    if ((dtype == 0 && n % 4 != 0) || (dtype != 0 && n % 8 != 0)) {
-        // the vector loads need 16-byte aligned rows
-        set_error("argmax_rows: row length %d not aligned for vector loads", n);
-        return -3;
-    }
     const int threads = 256;
     const unsigned blocks = static_cast<unsigned>((rows * 32 + threads - 1) / threads);
     if (rows == 0) return 0;
@@ -1094,6 +1107,25 @@ int cvt_f32_to_16(const float* in, void* out, long long n, int bf16, cudaStream_
     ProfScope prof_scope("cvt_f32_to_16", s);
     WFD_DISPATCH_BF16(bf16, (cvt_f32_to_16_k<BF16><<<ew_blocks(n, 256), 256, 0, s>>>(in, static_cast<uint16_t*>(out), n)));
     WFD_CHECK_LAUNCH("cvt_f32_to_16");
+    return 0;
+}
+template <bool BF16>
+__global__ void cvt_f32_to_16_2d_k(const float* __restrict__ in, long long ld_in, uint16_t* __restrict__ out,
+                                   long long ld_out, long long rows, int cols) {
+    const long long n = rows * cols;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / cols;
+        const int c = static_cast<int>(i - r * cols);
+        out[r * ld_out + c] = f_to_u16<BF16>(in[r * ld_in + c]);
+    }
+}
+int cvt_f32_to_16_2d(const float* in, long long ld_in, void* out, long long ld_out, long long rows, int cols, int bf16,
+                     cudaStream_t s) {
+    ProfScope prof_scope("cvt_f32_to_16_2d", s);
+    WFD_DISPATCH_BF16(bf16, (cvt_f32_to_16_2d_k<BF16><<<ew_blocks(rows * cols, 256), 256, 0, s>>>(
+                                in, ld_in, static_cast<uint16_t*>(out), ld_out, rows, cols)));
+    WFD_CHECK_LAUNCH("cvt_f32_to_16_2d");
     return 0;
 }
 int add16(const void* a, const void* b, void* out, long long n, int bf16, cudaStream_t s) {

@@ -12,15 +12,16 @@ namespace wfd {
 // sums: [B, G, 2] fixed-point (2^20) {sum, sumsq}, zeroed by the caller before accumulation.
 int gn_stats(const void* x, acc_t* sums, int B, int HW, int C, int G, int bf16, cudaStream_t s);
 // y = act((x - mean) * rstd * gamma + beta), act = SiLU if silu else identity
+// HW_stat: pixels per sample the statistics cover (0 = HW; larger when the plane is split into row bands)
 int gn_apply(const void* x, const acc_t* sums, const float* gamma, const float* beta, void* y, int B, int HW, int C,
-             int G, float eps, int silu, int bf16, cudaStream_t s);
+             int G, float eps, int silu, int bf16, cudaStream_t s, int HW_stat = 0);
 // red: [B, G, 2] fixed-point (2^40) {sum(du*gamma), sum(du*gamma*xhat)}, zeroed by the caller; du = dy * act'(u)
 int gn_bwd_reduce(const void* dy, const void* x, const acc_t* sums, const float* gamma, const float* beta, acc_t* red,
-                  int B, int HW, int C, int G, float eps, int silu, int bf16, cudaStream_t s);
+                  int B, int HW, int C, int G, float eps, int silu, int bf16, cudaStream_t s, int HW_stat = 0);
 // dx = rstd * (du*gamma - (red0 + xhat*red1)/n) (+ add)
 int gn_bwd_apply(const void* dy, const void* x, const acc_t* sums, const float* gamma, const float* beta,
                  const acc_t* red, const void* add, void* dx, int B, int HW, int C, int G, float eps, int silu,
-                 int bf16, cudaStream_t s);
+                 int bf16, cudaStream_t s, int HW_stat = 0);
 
 // reduce (optional: skipped when the producing contraction fused it) + apply, in L2-sized blocks of samples
 int gn_bwd(const void* dy, const void* x, const acc_t* sums, const float* gamma, const float* beta, acc_t* red,
@@ -30,11 +31,12 @@ int gn_bwd(const void* dy, const void* x, const acc_t* sums, const float* gamma,
 // ---- latent side (reference wf_vae.py:593 post_quant_conv 1x1 4->4, wf_vae.py:218 conv_in 3x3 4->Cm)
 // z: NCHW [B,4,h,w] fp32 (z_f16=0) or fp16 (z_f16=1); out: [B, h*w, Cm] 16-bit. pq_w [4,4], pq_b [4], w [Cm,4,3,3], b [Cm]
 int latent_in(const void* z, int z_f16, float in_scale, const float* pq_w, const float* pq_b, const float* w,
-              const float* b, void* out, int B, int h, int wd, int Cm, int bf16, cudaStream_t s);
+              const float* b, void* out, int B, int h, int wd, int Cm, int bf16, cudaStream_t s, int y_off = 0,
+              int h_total = 0);  // row bands: z is the whole [B,4,h_total,w] plane, rows [y_off, y_off+h) are produced
 // dz[b,c,y,x] (fp32 NCHW) = in_scale * pq_w^T conv_in^T(dy); dy: [B, h*w, Cm] 16-bit; scale_b: optional per-sample scale;
 // w must be the conv_in weight re-ordered to [ky][kx][ci][co]
 int latent_out(const void* dy, float in_scale, const float* scale_b, const float* pq_w, const float* w, float* dz,
-               int B, int h, int wd, int Cm, int bf16, cudaStream_t s);
+               int B, int h, int wd, int Cm, int bf16, cudaStream_t s, int y_off = 0, int h_total = 0);
 
 // ---- wave softmax over all T_pad channels (reference pipeline_wfd.py:405); rowsum[n] = sum_{i<T} p~[n,i] of the
 // rounded 16-bit values that feed the contraction.
@@ -44,12 +46,12 @@ int wave_softmax(const void* logits, void* wave, float* rowsum, long long rows, 
 int wave_rowsum(const void* wave, float* rowsum, long long rows, int T_pad, int T, int bf16, cudaStream_t s);
 // loss[b] = coef * 0.5 * sum_n (S_n * c_n - rowdot_a[n]),  c_n = sum of S over the <=4 in-map neighbours
 int wfc_loss_finish(const float* rowsum, const acc_t* rowdot, float* loss, int B, int H, int W, float coef,
-                    cudaStream_t s);
+                    cudaStream_t s, int y_off = 0, int H_total = 0);
 // grad wrt wave (no softmax): dwave[n,i] = coef*dloss[b] * ([i<T]*c_n - a[n,i]);
 // grad wrt logits (softmax bwd): dlogits[n,i] = coef*dloss[b] * p[n,i] * (([i<T]*c_n - a[n,i]) - (S_n*c_n - rowdot_a[n]))
 int wfc_grad_finish(const void* wave, const void* a, const float* rowsum, const acc_t* rowdot, const float* dloss,
                     void* dout, int B, int H, int W, int T_pad, int T, float coef, int through_softmax, int bf16,
-                    cudaStream_t s);
+                    cudaStream_t s, int y_off = 0, int H_total = 0);
 
 // ---- attention helpers (reference attention.py:354-368: scores -> fp32 softmax -> probs)
 int attn_softmax(const float* scores, void* probs, long long rows, int n, int bf16, cudaStream_t s);
@@ -68,6 +70,9 @@ int nhwc16_to_nchw(const void* in, void* out, int out_f16, int B, int C, int HW,
 // 16-bit -> fp32 (same layout) and generic helpers
 int cvt16_to_f32(const void* in, float* out, long long n, int bf16, cudaStream_t s);
 int cvt_f32_to_16(const float* in, void* out, long long n, int bf16, cudaStream_t s);
+// strided rows: out[r, c] (row stride ld_out, 16-bit) = in[r, c] (row stride ld_in, fp32)
+int cvt_f32_to_16_2d(const float* in, long long ld_in, void* out, long long ld_out, long long rows, int cols, int bf16,
+                     cudaStream_t s);
 int add16(const void* a, const void* b, void* out, long long n, int bf16, cudaStream_t s);
 
 }  // namespace wfd

@@ -300,7 +300,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         continue;
                     }
                     const int x0 = tc.tx * p.w_box * p.in_stride;
-                    const int y0 = tc.ty * p.h_box * p.in_stride;
+                    const int y0 = tc.ty * p.h_box * p.in_stride + p.a_y_off;
                     const int ab = tc.bb + tc.z * p.a_zmul;
                     const int bz = tc.z * p.b_zmul + tc.bb * p.b_bbmul;
                     const int n0 = tc.n_tile * p.BN + rank * (p.BN / CG);  // this CTA's rows of the B tile
@@ -762,7 +762,7 @@ __global__ void tapgemm_ref_kernel(const TapGemmParams p) {
     float acc = 0.f;
     for (int tap = 0; tap < p.n_taps; ++tap) {
         const int xi = x * p.in_stride + p.tap_dx[tap];
-        const int yi = y * p.in_stride + p.tap_dy[tap];
+        const int yi = y * p.in_stride + p.tap_dy[tap] + p.a_y_off;
         if (xi < 0 || xi >= p.a_W || yi < 0 || yi >= p.a_H || ab >= p.a_B) continue;
         const uint16_t* arow = A + ((static_cast<long long>(ab) * p.a_H + yi) * p.a_W + xi) * p.a_ld;
         for (int cc = 0; cc < p.cpt; ++cc) {

@@ -39,6 +39,7 @@ struct TapGemmParams {
     int w_box, h_box;       // w_box * h_box == 128
     int W, H;               // output plane (pixel index = (bb*H + y)*W + x)
     int in_stride;          // input coordinate = out coordinate * in_stride + tap offset
+    int a_y_off;            // added to every input row coordinate (row-band plans: the A view starts one halo row early)
     // ---- K loop
     int n_taps, cpt;        // taps, 64-wide chunks per tap
     int kk_last;            // 16-channel MMA steps needed in the last chunk of a tap (0 = all four)

@@ -64,9 +64,25 @@ int Wfc::init(const uint8_t* mx, const uint8_t* my, int T_, int T_pad_, int dtyp
 
 static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
+// Row bands keep one halo row of the wave and of the row sums above and below the band (vertical pairs, losses.py:60-66).
 size_t Wfc::saved_bytes(int B, int H, int W) const {
     const size_t rows = static_cast<size_t>(B) * H * W;
-    return 256 + 2 * align256(rows * T_pad * 2) + align256(rows * 4) + align256(rows * sizeof(acc_t));
+    const size_t pad = band ? 2 * (align256(static_cast<size_t>(W) * T_pad * 2) + align256(static_cast<size_t>(W) * 4)) : 0;
+    return 256 + 2 * align256(rows * T_pad * 2) + align256(rows * 4) + align256(rows * sizeof(acc_t)) + pad;
+}
+
+int Wfc::set_band(Comm* c, int H_total_) {
+    if (!c || H_total_ < 1 || H_total_ % c->nranks != 0) {
+        set_error("wfc: row bands need a communicator and a map height divisible by the rank count");
+        return -3;
+    }
+    comm = c;
+    band = true;
+    band_R = c->nranks;
+    band_r = c->rank;
+    H_total = H_total_;
+    op_wave = nullptr;
+    return 0;
 }
 
 struct SavedView {
@@ -76,17 +92,17 @@ struct SavedView {
     float* rowsum;
     acc_t* rowdot;  // fixed point 2^40
 };
-static SavedView view_saved(void* saved, size_t rows, int T_pad) {
+static SavedView view_saved(void* saved, size_t rows, int T_pad, size_t halo_wave = 0, size_t halo_sum = 0) {
     SavedView v;
     uint8_t* p = static_cast<uint8_t*>(saved);
     v.hdr = reinterpret_cast<WfcSavedHeader*>(p);
-    p += 256;
+    p += 256 + halo_wave;
     v.wave = p;
-    p += align256(rows * T_pad * 2);
+    p += align256(rows * T_pad * 2) + halo_wave;
     v.a = p;
-    p += align256(rows * T_pad * 2);
+    p += align256(rows * T_pad * 2) + halo_sum;
     v.rowsum = reinterpret_cast<float*>(p);
-    p += align256(rows * 4);
+    p += align256(rows * 4) + halo_sum;
     v.rowdot = reinterpret_cast<acc_t*>(p);
     return v;
 }
@@ -110,19 +126,35 @@ int Wfc::forward(const void* in, int is_logits, int B, int H, int W, float stren
         return -3;
     }
     const size_t rows = static_cast<size_t>(B) * H * W;
-    SavedView v = view_saved(saved, rows, T_pad);
+    const size_t halo_wave = band ? align256(static_cast<size_t>(W) * T_pad * 2) : 0;
+    const size_t halo_sum = band ? align256(static_cast<size_t>(W) * 4) : 0;
+    if (band && (B != 1 || !is_logits || H * band_R != H_total)) {
+        set_error("wfc: a row-band handle scores logits of one map, %d rows per band (got B=%d H=%d is_logits=%d)",
+                  H_total / band_R, B, H, is_logits);
+        return -3;
+    }
+    SavedView v = view_saved(saved, rows, T_pad, halo_wave, halo_sum);
     const void* wave = is_logits ? v.wave : in;
+    const int Hm = band ? H_total : H;        // rows of the whole map
+    const int y_off = band ? band_r * H : 0;  // first row of this band
     // the header lives in caller memory on the device side of `saved`; keep the host copy in the handle instead
     hdr_host.B = B;
     hdr_host.H = H;
     hdr_host.W = W;
     hdr_host.is_logits = is_logits;
-    hdr_host.coef = strength / static_cast<float>(H * (W - 1) + (H - 1) * W);
+    hdr_host.coef = strength / static_cast<float>(Hm * (W - 1) + (Hm - 1) * W);
     hdr_host.wave = wave;
     hdr_saved = saved;
     if (is_logits) CK(wave_softmax(in, v.wave, v.rowsum, static_cast<long long>(rows), T_pad, T, bf16, s));
     else CK(wave_rowsum(in, v.rowsum, static_cast<long long>(rows), T_pad, T, bf16, s));
     CUDA_CK(cudaMemsetAsync(v.rowdot, 0, rows * sizeof(acc_t), s));
+    if (band) {
+        const size_t wb_ = static_cast<size_t>(W) * T_pad * 2, sb_ = static_cast<size_t>(W) * 4;
+        uint8_t* wv = v.wave;
+        uint8_t* rs = reinterpret_cast<uint8_t*>(v.rowsum);
+        CK(comm->halo(wv - wb_, wv, wv + static_cast<size_t>(H - 1) * wb_, wv + static_cast<size_t>(H) * wb_, wb_, s));
+        CK(comm->halo(rs - sb_, rs, rs + static_cast<size_t>(H - 1) * sb_, rs + static_cast<size_t>(H) * sb_, sb_, s));
+    }
     if (op_wave != wave || op_a != v.a || op_B != B || op_H != H || op_W != W) {
         memset(&op, 0, sizeof(op));
         TapGemmParams& p = op.p;
@@ -159,6 +191,11 @@ int Wfc::forward(const void* in, int is_logits, int B, int H, int W, float stren
         p.a_C = T_pad;
         p.a_W = W;
         p.a_H = H;
+        if (band) {  // the view starts at the top halo row
+            p.a_ptr = static_cast<const uint8_t*>(wave) - static_cast<size_t>(W) * T_pad * 2;
+            p.a_H = H + 2;
+            p.a_y_off = 1;
+        }
         p.a_B = B;
         p.a_ld = T_pad;
         p.b_ptr = Bm;
@@ -173,7 +210,8 @@ int Wfc::forward(const void* in, int is_logits, int B, int H, int W, float stren
         op_W = W;
     }
     CK(debug_ref_gemm() ? tapgemm_launch_ref(&op, s) : tapgemm_launch(&op, s));
-    CK(wfc_loss_finish(v.rowsum, v.rowdot, loss, B, H, W, hdr_host.coef, s));
+    CK(wfc_loss_finish(v.rowsum, v.rowdot, loss, B, H, W, hdr_host.coef, s, y_off, Hm));
+    if (band) CK(comm->allreduce_f32(loss, 1, s));  // every band holds the map's loss
     return 0;
 }
 
@@ -183,9 +221,12 @@ int Wfc::backward(void* saved, const float* dloss, void* dout, cudaStream_t s) {
         return -3;
     }
     const size_t rows = static_cast<size_t>(hdr_host.B) * hdr_host.H * hdr_host.W;
-    SavedView v = view_saved(saved, rows, T_pad);
+    const size_t halo_wave = band ? align256(static_cast<size_t>(hdr_host.W) * T_pad * 2) : 0;
+    const size_t halo_sum = band ? align256(static_cast<size_t>(hdr_host.W) * 4) : 0;
+    SavedView v = view_saved(saved, rows, T_pad, halo_wave, halo_sum);
     return wfc_grad_finish(hdr_host.wave, v.a, v.rowsum, v.rowdot, dloss, dout, hdr_host.B, hdr_host.H, hdr_host.W,
-                           T_pad, T, hdr_host.coef, hdr_host.is_logits, bf16, s);
+                           T_pad, T, hdr_host.coef, hdr_host.is_logits, bf16, s, band ? band_r * hdr_host.H : 0,
+                           band ? H_total : hdr_host.H);
 }
 
 }  // namespace wfd

@@ -40,9 +40,12 @@ def _z_dtype_code(z):
 
 
 class DecoderPlan:
-    """One wfd_decoder handle + its workspace for a fixed (h, w, B_max, dtype16)."""
+    """One wfd_decoder handle + its workspace for a fixed (h, w, B_max, dtype16).
 
-    def __init__(self, model, h, w, b_max, dtype16, device):
+    band=(rank, nranks) builds a row-band plan instead (see rowband.py): h is then the height of the whole latent
+    plane, the plan decodes rows [rank*h/nranks, (rank+1)*h/nranks) of ONE map and needs a communicator attached."""
+
+    def __init__(self, model, h, w, b_max, dtype16, device, band=None):
         lib = nat.lib()
         cfg = model.config
         c = nat.DecoderConfig()
@@ -62,7 +65,17 @@ class DecoderPlan:
         self.h, self.w, self.b_max, self.dtype16 = h, w, b_max, dtype16
         self.t_pad = cfg.out_channels
         with torch.cuda.device(device):
-            nat.check(lib.wfd_decoder_create(C.byref(c), h, w, b_max, dtype16, C.byref(self.handle)), "wfd_decoder_create")
+            if band is None:
+                nat.check(lib.wfd_decoder_create(C.byref(c), h, w, b_max, dtype16, C.byref(self.handle)),
+                          "wfd_decoder_create")
+            else:
+                if b_max != 1:
+                    raise nat.WfdError("row-band plans decode one map (batch 1)")
+                nat.check(lib.wfd_decoder_create_band(C.byref(c), h, w, band[0], band[1], dtype16, C.byref(self.handle)),
+                          "wfd_decoder_create_band")
+                self.h_total = h
+                self.h = h // band[1]
+            self.band = band
             for key, t in model.state_dict().items():
                 if not (key.startswith("decoder.") or key.startswith("post_quant_conv.")):
                     continue
@@ -225,7 +238,8 @@ class WfcHandle:
                                              C.c_void_p(out_ptr), nat.stream_ptr()), "wfd_wfc_backward")
 
     def wave_view(self, B, H, W):
-        off = self._saved_ptr + 256 - self._saved.data_ptr()
+        ptr = nat.lib().wfd_wfc_saved_wave(self.handle, C.c_void_p(self._saved_ptr), B, H, W)
+        off = ptr - self._saved.data_ptr()
         n = B * H * W * self.t_pad
         return self._saved[off:off + 2 * n].view(_torch16(self.dtype16)).view(B, H, W, self.t_pad)
 
