@@ -363,6 +363,155 @@ def run_native(args):
         dist.destroy_process_group()
 
 
+def run_rowband(args):
+    """ONE map split into row bands over the ranks (BASELINE config 4, strong scaling; wf_diffusers/rowband.py)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    ge.build()
+    from wavefunctiondiffusion_b200 import _native as nat
+    from wavefunctiondiffusion_b200.wf_diffusers.rowband import BandComm, BandGuidance, LoopbackGroup, gather_rows
+    from wavefunctiondiffusion_b200.wf_diffusers.wf_vae import AutoencoderTile
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        comm = BandComm.from_torch_distributed(dev)
+    else:
+        comm = LoopbackGroup(1).comm(0)
+    mx, my, T, t_pad, cfg = load_workload(args)
+    torch.manual_seed(0)
+    tile_vae = AutoencoderTile(**cfg).eval().to(dev)
+    L = args.latent
+    parity = None
+    gold = os.path.join(ROOT, "tests", "golden", "ice_c1_step.npz")
+    if L == 64 and args.tileset == "ice_64x64" and args.arch == "64x64":
+        z = np.load(gold)
+        lat_host = torch.from_numpy(z["latents"]).pin_memory()
+    else:
+        z = None
+        lat_host = torch.randn(1, 4, L, L, generator=torch.Generator().manual_seed(1234)).pin_memory()
+    bg = BandGuidance(tile_vae, mx, my, L, L, comm, dev)
+    lat = lat_host.to(dev)
+    dz_host = torch.empty(1, 4, bg.h_band, L).pin_memory()
+    lib = nat.lib()
+
+    def step_resident():
+        return bg.step(lat, 1.0 / LATENT_SCALE, STRENGTH)
+
+    def step_e2e():
+        l = lat_host.to(dev, non_blocking=True)
+        loss, dz = bg.step(l, 1.0 / LATENT_SCALE, STRENGTH)
+        dz_host.copy_(dz, non_blocking=True)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    loss, dz = step_resident()
+    full = gather_rows(dz, 2) if world > 1 else dz
+    if z is not None and rank == 0:
+        ref_l = float(np.asarray(z["loss_f64"]).reshape(-1)[0])
+        g = torch.from_numpy(z["grad_f64"])
+        parity = {"against": "tests/golden/ice_c1_step.npz (unmodified reference, fp64)",
+                  "loss": loss.item(), "loss_ref": ref_l,
+                  "grad_rel_l2": ((full.cpu().double() - g).norm() / g.norm()).item()}
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.wfd_launch_count()
+    W = max(args.warmup, 3)
+    ms = timed(step_resident, args.steps, W)
+    launches = (lib.wfd_launch_count() - n0) // (args.steps + W) * args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps, W)
+    prof = {}
+    if rank == 0:
+        lib.wfd_profile_enable(1)
+    psteps = 2
+    for _ in range(psteps):  # every rank must take part in the exchanges
+        step_resident()
+    torch.cuda.synchronize()
+    if rank == 0:
+        buf = C.create_string_buffer(1 << 16)
+        lib.wfd_profile_report(buf, len(buf))
+        lib.wfd_profile_enable(0)
+        for line in buf.value.decode().splitlines():
+            name, cnt, tot = line.rsplit(" ", 2)
+            prof[name] = (int(cnt) / psteps, float(tot) / psteps)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    fl = step_flops(cfg, L, L, T)
+    tg_ms = sum(t for n, (c, t) in prof.items() if n.startswith("tapgemm"))
+    tg_launches = sum(c for n, (c, t) in prof.items() if n.startswith("tapgemm"))
+    all_ms = sum(t for c, t in prof.values())
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    achieved = fl["F_step"] / world / (tg_ms / 1e3) / 1e12 if tg_ms > 0 else None
+    top = sorted(prof.items(), key=lambda kv: -kv[1][1])[:args.top]
+    if args.verbose:
+        for n, (c, t) in top:
+            print("  %-60s %6.1f launches %9.3f ms/step" % (n, c, t), file=sys.stderr)
+        print("  profiled total %.3f ms/step, tapgemm %.3f ms" % (all_ms, tg_ms), file=sys.stderr)
+    out = {
+        "metric": "wfc_guidance_map_steps_per_s", "value": args.steps / (ms / 1e3), "unit": "maps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "ONE %s tileset %dx%d map (batch 1) split into %d row bands of %d rows, one per GPU; "
+                               "tilenet_sc_space_%s random init (seed 0), one WFC-guidance step, strength %g"
+                               % (args.tileset, L, L, world, bg.h_band, args.arch, STRENGTH),
+                   "tileset": args.tileset, "T": T, "T_pad": t_pad, "latent_hw": L, "row_bands": world,
+                   "exchange": "NCCL send/recv halos, all-reduce of GroupNorm sums and loss, all-gather of keys/values, "
+                               "reduce-scatter of their gradients" if world > 1 else "none (one band)",
+                   "l2": "working set per step exceeds the 126 MB L2; no flush needed"},
+        "e2e": {"value": args.steps / (ms_e2e / 1e3), "unit": "maps/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": lat_host.numel() * 4, "d2h_bytes_per_step": dz_host.numel() * 4,
+                "api": "rowband.BandGuidance.step with pinned host latents; this rank's dz rows read back"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "tapgemm_kernel (rank 0's share of the step's contractions)",
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if achieved else None,
+                     "algorithmic_flops_per_step": fl["F_step"] / world, "launches_per_step": tg_launches,
+                     "kernel_ms_per_step": tg_ms, "share_of_step": tg_ms / all_ms if all_ms else None, "traffic": None},
+        "cpu_baseline": None, "parity": parity, "loss_check": [loss.item()],
+        "profile_top": [{"kernel": n, "launches_per_step": c, "ms_per_step": t} for n, (c, t) in top],
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -377,6 +526,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--top", type=int, default=12, help="kernels listed in profile_top")
+    ap.add_argument("--rowband", action="store_true",
+                    help="strong scaling: ONE --latent x --latent map split into row bands over the GPUs (config 4)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -387,6 +538,9 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    if args.rowband:
+        run_rowband(args)
+        return
     run_native(args)
 
 
