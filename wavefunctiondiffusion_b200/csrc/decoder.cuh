@@ -135,6 +135,9 @@ struct Wfc {
     WfcSavedHeader hdr_host;
     void* hdr_saved = nullptr;
     uint16_t* Bm = nullptr;
+    int* kc_list = nullptr;  // K chunks of each N tile that hold at least one allowed pair (see Wfc::init)
+    int* kc_cnt = nullptr;
+    double kc_kept = 1.0;    // fraction of the K chunks that are visited
     // last prepared contraction (tensor maps depend on the buffers of the call)
     TapGemmOp op;
     const void* op_wave = nullptr;

@@ -65,7 +65,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if ((++spins & 0x3FFu) == 0 && clock64() - t0 > 4000000000LL) {
+#ifdef WFD_WATCHDOG_PRINTF
+            // a printf is a call: it makes the compiler save/restore convergence barriers (BMOV) around every wait of
+            // the hot loops, which slowed the TMA producer warps measurably - compile it in only to chase a hang
             printf("wfd: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+#endif
             asm volatile("trap;");
         }
     }

@@ -304,52 +304,86 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int ab = tc.bb + tc.z * p.a_zmul;
                     const int bz = tc.z * p.b_zmul + tc.bb * p.b_bbmul;
                     const int n0 = tc.n_tile * p.BN + rank * (p.BN / CG);  // this CTA's rows of the B tile
-                    const int n_outer = p.reuse ? 3 : p.n_taps;
-                    int it = 0;
-                    for (int o = 0; o < n_outer; ++o) {
-                        const int xx = p.reuse ? x0 + o - 1 : x0 + p.tap_dx[o];
-                        const int yy = p.reuse ? y0 - 1 : y0 + p.tap_dy[o];
-                        for (int cc = 0; cc < p.cpt; ++cc, ++it) {
-                            const int bk = p.reuse ? it * 3 : it * TG_KC;  // chunk / element coordinate of the weights
-                            if (p.dbg) {
-                                const long long w0 = clock64();
-                                mbar_wait(&empty_bar[stage], phase ^ 1);
-                                w_empty += clock64() - w0;
+                    // The producer warps sit on the critical path of short-K and block-sparse contractions (one warp issues
+                    // dependent instructions every few cycles): the three walks below keep their per-chunk work minimal, and
+                    // each warp only computes the coordinates of its own operand.
+                    auto slot_wait = [&]() {
+                        if (p.dbg) {
+                            const long long w0 = clock64();
+                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                            w_empty += clock64() - w0;
+                        } else {
+                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                        }
+                    };
+                    auto slot_next = [&]() {
+                        __syncwarp();
+                        if (++stage == stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    };
+                    auto issue_a = [&](int ca, int xx, int yy) {
+                        slot_wait();
+                        const long long i0 = p.dbg ? clock64() : 0;
+                        if (elect_one()) {
+                            if (CG == 2) {  // both CTAs load into their own shared memory; the leader's barrier counts all bytes
+                                if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * a_stage_bytes);
+                                tma_load_4d_2sm(smA + static_cast<size_t>(stage) * a_stage_bytes, &tmA, &full_bar[stage], ca,
+                                                xx, yy, ab);
                             } else {
-                                mbar_wait(&empty_bar[stage], phase ^ 1);
-                            }
-                            const long long i0 = p.dbg ? clock64() : 0;
-                            if (elect_one()) {
-                                if (CG == 2) {
-                                    // both CTAs load into their own shared memory; the leader's barrier counts all bytes
-                                    if (load_a) {
-                                        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * a_stage_bytes);
-                                        tma_load_4d_2sm(smA + static_cast<size_t>(stage) * a_stage_bytes, &tmA,
-                                                        &full_bar[stage], c0 + cc * TG_KC, xx, yy, ab);
-                                    } else {
-                                        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * b_stage_bytes);
-                                        tma_load_3d_2sm(smB + static_cast<size_t>(stage) * b_stage_bytes, &tmB,
-                                                        &full_bar[stage], bk, n0, bz);
-                                    }
-                                } else if (load_a) {
-                                    mbar_expect_tx(&full_bar[stage], a_stage_bytes);
-                                    tma_load_4d(smA + static_cast<size_t>(stage) * a_stage_bytes, &tmA, &full_bar[stage],
-                                                c0 + cc * TG_KC, xx, yy, ab);
-                                } else {
-                                    mbar_expect_tx(&full_bar[stage], b_stage_bytes);
-                                    if (p.reuse)
-                                        tma_load_3d(smB + static_cast<size_t>(stage) * b_stage_bytes, &tmB, &full_bar[stage], 0, n0, bk);
-                                    else
-                                        tma_load_3d(smB + static_cast<size_t>(stage) * b_stage_bytes, &tmB, &full_bar[stage], bk, n0, bz);
-                                }
-                            }
-                            __syncwarp();
-                            if (p.dbg) w_issue += clock64() - i0;
-                            if (++stage == stages) {
-                                stage = 0;
-                                phase ^= 1;
+                                mbar_expect_tx(&full_bar[stage], a_stage_bytes);
+                                tma_load_4d(smA + static_cast<size_t>(stage) * a_stage_bytes, &tmA, &full_bar[stage], ca, xx, yy, ab);
                             }
                         }
+                        if (p.dbg) w_issue += clock64() - i0;
+                        slot_next();
+                    };
+                    auto issue_b = [&](int k0, int k2) {  // weights box at (k0, n0, k2)
+                        slot_wait();
+                        const long long i0 = p.dbg ? clock64() : 0;
+                        if (elect_one()) {
+                            if (CG == 2) {
+                                if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * b_stage_bytes);
+                                tma_load_3d_2sm(smB + static_cast<size_t>(stage) * b_stage_bytes, &tmB, &full_bar[stage], k0, n0, k2);
+                            } else {
+                                mbar_expect_tx(&full_bar[stage], b_stage_bytes);
+                                tma_load_3d(smB + static_cast<size_t>(stage) * b_stage_bytes, &tmB, &full_bar[stage], k0, n0, k2);
+                            }
+                        }
+                        if (p.dbg) w_issue += clock64() - i0;
+                        slot_next();
+                    };
+                    if (p.kc_list) {
+                        // skip list (plain schedule): packed entries dx+1 | (dy+1) << 2 | chunk-in-tap << 4 | chunk << 16,
+                        // fetched 32 at a time (one per lane) and handed round by shuffle
+                        const int n_list = __ldg(p.kc_cnt + tc.n_tile);
+                        const int* list = p.kc_list + static_cast<long long>(tc.n_tile) * k_iters;
+                        // the batch after the current one is already in flight, so the load latency never stalls the ring
+                        int mine_e = 0, next_e = (lane < n_list) ? __ldg(list + lane) : 0;
+                        for (int j = 0; j < n_list; ++j) {
+                            if ((j & 31) == 0) {
+                                mine_e = next_e;
+                                next_e = (j + 32 + lane < n_list) ? __ldg(list + j + 32 + lane) : 0;
+                            }
+                            const int e = __shfl_sync(0xffffffffu, mine_e, j & 31);
+                            if (load_a) issue_a(c0 + ((e >> 4) & 0xfff) * TG_KC, x0 + (e & 3) - 1, y0 + ((e >> 2) & 3) - 1);
+                            else issue_b((e >> 16) * TG_KC, bz);
+                        }
+                    } else if (p.reuse) {
+                        if (load_a) {
+                            for (int o = 0; o < 3; ++o)
+                                for (int cc = 0; cc < p.cpt; ++cc) issue_a(c0 + cc * TG_KC, x0 + o - 1, y0 - 1);
+                        } else {
+                            for (int it = 0; it < k_iters; ++it) issue_b(0, it * 3);
+                        }
+                    } else if (load_a) {
+                        for (int o = 0; o < p.n_taps; ++o) {
+                            const int xx = x0 + p.tap_dx[o], yy = y0 + p.tap_dy[o];
+                            for (int cc = 0; cc < p.cpt; ++cc) issue_a(c0 + cc * TG_KC, xx, yy);
+                        }
+                    } else {
+                        for (int it = 0; it < k_iters; ++it) issue_b(it * TG_KC, bz);
                     }
                 }
             }
@@ -390,7 +424,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
             int cc = 0;  // chunk index within the tap (the last chunk of a tap may hold fewer than 64 useful channels)
-            for (int kc = 0; kc < k_iters; ++kc) {
+            const int k_walk = p.kc_cnt ? __ldg(p.kc_cnt + decode_tile(p, t, CG, rank).n_tile) : k_iters;
+            for (int kc = 0; kc < k_walk; ++kc) {
                 const int n_k = (cc == p.cpt - 1) ? kk_last : TG_KC / 16;
                 if (++cc == p.cpt) cc = 0;
                 w0 = p.dbg ? clock64() : 0;
@@ -418,10 +453,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     if (CG == 2) {  // release the stage / publish the accumulator in both CTAs of the pair
                         umma_commit_2sm(&empty_bar[stage]);
-                        if (kc == k_iters - 1) umma_commit_2sm(&tfull_bar[acc]);
+                        if (kc == k_walk - 1) umma_commit_2sm(&tfull_bar[acc]);
                     } else {
                         umma_commit(&empty_bar[stage]);
-                        if (kc == k_iters - 1) {
+                        if (kc == k_walk - 1) {
                             umma_commit(&tfull_bar[acc]);
                             if (b_res) umma_commit(tdone_bar);
                         }
@@ -864,6 +899,10 @@ int tapgemm_prepare(TapGemmOp* op) {
     }
     if ((p.residual ? 1 : 0) + (p.rowdot ? 1 : 0) + (p.gnb_red ? 1 : 0) > 1) {
         set_error("tapgemm_prepare: residual, row-dot and GroupNorm-backward epilogues are mutually exclusive");
+        return -3;
+    }
+    if (p.kc_list && (p.reuse || p.kk_last || !p.kc_cnt || p.b_resident)) {
+        set_error("tapgemm_prepare: a K-chunk skip list needs the plain schedule with whole 64-channel chunks");
         return -3;
     }
     if (p.reuse && !tapgemm_reuse_ok(p)) {

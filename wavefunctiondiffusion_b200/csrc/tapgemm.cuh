@@ -45,6 +45,11 @@ struct TapGemmParams {
     int kk_last;            // 16-channel MMA steps needed in the last chunk of a tap (0 = all four)
     int tap_dx[TG_MAX_TAPS], tap_dy[TG_MAX_TAPS];
     const int* a_c0;        // [n_tiles] first input channel of each N tile (nullptr => 0)
+    // optional K-chunk skip list (plain schedule, kk_last == 0, taps within +-1): for N tile n only the chunks named by
+    // kc_list[n * n_taps*cpt + j], j < kc_cnt[n] (>= 1), are visited - the others hold nothing but zeros in Bm
+    // (block-sparse adjacency operand). Entry = dx+1 | (dy+1) << 2 | chunk-in-tap << 4 | chunk << 16.
+    const int* kc_list;
+    const int* kc_cnt;
     int cg;                 // CTA group: 0 = let tapgemm_prepare choose, 1 = single CTA, 2 = CTA pair (cta_group::2)
     int b_resident;         // set by tapgemm_prepare: weights of the current N tile stay resident in shared memory
     int reuse;              // 1: row-reuse schedule (3x3 stride-1 taps; Bm chunks in (dx, cc, dy) order)
