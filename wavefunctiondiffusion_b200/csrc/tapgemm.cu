@@ -533,10 +533,18 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 side_ptr = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.gnb_x) + out_off + n0);
             const int n_chunks = (min(p.BN, p.N - n0) + 15) / 16;
             uint4 sb0[2], sb1[2], sb2[2];
+            auto load_side = [&](int chunk, uint4(&dst)[2]) {
+                if (p.wide_io) {
+                    ldg256(side_ptr + 2 * chunk, dst[0], dst[1]);
+                } else {
+                    dst[0] = __ldg(side_ptr + 2 * chunk);
+                    dst[1] = __ldg(side_ptr + 2 * chunk + 1);
+                }
+            };
             if (side_ptr) {
-                if (half < n_chunks) { sb0[0] = __ldg(side_ptr + 2 * half); sb0[1] = __ldg(side_ptr + 2 * half + 1); }
-                if (half + 2 < n_chunks) { sb1[0] = __ldg(side_ptr + 2 * (half + 2)); sb1[1] = __ldg(side_ptr + 2 * (half + 2) + 1); }
-                if (half + 4 < n_chunks) { sb2[0] = __ldg(side_ptr + 2 * (half + 4)); sb2[1] = __ldg(side_ptr + 2 * (half + 4) + 1); }
+                if (half < n_chunks) load_side(half, sb0);
+                if (half + 2 < n_chunks) load_side(half + 2, sb1);
+                if (half + 4 < n_chunks) load_side(half + 4, sb2);
             }
             {
                 const long long w0 = p.dbg ? clock64() : 0;
@@ -559,11 +567,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     side_cur[0] = sb0[0]; side_cur[1] = sb0[1];
                     sb0[0] = sb1[0]; sb0[1] = sb1[1];
                     sb1[0] = sb2[0]; sb1[1] = sb2[1];
-                    if (c + 6 < n_chunks) { sb2[0] = __ldg(side_ptr + 2 * (c + 6)); sb2[1] = __ldg(side_ptr + 2 * (c + 6) + 1); }
+                    if (c + 6 < n_chunks) load_side(c + 6, sb2);
                 }
                 uint32_t r[16];
                 tmem_ld16(taddr + j0, r);
-                tmem_ld_wait();
+                tmem_ld_wait(r);
                 float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
@@ -598,15 +606,27 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 if (p.out_fp32) {
                     float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + n);
+                    if (p.wide_io) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        for (int j = 0; j < 2; ++j)
+                            stg256(op + 2 * j,
+                                   make_uint4(__float_as_uint(v[8 * j]), __float_as_uint(v[8 * j + 1]), __float_as_uint(v[8 * j + 2]), __float_as_uint(v[8 * j + 3])),
+                                   make_uint4(__float_as_uint(v[8 * j + 4]), __float_as_uint(v[8 * j + 5]), __float_as_uint(v[8 * j + 6]), __float_as_uint(v[8 * j + 7])));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
                 } else {
                     uint32_t w[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) w[j] = pack2<BF16>(v[2 * j], v[2 * j + 1]);
                     uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + out_off + n);
-                    op[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                    op[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                    if (p.wide_io) {
+                        stg256(op, make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));
+                    } else {
+                        op[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                        op[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                    }
                     if (p.gn_sums) {
                         const int g = n / p.gn_cpg;
                         if (g != ggroup) {
@@ -901,6 +921,22 @@ int tapgemm_prepare(TapGemmOp* op) {
         set_error("tapgemm_prepare: residual, row-dot and GroupNorm-backward epilogues are mutually exclusive");
         return -3;
     }
+    {
+        // 256-bit epilogue accesses need every row piece 32-byte aligned
+        const long long es = p.out_fp32 ? 4 : 2;
+        auto al = [](long long v) { return (v & 31) == 0; };
+        bool ok = al(reinterpret_cast<long long>(p.out)) && al(p.out_sx * es) && al(p.out_sy * es) && al(p.out_sb * es) &&
+                  al(p.c_zstride * es);
+        if (p.residual) ok = ok && !p.out_fp32 && al(reinterpret_cast<long long>(p.residual));
+        if (p.gnb_red) ok = ok && !p.out_fp32 && al(reinterpret_cast<long long>(p.gnb_x));
+        if (p.rowdot) ok = ok && al(reinterpret_cast<long long>(p.dotsrc)) && al(p.ld_dot * 2);
+        static int no_wide = -1;
+        if (no_wide < 0) {
+            const char* e = getenv("WFD_NO_WIDE_IO");
+            no_wide = (e && e[0] == '1') ? 1 : 0;
+        }
+        p.wide_io = (ok && !no_wide) ? 1 : 0;
+    }
     if (p.kc_list && (p.reuse || p.kk_last || !p.kc_cnt || p.b_resident)) {
         set_error("tapgemm_prepare: a K-chunk skip list needs the plain schedule with whole 64-channel chunks");
         return -3;
@@ -918,7 +954,16 @@ int tapgemm_prepare(TapGemmOp* op) {
             no2 = (e && e[0] == '1') ? 1 : 0;
         }
         const bool pairs_ok = ((p.tiles_x * p.tiles_y) % 2 == 0) && !p.a_zmul;
-        p.cg = (!no2 && p.cg != 1 && !p.reuse && p.BN >= 128 && p.BN % 32 == 0 && pairs_ok) ? 2 : 1;
+        // row-reuse (grouped 3x3) contractions have narrow N tiles: their MMA-issuing thread is the bottleneck, and a pair
+        // halves the instructions per MAC (one 256 x BN MMA instead of two 128 x BN)
+        static int reuse2 = -1;
+        if (reuse2 < 0) {
+            const char* e = getenv("WFD_REUSE_2CTA");
+            reuse2 = (e && e[0] == '0') ? 0 : 1;
+        }
+        const bool wide = !p.reuse && p.BN >= 128 && p.BN % 32 == 0;
+        const bool narrow_reuse = p.reuse && reuse2 && p.BN % 16 == 0;
+        p.cg = (!no2 && p.cg != 1 && (wide || narrow_reuse) && pairs_ok) ? 2 : 1;
     }
     const CUtensorMapDataType dt = p.is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     {
@@ -943,7 +988,7 @@ int tapgemm_prepare(TapGemmOp* op) {
         // weights as (64 elements, rows, chunk): one box fetches the three vertical-tap chunks of a (dx, cc) pair
         cuuint64_t dims[3] = {(cuuint64_t)TG_KC, (cuuint64_t)p.b_rows, (cuuint64_t)(9 * p.cpt)};
         cuuint64_t strides[2] = {(cuuint64_t)p.ldb * 2, (cuuint64_t)TG_KC * 2};
-        cuuint32_t box[3] = {TG_KC, (cuuint32_t)p.BN, 3};
+        cuuint32_t box[3] = {TG_KC, (cuuint32_t)(p.BN / p.cg), 3};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(&op->tmB, dt, 3, const_cast<void*>(p.b_ptr), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1051,8 +1096,34 @@ int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream) {
                  p.gn_sums ? 1 : 0, cg);
     ProfScope prof_scope(g_prof_on ? pname : "", stream);
     cudaError_t e;
+    // WFD_TG_DBG=1 (diagnosis only): every launch runs with the per-role wait counters of CTA 0 and prints them
+    static int tg_dbg = -1;
+    static long long* tg_dbg_buf = nullptr;
+    if (tg_dbg < 0) {
+        const char* ev = getenv("WFD_TG_DBG");
+        tg_dbg = (ev && ev[0] == '1') ? 1 : 0;
+        if (tg_dbg && cudaMalloc(&tg_dbg_buf, 16 * sizeof(long long)) != cudaSuccess) tg_dbg = 0;
+    }
+    TapGemmOp dbg_op;
+    if (tg_dbg && !p.dbg) {
+        dbg_op = *op;
+        dbg_op.p.dbg = tg_dbg_buf;
+        cudaMemsetAsync(tg_dbg_buf, 0, 16 * sizeof(long long), stream);
+        op = &dbg_op;
+    }
     if (p.is_bf16) e = (cg == 2) ? launch_variant<true, 2>(op, grid, stream) : launch_variant<true, 1>(op, grid, stream);
     else e = (cg == 2) ? launch_variant<false, 2>(op, grid, stream) : launch_variant<false, 1>(op, grid, stream);
+    if (tg_dbg && op == &dbg_op && e == cudaSuccess) {
+        long long h[16];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, tg_dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        const TapGemmParams& q = op->p;
+        fprintf(stderr,
+                "tgdbg N=%d BN=%d taps=%d cpt=%d aC=%d reuse=%d cg=%d side=%d tiles=%d grid=%d stages=%d | A %lld we %lld is %lld | "
+                "B %lld we %lld is %lld | MMA %lld wte %lld wf %lld | EPI %lld wtf %lld busy %lld\n",
+                q.N, q.BN, q.n_taps, q.cpt, q.a_C, q.reuse, cg, q.residual ? 1 : (q.rowdot ? 2 : (q.gnb_red ? 3 : 0)), total, grid,
+                op->stages, h[0], h[1], h[10], h[8], h[9], h[11], h[2], h[3], h[4], h[5], h[6], h[7]);
+    }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("tapgemm launch: %s", cudaGetErrorString(e));

@@ -40,6 +40,7 @@ struct TapGemmParams {
     int W, H;               // output plane (pixel index = (bb*H + y)*W + x)
     int in_stride;          // input coordinate = out coordinate * in_stride + tap offset
     int a_y_off;            // added to every input row coordinate (row-band plans: the A view starts one halo row early)
+    int wide_io;            // set by tapgemm_prepare: output and side-input rows are 32-byte aligned (256-bit accesses)
     // ---- K loop
     int n_taps, cpt;        // taps, 64-wide chunks per tap
     int kk_last;            // 16-channel MMA steps needed in the last chunk of a tap (0 = all four)
