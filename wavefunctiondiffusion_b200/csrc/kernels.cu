@@ -186,12 +186,16 @@ gn_apply_k(const uint4* __restrict__ x, const acc_t* __restrict__ sums, const fl
     const int p0 = blockIdx.x * ppb, p1 = min(HW, p0 + ppb);
     const int tcol = threadIdx.x % m.nvt, trow = threadIdx.x / m.nvt;
     const int cpg = C / G;
+    // mean / rstd come out of double-precision math on the integer sums: once per group and block, not once per thread
+    __shared__ float s_mean[GN_MAXG], s_rstd[GN_MAXG];
+    if (threadIdx.x < G)
+        gn_finalize(sums, b, threadIdx.x, G, static_cast<double>(cpg) * HW_stat, eps, s_mean[threadIdx.x], s_rstd[threadIdx.x]);
+    __syncthreads();
     if (trow >= m.R) return;
     for (int k = 0; k < m.cpt; ++k) {
         const int col = tcol + k * m.nvt;
         if (col >= m.nv) break;
-        float mean, rstd;
-        gn_finalize(sums, b, (col * 8) / cpg, G, static_cast<double>(cpg) * HW_stat, eps, mean, rstd);
+        const float mean = s_mean[(col * 8) / cpg], rstd = s_rstd[(col * 8) / cpg];
         float sc[8], sh[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -233,15 +237,17 @@ gn_bwd_reduce_k(const uint4* __restrict__ dy, const uint4* __restrict__ x, const
     const int p0 = blockIdx.x * ppb, p1 = min(HW, p0 + ppb);
     const int tcol = threadIdx.x % m.nvt, trow = threadIdx.x / m.nvt;
     const int cpg = C / G;
+    __shared__ float s_mean[GN_MAXG], s_rstd[GN_MAXG];
     if (threadIdx.x < 2 * G) sh[threadIdx.x] = 0ull;
+    if (threadIdx.x < G)
+        gn_finalize(sums, b, threadIdx.x, G, static_cast<double>(cpg) * HW_stat, eps, s_mean[threadIdx.x], s_rstd[threadIdx.x]);
     __syncthreads();
     if (trow < m.R) {
         for (int k = 0; k < m.cpt; ++k) {
             const int col = tcol + k * m.nvt;
             if (col >= m.nv) break;
             const int g = (col * 8) / cpg;
-            float mean, rstd;
-            gn_finalize(sums, b, g, G, static_cast<double>(cpg) * HW_stat, eps, mean, rstd);
+            const float mean = s_mean[g], rstd = s_rstd[g];
             float ga[8], be[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -300,17 +306,21 @@ gn_bwd_apply_k(const uint4* __restrict__ dy, const uint4* __restrict__ x, const 
     const int p0 = blockIdx.x * ppb, p1 = min(HW, p0 + ppb);
     const int tcol = threadIdx.x % m.nvt, trow = threadIdx.x / m.nvt;
     const int cpg = C / G;
+    __shared__ float s_mean[GN_MAXG], s_rstd[GN_MAXG], s_r1[GN_MAXG], s_r2[GN_MAXG];
+    if (threadIdx.x < G) {
+        const int g = threadIdx.x;
+        const double n = static_cast<double>(cpg) * HW_stat;
+        gn_finalize(sums, b, g, G, n, eps, s_mean[g], s_rstd[g]);
+        s_r1[g] = static_cast<float>(static_cast<double>(red[(b * G + g) * 2]) * (1.0 / WFD_FX_GRAD) / n);
+        s_r2[g] = static_cast<float>(static_cast<double>(red[(b * G + g) * 2 + 1]) * (1.0 / WFD_FX_GRAD) / n);
+    }
+    __syncthreads();
     if (trow >= m.R) return;
     for (int k = 0; k < m.cpt; ++k) {
         const int col = tcol + k * m.nvt;
         if (col >= m.nv) break;
         const int g = (col * 8) / cpg;
-        float mean, rstd;
-        const double n = static_cast<double>(cpg) * HW_stat;
-        gn_finalize(sums, b, g, G, n, eps, mean, rstd);
-        const float inv_n = static_cast<float>(1.0 / n);
-        const float r1 = static_cast<float>(static_cast<double>(red[(b * G + g) * 2]) * (1.0 / WFD_FX_GRAD) / n);
-        const float r2 = static_cast<float>(static_cast<double>(red[(b * G + g) * 2 + 1]) * (1.0 / WFD_FX_GRAD) / n);
+        const float mean = s_mean[g], rstd = s_rstd[g], r1 = s_r1[g], r2 = s_r2[g];
         float ga[8], be[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -363,10 +373,18 @@ static int gn_check(int C, int G) {
     }
     return 0;
 }
-static void gn_grid(int B, int HW, int C, dim3& grid, int& ppb) {
+// One wave: the grid is sized to the number of blocks that are resident at once (blocks_per_sm comes from the occupancy
+// API for the kernel at hand). A grid of 1.33 waves - what "4 per SM" gave for kernels that fit 3 - runs as long as 2.
+template <typename K>
+static int gn_blocks_per_sm(K kernel) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, GN_THREADS, 0) != cudaSuccess || n < 1) n = 2;
+    return n;
+}
+static void gn_grid(int B, int HW, int C, int blocks_per_sm, dim3& grid, int& ppb) {
     const GnMap m = gn_map(C);
-    // aim at ~4 resident blocks per SM in total, each block looping over >= 8 of its row lanes
-    int blocks_x = (num_sms() * 4 + B - 1) / B;
+    int blocks_x = (num_sms() * blocks_per_sm) / B;
+    if (blocks_x < 1) blocks_x = 1;
     int min_ppb = m.R * 8;
     ppb = (HW + blocks_x - 1) / blocks_x;
     if (ppb < min_ppb) ppb = min_ppb;
@@ -380,7 +398,8 @@ int gn_stats(const void* x, acc_t* sums, int B, int HW, int C, int G, int bf16, 
     if (int r = gn_check(C, G)) return r;
     dim3 grid;
     int ppb;
-    gn_grid(B, HW, C, grid, ppb);
+    static const int bps = gn_blocks_per_sm(gn_stats_k<true>);
+    gn_grid(B, HW, C, bps, grid, ppb);
     WFD_DISPATCH_BF16(bf16, (gn_stats_k<BF16><<<grid, GN_THREADS, 0, s>>>(static_cast<const uint4*>(x), sums, HW, C, G, ppb)));
     WFD_CHECK_LAUNCH("gn_stats");
     return 0;
@@ -391,7 +410,8 @@ int gn_apply(const void* x, const acc_t* sums, const float* gamma, const float* 
     if (int r = gn_check(C, G)) return r;
     dim3 grid;
     int ppb;
-    gn_grid(B, HW, C, grid, ppb);
+    static const int bps = gn_blocks_per_sm(gn_apply_k<true>);
+    gn_grid(B, HW, C, bps, grid, ppb);
     WFD_DISPATCH_BF16(bf16, (gn_apply_k<BF16><<<grid, GN_THREADS, 0, s>>>(static_cast<const uint4*>(x), sums, gamma, beta,
                                                                          static_cast<uint4*>(y), HW, HW_stat > 0 ? HW_stat : HW, C, G, eps, silu, ppb)));
     WFD_CHECK_LAUNCH("gn_apply");
@@ -403,7 +423,8 @@ int gn_bwd_reduce(const void* dy, const void* x, const acc_t* sums, const float*
     if (int r = gn_check(C, G)) return r;
     dim3 grid;
     int ppb;
-    gn_grid(B, HW, C, grid, ppb);
+    static const int bps = gn_blocks_per_sm(gn_bwd_reduce_k<true>);
+    gn_grid(B, HW, C, bps, grid, ppb);
     WFD_DISPATCH_BF16(bf16, (gn_bwd_reduce_k<BF16><<<grid, GN_THREADS, 0, s>>>(
                                 static_cast<const uint4*>(dy), static_cast<const uint4*>(x), sums, gamma, beta, red, HW,
                                 HW_stat > 0 ? HW_stat : HW, C, G, eps, silu, ppb)));
@@ -417,7 +438,8 @@ int gn_bwd_apply(const void* dy, const void* x, const acc_t* sums, const float* 
     if (int r = gn_check(C, G)) return r;
     dim3 grid;
     int ppb;
-    gn_grid(B, HW, C, grid, ppb);
+    static const int bps = gn_blocks_per_sm(gn_bwd_apply_k<true>);
+    gn_grid(B, HW, C, bps, grid, ppb);
     WFD_DISPATCH_BF16(bf16, (gn_bwd_apply_k<BF16><<<grid, GN_THREADS, 0, s>>>(
                                 static_cast<const uint4*>(dy), static_cast<const uint4*>(x), sums, gamma, beta, red,
                                 static_cast<const uint4*>(add), static_cast<uint4*>(dx), HW, HW_stat > 0 ? HW_stat : HW,
