@@ -10,6 +10,7 @@ loaded) and an in-process loopback group (R bands on one GPU, one host thread pe
 """
 import ctypes as C
 import os
+import sys
 import threading
 
 import torch
@@ -112,11 +113,20 @@ class BandComm:
                   "wfd_comm_create_loopback")
         return BandComm(h, rank, group.nranks, keep=group)
 
+    def close(self):
+        """Destroy the communicator. Call it after every BandGuidance that captured CUDA graphs over it was closed: NCCL
+        keeps a communicator alive for the graphs that reference it, and tearing it down first can block."""
+        if self.handle:
+            nat.lib().wfd_comm_destroy(self.handle)
+            self.handle = None
+
     def __del__(self):
         try:
-            if self.handle:
-                nat.lib().wfd_comm_destroy(self.handle)
-                self.handle = None
+            import sys
+
+            if sys.is_finalizing():
+                return  # interpreter shutdown: destruction order is arbitrary, the process is going away anyway
+            self.close()
         except Exception:
             pass
 
@@ -141,6 +151,7 @@ class BandGuidance:
         self.wfc = WfcHandle(mat_x, mat_y, model.config.out_channels, self.dtype16, device)
         self.H_total = self.plan.H * self.nranks  # map rows (the ice/platform decoders keep the latent resolution)
         nat.check(lib.wfd_wfc_attach_comm(self.wfc.handle, comm.handle, self.H_total), "wfd_wfc_attach_comm")
+        self._graphs = {}
 
     def _check_z(self, z):
         _require_cuda(z, "row-band guidance")
@@ -154,17 +165,48 @@ class BandGuidance:
         self.plan.forward(z, in_scale)
         return self.plan.logits_view(1)
 
-    def step(self, z, in_scale=1.0, strength=1.0):
-        z = self._check_z(z)
-        lib = nat.lib()
-        loss = torch.empty(1, dtype=torch.float32, device=self.device)
-        dz = torch.empty((1, 4, self.h_band, self.w), dtype=torch.float32, device=self.device)
+    def _launch(self, z, in_scale, strength, loss, dz):
         self.plan.generation += 1
-        nat.check(lib.wfd_guidance_step(self.plan.handle, self.wfc.handle, C.c_void_p(z.data_ptr()), _z_dtype_code(z), 1,
-                                        float(in_scale), float(strength), self.wfc.saved_ptr(1, self.plan.H, self.plan.W),
-                                        C.c_void_p(loss.data_ptr()), C.c_void_p(dz.data_ptr()), nat.stream_ptr()),
-                  "wfd_guidance_step")
-        return loss, dz
+        nat.check(nat.lib().wfd_guidance_step(self.plan.handle, self.wfc.handle, C.c_void_p(z.data_ptr()), _z_dtype_code(z),
+                                              1, float(in_scale), float(strength),
+                                              self.wfc.saved_ptr(1, self.plan.H, self.plan.W), C.c_void_p(loss.data_ptr()),
+                                              C.c_void_p(dz.data_ptr()), nat.stream_ptr()), "wfd_guidance_step")
+
+    def step(self, z, in_scale=1.0, strength=1.0, graph=False):
+        """graph=True replays the step (kernels AND the NCCL exchanges between them) from a CUDA graph after two plain
+        warm-up calls: at 8 bands the ~290 short launches per step are otherwise bound by the host. Every rank must make
+        the same choice; the returned tensors are then static buffers that the next call overwrites."""
+        z = self._check_z(z)
+        if not graph:
+            loss = torch.empty(1, dtype=torch.float32, device=self.device)
+            dz = torch.empty((1, 4, self.h_band, self.w), dtype=torch.float32, device=self.device)
+            self._launch(z, in_scale, strength, loss, dz)
+            return loss, dz
+        key = (z.dtype, float(in_scale), float(strength))
+        g = self._graphs.get(key)
+        if g is None:
+            g = {"z": torch.zeros_like(z), "loss": torch.empty(1, dtype=torch.float32, device=self.device),
+                 "dz": torch.empty((1, 4, self.h_band, self.w), dtype=torch.float32, device=self.device), "calls": 0,
+                 "graph": None}
+            self._graphs[key] = g
+        g["z"].copy_(z)
+        if g["graph"] is None and g["calls"] >= 2:
+            torch.cuda.synchronize(self.device)
+            graph_obj = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_obj, capture_error_mode="thread_local"):
+                self._launch(g["z"], in_scale, strength, g["loss"], g["dz"])
+            g["graph"] = graph_obj
+        if g["graph"] is not None:
+            g["graph"].replay()
+        else:
+            self._launch(g["z"], in_scale, strength, g["loss"], g["dz"])
+        g["calls"] += 1
+        return g["loss"], g["dz"]
+
+    def close(self):
+        """Release the captured graphs (they hold the NCCL exchanges) before the communicator goes away."""
+        self._graphs.clear()
+        torch.cuda.synchronize(self.device)
 
     def wave(self):
         """(1, h_band, w, T_pad) wave of this band after step()."""
