@@ -234,7 +234,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_init(tdone_bar, 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], TG_EPI_THREADS * CG);
+            mbar_init(&tempty_bar[a], (p.epi_split ? TG_EPI_THREADS / 2 : TG_EPI_THREADS) * CG);
         }
         fence_barrier_init();
     }
@@ -482,9 +482,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // warps that take the even / odd 16-column chunks of the tile)
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        const int etid = threadIdx.x - 64;   // 0..255 among the epilogue threads
-        const int half = (warp - 2) >> 2;    // 0: even chunks, 1: odd chunks
-        int acc = 0;
+        const int half = (warp - 2) >> 2;    // 0: even chunks, 1: odd chunks (tile-split mode: even / odd tiles)
+        // Narrow tiles (a few 16-column chunks) are bound by the per-tile bookkeeping of the epilogue, not by its columns:
+        // in tile-split mode each half-set of four warps owns one accumulator stage and drains every other tile on its own
+        const bool split = p.epi_split != 0;
+        const int etid = split ? (threadIdx.x - 64) & 127 : threadIdx.x - 64;  // index among the threads that share a tile
+        const int eset = split ? TG_EPI_THREADS / 2 : TG_EPI_THREADS;
+        const int c_first = split ? 0 : half, c_step = split ? 1 : 2;
+        int acc = 0, my_tiles = 0;
         uint32_t acc_phase = 0;
         long long w_tfull = 0, e_busy = 0;
         const long long t_begin = clock64();
@@ -500,6 +505,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc.bb = __shfl_sync(0xffffffffu, mine.bb, l);
             tc.ty = __shfl_sync(0xffffffffu, mine.ty, l);
             tc.tx = __shfl_sync(0xffffffffu, mine.tx, l);
+            if (split && acc != half) {  // the other half-set's tile
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+                continue;
+            }
             const long long pixel =
                 (static_cast<long long>(tc.bb) * p.H + tc.ty * p.h_box + yy) * p.W + tc.tx * p.w_box + xx;
             const int n0 = tc.n_tile * p.BN;
@@ -507,19 +517,28 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                       static_cast<long long>(tc.ty * p.h_box + yy) * p.out_sy +
                                       static_cast<long long>(tc.tx * p.w_box + xx) * p.out_sx;
             // stage this tile's bias in shared memory while the MMAs are still running
-            float* bs = bias_s + acc * 256;
+            // tile-split mode: a half-set always drains the same accumulator, so its staging buffers alternate with its own
+            // tile count instead (four 64-float slices of each 2 x 256 array; BN <= 64 there)
+            const int stage_off = split ? (half * 2 + (my_tiles & 1)) * 64 : acc * 256;
+            ++my_tiles;
+            float* bs = bias_s + stage_off;
             if (p.bias) {
-                for (int j = etid; j < p.BN; j += TG_EPI_THREADS) bs[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+                for (int j = etid; j < p.BN; j += eset) bs[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
             }
-            float* gms = gam_s + acc * 256;
-            float* bts = bet_s + acc * 256;
+            float* gms = gam_s + stage_off;
+            float* bts = bet_s + stage_off;
             if (p.gnb_red) {
-                for (int j = etid; j < p.BN; j += TG_EPI_THREADS) {
+                for (int j = etid; j < p.BN; j += eset) {
                     gms[j] = (n0 + j < p.N) ? __ldg(p.gnb_gamma + n0 + j) : 0.f;
                     bts[j] = (n0 + j < p.N) ? __ldg(p.gnb_beta + n0 + j) : 0.f;
                 }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(TG_EPI_THREADS) : "memory");
+            if (split) {
+                if (half == 0) asm volatile("bar.sync 2, %0;" ::"n"(TG_EPI_THREADS / 2) : "memory");
+                else asm volatile("bar.sync 3, %0;" ::"n"(TG_EPI_THREADS / 2) : "memory");
+            } else {
+                asm volatile("bar.sync 1, %0;" ::"n"(TG_EPI_THREADS) : "memory");
+            }
             // one row-wise side input per launch: residual (forward), dot operand (WFC) or saved activation (GroupNorm
             // backward). Its 32-byte pieces are prefetched three chunks deep, the first three before the accumulator wait,
             // so that DRAM latency overlaps the MMAs instead of serialising the column loop.
@@ -542,9 +561,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             };
             if (side_ptr) {
-                if (half < n_chunks) load_side(half, sb0);
-                if (half + 2 < n_chunks) load_side(half + 2, sb1);
-                if (half + 4 < n_chunks) load_side(half + 4, sb2);
+                if (c_first < n_chunks) load_side(c_first, sb0);
+                if (c_first + c_step < n_chunks) load_side(c_first + c_step, sb1);
+                if (c_first + 2 * c_step < n_chunks) load_side(c_first + 2 * c_step, sb2);
             }
             {
                 const long long w0 = p.dbg ? clock64() : 0;
@@ -559,7 +578,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int ggroup = -1;
             float b1 = 0.f, b2 = 0.f, bmean = 0.f, brstd = 0.f;
             int bgroup = -1;
-            for (int c = half; c < n_chunks; c += 2) {
+            for (int c = c_first; c < n_chunks; c += c_step) {
                 const int j0 = c * 16;
                 const int n = n0 + j0;
                 uint4 side_cur[2];
@@ -567,7 +586,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     side_cur[0] = sb0[0]; side_cur[1] = sb0[1];
                     sb0[0] = sb1[0]; sb0[1] = sb1[1];
                     sb1[0] = sb2[0]; sb1[1] = sb2[1];
-                    if (c + 6 < n_chunks) load_side(c + 6, sb2);
+                    if (c + 3 * c_step < n_chunks) load_side(c + 3 * c_step, sb2);
                 }
                 uint32_t r[16];
                 tmem_ld16(taddr + j0, r);
@@ -936,6 +955,14 @@ int tapgemm_prepare(TapGemmOp* op) {
             no_wide = (e && e[0] == '1') ? 1 : 0;
         }
         p.wide_io = (ok && !no_wide) ? 1 : 0;
+    }
+    {
+        static int no_split = -1;
+        if (no_split < 0) {
+            const char* e = getenv("WFD_NO_EPI_SPLIT");
+            no_split = (e && e[0] == '1') ? 1 : 0;
+        }
+        p.epi_split = (!no_split && p.BN <= 64) ? 1 : 0;
     }
     if (p.kc_list && (p.reuse || p.kk_last || !p.kc_cnt || p.b_resident)) {
         set_error("tapgemm_prepare: a K-chunk skip list needs the plain schedule with whole 64-channel chunks");

@@ -41,6 +41,8 @@ struct TapGemmParams {
     int in_stride;          // input coordinate = out coordinate * in_stride + tap offset
     int a_y_off;            // added to every input row coordinate (row-band plans: the A view starts one halo row early)
     int wide_io;            // set by tapgemm_prepare: output and side-input rows are 32-byte aligned (256-bit accesses)
+    int epi_split;          // set by tapgemm_prepare: narrow tiles - the two epilogue warps of a TMEM lane quarter take alternate
+                            // TILES (all chunks of them) instead of alternate 16-column chunks of every tile
     // ---- K loop
     int n_taps, cpt;        // taps, 64-wide chunks per tap
     int kk_last;            // 16-channel MMA steps needed in the last chunk of a tap (0 = all four)
