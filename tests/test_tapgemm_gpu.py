@@ -212,6 +212,47 @@ def test_four_tap_neighbour_contraction(use_ref):
     assert _rel(out, want) < 6e-3
 
 
+@pytest.mark.parametrize("n_group", [0, 4])
+def test_block_sparse_skip_list_is_bit_identical(n_group):
+    """The WFC contraction visits only the K chunks of the adjacency operand that hold an allowed pair (wfc.cu): the
+    skipped chunks are all zero, so the result must equal the dense walk bit for bit (and the CUDA-core checker)."""
+    torch.manual_seed(6)
+    Bn, H, W, T, BN = 4, 32, 32, 512, 256
+    p = torch.rand(Bn, H, W, T, device="cuda").bfloat16()
+    mats = (torch.rand(4, T, T, device="cuda") < 0.02).bfloat16()
+    keep = torch.rand(4, T // BN, T // 64, device="cuda") < 0.4          # [tap][N tile][chunk] blocks that survive
+    keep[:, 1, :] = False
+    keep[0, 1, 3] = False                                                  # N tile 1 ends up with no chunk at all
+    mask = keep.repeat_interleave(BN, 1).repeat_interleave(64, 2).to(mats.dtype)
+    mats = mats * mask
+    Bm = torch.cat([mats[t] for t in range(4)], dim=1).contiguous()      # [T, 4T]
+    cpt, k_iters, n_tiles = T // 64, 4 * (T // 64), T // BN
+    tdx, tdy = [1, -1, 0, 0], [0, 0, 1, -1]
+    lst = torch.zeros(n_tiles, k_iters, dtype=torch.int32)
+    cnt = torch.zeros(n_tiles, dtype=torch.int32)
+    for n in range(n_tiles):
+        c = 0
+        for kc in range(k_iters):
+            tap, cc = divmod(kc, cpt)
+            if bool(Bm[n * BN:(n + 1) * BN, kc * 64:(kc + 1) * 64].any()):
+                lst[n, c] = (tdx[tap] + 1) | ((tdy[tap] + 1) << 2) | (cc << 4) | (kc << 16)
+                c += 1
+        cnt[n] = max(c, 1)
+    assert cnt.min().item() == 1 and cnt.sum().item() < n_tiles * k_iters
+    lst, cnt = lst.cuda(), cnt.cuda()
+    outs = []
+    for use_list, use_ref in ((True, 0), (False, 0), (False, 1)):
+        out = torch.zeros(Bn, H, W, T, device="cuda", dtype=torch.bfloat16)
+        d = _desc(a=p.data_ptr(), a_C=T, a_W=W, a_H=H, a_B=Bn, a_ld=T, b=Bm.data_ptr(), b_rows=T, ldb=4 * T, b_zstride=0,
+                  b_Z=1, n_taps=4, cpt=cpt, tap_dx=tdx, tap_dy=tdy, BN=BN, N=T, W=W, H=H, B=Bn, w_box=32, h_box=4,
+                  in_stride=1, z_count=1, out=out.data_ptr(), out_fp32=0, ldc=T, alpha=1.0, dtype16=1, n_group=n_group,
+                  kc_list=lst.data_ptr() if use_list else None, kc_cnt=cnt.data_ptr() if use_list else None)
+        _run(d, use_ref)
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    assert _rel(outs[0], outs[2]) < 6e-3
+
+
 @pytest.mark.parametrize("use_ref", [1, 0])
 @pytest.mark.parametrize("n_group", [0, 4])
 def test_persistent_many_tiles_per_cta(use_ref, n_group):
