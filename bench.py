@@ -332,6 +332,15 @@ def run_native(args):
                 "algorithmic_flops_per_step": fl["F_step"] * B, "launches_per_step": tg_launches,
                 "avg_launch_ms": tg_ms / tg_launches if tg_launches else None, "kernel_ms_per_step": tg_ms,
                 "share_of_step": tg_ms / all_ms if all_ms else None, "traffic": None}
+    # DRAM bytes per launch come from the committed ncu capture of the same workload (they cannot be measured live)
+    if args.tileset == "ice_64x64" and args.latent == 64 and args.arch == "64x64" and B == 8:
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01c_tapgemm_dram.json")))
+            roofline["traffic"] = tr["traffic_bytes_per_launch"]
+            roofline["traffic_unit"] = "bytes per launch (dram read + write, mean over the %d launches of one step)" % tr["launches"]
+            roofline["traffic_source"] = "profiles/r01c_tapgemm_dram.json: " + tr["source"]
+        except Exception:
+            pass
     top = sorted(prof.items(), key=lambda kv: -kv[1][1])[:args.top]
     if args.verbose:
         for n, (c, t) in top:
