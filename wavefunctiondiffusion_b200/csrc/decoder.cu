@@ -59,6 +59,13 @@ static int choose_bn(int rpg) {
     return 64;
 }
 
+// Few-tile launches (batch 1, or one row band of a large map): a 128-pixel x BN tiling that yields fewer tiles than
+// there are SMs leaves most of the GPU idle, so BN is halved (down to 48..96) until the launch has ~100 tiles.
+static int fit_bn(int BN, long long m_tiles, int N) {
+    while (BN >= 96 && (BN / 2) % 16 == 0 && N % (BN / 2) == 0 && m_tiles * ((N + BN - 1) / BN) < 100) BN /= 2;
+    return BN;
+}
+
 void PackedB::release() {
     if (Bm) cudaFree(Bm);
     if (a_c0) cudaFree(a_c0);
@@ -407,9 +414,14 @@ int Decoder::pack_named_conv(const std::string& name, int cout, int cin, int gro
         const size_t per_stage = static_cast<size_t>(hb + 2) * wb * 128 + 3 * static_cast<size_t>(BN) * 128;
         return per_stage * 3 <= 216 * 1024;
     };
-    CK(pack_conv(wv->data(), cout, cin, groups, k, fwd_mode, bf16 != 0, 0, &cw.fwd, nullptr, want_reuse(cout / groups)));
+    // dense (groups == 1) layers may use a narrower N tile when the plan has few 128-pixel tiles
+    const long long m_tiles = ph > 0 ? static_cast<long long>(B_max) * ((static_cast<long long>(ph) * pw) / TG_BM)
+                                     : static_cast<long long>(B_max) * ((static_cast<long long>(h) * w) / TG_BM);
+    const int bn_f = groups == 1 ? fit_bn(choose_bn(cout), m_tiles, cout) : 0;
+    const int bn_b = groups == 1 ? fit_bn(choose_bn(cin), m_tiles, cin) : 0;
+    CK(pack_conv(wv->data(), cout, cin, groups, k, fwd_mode, bf16 != 0, bn_f, &cw.fwd, nullptr, want_reuse(cout / groups)));
     if (want_bwd && fwd_mode == 0)
-        CK(pack_conv(wv->data(), cout, cin, groups, k, 1, bf16 != 0, 0, &cw.bwd, nullptr, want_reuse(cin / groups)));
+        CK(pack_conv(wv->data(), cout, cin, groups, k, 1, bf16 != 0, bn_b, &cw.bwd, nullptr, want_reuse(cin / groups)));
     CK(upload_f32(*bv, &cw.bias));
     return 0;
 }
@@ -850,7 +862,8 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
                         Cm, G, eps, 0, bf16, s, N * band_R));
         }
         const ConvW& cq = convs["attn.qkv"];
-        const int bn_c = Cm % 192 == 0 ? 192 : (Cm % 128 == 0 ? 128 : (Cm % 64 == 0 ? 64 : 16));
+        const int bn_c = fit_bn(Cm % 192 == 0 ? 192 : (Cm % 128 == 0 ? 128 : (Cm % 64 == 0 ? 64 : 16)),
+                                static_cast<long long>(B_max) * (N / TG_BM), Cm);
         const int bn_n = Nk % 256 == 0 ? 256 : 128;
         PlainGemm g;
         memset(&g, 0, sizeof(g));
@@ -1059,7 +1072,8 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         uint8_t* dqkv = ws + o_dqkv;
         uint8_t* dkv = ws + o_dkv;
         const ConvW& cp = convs[a + "proj_attn"];
-        const int bn_c = Cm % 192 == 0 ? 192 : (Cm % 128 == 0 ? 128 : (Cm % 64 == 0 ? 64 : 16));
+        const int bn_c = fit_bn(Cm % 192 == 0 ? 192 : (Cm % 128 == 0 ? 128 : (Cm % 64 == 0 ? 64 : 16)),
+                                static_cast<long long>(B_max) * (N / TG_BM), Cm);
         const int bn_n = Nk % 256 == 0 ? 256 : 128;
         PlainGemm g;
         // dO = dout Wp
