@@ -176,8 +176,8 @@ __device__ __forceinline__ float sigmoidf_(float u) {
     return fmaf(0.5f, t, 0.5f);
 }
 
-template <bool BF16>
-__global__ void __launch_bounds__(GN_THREADS, 3)
+template <bool BF16, int U>
+__global__ void __launch_bounds__(GN_THREADS, U <= 2 ? 3 : 2)
 gn_apply_k(const uint4* __restrict__ x, const acc_t* __restrict__ sums, const float* __restrict__ gamma,
            const float* __restrict__ beta, uint4* __restrict__ y, int HW, int HW_stat, int C, int G, float eps, int silu,
            int ppb) {
@@ -204,7 +204,7 @@ gn_apply_k(const uint4* __restrict__ x, const acc_t* __restrict__ sums, const fl
             sh[j] = __ldg(beta + col * 8 + j) - mean * rstd * ga;
         }
         const long long base = (static_cast<long long>(b) * HW) * m.nv + col;
-        constexpr int U = 2;  // independent 16-byte loads in flight per thread
+        // U independent 16-byte loads in flight per thread
         for (int p = p0 + trow; p < p1; p += U * m.R) {
             uint4 raw[U];
 #pragma unroll
@@ -410,10 +410,28 @@ int gn_apply(const void* x, const acc_t* sums, const float* gamma, const float* 
     if (int r = gn_check(C, G)) return r;
     dim3 grid;
     int ppb;
-    static const int bps = gn_blocks_per_sm(gn_apply_k<true>);
-    gn_grid(B, HW, C, bps, grid, ppb);
-    WFD_DISPATCH_BF16(bf16, (gn_apply_k<BF16><<<grid, GN_THREADS, 0, s>>>(static_cast<const uint4*>(x), sums, gamma, beta,
-                                                                         static_cast<uint4*>(y), HW, HW_stat > 0 ? HW_stat : HW, C, G, eps, silu, ppb)));
+    // loads in flight per thread: WFD_GN_APPLY_U = 2 (3 blocks per SM), 4 or 6 (2 blocks per SM)
+    static int u_sel = -1;
+    if (u_sel < 0) {
+        const char* e = getenv("WFD_GN_APPLY_U");
+        u_sel = e ? atoi(e) : 4;  // measured on B200: 1.045 / 0.993 / 0.990 ms per step for 2 / 4 / 6
+    }
+    if (u_sel == 4) {
+        static const int bps = gn_blocks_per_sm(gn_apply_k<true, 4>);
+        gn_grid(B, HW, C, bps, grid, ppb);
+        WFD_DISPATCH_BF16(bf16, (gn_apply_k<BF16, 4><<<grid, GN_THREADS, 0, s>>>(static_cast<const uint4*>(x), sums, gamma, beta,
+                                                                                static_cast<uint4*>(y), HW, HW_stat > 0 ? HW_stat : HW, C, G, eps, silu, ppb)));
+    } else if (u_sel == 6) {
+        static const int bps = gn_blocks_per_sm(gn_apply_k<true, 6>);
+        gn_grid(B, HW, C, bps, grid, ppb);
+        WFD_DISPATCH_BF16(bf16, (gn_apply_k<BF16, 6><<<grid, GN_THREADS, 0, s>>>(static_cast<const uint4*>(x), sums, gamma, beta,
+                                                                                static_cast<uint4*>(y), HW, HW_stat > 0 ? HW_stat : HW, C, G, eps, silu, ppb)));
+    } else {
+        static const int bps = gn_blocks_per_sm(gn_apply_k<true, 2>);
+        gn_grid(B, HW, C, bps, grid, ppb);
+        WFD_DISPATCH_BF16(bf16, (gn_apply_k<BF16, 2><<<grid, GN_THREADS, 0, s>>>(static_cast<const uint4*>(x), sums, gamma, beta,
+                                                                                static_cast<uint4*>(y), HW, HW_stat > 0 ? HW_stat : HW, C, G, eps, silu, ppb)));
+    }
     WFD_CHECK_LAUNCH("gn_apply");
     return 0;
 }
