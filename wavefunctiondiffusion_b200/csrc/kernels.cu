@@ -226,8 +226,8 @@ gn_apply_k(const uint4* __restrict__ x, const acc_t* __restrict__ sums, const fl
     }
 }
 
-template <bool BF16>
-__global__ void __launch_bounds__(GN_THREADS, 3)
+template <bool BF16, int U>
+__global__ void __launch_bounds__(GN_THREADS, U <= 2 ? 3 : 2)
 gn_bwd_reduce_k(const uint4* __restrict__ dy, const uint4* __restrict__ x, const acc_t* __restrict__ sums,
                 const float* __restrict__ gamma, const float* __restrict__ beta, acc_t* __restrict__ red, int HW,
                 int HW_stat, int C, int G, float eps, int silu, int ppb) {
@@ -256,7 +256,6 @@ gn_bwd_reduce_k(const uint4* __restrict__ dy, const uint4* __restrict__ x, const
             }
             float s1 = 0.f, s2 = 0.f;
             const long long base = (static_cast<long long>(b) * HW) * m.nv + col;
-            constexpr int U = 2;
             for (int p = p0 + trow; p < p1; p += U * m.R) {
                 uint4 rx[U], rd[U];
 #pragma unroll
@@ -441,11 +440,24 @@ int gn_bwd_reduce(const void* dy, const void* x, const acc_t* sums, const float*
     if (int r = gn_check(C, G)) return r;
     dim3 grid;
     int ppb;
-    static const int bps = gn_blocks_per_sm(gn_bwd_reduce_k<true>);
-    gn_grid(B, HW, C, bps, grid, ppb);
-    WFD_DISPATCH_BF16(bf16, (gn_bwd_reduce_k<BF16><<<grid, GN_THREADS, 0, s>>>(
-                                static_cast<const uint4*>(dy), static_cast<const uint4*>(x), sums, gamma, beta, red, HW,
-                                HW_stat > 0 ? HW_stat : HW, C, G, eps, silu, ppb)));
+    static int u_sel = -1;  // (x, dy) row pairs in flight per thread: WFD_GN_REDUCE_U = 2 (3 blocks per SM) or 4 (2 per SM)
+    if (u_sel < 0) {
+        const char* e = getenv("WFD_GN_REDUCE_U");
+        u_sel = e ? atoi(e) : 4;  // measured on B200: 0.903 / 0.853 ms per step for 2 / 4
+    }
+    if (u_sel == 4) {
+        static const int bps = gn_blocks_per_sm(gn_bwd_reduce_k<true, 4>);
+        gn_grid(B, HW, C, bps, grid, ppb);
+        WFD_DISPATCH_BF16(bf16, (gn_bwd_reduce_k<BF16, 4><<<grid, GN_THREADS, 0, s>>>(
+                                    static_cast<const uint4*>(dy), static_cast<const uint4*>(x), sums, gamma, beta, red, HW,
+                                    HW_stat > 0 ? HW_stat : HW, C, G, eps, silu, ppb)));
+    } else {
+        static const int bps = gn_blocks_per_sm(gn_bwd_reduce_k<true, 2>);
+        gn_grid(B, HW, C, bps, grid, ppb);
+        WFD_DISPATCH_BF16(bf16, (gn_bwd_reduce_k<BF16, 2><<<grid, GN_THREADS, 0, s>>>(
+                                    static_cast<const uint4*>(dy), static_cast<const uint4*>(x), sums, gamma, beta, red, HW,
+                                    HW_stat > 0 ? HW_stat : HW, C, G, eps, silu, ppb)));
+    }
     WFD_CHECK_LAUNCH("gn_bwd_reduce");
     return 0;
 }
