@@ -108,3 +108,52 @@ def test_band_shape_errors():
         DecoderPlan(net, 30, 32, 1, 1, torch.device("cuda"), band=(0, 4))  # 30 rows do not split into 4 bands
     with pytest.raises(nat.WfdError):
         DecoderPlan(net, 32, 32, 2, 1, torch.device("cuda"), band=(0, 2))  # one map per band plan
+
+
+def test_pipeline_guidance_block_in_row_bands(tmp_path):
+    """`WaveFunctionDiffusionPipeline.wfc_guidance` with `enable_row_bands`: the guided latents of every band rank equal
+    those of the single-device pipeline (same scheduler chain factor, gradient gathered from the bands)."""
+    from wavefunctiondiffusion_b200.utils.harness import (AffineDDIMScheduler, ConstantTextEncoder, RandomNoiseUNet,
+                                                          TinyImageVAE, WhitespaceTokenizer)
+    from wavefunctiondiffusion_b200.wf_diffusers.pipeline_wfd import WaveFunctionDiffusionPipeline
+
+    z = np.load(os.path.join(GOLD, "tiny_step.npz"))
+    cfg = json.loads(str(z["cfg_json"]))
+    T = int(z["T"])
+    mats = np.unpackbits(z["mats"])[: 2 * T * T].reshape(2, T, T).astype(bool)
+    torch.manual_seed(int(z["seed"]))
+    net = AutoencoderTile(**cfg).eval().cuda()
+    npz = str(tmp_path / "wfc.npz")
+    np.savez(npz, wfc_mats=mats)
+
+    def make_pipe():
+        pipe = WaveFunctionDiffusionPipeline(TinyImageVAE(), ConstantTextEncoder(), WhitespaceTokenizer(), net,
+                                             RandomNoiseUNet(4, 32), AffineDDIMScheduler(), None, None, wfc_data_path=npz)
+        pipe.set_progress_bar_config(disable=True)
+        pipe.to("cuda")
+        pipe.scheduler.set_timesteps(50, device="cuda")
+        return pipe
+
+    g = torch.Generator().manual_seed(21)
+    lat = (torch.randn(1, 4, 32, 32, generator=g) * 0.8).cuda()
+    eps = torch.randn(1, 4, 32, 32, generator=g).cuda()
+    ref_pipe = make_pipe()
+    t = ref_pipe.scheduler.timesteps[25]
+    want = ref_pipe.wfc_guidance(lat, eps, t, 5.0)
+    pipes = [make_pipe() for _ in range(2)]
+    torch.cuda.synchronize()
+
+    def fn(rank, comm):
+        pipes[rank].enable_row_bands(comm)
+        out = pipes[rank].wfc_guidance(lat, eps, t, 5.0)
+        with pytest.raises(ValueError):
+            pipes[rank].guidance_loss(torch.cat([lat, lat]), 5.0)
+        torch.cuda.current_stream().synchronize()
+        pipes[rank].disable_row_bands()
+        return out.cpu()
+
+    outs = run_loopback(2, fn)
+    assert torch.equal(outs[0], outs[1])
+    # the guidance step is ~1e-5 of the latents: compared as a difference of fp32 latents it carries their rounding noise
+    assert _rel(outs[0], want.cpu()) < 1e-6
+    assert _rel(outs[0] - lat.cpu(), (want - lat).cpu()) < 2e-2

@@ -121,10 +121,36 @@ class WaveFunctionDiffusionPipeline:
             return image.cpu().permute(0, 2, 3, 1).float().numpy()
         return image
 
+    def enable_row_bands(self, comm, graph=False):
+        """Compute the guidance of ONE large map in row bands over the ranks of `comm` (rowband.BandComm): every rank
+        runs this pipeline on the same latents (the UNet and the schedulers stay replicated, as in the reference) and
+        the tile-VAE decode / WFC loss / backward of the guidance block are split along y. Batch must be 1."""
+        self._row_bands = {"comm": comm, "graph": bool(graph), "plans": {}}
+
+    def disable_row_bands(self):
+        rb = getattr(self, "_row_bands", None)
+        if rb:
+            for bg in rb["plans"].values():
+                bg.close()
+        self._row_bands = None
+
     def guidance_loss(self, latents, strength):
         """strength * wfc_loss(decode_latents_tile(latents)) as ONE fused library call, differentiable w.r.t.
         `latents`: decode, softmax, the four-direction adjacency contraction and the whole backward never leave the
         device library (the wave is not materialised in torch)."""
+        rb = getattr(self, "_row_bands", None)
+        if rb:
+            from .rowband import BandGuidance, BandGuidanceFunction
+
+            if latents.shape[0] != 1:
+                raise ValueError("row bands split ONE map: batch size must be 1, got %d" % latents.shape[0])
+            key = (latents.shape[2], latents.shape[3], str(latents.device))
+            bg = rb["plans"].get(key)
+            if bg is None:
+                ax, ay = self.wfc_loss._mats()
+                bg = BandGuidance(self.tile_vae, ax, ay, latents.shape[2], latents.shape[3], rb["comm"], latents.device)
+                rb["plans"][key] = bg
+            return BandGuidanceFunction.apply(latents, bg, 1.0 / LATENT_SCALE, float(strength), rb["graph"])
         t_pad = self.tile_vae.config.out_channels
         handle = self.wfc_loss.native_handle(t_pad, latents.device)
         return GuidanceLossFunction.apply(latents, self.tile_vae._native, handle, 1.0 / LATENT_SCALE, float(strength))

@@ -65,6 +65,18 @@ class LoopbackGroup:
         self.handle = nat.lib().wfd_loop_group_create(nranks)
         if not self.handle:
             raise nat.WfdError("wfd_loop_group_create failed")
+        self._slots = [None] * nranks
+        self._barrier = threading.Barrier(nranks)
+
+    def gather_rows(self, rank, t, dim):
+        """Host-side counterpart of the all-gather: every thread leaves its band, all read the concatenation."""
+        torch.cuda.current_stream().synchronize()
+        self._slots[rank] = t
+        self._barrier.wait(timeout=120)
+        out = torch.cat([x.clone() for x in self._slots], dim=dim)
+        torch.cuda.current_stream().synchronize()
+        self._barrier.wait(timeout=120)
+        return out
 
     def comm(self, rank):
         return BandComm._loopback(self, rank)
@@ -112,6 +124,13 @@ class BandComm:
         nat.check(nat.lib().wfd_comm_create_loopback(C.c_void_p(group.handle), rank, C.byref(h)),
                   "wfd_comm_create_loopback")
         return BandComm(h, rank, group.nranks, keep=group)
+
+    def gather_rows(self, t, dim):
+        """Concatenate every rank's band along `dim`: torch.distributed all_gather between processes, a host-side
+        exchange between the threads of a loopback group."""
+        if self._keep is not None:
+            return self._keep.gather_rows(self.rank, t, dim)
+        return gather_rows(t, dim)
 
     def close(self):
         """Destroy the communicator. Call it after every BandGuidance that captured CUDA graphs over it was closed: NCCL
@@ -211,6 +230,24 @@ class BandGuidance:
     def wave(self):
         """(1, h_band, w, T_pad) wave of this band after step()."""
         return self.wfc.wave_view(1, self.plan.H, self.plan.W)
+
+
+class BandGuidanceFunction(torch.autograd.Function):
+    """strength * wfc_loss(softmax(decode(latents / 0.18215))) of ONE map computed in row bands: the loss is the map's
+    loss on every rank, the gradient is gathered from the bands, so `torch.autograd.grad(loss, latents)` behaves exactly
+    as with the single-device GuidanceLossFunction (reference pipeline_wfd.py:609-613)."""
+
+    @staticmethod
+    def forward(ctx, latents, bands, in_scale, strength, graph):
+        loss, dz = bands.step(latents.detach(), in_scale, strength, graph=graph)
+        ctx.save_for_backward(bands.comm.gather_rows(dz, 2))
+        ctx.zdtype = latents.dtype
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dz,) = ctx.saved_tensors
+        return (dz * dloss.float().view(-1, 1, 1, 1)).to(ctx.zdtype), None, None, None, None
 
 
 def gather_rows(t, dim):
