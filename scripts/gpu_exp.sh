@@ -1,9 +1,8 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-for u in 2 4; do
-  WFD_GN_REDUCE_U=$u python bench.py --steps 10 --warmup 3 --no-cpu-baseline --verbose --top 8 2> gpurun_out/exp.err | python -c "
+for m in 64 96 128 0; do
+  WFD_EPI_SPLIT_MAX=$m python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('gn_reduce U=$u: ms/step %.3f'%d['ms_per_step'])"
-  grep "gn_bwd_reduce" gpurun_out/exp.err
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('epi_split_max $m: ms/step %.3f loss %s'%(d['ms_per_step'], d['loss_check']))"
 done

@@ -518,8 +518,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                       static_cast<long long>(tc.tx * p.w_box + xx) * p.out_sx;
             // stage this tile's bias in shared memory while the MMAs are still running
             // tile-split mode: a half-set always drains the same accumulator, so its staging buffers alternate with its own
-            // tile count instead (four 64-float slices of each 2 x 256 array; BN <= 64 there)
-            const int stage_off = split ? (half * 2 + (my_tiles & 1)) * 64 : acc * 256;
+            // tile count instead (four 128-float slices of each 2 x 256 array; BN <= 128 there)
+            const int stage_off = split ? (half * 2 + (my_tiles & 1)) * 128 : acc * 256;
             ++my_tiles;
             float* bs = bias_s + stage_off;
             if (p.bias) {
@@ -957,12 +957,13 @@ int tapgemm_prepare(TapGemmOp* op) {
         p.wide_io = (ok && !no_wide) ? 1 : 0;
     }
     {
-        static int no_split = -1;
-        if (no_split < 0) {
-            const char* e = getenv("WFD_NO_EPI_SPLIT");
-            no_split = (e && e[0] == '1') ? 1 : 0;
+        static int split_max = -1;  // widest N tile drained in tile-split mode (WFD_EPI_SPLIT_MAX, 0 = never; <= 128)
+        if (split_max < 0) {
+            const char* e = getenv("WFD_EPI_SPLIT_MAX");
+            split_max = e ? atoi(e) : 96;  // measured on B200: 13.76 / 13.49 / 13.31 / 13.39 ms per step for 0 / 64 / 96 / 128
+            if (split_max > 128) split_max = 128;
         }
-        p.epi_split = (!no_split && p.BN <= 64) ? 1 : 0;
+        p.epi_split = (p.BN <= split_max) ? 1 : 0;
     }
     if (p.kc_list && (p.reuse || p.kk_last || !p.kc_cnt || p.b_resident)) {
         set_error("tapgemm_prepare: a K-chunk skip list needs the plain schedule with whole 64-channel chunks");
