@@ -177,7 +177,9 @@ def run_reference(args):
         "impl": "reference", "metric": "wfc_guidance_map_steps_per_s", "value": v, "unit": "maps/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, T, t_pad, per_gpu_batch=1),
+        "config": dict(workload_config(args, T, t_pad, per_gpu_batch=args.batch),
+                       reference_sample="each step runs ONE map of the batch of %d (maps are independent; the metric is "
+                                        "per map)" % args.batch),
         "cpu_baseline": {"value": v, "unit": "maps/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
