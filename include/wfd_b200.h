@@ -179,6 +179,7 @@ typedef struct {
     int n_group;      /* >1: tile rasterisation in bands of n_group N tiles */
     int reuse;        /* 1: row-reuse schedule (3x3 stride-1 taps, b packed in (dx, cc, dy) chunk order) */
     long long* dbg;   /* optional device int64[8]: cycle counters of CTA 0 per warp role (profiling aid) */
+    int a_mn_major;     /* A given transposed in memory: [a_B][a_C = K rows][a_W = M columns], M contiguous, pitch a_ld */
     const int* kc_list; /* optional K-chunk skip list (device), entries dx+1 | (dy+1)<<2 | chunk-in-tap<<4 | chunk<<16; */
     const int* kc_cnt;  /* [n_tiles] entries used per N tile (>= 1); rows n*n_taps*cpt.. of kc_list belong to N tile n */
 } wfd_tapgemm_desc;

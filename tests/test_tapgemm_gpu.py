@@ -212,6 +212,24 @@ def test_four_tap_neighbour_contraction(use_ref):
     assert _rel(out, want) < 6e-3
 
 
+@pytest.mark.parametrize("use_ref", [1, 0])
+@pytest.mark.parametrize("M,K,N,BN,Bn", [(256, 128, 64, 64, 1), (512, 256, 384, 192, 2), (1024, 192, 48, 48, 1)])
+def test_m_major_a_operand(M, K, N, BN, Bn, use_ref):
+    """A handed over transposed in memory ([K][M], M contiguous) - the attention backward products dV = P^T dO and
+    dK = dS^T Q read P / dS as they are stored instead of going through a transpose pass."""
+    torch.manual_seed(7)
+    At = torch.randn(Bn, K, M, device="cuda").bfloat16()          # [sample][k][m]
+    Bm = torch.randn(Bn, N, K, device="cuda").bfloat16()
+    out = torch.zeros(Bn, M, N, device="cuda", dtype=torch.bfloat16)
+    d = _desc(a=At.data_ptr(), a_C=K, a_W=M, a_H=1, a_B=Bn, a_ld=M, b=Bm.data_ptr(), b_rows=N, ldb=K, b_zstride=N * K,
+              b_Z=Bn, n_taps=1, cpt=K // 64, tap_dx=[0], tap_dy=[0], a_c0=None, BN=BN, N=N, W=M, H=1, B=Bn, w_box=128,
+              h_box=1, in_stride=1, z_count=1, b_bbmul=1, out=out.data_ptr(), out_fp32=0, ldc=N, alpha=1.0, dtype16=1,
+              a_mn_major=1)
+    _run(d, use_ref)
+    want = torch.einsum("bkm,bnk->bmn", At.float(), Bm.float())
+    assert _rel(out, want) < 6e-3
+
+
 @pytest.mark.parametrize("n_group", [0, 4])
 def test_block_sparse_skip_list_is_bit_identical(n_group):
     """The WFC contraction visits only the K chunks of the adjacency operand that hold an allowed pair (wfc.cu): the

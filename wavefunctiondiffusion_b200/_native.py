@@ -45,6 +45,7 @@ class TapGemmDesc(C.Structure):
         ("n_group", C.c_int),
         ("reuse", C.c_int),
         ("dbg", C.c_void_p),
+        ("a_mn_major", C.c_int),
         ("kc_list", C.c_void_p),
         ("kc_cnt", C.c_void_p),
     ]

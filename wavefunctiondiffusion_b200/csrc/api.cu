@@ -359,6 +359,7 @@ int wfd_test_tapgemm(const wfd_tapgemm_desc* t, int use_ref, void* stream) {
     p.gn_G = 8;
     p.is_bf16 = t->dtype16;
     p.dbg = t->dbg;
+    p.a_mn_major = t->a_mn_major;
     p.kc_list = t->kc_list;
     p.kc_cnt = t->kc_cnt;
     p.a_ptr = t->a;

@@ -234,6 +234,8 @@ int Decoder::init(const wfd_decoder_config& c, int h_, int w_, int Bmax, int dty
         conv_n_group = ng ? atoi(ng) : 0;
         const char* m = getenv("WFD_FUSE_BWD_MAX_C");
         fuse_bwd_max_c = m ? atoi(m) : 768;
+        const char* mm = getenv("WFD_NO_MMAJOR");
+        mmajor_a = !(mm && mm[0] == '1');
     }
     if (c.latent_channels != 4) {
         set_error("decoder: latent_channels must be 4 (got %d)", c.latent_channels);
@@ -352,9 +354,9 @@ void Decoder::layout_workspace() {
     o_P = take(B * N * Nk * e);
     o_O = take(B * N * Cm * e);
     // backward-only attention scratch
-    o_PT = take(B * N * Nk * e);
+    o_PT = mmajor_a ? 0 : take(B * N * Nk * e);  // transposed copies only without the M-major A operand
     o_dS = take(B * N * Nk * e);
-    o_dST = take(B * N * Nk * e);
+    o_dST = mmajor_a ? 0 : take(B * N * Nk * e);
     o_dO = take(B * N * Cm * e);
     o_dOT = take(B * Cm * N * e);
     o_KT = take(B * Cm * Nk * e);
@@ -649,6 +651,7 @@ int Decoder::conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int 
 // plain batched GEMM: D[rows, N] = alpha * A[rows, K] * Bm[N, K]^T (+bias)(+residual); rows are tokens of sample bb
 struct PlainGemm {
     const void* A; int K; long long a_ld; int rows_per_sample; int a_B;   // A: [a_B, rows_per_sample, a_ld]
+    bool a_mn_major;                                                      // A stored transposed: [a_B, K, a_ld >= rows]
     bool a_shared;                                                        // A identical for every z (weights as A)
     const void* Bm; int b_rows; long long ldb, b_zstride; int b_Z;        // Bm: [b_Z][b_rows][ldb]
     bool b_per_sample;                                                    // Bm slice = sample index
@@ -718,6 +721,7 @@ int Decoder::plain_gemm(Exec& ex, const PlainGemm& g) {
             p.gnb_eps = g.gb->eps;
         }
         p.is_bf16 = bf16;
+        p.a_mn_major = g.a_mn_major ? 1 : 0;
         p.a_ptr = g.A;
         p.a_C = g.K;
         p.a_W = g.rows_per_sample;
@@ -1084,14 +1088,17 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         CK(plain_gemm(ex, g));
         if (!ex.prepare) {
             CK(transpose16(ws + o_dO, ws + o_dOT, B, N, Cm, Cm, static_cast<long long>(N) * Cm, s));
-            CK(transpose16(ws + o_P, ws + o_PT, B, N, Nk, Nk, static_cast<long long>(N) * Nk, s));
+            if (!mmajor_a) CK(transpose16(ws + o_P, ws + o_PT, B, N, Nk, Nk, static_cast<long long>(N) * Nk, s));
             CK(transpose16(qkv, ws + o_QT, B, N, Cm, 3 * Cm, static_cast<long long>(N) * 3 * Cm, s));
             CK(transpose16(qkv_all + static_cast<size_t>(Cm) * 2, ws + o_KT, B, Nk, Cm, 3 * Cm,
                            static_cast<long long>(Nk) * 3 * Cm, s));
         }
         // dV = P^T dO  -> dqkv[:, 2C:3C] (band plan: partial over this band's queries, fp32)
         memset(&g, 0, sizeof(g));
-        g.A = ws + o_PT; g.K = N; g.a_ld = N; g.rows_per_sample = Nk; g.a_B = B_max;
+        // (P is read as stored, M-major: no transposed copy of the N x Nk matrix)
+        if (mmajor_a) { g.A = ws + o_P; g.a_ld = Nk; g.a_mn_major = true; }
+        else { g.A = ws + o_PT; g.a_ld = N; }
+        g.K = N; g.rows_per_sample = Nk; g.a_B = B_max;
         g.Bm = ws + o_dOT; g.b_rows = Cm; g.ldb = N; g.b_zstride = static_cast<long long>(Cm) * N; g.b_Z = B_max;
         g.b_per_sample = true; g.BN = bn_c; g.N = Cm; g.alpha = 1.f;
         if (split) { g.out = dkv + static_cast<size_t>(Cm) * 4; g.out_fp32 = 1; g.ldc = 2 * Cm; }
@@ -1107,7 +1114,7 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         if (!ex.prepare) {
             CK(attn_softmax_bwd(ws + o_P, reinterpret_cast<const float*>(ws + o_S), ws + o_dS, static_cast<long long>(B) * N,
                                 Nk, 1.f / sqrtf(static_cast<float>(Cm)), bf16, s));
-            CK(transpose16(ws + o_dS, ws + o_dST, B, N, Nk, Nk, static_cast<long long>(N) * Nk, s));
+            if (!mmajor_a) CK(transpose16(ws + o_dS, ws + o_dST, B, N, Nk, Nk, static_cast<long long>(N) * Nk, s));
         }
         // dQ = dS K -> dqkv[:, 0:C]
         memset(&g, 0, sizeof(g));
@@ -1117,7 +1124,9 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         CK(plain_gemm(ex, g));
         // dK = dS^T Q -> dqkv[:, C:2C]
         memset(&g, 0, sizeof(g));
-        g.A = ws + o_dST; g.K = N; g.a_ld = N; g.rows_per_sample = Nk; g.a_B = B_max;
+        if (mmajor_a) { g.A = ws + o_dS; g.a_ld = Nk; g.a_mn_major = true; }
+        else { g.A = ws + o_dST; g.a_ld = N; }
+        g.K = N; g.rows_per_sample = Nk; g.a_B = B_max;
         g.Bm = ws + o_QT; g.b_rows = Cm; g.ldb = N; g.b_zstride = static_cast<long long>(Cm) * N; g.b_Z = B_max;
         g.b_per_sample = true; g.BN = bn_c; g.N = Cm; g.alpha = 1.f;
         if (split) { g.out = dkv; g.out_fp32 = 1; g.ldc = 2 * Cm; }

@@ -244,7 +244,22 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_
     return d;
 }
 
+// MN-major operand tile with the 128-byte swizzle (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>): in 16-byte
+// units the canonical layout is Swizzle<3,4,3> o ((8,n),(8,k)):((1,LBO),(8,SBO)) - 64 elements of M (or N) are contiguous
+// in a 128-byte row, 8 consecutive K rows form a 1024-byte atom, atoms along K are SBO apart and blocks of 64 along M
+// are LBO apart. A TMA box [64 m][64 k] with SWIZZLE_128B is 8 such atoms back to back (SBO = 1024).
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= static_cast<uint64_t>(1) << 46;  // descriptor version 1 (sm_100)
+    d |= 2ull << 61;                      // SWIZZLE_128B
+    return d;
+}
+
 // Instruction descriptor for kind::f16: fp32 accumulate, both operands K-major, dense.
+
 // is_bf16: 1 = bf16 operands, 0 = fp16 operands.
 __device__ __host__ __forceinline__ uint32_t make_idesc_f16(uint32_t m, uint32_t n, uint32_t is_bf16) {
     uint32_t d = 0;
@@ -255,5 +270,6 @@ __device__ __host__ __forceinline__ uint32_t make_idesc_f16(uint32_t m, uint32_t
     d |= (m >> 4) << 24;       // m_dim
     return d;
 }
+constexpr uint32_t IDESC_A_MN_MAJOR = 1u << 15;  // A operand is M-major (see make_mnmajor_desc)
 
 }  // namespace wfd

@@ -377,6 +377,24 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         } else {
                             for (int it = 0; it < k_iters; ++it) issue_b(0, it * 3);
                         }
+                    } else if (load_a && p.a_mn_major) {
+                        // M-major A: two [64 m][64 k] boxes per stage (m contiguous), coordinates (m, k, 0, sample)
+                        for (int cc = 0; cc < p.cpt; ++cc) {
+                            slot_wait();
+                            if (elect_one()) {
+                                uint8_t* dst = smA + static_cast<size_t>(stage) * a_stage_bytes;
+                                if (CG == 2) {
+                                    if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * a_stage_bytes);
+                                    tma_load_4d_2sm(dst, &tmA, &full_bar[stage], x0, cc * TG_KC, 0, ab);
+                                    tma_load_4d_2sm(dst + 8192, &tmA, &full_bar[stage], x0 + 64, cc * TG_KC, 0, ab);
+                                } else {
+                                    mbar_expect_tx(&full_bar[stage], a_stage_bytes);
+                                    tma_load_4d(dst, &tmA, &full_bar[stage], x0, cc * TG_KC, 0, ab);
+                                    tma_load_4d(dst + 8192, &tmA, &full_bar[stage], x0 + 64, cc * TG_KC, 0, ab);
+                                }
+                            }
+                            slot_next();
+                        }
                     } else if (load_a) {
                         for (int o = 0; o < p.n_taps; ++o) {
                             const int xx = x0 + p.tap_dx[o], yy = y0 + p.tap_dy[o];
@@ -396,7 +414,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
       // ===================================================== MMA issuer (one thread; with CG == 2 only in the leader CTA)
       if (rank == 0) {
-        const uint32_t idesc = make_idesc_f16(TG_BM * CG, static_cast<uint32_t>(p.BN), BF16 ? 1u : 0u);
+        const uint32_t idesc = make_idesc_f16(TG_BM * CG, static_cast<uint32_t>(p.BN), BF16 ? 1u : 0u) |
+                               (p.a_mn_major ? IDESC_A_MN_MAJOR : 0u);
         const int n_sub = p.reuse ? 3 : 1;                        // vertical taps served by one stage
         const int kk_last = (p.kk_last > 0 && p.kk_last < TG_KC / 16) ? p.kk_last : TG_KC / 16;
         const uint32_t a_sub_bytes = static_cast<uint32_t>(p.w_box) * 128;  // one image row of the patch
@@ -437,17 +456,20 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t b_base = b_res ? smem_u32(smB) + static_cast<uint32_t>(kc) * 3u * b_box_bytes
                                                   : smem_u32(smB + static_cast<size_t>(stage) * b_stage_bytes);
                     for (int sub = 0; sub < n_sub; ++sub) {
-                        const uint64_t adesc = make_kmajor_desc(a_base + sub * a_sub_bytes, 128);
+                        // K-major A: 16 elements along K are 32 bytes inside the swizzle atom (+2 in 16-byte units);
+                        // M-major A: 16 K rows are two 1024-byte atoms (+128)
+                        const uint64_t adesc = p.a_mn_major ? make_mnmajor_desc(a_base, 8192, 1024)
+                                                            : make_kmajor_desc(a_base + sub * a_sub_bytes, 128);
+                        const uint64_t a_step = p.a_mn_major ? 128 : 2;
                         const uint64_t bdesc = make_kmajor_desc(b_base + sub * b_box_bytes, 128);
 #pragma unroll
                         for (int k = 0; k < TG_KC / 16; ++k) {
-                            // advancing 16 elements (32 bytes) along K inside the swizzle atom: +2 in 16-byte units;
                             // 16-channel steps that only meet zero-padded weights are skipped
                             if (k < n_k) {
                                 if (CG == 2)
-                                    umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc > 0 || sub > 0 || k > 0) ? 1u : 0u);
+                                    umma_f16_2sm(d_tmem, adesc + a_step * k, bdesc + 2 * k, idesc, (kc > 0 || sub > 0 || k > 0) ? 1u : 0u);
                                 else
-                                    umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc > 0 || sub > 0 || k > 0) ? 1u : 0u);
+                                    umma_f16(d_tmem, adesc + a_step * k, bdesc + 2 * k, idesc, (kc > 0 || sub > 0 || k > 0) ? 1u : 0u);
                             }
                         }
                     }
@@ -839,12 +861,14 @@ __global__ void tapgemm_ref_kernel(const TapGemmParams p) {
         const int yi = y * p.in_stride + p.tap_dy[tap] + p.a_y_off;
         if (xi < 0 || xi >= p.a_W || yi < 0 || yi >= p.a_H || ab >= p.a_B) continue;
         const uint16_t* arow = A + ((static_cast<long long>(ab) * p.a_H + yi) * p.a_W + xi) * p.a_ld;
+        if (p.a_mn_major) arow = A + static_cast<long long>(ab) * p.a_C * p.a_ld + xi;  // column xi of the [K][M] sample
+        const long long a_kstride = p.a_mn_major ? p.a_ld : 1;
         for (int cc = 0; cc < p.cpt; ++cc) {
             const uint16_t* brow = Bm + static_cast<long long>(b_chunk_index(p, tap, cc)) * TG_KC;
             for (int k = 0; k < TG_KC; ++k) {
                 const int c = c0 + cc * TG_KC + k;
                 if (c >= p.a_C) break;
-                acc = fmaf(lo16_to_f<BF16>(arow[c]), lo16_to_f<BF16>(brow[k]), acc);
+                acc = fmaf(lo16_to_f<BF16>(arow[c * a_kstride]), lo16_to_f<BF16>(brow[k]), acc);
             }
         }
     }
@@ -994,7 +1018,23 @@ int tapgemm_prepare(TapGemmOp* op) {
         p.cg = (!no2 && p.cg != 1 && (wide || narrow_reuse) && pairs_ok) ? 2 : 1;
     }
     const CUtensorMapDataType dt = p.is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    {
+    if (p.a_mn_major) {
+        if (p.n_taps != 1 || p.reuse || p.a_H != 1 || p.w_box != TG_BM || p.a_c0 || p.kk_last || p.in_stride != 1 || p.a_zmul) {
+            set_error("tapgemm_prepare: an M-major A operand needs a plain one-tap GEMM over whole 64-row K chunks");
+            return -3;
+        }
+        // A as stored: [a_B][a_C = K rows][a_W = M columns], M contiguous; box = 64 m x 64 k
+        cuuint64_t dims[4] = {(cuuint64_t)p.a_W, (cuuint64_t)p.a_C, 1, (cuuint64_t)p.a_B};
+        cuuint64_t strides[3] = {(cuuint64_t)p.a_ld * 2, (cuuint64_t)p.a_ld * 2 * p.a_C, (cuuint64_t)p.a_ld * 2 * p.a_C};
+        cuuint32_t box[4] = {64, TG_KC, 1, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&op->tmA, dt, 4, const_cast<void*>(p.a_ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled(A, M-major) failed: %d (M=%d K=%d B=%d ld=%lld)", (int)r, p.a_W, p.a_C, p.a_B, p.a_ld);
+            return -4;
+        }
+    } else {
         cuuint64_t dims[4] = {(cuuint64_t)p.a_C, (cuuint64_t)p.a_W, (cuuint64_t)p.a_H, (cuuint64_t)p.a_B};
         cuuint64_t strides[3] = {(cuuint64_t)p.a_ld * 2, (cuuint64_t)p.a_ld * 2 * p.a_W,
                                  (cuuint64_t)p.a_ld * 2 * p.a_W * p.a_H};

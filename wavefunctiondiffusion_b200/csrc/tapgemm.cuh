@@ -40,6 +40,8 @@ struct TapGemmParams {
     int W, H;               // output plane (pixel index = (bb*H + y)*W + x)
     int in_stride;          // input coordinate = out coordinate * in_stride + tap offset
     int a_y_off;            // added to every input row coordinate (row-band plans: the A view starts one halo row early)
+    int a_mn_major;         // plain one-tap GEMMs only: A is given TRANSPOSED in memory, [a_C = K rows][a_W = M columns] per
+                            // sample with row pitch a_ld (M contiguous) - D = A^T-as-stored x Bm^T without a transpose pass
     int wide_io;            // set by tapgemm_prepare: output and side-input rows are 32-byte aligned (256-bit accesses)
     int epi_split;          // set by tapgemm_prepare: narrow tiles - the two epilogue warps of a TMEM lane quarter take alternate
                             // TILES (all chunks of them) instead of alternate 16-column chunks of every tile
