@@ -236,6 +236,8 @@ int Decoder::init(const wfd_decoder_config& c, int h_, int w_, int Bmax, int dty
         fuse_bwd_max_c = m ? atoi(m) : 768;
         const char* mm = getenv("WFD_NO_MMAJOR");
         mmajor_a = !(mm && mm[0] == '1');
+        const char* rh = getenv("WFD_REUSE_HBOX");
+        reuse_hbox = rh ? atoi(rh) : 2;
     }
     if (c.latent_channels != 4) {
         set_error("decoder: latent_channels must be 4 (got %d)", c.latent_channels);
@@ -580,6 +582,17 @@ int Decoder::conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int 
         if (!pick_box(Wout, Hout, &wb, &hb)) {
             set_error("decoder: cannot tile %dx%d plane", Hout, Wout);
             return -3;
+        }
+        // Row-reuse contractions fetch (h_box + 2) image rows per horizontal shift: a taller, narrower patch re-reads
+        // fewer halo rows from L2 (3 x 2.0 of the activation bytes at 64 x 2, 3 x 1.25 at 16 x 8). Measured on B200
+        // (WFD_REUSE_HBOX = 2 / 4 / 8: 1.00 / 1.14 / 1.12 ms for the five 3072-channel groups=64 launches): no gain, so
+        // L2 delivery is not what bounds them and the default stays the widest patch.
+        if (pk.reuse && reuse_hbox > hb) {
+            const int hb2 = reuse_hbox, wb2 = TG_BM / reuse_hbox;
+            if (wb2 >= 8 && wb2 * hb2 == TG_BM && Wout % wb2 == 0 && Hout % hb2 == 0) {
+                wb = wb2;
+                hb = hb2;
+            }
         }
         p.BN = pk.BN;
         p.n_tiles = pk.n_tiles;
