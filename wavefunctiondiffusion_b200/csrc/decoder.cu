@@ -237,7 +237,7 @@ int Decoder::init(const wfd_decoder_config& c, int h_, int w_, int Bmax, int dty
         const char* mm = getenv("WFD_NO_MMAJOR");
         mmajor_a = !(mm && mm[0] == '1');
         const char* rh = getenv("WFD_REUSE_HBOX");
-        reuse_hbox = rh ? atoi(rh) : 2;
+        reuse_hbox = rh ? atoi(rh) : 0;  // 0: keep the widest patch pick_box() finds
     }
     if (c.latent_channels != 4) {
         set_error("decoder: latent_channels must be 4 (got %d)", c.latent_channels);

@@ -68,7 +68,7 @@ struct Decoder {
     int conv_n_group = 0;  // tile rasterisation of the convs: 0/1 = M fastest (default), k = bands of k N tiles (WFD_CONV_NGROUP)
     int fuse_bwd_max_c = 768;  // largest channel count whose GroupNorm-backward reduction is fused into the conv epilogue
     bool mmajor_a = true;  // attention backward reads P / dS as stored (M-major A operand) instead of transposed copies
-    int reuse_hbox = 2;    // preferred patch height of the row-reuse contractions (WFD_REUSE_HBOX: 2, 4, 8 or 16)
+    int reuse_hbox = 0;    // preferred patch height of the row-reuse contractions (WFD_REUSE_HBOX: 0 = widest patch, 2, 4, 8, 16)
     int use_reuse = 1;  // row-reuse schedule for 3x3 convs whose stage fits (WFD_NO_REUSE=1 disables, for A/B runs)
     // row bands (one map split along y over band_R ranks): h is the local band height, h_total the map's
     bool band = false;
