@@ -154,6 +154,13 @@ WFD_API int wfd_wfc_attach_comm(wfd_wfc* h, wfd_comm* c, int H_total);
  * ---------------------------------------------------------------------------------------------------------------- */
 WFD_API int wfd_argmax_tiles(const void* x, int dtype, long long rows, int n, long long* out, void* stream);
 
+/* Rule violations of integer tile maps (what the reference's users check after the argmax; it is WFCLossEinsum of the
+ * one-hot wave, losses.py:63-75, times the pair count): tiles int64 [B, H, W] on the device, out int64 [B, 2] =
+ * {horizontal pairs with mat_x[left, right] == 0, vertical pairs with mat_y[top, bottom] == 0}; ids outside [0, T)
+ * (padded channels) always violate. */
+WFD_API int wfd_wfc_count_violations(const wfd_wfc* h, const long long* tiles, int B, int H, int W, long long* out,
+                                     void* stream);
+
 /* layout helpers used by the Python layer: NCHW (fp32/fp16) <-> nhwc16, 16-bit -> fp32 */
 WFD_API int wfd_nchw_to_nhwc16(const void* in, int in_dtype, void* out, int B, int C, int HW, int dtype16, void* stream);
 WFD_API int wfd_nhwc16_to_nchw(const void* in, void* out, int out_dtype, int B, int C, int HW, int dtype16, void* stream);

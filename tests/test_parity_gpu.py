@@ -241,3 +241,29 @@ def test_batch_properties_full_size():
     (grad1,) = torch.autograd.grad(loss1.sum(), z1)
     assert abs(loss1.item() - 2 * loss[0].item()) <= 1e-4 * abs(loss1.item())
     assert _rel(grad1[0].cpu(), 2 * grad[0].cpu()) < TOL_GRAD
+
+
+def test_rule_violation_count_of_tile_maps():
+    """Integer work, bit-exact: forbidden adjacent pairs of argmax tile maps against the oracle's count (which is the
+    reference loss of the one-hot wave times the pair count), including ids in the padded channels and ragged sizes."""
+    rng = np.random.RandomState(9)
+    T = 100
+    mats = rng.rand(2, T, T) < 0.3
+    loss = WFCLossEinsum(mats[0], mats[1]).cuda()
+    for (B, H, W) in ((1, 1, 2), (2, 7, 5), (3, 64, 64)):
+        tiles = rng.randint(0, T, size=(B, H, W)).astype(np.int64)
+        got = loss.count_violations(torch.from_numpy(tiles).cuda()).cpu().numpy()
+        for b in range(B):
+            P = H * (W - 1) + (H - 1) * W
+            want = orc.forbidden_pair_fraction(tiles[b], mats[0], mats[1]) * P
+            assert got[b].sum() == round(want)
+            assert got[b, 0] == np.count_nonzero(~mats[0][tiles[b][:, :-1], tiles[b][:, 1:]])
+            assert got[b, 1] == np.count_nonzero(~mats[1][tiles[b][:-1], tiles[b][1:]])
+    # ids in the padded channels (>= T) can come out of an argmax over T_pad channels: every pair they touch violates
+    tiles = np.zeros((1, 2, 3), dtype=np.int64)
+    tiles[0, 0, 1] = T + 5
+    allow = np.ones((2, T, T), dtype=bool)
+    got = WFCLossEinsum(allow[0], allow[1]).cuda().count_violations(torch.from_numpy(tiles).cuda()).cpu().numpy()
+    assert got.tolist() == [[2, 1]]
+    # (H, W) input is treated as a batch of one
+    assert loss.count_violations(torch.zeros(4, 4, dtype=torch.int64, device="cuda")).shape == (1, 2)

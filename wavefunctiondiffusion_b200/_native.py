@@ -88,6 +88,7 @@ SIGNATURES = {
                                           C.POINTER(C.c_void_p)]),
     "wfd_decoder_attach_comm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "wfd_wfc_attach_comm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "wfd_wfc_count_violations": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "wfd_argmax_tiles": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "wfd_nchw_to_nhwc16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "wfd_nhwc16_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -294,6 +294,15 @@ int wfd_guidance_step(wfd_decoder* d, wfd_wfc* h, const void* z, int z_dtype, in
     return D.backward(nullptr, B, nullptr, dz, S(stream));
 }
 
+int wfd_wfc_count_violations(const wfd_wfc* h, const long long* tiles, int B, int H, int W, long long* out, void* stream) {
+    if (!h || !tiles || !out) {
+        set_error("wfd_wfc_count_violations: null argument");
+        return -1;
+    }
+    const Wfc& w = h->w;
+    return count_violations(tiles, w.rules, w.rules + static_cast<size_t>(w.T) * w.T, w.T, B, H, W, out, S(stream));
+}
+
 int wfd_argmax_tiles(const void* x, int dtype, long long rows, int n, long long* out, void* stream) {
     if (!x || !out) {
         set_error("wfd_argmax_tiles: null argument");

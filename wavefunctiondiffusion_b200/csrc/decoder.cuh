@@ -137,6 +137,7 @@ struct Wfc {
     WfcSavedHeader hdr_host;
     void* hdr_saved = nullptr;
     uint16_t* Bm = nullptr;
+    uint8_t* rules = nullptr;  // device copy of the 0/1 rule matrices [2][T][T] (x then y) for count_violations
     int* kc_list = nullptr;  // K chunks of each N tile that hold at least one allowed pair (see Wfc::init)
     int* kc_cnt = nullptr;
     double kc_kept = 1.0;    // fraction of the K chunks that are visited

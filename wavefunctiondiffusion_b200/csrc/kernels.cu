@@ -1062,6 +1062,56 @@ int argmax_rows(const void* x, int dtype, long long rows, int n, long long* out,
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ rule violations
+__global__ void __launch_bounds__(256)
+count_violations_k(const long long* __restrict__ tiles, const uint8_t* __restrict__ mat_x,
+                   const uint8_t* __restrict__ mat_y, int T, int H, int W, unsigned long long* __restrict__ out) {
+    __shared__ unsigned int sh[2];
+    const int b = blockIdx.y;
+    if (threadIdx.x < 2) sh[threadIdx.x] = 0u;
+    __syncthreads();
+    const long long* tb = tiles + static_cast<long long>(b) * H * W;
+    unsigned int bad_x = 0u, bad_y = 0u;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+        const int y = i / W, x = i - y * W;
+        const long long t = tb[i];
+        const bool t_ok = t >= 0 && t < T;
+        if (x + 1 < W) {
+            const long long r = tb[i + 1];
+            const bool ok = t_ok && r >= 0 && r < T && mat_x[t * T + r] != 0;
+            bad_x += ok ? 0u : 1u;
+        }
+        if (y + 1 < H) {
+            const long long d = tb[i + W];
+            const bool ok = t_ok && d >= 0 && d < T && mat_y[t * T + d] != 0;
+            bad_y += ok ? 0u : 1u;
+        }
+    }
+    atomicAdd(&sh[0], bad_x);
+    atomicAdd(&sh[1], bad_y);
+    __syncthreads();
+    if (threadIdx.x < 2 && sh[threadIdx.x] != 0u)
+        atomicAdd(out + static_cast<long long>(b) * 2 + threadIdx.x, static_cast<unsigned long long>(sh[threadIdx.x]));
+}
+int count_violations(const long long* tiles, const uint8_t* mat_x, const uint8_t* mat_y, int T, int B, int H, int W,
+                     long long* out, cudaStream_t s) {
+    ProfScope prof_scope("count_violations", s);
+    if (B < 1 || H < 1 || W < 1 || T < 1) {
+        set_error("count_violations: bad shape B=%d H=%d W=%d T=%d", B, H, W, T);
+        return -3;
+    }
+    cudaError_t e = cudaMemsetAsync(out, 0, static_cast<size_t>(B) * 2 * sizeof(long long), s);
+    if (e != cudaSuccess) {
+        set_error("count_violations: %s", cudaGetErrorString(e));
+        return -8;
+    }
+    int bx = (H * W + 255) / 256;
+    if (bx > 64) bx = 64;
+    count_violations_k<<<dim3(bx, B), 256, 0, s>>>(tiles, mat_x, mat_y, T, H, W, reinterpret_cast<unsigned long long*>(out));
+    WFD_CHECK_LAUNCH("count_violations");
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ layout conversion
 template <bool BF16>
 __global__ void __launch_bounds__(256)

@@ -64,6 +64,12 @@ int transpose16(const void* in, void* out, int Z, int R, int C, long long ld_in,
 // ---- argmax over the last axis, numpy semantics (first max wins, NaN is max); dtype: 0 fp32, 1 fp16, 2 bf16
 int argmax_rows(const void* x, int dtype, long long rows, int n, long long* out, cudaStream_t s);
 
+// ---- rule violations of an integer tile map (the one-hot case of the loss): out[b] = {pairs (x, x+1) with
+// mat_x[left, right] == 0, pairs (y, y+1) with mat_y[top, bottom] == 0}; tile ids outside [0, T) always violate.
+// tiles: int64 [B, H, W]; mat_x / mat_y: uint8 [T, T] on the device; out: int64 [B, 2], overwritten.
+int count_violations(const long long* tiles, const uint8_t* mat_x, const uint8_t* mat_y, int T, int B, int H, int W,
+                     long long* out, cudaStream_t s);
+
 // ---- layout conversion at the API boundary: NCHW (fp32/fp16) <-> channels-last 16-bit
 int nchw_to_nhwc16(const void* in, int in_f16, void* out, int B, int C, int HW, int bf16, cudaStream_t s);
 int nhwc16_to_nchw(const void* in, void* out, int out_f16, int B, int C, int HW, int bf16, cudaStream_t s);

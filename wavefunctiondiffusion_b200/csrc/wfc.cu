@@ -36,6 +36,7 @@ constexpr int WFC_BN = 256;
 
 Wfc::~Wfc() {
     if (Bm) cudaFree(Bm);
+    if (rules) cudaFree(rules);
     if (kc_list) cudaFree(kc_list);
     if (kc_cnt) cudaFree(kc_cnt);
 }
@@ -63,6 +64,16 @@ int Wfc::init(const uint8_t* mx, const uint8_t* my, int T_, int T_pad_, int dtyp
     }
     CUDA_CK(cudaMalloc(&Bm, hb.size() * 2));
     CUDA_CK(cudaMemcpy(Bm, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice));
+    {
+        const size_t tt = static_cast<size_t>(T) * T;
+        std::vector<uint8_t> r(2 * tt);
+        for (size_t i = 0; i < tt; ++i) {
+            r[i] = mx[i] ? 1 : 0;
+            r[tt + i] = my[i] ? 1 : 0;
+        }
+        CUDA_CK(cudaMalloc(&rules, r.size()));
+        CUDA_CK(cudaMemcpy(rules, r.data(), r.size(), cudaMemcpyHostToDevice));
+    }
     // Adjacency is very sparse (0.2 % for the StarCraft tilesets): about half of the [256 tiles] x [64 neighbour tiles]
     // blocks of the packed operand hold no allowed pair at all. Those K chunks are skipped - they add exact zeros, so the
     // result is bit-identical to the dense contraction (WFD_WFC_DENSE=1 keeps every chunk, for A/B runs).

@@ -237,6 +237,18 @@ class WfcHandle:
                                              None if dloss is None else C.c_void_p(dloss.data_ptr()),
                                              C.c_void_p(out_ptr), nat.stream_ptr()), "wfd_wfc_backward")
 
+    def count_violations(self, tiles):
+        """tiles: int64 (B, H, W) or (H, W) on the device -> int64 (B, 2): forbidden horizontal / vertical pairs."""
+        _require_cuda(tiles, "count_violations")
+        t = tiles if tiles.dim() == 3 else tiles.unsqueeze(0)
+        t = t.to(torch.int64).contiguous()
+        B, H, W = t.shape
+        out = torch.empty((B, 2), dtype=torch.int64, device=t.device)
+        nat.check(nat.lib().wfd_wfc_count_violations(self.handle, C.c_void_p(t.data_ptr()), B, H, W,
+                                                     C.c_void_p(out.data_ptr()), nat.stream_ptr()),
+                  "wfd_wfc_count_violations")
+        return out
+
     def wave_view(self, B, H, W):
         ptr = nat.lib().wfd_wfc_saved_wave(self.handle, C.c_void_p(self._saved_ptr), B, H, W)
         off = ptr - self._saved.data_ptr()

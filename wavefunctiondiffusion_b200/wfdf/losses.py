@@ -42,6 +42,13 @@ class WFCLossEinsum(torch.nn.Module):
             self._handles[key] = h
         return h
 
+    def count_violations(self, tiles):
+        """Forbidden adjacent pairs of integer tile maps (B, H, W) -> int64 (B, 2) = (horizontal, vertical): the
+        one-hot case of forward(), counted on the device (not part of the reference API)."""
+        _require_cuda(tiles, "WFCLossEinsum.count_violations")
+        t_pad = (self.count + 127) // 128 * 128
+        return self.native_handle(t_pad, tiles.device).count_violations(tiles)
+
     def forward(self, t, softmax=False):
         if t.dim() != 4 or t.size(1) < self.count:
             raise ValueError(f"wave must be (B, C>={self.count}, H, W), got {tuple(t.shape)}")
