@@ -31,6 +31,7 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    extra = os.environ.get("WFD_NVCC_EXTRA", "").split()  # e.g. -DWFD_UNIFORM_WARP=1 (use with --force)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     objs = []
     procs = []
@@ -39,7 +40,7 @@ def build(force=False, verbose=False):
         o = os.path.join(HERE, "build", src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [_nvcc()] + NVCC_FLAGS + ["-c", s, "-o", o]
+            cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd))
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
