@@ -9,6 +9,7 @@ AutoencoderTile, whose initialisation order is checked to be bit-identical to th
   tiny_step.npz            reference decode+softmax+loss+grad on a small config, fp64 and fp32
   tiny_down_step.npz       same with a DownDecoderBlock2D (the 32x32-style config)
   ice_c1_step.npz          BASELINE config 1: ice 64x64, batch 1, tilenet_sc_space_64x64, strength 5
+  ice_c2_step.npz          BASELINE config 2's benchmarked shape: the same weights, batch 8 (slot 0 = the C1 latents)
 """
 import glob
 import json
@@ -129,12 +130,41 @@ def full_fixture(vae, losses):
     np.savez_compressed(os.path.join(GOLD, "ice_c1_step.npz"), **out)
 
 
+def batch8_fixture(vae, losses):
+    """BASELINE config 2's shape (ice 64x64, batch 8): slot 0 carries the C1 latents, slots 1-7 are fresh draws, slot 5
+    repeats slot 2 (identical maps must give identical results). loss (8,) and latent gradient, fp64 and fp32."""
+    cfg = json.load(open(REFERENCE_ROOT + "/configs/tilenet/tilenet_sc_space_64x64.json"))
+    mats = np.load(REFERENCE_ROOT + "/wfd/scmap/tile_data/wfc/ice_64x64.npz")["wfc_mats"]
+    T = mats.shape[1]
+    t_pad = (T + 127) // 128 * 128
+    cfg["in_channels"] = cfg["out_channels"] = t_pad
+    c1 = np.load(os.path.join(GOLD, "ice_c1_step.npz"))
+    g = torch.Generator().manual_seed(4321)
+    lat = torch.randn(8, 4, 64, 64, generator=g)
+    lat[0] = torch.from_numpy(c1["latents"])[0]
+    lat[5] = lat[2]
+    out = {"latents": lat.numpy(), "seed": 0, "strength": 5.0, "cfg_json": json.dumps(cfg), "tileset": "ice_64x64"}
+    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        _, logits, wave, loss, grad, dt = reference_step(vae, losses, cfg, mats, lat, 5.0, dtype, 0)
+        out["loss_" + tag] = loss.numpy().astype(np.float64)
+        out["grad_" + tag] = grad.numpy().astype(np.float32)
+        out["seconds_" + tag] = dt
+        print("ice C2", tag, "loss", loss.numpy(), "grad L2", grad.norm().item(), "%.1fs" % dt)
+    # the reference's own batch independence: slot 0 of the batch equals the batch-1 run of the same latents
+    assert abs(out["loss_f64"][0] - float(np.asarray(c1["loss_f64"]).reshape(-1)[0])) < 1e-9
+    np.savez_compressed(os.path.join(GOLD, "ice_c2_step.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     vae, losses = load_reference()
+    if "--only-c2" in sys.argv:
+        batch8_fixture(vae, losses)
+        sys.exit(0)
     wfc_mats_fixtures()
     small_fixture(vae, losses, "tiny_step.npz", TINY, 16, 2, 100, 7)
     small_fixture(vae, losses, "tiny_down_step.npz", TINY_DOWN, 32, 2, 100, 11)
     if "--skip-full" not in sys.argv:
         full_fixture(vae, losses)
+        batch8_fixture(vae, losses)

@@ -1,0 +1,119 @@
+// Micro-benchmark (diagnosis only, not part of the library): cycles per tcgen05.mma (kind::f16, K = 16) as a function of
+// the N extent and the CTA group, issued back to back by one thread with operands resident in shared memory (no TMA).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I wavefunctiondiffusion_b200/csrc scripts/ubench/mma_rate.cu -o /tmp/mma_rate
+#include "ptx.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+using namespace wfd;
+
+template <int CG>
+__global__ void __launch_bounds__(128, 1) mma_rate_k(int N, int n_mma, int reps, int a_stride16, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
+    for (int i = threadIdx.x; i < 128 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        if (CG == 2) { tmem_alloc_2sm(&tmem_slot, 512); tmem_relinquish_2sm(); }
+        else { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (CG == 2) cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    if (warp == 0 && rank == 0) {
+        const uint32_t idesc = make_idesc_f16(128 * CG, (uint32_t)N, 1u);
+        const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem + 80 * 1024);
+        long long best = 1ll << 60;
+        uint32_t phase = 0;
+        for (int r = 0; r < reps; ++r) {
+            const long long t0 = clock64();
+            if (elect_one()) {
+                for (int i = 0; i < n_mma; ++i) {
+                    // operand addresses walk through a 48 KB window like the stages of the real kernel
+                    const uint32_t off = (uint32_t)((i * a_stride16) & 0xBFF) << 4;
+                    const uint64_t adesc = make_kmajor_desc(a_base + off, 128);
+                    const uint64_t bdesc = make_kmajor_desc(b_base + (off & 0x1FFF), 128);
+                    if (CG == 2) umma_f16_2sm(tmem_base, adesc, bdesc, idesc, i > 0 ? 1u : 0u);
+                    else umma_f16(tmem_base, adesc, bdesc, idesc, i > 0 ? 1u : 0u);
+                }
+                if (CG == 2) umma_commit_2sm(&bar);
+                else umma_commit(&bar);
+            }
+            __syncwarp();
+            mbar_wait(&bar, phase);
+            phase ^= 1;
+            const long long dt = clock64() - t0;
+            if (dt < best) best = dt;
+        }
+        if (lane == 0 && blockIdx.x == 0) out[0] = best;
+    } else if (CG == 2 && warp == 0 && rank == 1) {
+        // the peer's barrier receives the multicast commit too: consume the phases so the barrier never overflows
+        uint32_t phase = 0;
+        for (int r = 0; r < reps; ++r) {
+            mbar_wait(&bar, phase);
+            phase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (CG == 2) cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        if (CG == 2) tmem_dealloc_2sm(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
+    }
+}
+
+template <int CG>
+static long long run(int N, int n_mma, int a_stride16, int grid) {
+    long long* d;
+    cudaMalloc(&d, 8);
+    cudaFuncSetAttribute(mma_rate_k<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = 130 * 1024;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, mma_rate_k<CG>, N, n_mma, 20, a_stride16, d);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    long long h = -1;
+    if (e != cudaSuccess) printf("error: %s\n", cudaGetErrorString(e));
+    else cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return h;
+}
+
+int main() {
+    const int ns[] = {16, 32, 48, 64, 96, 128, 192, 256};
+    printf("cycles per tcgen05.mma kind::f16 K=16 (best of 20 batches), operands in shared memory\n");
+    printf("%5s %5s %8s | %10s %10s | %10s %10s\n", "cg", "N", "n_mma", "1 CTA", "full grid", "cyc/mma", "cyc/mma(g)");
+    for (int cg = 1; cg <= 2; ++cg)
+        for (int N : ns) {
+            if (cg == 2 && N % 16) continue;
+            for (int n_mma : {32, 256}) {
+                const long long a = cg == 1 ? run<1>(N, n_mma, 2, 1) : run<2>(N, n_mma, 2, 2);
+                const long long b = cg == 1 ? run<1>(N, n_mma, 2, 148) : run<2>(N, n_mma, 2, 148);
+                printf("%5d %5d %8d | %10lld %10lld | %10.1f %10.1f\n", cg, N, n_mma, a, b, (double)a / n_mma, (double)b / n_mma);
+            }
+        }
+    // A rows read with a large stride between consecutive MMAs (different swizzle atoms) vs the same 32 bytes
+    for (int s : {0, 2, 64, 130})
+        printf("cg=2 N=48 a_stride16=%d: %.1f cyc/mma\n", s, (double)run<2>(48, 256, s, 148) / 256);
+    return 0;
+}

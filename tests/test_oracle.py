@@ -91,6 +91,27 @@ def test_oracle_matches_reference_ice_c1():
     assert (tiles != z["tiles_f64"]).mean() < 0.002
 
 
+@pytest.mark.slow
+def test_oracle_matches_reference_ice_c2_batch8_slot():
+    """BASELINE config 2's shape (batch 8): the golden run of the unmodified reference on the whole batch against the
+    oracle on two of its maps (maps are independent: the loss is per map, GroupNorm and attention are per sample)."""
+    z = np.load(os.path.join(GOLD, "ice_c2_step.npz"))
+    c1 = np.load(os.path.join(GOLD, "ice_c1_step.npz"))
+    cfg = json.loads(str(z["cfg_json"]))
+    mx, my = load_wfc_mats("ice_64x64")
+    assert z["latents"].shape == (8, 4, 64, 64) and np.array_equal(z["latents"][0], c1["latents"][0])
+    assert np.array_equal(z["latents"][5], z["latents"][2])
+    assert abs(z["loss_f64"][0] - float(np.asarray(c1["loss_f64"]).reshape(-1)[0])) < 1e-9
+    assert z["loss_f64"][5] == z["loss_f64"][2]
+    torch.manual_seed(int(z["seed"]))
+    net = AutoencoderTile(**cfg)
+    lat = torch.from_numpy(z["latents"][[3, 7]])
+    r = orc.guidance_step(net.state_dict(), cfg, mx, my, lat, 5.0, torch.float32)
+    assert np.allclose(r["loss"].numpy(), z["loss_f64"][[3, 7]], rtol=2e-6)
+    g = z["grad_f64"][[3, 7]].astype(np.float64)
+    assert np.linalg.norm(r["grad"].numpy() - g) <= 1e-3 * np.linalg.norm(g)
+
+
 def test_ddim_coefficients_shape():
     a, b = orc.ddim_coefficients(50)
     assert a.shape == (50,) and b.shape == (50,) and (a > 1.0).all() and a[0] > a[-1] and (b < 0).all()

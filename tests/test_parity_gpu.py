@@ -123,6 +123,52 @@ def test_ice_config1_against_reference_golden():
     assert (tiles[0].cpu().numpy()[clear] == z["tiles_f64"][clear]).mean() > 0.99
 
 
+def test_ice_config2_batch8_against_reference_golden():
+    """BASELINE config 2's benchmarked shape: ice 64x64, BATCH 8, against the unmodified reference's fp64 loss (8,) and
+    latent gradient; slot 0 carries the config-1 latents and must reproduce the batch-1 run of this plan bit for bit."""
+    z = np.load(os.path.join(GOLD, "ice_c2_step.npz"))
+    cfg = json.loads(str(z["cfg_json"]))
+    mx, my = load_wfc_mats("ice_64x64")
+    torch.manual_seed(int(z["seed"]))
+    net = AutoencoderTile(**cfg).eval().cuda()
+    wfc_loss = WFCLossEinsum(mx, my).cuda()
+    handle = wfc_loss.native_handle(cfg["out_channels"], torch.device("cuda:0"))
+    lat = torch.from_numpy(z["latents"]).cuda()
+    x = lat.clone().requires_grad_()
+    loss = GuidanceLossFunction.apply(x, net._native, handle, 1.0 / 0.18215, 5.0)
+    (grad,) = torch.autograd.grad(loss.sum(), x)
+    rel_l = np.abs(loss.cpu().numpy().astype(np.float64) - z["loss_f64"]) / np.abs(z["loss_f64"])
+    rel_g = [_rel(grad[b].cpu(), z["grad_f64"][b]) for b in range(8)]
+    print("ice C2: loss rel max", rel_l.max(), "grad rel-L2 per map", ["%.3e" % r for r in rel_g])
+    assert rel_l.max() < TOL_LOSS
+    assert max(rel_g) < TOL_GRAD and _rel(grad.cpu(), z["grad_f64"]) < TOL_GRAD
+    assert loss[5].item() == loss[2].item() and torch.equal(grad[5], grad[2])
+    # the same plan on the config-1 latents alone: bitwise the batch's slot 0 (integer cross-CTA sums, fixed tile walk)
+    x1 = lat[:1].clone().requires_grad_()
+    loss1 = GuidanceLossFunction.apply(x1, net._native, handle, 1.0 / 0.18215, 5.0)
+    (grad1,) = torch.autograd.grad(loss1.sum(), x1)
+    assert loss1.item() == loss[0].item() and torch.equal(grad1[0], grad[0])
+    c1 = np.load(os.path.join(GOLD, "ice_c1_step.npz"))
+    assert abs(loss1.item() - float(np.asarray(c1["loss_f64"]).reshape(-1)[0])) < TOL_LOSS * loss1.item()
+
+
+def test_fp16_operand_mode_small(monkeypatch):
+    """WFD_DTYPE16=fp16 (the reference's set_precision('half') operand type) through the whole step: same tolerances
+    for logits and loss; the gradient is held to the same bound thanks to the power-of-two gradient scale of fp16 plans."""
+    monkeypatch.setenv("WFD_DTYPE16", "fp16")
+    z, cfg, mats, net = _load_small("tiny_step.npz")
+    wfc_loss = WFCLossEinsum(mats[0], mats[1]).cuda()
+    lat = torch.from_numpy(z["latents"]).cuda().requires_grad_()
+    loss = GuidanceLossFunction.apply(lat, net._native, wfc_loss.native_handle(cfg["out_channels"], lat.device),
+                                      1.0 / 0.18215, 5.0)
+    (grad,) = torch.autograd.grad(loss.sum(), lat)
+    with torch.no_grad():
+        logits = net.decode(lat.detach() / 0.18215).sample
+    assert _rel(logits.cpu(), z["logits_f64"]) < TOL_LOGITS
+    assert _rel(loss.cpu(), z["loss_f64"]) < TOL_LOSS
+    assert _rel(grad.cpu(), z["grad_f64"]) < TOL_GRAD
+
+
 ALL_TILESETS = ["ashworld_64x64", "badlands_64x64", "desert_64x64", "ice_64x64", "install_64x64", "jungle_64x64",
                 "platform_32x32", "platform_64x64", "twilight_64x64"]
 

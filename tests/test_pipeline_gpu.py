@@ -102,10 +102,14 @@ def test_micro_batching_matches_one_call(tmp_path, monkeypatch):
 
 
 @pytest.mark.parametrize("arch,tileset,latent", [("32x32", "platform_32x32", 64), ("64x64", "install_64x64", 128),
-                                                 ("64x64", "twilight_64x64", 64), ("64x64", "ashworld_64x64", 64)])
+                                                 ("64x64", "twilight_64x64", 64), ("64x64", "ashworld_64x64", 64),
+                                                 ("64x64", "badlands_64x64", 64), ("64x64", "desert_64x64", 64),
+                                                 ("64x64", "jungle_64x64", 64), ("64x64", "platform_64x64", 64),
+                                                 ("64x64", "install_64x64", 64)])
 def test_other_configs_against_the_oracle(arch, tileset, latent):
-    """BASELINE config 5's architecture (DownDecoderBlock2D, 32x32 map from 64x64 latents), a 128x128 map, and the
-    largest / smallest-but-one tilesets of config 3 (T_pad 4352 and 1536)."""
+    """BASELINE config 5's architecture (DownDecoderBlock2D, 32x32 map from 64x64 latents), a 128x128 map, and the full
+    architecture on EVERY tileset of config 3 (ice has its own golden tests): T_pad 1024 ... 4352 changes conv_out's
+    channels per group, the N tiling of the WFC contraction and its K-chunk skip lists."""
     mx, my = load_wfc_mats(tileset)
     t_pad = round_up_channels(mx.shape[0])
     cfg = tilenet_config(arch, t_pad)
@@ -121,21 +125,6 @@ def test_other_configs_against_the_oracle(arch, tileset, latent):
     print(arch, tileset, latent, "loss", loss.item(), want["loss"].item(), "grad rel", _rel(grad.cpu(), want["grad"]))
     assert _rel(loss.cpu(), want["loss"]) < 1e-3
     assert _rel(grad.cpu(), want["grad"]) < 5e-2
-
-
-def test_large_map_256_runs():
-    """BASELINE config 4's map size on one GPU (the CPU oracle cannot hold its 65 536^2 attention matrix): finite results
-    and the uniform-logit invariants."""
-    mx, my = load_wfc_mats("install_64x64")
-    t_pad = round_up_channels(mx.shape[0])
-    torch.manual_seed(0)
-    net = AutoencoderTile(**tilenet_config("64x64", t_pad)).eval().cuda()
-    wfc = WFCLossEinsum(mx, my).cuda()
-    z = torch.randn(1, 4, 256, 256, generator=torch.Generator().manual_seed(4)).cuda().requires_grad_()
-    loss = GuidanceLossFunction.apply(z, net._native, wfc.native_handle(t_pad, z.device), 1 / 0.18215, 5.0)
-    (grad,) = torch.autograd.grad(loss.sum(), z)
-    assert torch.isfinite(loss).all() and torch.isfinite(grad).all() and grad.abs().max() > 0
-    assert 0.5 * 5 < loss.item() < 5.0
 
 
 def test_img2img_from_a_tile_map(tmp_path):

@@ -1,7 +1,8 @@
 """Row-band plans (one map split along y) against the single-plan path and the reference's golden vectors.
 
 The bands run on ONE GPU here, each on its own host thread and CUDA stream, exchanging through the library's in-process
-loopback transport; `scripts/band_nccl_check.py` repeats the comparison over NCCL with one process per GPU.
+loopback transport; `test_band_plan_over_nccl` repeats the comparison over NCCL with one process per GPU
+(tests/band_nccl_worker.py under torchrun; skipped on a one-GPU box).
 
 What must hold: cutting the plane changes no arithmetic in the forward pass (GroupNorm sums are fixed-point integers,
 every conv / attention row accumulates in the same order), so the band logits are BIT-EXACT against the single plan;
@@ -44,7 +45,7 @@ def _single(net, mats, lat, in_scale, strength, t_pad):
     return loss.cpu(), grad.cpu(), logits.cpu(), tiles.cpu()
 
 
-def _banded(net, mats, lat, in_scale, strength, R):
+def _banded(net, mats, lat, in_scale, strength, R, keep16=False):
     h, w = lat.shape[2], lat.shape[3]
     T = mats[0].shape[0]
     torch.cuda.synchronize()
@@ -52,7 +53,7 @@ def _banded(net, mats, lat, in_scale, strength, R):
     def fn(rank, comm):
         bg = BandGuidance(net, mats[0], mats[1], h, w, comm, lat.device)
         loss, dz = bg.step(lat, in_scale, strength)
-        logits = bg.plan.logits_view(1).float().clone()
+        logits = bg.plan.logits_view(1).clone() if keep16 else bg.plan.logits_view(1).float().clone()
         tiles = argmax_tiles(bg.wave()[..., :T].float().contiguous())
         torch.cuda.current_stream().synchronize()
         return loss.cpu(), dz.cpu(), logits.cpu(), tiles.cpu()
@@ -95,6 +96,62 @@ def test_band_plan_ice_config1_against_reference_golden(R):
     loss, grad, _, _ = _banded(net, mats, lat, 1.0 / 0.18215, 5.0, R)
     assert abs(loss.item() - float(np.asarray(z["loss_f64"]).reshape(-1)[0])) <= 1e-3 * abs(float(np.asarray(z["loss_f64"]).reshape(-1)[0]))
     assert _rel(grad, z["grad_f64"]) < 5e-2
+
+
+def test_large_map_256_single_plan_bands_and_sparse_loss():
+    """BASELINE config 4's map size (256x256, one map). The CPU oracle cannot hold the 65 536^2 attention matrix, so the
+    checks are the ones SURVEY App. D names: (i) the loss against the oracle's sparse/complement formulation evaluated on
+    the DEVICE wave (fp64, the reference's losses.py:63-75 arithmetic on identical inputs); (ii) the map cut into 2 and 4
+    row bands reproduces the single plan: logits and argmax tiles bit-exact, loss and gradient within fp32 summation
+    order of the key/value gradients."""
+    from oracle import wfd_oracle as orc
+    from wavefunctiondiffusion_b200.utils.tilesets import round_up_channels, tilenet_config
+
+    mats = load_wfc_mats("install_64x64")
+    T = mats[0].shape[0]
+    t_pad = round_up_channels(T)
+    torch.manual_seed(0)
+    net = AutoencoderTile(**tilenet_config("64x64", t_pad)).eval().cuda()
+    lat = torch.randn(1, 4, 256, 256, generator=torch.Generator().manual_seed(4)).cuda()
+    wfc_loss = WFCLossEinsum(mats[0], mats[1]).cuda()
+    handle = wfc_loss.native_handle(t_pad, lat.device)
+    x = lat.clone().requires_grad_()
+    loss = GuidanceLossFunction.apply(x, net._native, handle, 1.0 / 0.18215, 5.0)
+    (grad,) = torch.autograd.grad(loss.sum(), x)
+    assert torch.isfinite(loss).all() and torch.isfinite(grad).all() and grad.abs().max() > 0
+    plan = net._native.plan(1, 256, 256, lat.device)
+    logits = plan.logits_view(1).clone()                      # (1, T_pad, 256, 256) 16-bit, channels-last
+    wave = handle.wave_view(1, plan.H, plan.W)                  # (1, 256, 256, T_pad) as the contraction read it
+    tiles = argmax_tiles(wave[..., :T].float().contiguous()).cpu()
+    want = orc.wfc_loss_sparse(wave.float().cpu().permute(0, 3, 1, 2), mats[0], mats[1]) * 5.0
+    print("256x256: loss", loss.item(), "sparse fp64 on the device wave", want.item())
+    assert abs(loss.item() - want.item()) <= 2e-5 * abs(want.item())
+    ref = (loss.cpu(), grad.cpu(), logits.cpu(), tiles)
+    del plan, wave, x, grad
+    net._native.invalidate()                                    # frees the single plan's ~45 GB workspace
+    torch.cuda.empty_cache()
+    for R in (2, 4):
+        got = _banded(net, mats, lat, 1.0 / 0.18215, 5.0, R, keep16=True)
+        assert torch.equal(got[2], ref[2]), "band logits must be bit-exact at 256x256 (R=%d)" % R
+        assert torch.equal(got[3], ref[3])
+        assert abs(got[0].item() - ref[0].item()) <= 1e-6 * abs(ref[0].item())
+        assert _rel(got[1], ref[1]) < 2e-3
+        torch.cuda.empty_cache()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="the NCCL transport needs two GPUs")
+def test_band_plan_over_nccl():
+    """One process per GPU, exchanges over NCCL (halo send/recv, all-reduce, all-gather, reduce-scatter), plain launches
+    and CUDA-graph replay: tests/band_nccl_worker.py compares with the single plan on rank 0."""
+    import subprocess
+    import sys
+
+    n = 4 if torch.cuda.device_count() >= 4 else 2
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "band_nccl_worker.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+                        "--master-addr", "127.0.0.1", "--master-port", "29643", worker], capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0 and "NCCL_BAND_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
 def test_band_shape_errors():

@@ -216,12 +216,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // of tiles would otherwise hammer the same few global addresses with atomics
     unsigned long long* stat_s = reinterpret_cast<unsigned long long*>(bet_s + 512);  // [2][TG_STAT_SLOTS] fixed point
 
-#ifdef WFD_UNIFORM_WARP
+#ifndef WFD_NO_UNIFORM_WARP
     // The warp index through a shuffle: the compiler then knows it is warp-uniform, the role branches below become uniform
     // branches, and the loop state of the single-thread roles (stage, phase, MMA descriptors) lives in uniform registers:
-    // R2UR moves in the kernel drop from 91 to 12 and the MMA-issue loop has none left (cuobjdump). Found at the very end
-    // of round 1 with no GPU time left to run the test suite on it, so it is compiled in only on request
-    // (WFD_NVCC_EXTRA=-DWFD_UNIFORM_WARP=1 python -m wavefunctiondiffusion_b200.build --force); see profiles/r01c_summary.md.
+    // R2UR moves in the kernel drop from 91 to 12 and the MMA-issue loop has none left (cuobjdump, profiles/r02_sass.txt).
+    // Round 1 measured 13.3 -> 12.85 ms per batch-8 step; -DWFD_NO_UNIFORM_WARP=1 restores the plain index for A/B runs.
     const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
 #else
     const int warp = threadIdx.x >> 5;
