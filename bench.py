@@ -29,7 +29,8 @@ LATENT_SCALE = 0.18215
 
 # --------------------------------------------------------------------------------------------------- flop model
 def decoder_layers(cfg, h, w):
-    """(name, macs) per tensor-core layer of one decode, from the architecture (SURVEY §8d closed form)."""
+    """(name, macs) per tensor-core layer of one decode, from the architecture (SURVEY §8d closed form). The launch class
+    of a layer (the tag the library stamps on its contractions) follows from its name: see layer_class()."""
     rev = list(reversed(cfg["block_out_channels"]))
     rev_g = list(reversed(cfg["conv_groups"]))
     n_res = cfg["layers_per_block"] + 1
@@ -57,6 +58,65 @@ def decoder_layers(cfg, h, w):
             out.append(("up%d.down" % i, px * ch * (ch // rev_g[i]) * 9))
     out.append(("conv_out", px * cfg["out_channels"] * (ch // cfg["conv_init_groups"]) * 9))
     return out, px
+
+
+def layer_class(cfg, name):
+    """dense / g4 / g16 / g64 (resnet convs by conv group count), conv_out, attn, down - the tags of csrc/decoder.cu."""
+    rev_g = list(reversed(cfg["conv_groups"]))
+    if name.startswith("mid."):
+        return "dense"
+    if name.startswith("attn."):
+        return "attn"
+    if name == "conv_out":
+        return "conv_out"
+    if name.endswith(".down"):
+        return "down"
+    if name.startswith("up"):
+        g = rev_g[int(name[2:name.index(".")])]
+        return "dense" if g == 1 else "g%d" % g
+    return "other"
+
+
+def class_flops(cfg, h, w, T, t_pad, kc_kept):
+    """Tensor-core flops of ONE map-step per launch class (2 flops per MAC): `algorithmic` as SURVEY §8d counts them
+    (forward + backward-data of every decoder contraction, one extra attention product pair in backward, the dense
+    4 T^2 P loss), and `executed` where the kernel provably does less or more: the WFC contraction visits only the K
+    chunks of the packed adjacency operand that hold an allowed pair (kc_kept of them, over T_pad-padded operands)."""
+    layers, px = decoder_layers(cfg, h, w)
+    alg = {}
+    for name, macs in layers:
+        if name == "conv_in":
+            continue  # 4-channel latent conv: a CUDA-core kernel (latent_in / latent_out), 0.1 GF
+        c = layer_class(cfg, name)
+        alg[c] = alg.get(c, 0.0) + 2 * 2.0 * macs           # forward + backward-data
+    cm = list(reversed(cfg["block_out_channels"]))[0]
+    alg["attn"] = alg.get("attn", 0.0) + 4.0 * (h * w) ** 2 * cm   # attention backward needs 4 products, forward 2
+    side = int(round(px ** 0.5))
+    P = 2 * side * (side - 1)
+    alg["wfc"] = 4.0 * T * T * P
+    exe = dict(alg)
+    n_tiles = (t_pad + 255) // 256
+    exe["wfc"] = 2.0 * px * (n_tiles * 256) * (4 * t_pad) * kc_kept
+    return alg, exe
+
+
+def gn_pass_bytes(cfg, h, w):
+    """Algorithmic HBM bytes per map-step of the standalone GroupNorm passes (16-bit activations): every
+    GN layer reads x and writes y forward; backward reads dy and x (reduce) and dy, x (+ residual gradient), writes dx."""
+    rev = list(reversed(cfg["block_out_channels"]))
+    n_res = cfg["layers_per_block"] + 1
+    hw = h * w
+    elems, px, ch = 0, hw, rev[0]
+    elems += 2 * 2 * rev[0] * hw + rev[0] * hw          # mid resnets (2 x 2 GN) + attention group_norm
+    for i, kind in enumerate(cfg["up_block_types"]):
+        for j in range(n_res):
+            cin = ch if j == 0 else rev[i]
+            elems += (cin + rev[i]) * px
+        ch = rev[i]
+        if kind == "DownDecoderBlock2D":
+            px //= 4
+    elems += ch * px                                      # conv_norm_out
+    return {"gn_apply": 2.0 * 2 * elems, "gn_bwd_apply": 2.0 * 3.5 * elems, "gn_bwd_reduce": 2.0 * 2 * elems}
 
 
 def step_flops(cfg, h, w, T):
@@ -327,13 +387,45 @@ def run_native(args):
     except Exception:
         pass
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
-    achieved = fl["F_step"] * B / (tg_ms / 1e3) / 1e12 if tg_ms > 0 else None
+    # flops the tensor-core launches EXECUTE (the block-sparse WFC walk skips provably-zero K chunks), per launch class
+    kc_kept = float(lib.wfd_wfc_kc_kept(handle.handle))
+    alg, exe = class_flops(cfg, args.latent, args.latent, T, t_pad, kc_kept)
+    cls_ms = {}
+    for n, (c, t) in prof.items():
+        if n.startswith("tapgemm["):
+            k = n[len("tapgemm["):n.index("]")]
+            cls_ms[k] = cls_ms.get(k, 0.0) + t
+    classes = {}
+    for k in sorted(set(cls_ms) | set(exe)):
+        ms_k, f_k = cls_ms.get(k, 0.0), exe.get(k, 0.0) * B
+        classes[k] = {"ms_per_step": ms_k, "executed_tflop_per_step": f_k / 1e12,
+                      "tflops": f_k / (ms_k / 1e3) / 1e12 if ms_k > 0 else None,
+                      "frac": f_k / (ms_k / 1e3) / 1e12 / peak if ms_k > 0 else None}
+    f_exec = sum(exe.values()) * B
+    achieved = f_exec / (tg_ms / 1e3) / 1e12 if tg_ms > 0 else None
+    dense_eq = fl["F_step"] * B / (tg_ms / 1e3) / 1e12 if tg_ms > 0 else None
+    weakest = min((k for k in classes if classes[k]["frac"] is not None and classes[k]["ms_per_step"] > 0.2),
+                  key=lambda k: classes[k]["frac"], default=None)
     roofline = {"bound": "tensor", "kernel": "tapgemm_kernel (all tensor-core contractions of the step)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if achieved else None,
+                "flops": "EXECUTED flops: algorithmic decoder flops (fwd + bwd-data, SURVEY 8d) + the WFC contraction over the "
+                         "%.1f%% of its K chunks that hold an allowed pair (the rest are exact zeros and are skipped)" % (100 * kc_kept),
+                "frac_dense_equivalent": dense_eq / peak if dense_eq else None,
+                "wfc_chunks_kept": kc_kept,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)",
-                "algorithmic_flops_per_step": fl["F_step"] * B, "launches_per_step": tg_launches,
+                "executed_flops_per_step": f_exec, "algorithmic_flops_per_step": fl["F_step"] * B,
+                "launches_per_step": tg_launches,
                 "avg_launch_ms": tg_ms / tg_launches if tg_launches else None, "kernel_ms_per_step": tg_ms,
-                "share_of_step": tg_ms / all_ms if all_ms else None, "traffic": None}
+                "share_of_step": tg_ms / all_ms if all_ms else None, "classes": classes, "weakest_class": weakest,
+                "whole_step_frac_of_ideal": (fl["F_step"] * B / (peak * 1e12)) / (ms / args.steps / 1e3),
+                "traffic": None}
+    hbm_peak = peaks.get("hbm_gbs", 6551.4)
+    gn_bytes = {k: v * B for k, v in gn_pass_bytes(cfg, args.latent, args.latent).items()}
+    roofline["hbm_kernels"] = {
+        k: {"ms_per_step": prof[k][1], "algorithmic_gb_per_step": gb / 1e9,
+            "gbps": gb / (prof[k][1] / 1e3) / 1e9 if prof[k][1] > 0 else None,
+            "frac": gb / (prof[k][1] / 1e3) / 1e9 / hbm_peak if prof[k][1] > 0 else None}
+        for k, gb in gn_bytes.items() if k in prof}
     # DRAM bytes per launch come from the committed ncu capture of the same workload (they cannot be measured live)
     if args.tileset == "ice_64x64" and args.latent == 64 and args.arch == "64x64" and B == 8:
         try:

@@ -10,6 +10,7 @@ import functools
 import importlib
 import importlib.util
 import inspect
+import os
 import sys
 import types
 from collections import OrderedDict
@@ -18,12 +19,28 @@ from dataclasses import fields
 import torch
 
 REFERENCE_ROOT = "/root/reference"
+# The one offline install of the reference (`pip install --no-deps --target baseline/_ref`): git-ignored,
+# but it travels to the GPU box with the snapshot, so the UNMODIFIED reference modules can also be executed there
+# (reference arm of bench.py, tests/test_patch_reference_gpu.py).
+INSTALLED_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
 
 
-def load_reference(ref=REFERENCE_ROOT):
+def reference_root():
+    """Directory that holds the reference's `wfd/` package: the read-only tree in the authoring container, else the
+    installed copy; None when neither exists."""
+    for root in (REFERENCE_ROOT, INSTALLED_ROOT):
+        if os.path.exists(os.path.join(root, "wfd", "wf_diffusers", "wf_vae.py")):
+            return root
+    return None
+
+
+def load_reference(ref=None):
     """Returns (wf_vae module, losses module) of the reference."""
     if "ref_wf_diffusers.wf_vae" in sys.modules:
         return sys.modules["ref_wf_diffusers.wf_vae"], sys.modules["ref_losses"]
+    ref = ref or reference_root()
+    if ref is None:
+        raise FileNotFoundError("the reference is neither at %s nor installed under %s" % (REFERENCE_ROOT, INSTALLED_ROOT))
 
     def mod(name, package=False):
         m = types.ModuleType(name)

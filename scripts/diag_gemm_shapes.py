@@ -1,4 +1,5 @@
 """Plain GEMM with the dense-conv problem size vs the conv itself: is the activation box pattern the limiter?"""
+import os; os.environ.setdefault("WFD_ENABLE_TEST_HOOKS", "1")
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))

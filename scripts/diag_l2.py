@@ -1,4 +1,5 @@
 """Is the k-iteration rate of the big GEMMs limited per SM or chip-wide? Same GEMM on 148 / 74 / 37 CTAs."""
+import os; os.environ.setdefault("WFD_ENABLE_TEST_HOOKS", "1")
 import ctypes as C, os, sys, subprocess
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))

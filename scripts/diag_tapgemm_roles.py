@@ -1,4 +1,5 @@
 """Where does a tapgemm launch spend its time? Cycle counters of CTA 0 per warp role for decoder-like conv shapes."""
+import os; os.environ.setdefault("WFD_ENABLE_TEST_HOOKS", "1")
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))

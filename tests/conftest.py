@@ -3,6 +3,8 @@ import sys
 
 import pytest
 
+os.environ.setdefault("WFD_ENABLE_TEST_HOOKS", "1")  # include/wfd_b200_test.h: hooks answer only with this set at load
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

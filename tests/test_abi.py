@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared():
-    src = open(os.path.join(ROOT, "include", "wfd_b200.h")).read()
+    src = open(os.path.join(ROOT, "include", "wfd_b200.h")).read() + open(os.path.join(ROOT, "include", "wfd_b200_test.h")).read()
     return sorted(set(re.findall(r"WFD_API[^;(]*?\b(wfd_[a-z0-9_]+)\s*\(", src)))
 
 
@@ -28,6 +28,22 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), "missing export %s" % n
     assert sorted(nat.SIGNATURES) == names
     assert nat.lib().wfd_version() == 1
+    # the product header carries no test hook
+    product = open(os.path.join(ROOT, "include", "wfd_b200.h")).read()
+    assert "wfd_test_tapgemm" not in product and "wfd_debug_set_ref_gemm" not in product
+
+
+def test_hooks_need_the_environment_switch():
+    """include/wfd_b200_test.h: a process started without WFD_ENABLE_TEST_HOOKS=1 cannot reroute its contractions."""
+    import subprocess
+    import sys
+
+    code = ("import os; os.environ.pop('WFD_ENABLE_TEST_HOOKS', None); "
+            "from wavefunctiondiffusion_b200 import _native as nat; l = nat.lib(); "
+            "assert l.wfd_debug_set_ref_gemm(1) == -13 and b'WFD_ENABLE_TEST_HOOKS' in l.wfd_last_error(); print('ok')")
+    env = {k: v for k, v in os.environ.items() if k != "WFD_ENABLE_TEST_HOOKS"}
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
 
 
 def test_state_dict_keys_and_config():

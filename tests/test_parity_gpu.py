@@ -137,7 +137,7 @@ def test_ice_config2_batch8_against_reference_golden():
     x = lat.clone().requires_grad_()
     loss = GuidanceLossFunction.apply(x, net._native, handle, 1.0 / 0.18215, 5.0)
     (grad,) = torch.autograd.grad(loss.sum(), x)
-    rel_l = np.abs(loss.cpu().numpy().astype(np.float64) - z["loss_f64"]) / np.abs(z["loss_f64"])
+    rel_l = np.abs(loss.detach().cpu().numpy().astype(np.float64) - z["loss_f64"]) / np.abs(z["loss_f64"])
     rel_g = [_rel(grad[b].cpu(), z["grad_f64"][b]) for b in range(8)]
     print("ice C2: loss rel max", rel_l.max(), "grad rel-L2 per map", ["%.3e" % r for r in rel_g])
     assert rel_l.max() < TOL_LOSS

@@ -51,7 +51,8 @@ class TapGemmDesc(C.Structure):
     ]
 
 
-# name -> (restype, argtypes); must list every symbol include/wfd_b200.h declares (tests check this against the header)
+# name -> (restype, argtypes); must list every symbol include/wfd_b200.h and include/wfd_b200_test.h declare (tests check
+# this against the headers)
 SIGNATURES = {
     "wfd_version": (C.c_int, []),
     "wfd_last_error": (C.c_char_p, []),
@@ -88,6 +89,7 @@ SIGNATURES = {
                                           C.POINTER(C.c_void_p)]),
     "wfd_decoder_attach_comm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "wfd_wfc_attach_comm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "wfd_wfc_kc_kept": (C.c_double, [C.c_void_p]),
     "wfd_wfc_count_violations": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "wfd_argmax_tiles": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "wfd_nchw_to_nhwc16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

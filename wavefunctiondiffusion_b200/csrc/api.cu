@@ -1,6 +1,8 @@
 // extern "C" surface of libwfd_b200.so (declared in include/wfd_b200.h).
 #include "decoder.cuh"
 #include "kernels.cuh"
+#include "../../include/wfd_b200_test.h"
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 
@@ -30,6 +32,17 @@ struct wfd_loop_group {
     } while (0)
 
 static inline cudaStream_t S(void* stream) { return static_cast<cudaStream_t>(stream); }
+
+// include/wfd_b200_test.h: the hooks answer only in a process started with WFD_ENABLE_TEST_HOOKS=1
+static int test_hooks_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("WFD_ENABLE_TEST_HOOKS");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (!v) set_error("test hooks are disabled (start the process with WFD_ENABLE_TEST_HOOKS=1)");
+    return v;
+}
 
 
 extern "C" {
@@ -294,6 +307,7 @@ int wfd_guidance_step(wfd_decoder* d, wfd_wfc* h, const void* z, int z_dtype, in
     return D.backward(nullptr, B, nullptr, dz, S(stream));
 }
 
+double wfd_wfc_kc_kept(const wfd_wfc* h) { return h ? h->w.kc_kept : 0.0; }
 int wfd_wfc_count_violations(const wfd_wfc* h, const long long* tiles, int B, int H, int W, long long* out, void* stream) {
     if (!h || !tiles || !out) {
         set_error("wfd_wfc_count_violations: null argument");
@@ -322,6 +336,7 @@ int wfd_cvt16_to_f32(const void* in, float* out, long long n, int dtype16, void*
 }
 
 int wfd_test_tapgemm(const wfd_tapgemm_desc* t, int use_ref, void* stream) {
+    if (!test_hooks_enabled()) return -13;
     if (!t) return -1;
     TapGemmOp op;
     memset(&op, 0, sizeof(op));
@@ -392,6 +407,7 @@ int wfd_profile_enable(int on) {
 }
 int wfd_profile_report(char* buf, size_t cap) { return profile_report(buf, cap); }
 int wfd_debug_set_ref_gemm(int on) {
+    if (!test_hooks_enabled()) return -13;
     debug_set_ref_gemm(on);
     return 0;
 }

@@ -554,6 +554,7 @@ int Decoder::prepare_ops() {
 int Decoder::run_gemm(Exec& ex, TapGemmOp& tmpl, bool z_is_batch) {
     if (ex.prepare) {
         CK(tapgemm_prepare(&tmpl));
+        snprintf(tmpl.tag, sizeof(tmpl.tag), "%s", cur_tag);
         ex.ops->push_back(tmpl);
         return 0;
     }
@@ -815,8 +816,11 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
     int cur_h = h, cur_w = w;
     int ri = 0;
     auto fused_ok = [&](int C) { return fuse_gn && (C / G) % 16 == 0; };
+    static const char* const group_tag[] = {"dense", "g4", "g16", "g64", "grouped"};
+    auto tag_of = [&](int groups) { return group_tag[groups == 1 ? 0 : groups == 4 ? 1 : groups == 16 ? 2 : groups == 64 ? 3 : 4]; };
     auto resnet = [&](int idx, uint8_t* xin, bool stats_ready) -> int {
         const ResnetDesc& r = resnets[idx];
+        cur_tag = tag_of(r.groups);
         const int phw = r.h * r.w;
         uint8_t* act = ws + o_act;
         uint8_t* act2 = ws + o_act2;
@@ -868,6 +872,7 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
         // AttentionBlock.forward (attention.py:329-380), one head of Cm channels. N queries (this band's pixels)
         // attend over Nk keys; in a band plan the q|k|v rows of all bands are gathered into one [Nk, 3*Cm] block
         const int N = hw, Nk = hw * band_R;
+        cur_tag = "attn";
         uint8_t* xn = ws + o_xn;
         uint8_t* qkv_all = ws + o_qkv;
         uint8_t* qkv = qkv_all + static_cast<size_t>(band_r) * N * 3 * Cm * 2;  // this band's rows
@@ -935,6 +940,7 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
             char buf[128];
             snprintf(buf, sizeof(buf), "decoder.up_blocks.%d.downsamplers.0.conv", i);
             const ConvW& cd = convs[buf];
+            cur_tag = "down";
             CK(conv_gemm(ex, cd.fwd, x, cd.cin, cur_h, cur_w, cur_h / 2, cur_w / 2, ws + o_down_out[i], cd.cout,
                          cd.bias, nullptr, nullptr, 0, nullptr, nullptr));
             x = ws + o_down_out[i];
@@ -952,6 +958,7 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
                     ws + o_act, B, H_out * W_out, C_last, G, eps, 1, bf16, s, H_out * W_out * band_R));
     }
     const ConvW& co = convs["decoder.conv_out"];
+    cur_tag = "conv_out";
     CK(conv_gemm(ex, co.fwd, ws + o_act, C_last, H_out, W_out, H_out, W_out, ws + o_logits, T_pad, co.bias, nullptr,
                  nullptr, 0, nullptr, nullptr));
     return 0;
@@ -991,6 +998,9 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
     auto gbuf = [&](int i) { return ws + o_g[i & 3]; };
     // conv_out^T, then conv_norm_out + SiLU backward
     const ConvW& co = convs["decoder.conv_out"];
+    cur_tag = "conv_out";
+    static const char* const group_tag[] = {"dense", "g4", "g16", "g64", "grouped"};
+    auto tag_of = [&](int groups) { return group_tag[groups == 1 ? 0 : groups == 4 ? 1 : groups == 16 ? 2 : groups == 64 ? 3 : 4]; };
     {
         const GnBwdFuse gb = make_gb(n_gn - 1, x_last, "decoder.conv_norm_out", C_last, H_out * W_out, 1);
         CK(conv_gemm(ex, co.bwd, dlog, T_pad, H_out, W_out, H_out, W_out, gbuf(cur), C_last, nullptr, nullptr, nullptr, 0,
@@ -1003,6 +1013,7 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
     }
     auto resnet_bwd = [&](int idx, const uint8_t* xin) -> int {
         const ResnetDesc& r = resnets[idx];
+        cur_tag = tag_of(r.groups);
         const int phw = r.h * r.w;
         uint8_t* dout = gbuf(cur);
         uint8_t* t1 = gbuf(cur + 1);
@@ -1046,6 +1057,7 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
             const int last_idx = 2 + i * n_res + n_res - 1;
             if (down_after[i]) {
                 const ResnetDesc& r = resnets[last_idx];  // its plane is the conv's input plane
+                cur_tag = "down";
                 char buf[128];
                 uint8_t* dout = gbuf(cur);
                 uint8_t* dxin = gbuf(cur + 1);
@@ -1079,6 +1091,7 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         // attention backward. In a band plan (N local queries, Nk keys) dQ is complete locally, while dK and dV collect a
         // term from every band's queries: the fp32 partials [Nk, dK | dV] are reduce-scattered over the bands.
         const int N = hw, Nk = hw * band_R;
+        cur_tag = "attn";
         const bool split = band_R > 1;
         const std::string a = "decoder.mid_block.attentions.0.";
         uint8_t* dout = gbuf(cur);

@@ -94,6 +94,7 @@ struct Decoder {
     float last_in_scale = 1.f;
     int last_B = 0;
     std::vector<TapGemmOp> fwd_ops, bwd_ops;
+    const char* cur_tag = "";  // launch class stamped on the contractions prepared next (per-launch profile of bench.py)
 
     ~Decoder();
     int init(const wfd_decoder_config& c, int h, int w, int B_max, int dtype16, int band_rank = -1, int band_nranks = 1);

@@ -204,6 +204,52 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// NK back-to-back MMAs over consecutive 16-element K steps of one operand pair, issued by ONE thread: the descriptors
+// advance by a_step / 2 (16-byte units) inside the asm block, so the issuing thread spends two 32-bit adds per MMA instead
+// of rebuilding both descriptors (the issue loop, not the tensor pipe, bounds narrow-N contractions: ~4 cycles per
+// dependent uniform instruction, profiles/r02_summary.md). acc_first: accumulate flag of the first MMA; the rest accumulate.
+#define WFD_UMMA_RUN_BODY(GROUP)                                                                     \
+    asm volatile(                                                                                     \
+        "{\n\t"                                                                                       \
+        ".reg .pred p, t;\n\t"                                                                        \
+        ".reg .b32 al, bl;\n\t"                                                                       \
+        ".reg .b64 a, b;\n\t"                                                                         \
+        "setp.ne.b32 p, %6, 0;\n\t"                                                                   \
+        "setp.eq.u32 t, 0, 0;\n\t"                                                                    \
+        "mov.b64 a, {%1, %2};\n\t"                                                                    \
+        "mov.b64 b, {%3, %4};\n\t"                                                                    \
+        "tcgen05.mma.cta_group::" GROUP ".kind::f16 [%0], a, b, %5, p;\n\t"                           \
+        "setp.gt.s32 p, %8, 1;\n\t"                                                                   \
+        "add.u32 al, %1, %7;\n\t"                                                                     \
+        "add.u32 bl, %3, 2;\n\t"                                                                      \
+        "mov.b64 a, {al, %2};\n\t"                                                                    \
+        "mov.b64 b, {bl, %4};\n\t"                                                                    \
+        "@p tcgen05.mma.cta_group::" GROUP ".kind::f16 [%0], a, b, %5, t;\n\t"                        \
+        "setp.gt.s32 p, %8, 2;\n\t"                                                                   \
+        "add.u32 al, al, %7;\n\t"                                                                     \
+        "add.u32 bl, bl, 2;\n\t"                                                                      \
+        "mov.b64 a, {al, %2};\n\t"                                                                    \
+        "mov.b64 b, {bl, %4};\n\t"                                                                    \
+        "@p tcgen05.mma.cta_group::" GROUP ".kind::f16 [%0], a, b, %5, t;\n\t"                        \
+        "setp.gt.s32 p, %8, 3;\n\t"                                                                   \
+        "add.u32 al, al, %7;\n\t"                                                                     \
+        "add.u32 bl, bl, 2;\n\t"                                                                      \
+        "mov.b64 a, {al, %2};\n\t"                                                                    \
+        "mov.b64 b, {bl, %4};\n\t"                                                                    \
+        "@p tcgen05.mma.cta_group::" GROUP ".kind::f16 [%0], a, b, %5, t;\n\t"                        \
+        "}\n" ::"r"(d_tmem),                                                                          \
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first), "r"(a_step), "r"(n_k)  \
+        : "memory")
+// n_k in 1..4 MMAs (K steps of one 64-element chunk)
+// descriptors are passed as (low word, high word): only the address field in the low word moves
+__device__ __forceinline__ void umma_f16_run(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t acc_first, uint32_t a_step, int n_k) {
+    WFD_UMMA_RUN_BODY("1");
+}
+__device__ __forceinline__ void umma_f16_run_2sm(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                 uint32_t idesc, uint32_t acc_first, uint32_t a_step, int n_k) {
+    WFD_UMMA_RUN_BODY("2");
+}
 // Arrives on the mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

@@ -334,7 +334,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     auto issue_a = [&](int ca, int xx, int yy) {
                         slot_wait();
                         const long long i0 = p.dbg ? clock64() : 0;
-                        if (elect_one()) {
+                        if (p.dbg_skip & 1) {
+                            if (elect_one() && rank == 0) mbar_arrive(&full_bar[stage]);
+                        } else if (elect_one()) {
                             if (CG == 2) {  // both CTAs load into their own shared memory; the leader's barrier counts all bytes
                                 if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * a_stage_bytes);
                                 tma_load_4d_2sm(smA + static_cast<size_t>(stage) * a_stage_bytes, &tmA, &full_bar[stage], ca,
@@ -350,7 +352,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     auto issue_b = [&](int k0, int k2) {  // weights box at (k0, n0, k2)
                         slot_wait();
                         const long long i0 = p.dbg ? clock64() : 0;
-                        if (elect_one()) {
+                        if (p.dbg_skip & 2) {
+                            if (elect_one() && rank == 0) mbar_arrive(&full_bar[stage]);
+                        } else if (elect_one()) {
                             if (CG == 2) {
                                 if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * b_stage_bytes);
                                 tma_load_3d_2sm(smB + static_cast<size_t>(stage) * b_stage_bytes, &tmB, &full_bar[stage], k0, n0, k2);
@@ -426,9 +430,24 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                (p.a_mn_major ? IDESC_A_MN_MAJOR : 0u);
         const int n_sub = p.reuse ? 3 : 1;                        // vertical taps served by one stage
         const int kk_last = (p.kk_last > 0 && p.kk_last < TG_KC / 16) ? p.kk_last : TG_KC / 16;
-        const uint32_t a_sub_bytes = static_cast<uint32_t>(p.w_box) * 128;  // one image row of the patch
+        // The issuing thread is the busy role of every narrow-N launch (~4 cycles per dependent uniform instruction), so
+        // the loop keeps running descriptors: everything that moves between MMAs is the 14-bit address field (16-byte
+        // units) in the low word of a descriptor, advanced by plain 64-bit adds. Shared memory ends below 256 KB, so the
+        // field never carries into its neighbours.
+        // K-major A: 16 elements along K are 32 bytes inside the swizzle atom (+2); M-major A: 16 K rows are two
+        // 1024-byte atoms (+128)
+        const uint32_t a_step = p.a_mn_major ? 128 : 2;
+        const uint64_t a_desc0 = p.a_mn_major ? make_mnmajor_desc(smem_u32(smA), 8192, 1024) : make_kmajor_desc(smem_u32(smA), 128);
+        const uint64_t b_desc0 = make_kmajor_desc(smem_u32(smB), 128);
+        const uint32_t a_hi = static_cast<uint32_t>(a_desc0 >> 32), b_hi = static_cast<uint32_t>(b_desc0 >> 32);
+        const uint32_t a_lo0 = static_cast<uint32_t>(a_desc0), b_lo0 = static_cast<uint32_t>(b_desc0);
+        const uint32_t a_stage16 = a_stage_bytes >> 4, b_stage16 = b_stage_bytes >> 4;
+        const uint32_t a_sub16 = (static_cast<uint32_t>(p.w_box) * 128u) >> 4;  // one image row of the patch
+        const uint32_t b_box16 = b_box_bytes >> 4;
+        const int skip_mma = p.dbg_skip & 4;
         int stage = 0;
         uint32_t phase = 0;
+        uint32_t a_cur = a_lo0, b_cur = b_lo0;  // low descriptor words of the current stage
         int acc = 0;
         uint32_t acc_phase = 0;
         long long w_tempty = 0, w_full = 0;
@@ -460,25 +479,19 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (p.dbg) w_full += clock64() - w0;
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t a_base = smem_u32(smA + static_cast<size_t>(stage) * a_stage_bytes);
-                    const uint32_t b_base = b_res ? smem_u32(smB) + static_cast<uint32_t>(kc) * 3u * b_box_bytes
-                                                  : smem_u32(smB + static_cast<size_t>(stage) * b_stage_bytes);
-                    for (int sub = 0; sub < n_sub; ++sub) {
-                        // K-major A: 16 elements along K are 32 bytes inside the swizzle atom (+2 in 16-byte units);
-                        // M-major A: 16 K rows are two 1024-byte atoms (+128)
-                        const uint64_t adesc = p.a_mn_major ? make_mnmajor_desc(a_base, 8192, 1024)
-                                                            : make_kmajor_desc(a_base + sub * a_sub_bytes, 128);
-                        const uint64_t a_step = p.a_mn_major ? 128 : 2;
-                        const uint64_t bdesc = make_kmajor_desc(b_base + sub * b_box_bytes, 128);
-#pragma unroll
-                        for (int k = 0; k < TG_KC / 16; ++k) {
-                            // 16-channel steps that only meet zero-padded weights are skipped
-                            if (k < n_k) {
-                                if (CG == 2)
-                                    umma_f16_2sm(d_tmem, adesc + a_step * k, bdesc + 2 * k, idesc, (kc > 0 || sub > 0 || k > 0) ? 1u : 0u);
-                                else
-                                    umma_f16(d_tmem, adesc + a_step * k, bdesc + 2 * k, idesc, (kc > 0 || sub > 0 || k > 0) ? 1u : 0u);
-                            }
+                    uint32_t ad = a_cur;
+                    uint32_t bd = b_res ? b_lo0 + static_cast<uint32_t>(kc) * 3u * b_box16 : b_cur;
+                    if (!skip_mma) {
+                        // 16-channel steps that only meet zero-padded weights are skipped (n_k < 4)
+                        if (CG == 2) umma_f16_run_2sm(d_tmem, ad, a_hi, bd, b_hi, idesc, kc > 0 ? 1u : 0u, a_step, n_k);
+                        else umma_f16_run(d_tmem, ad, a_hi, bd, b_hi, idesc, kc > 0 ? 1u : 0u, a_step, n_k);
+                        if (n_sub == 3) {  // the other two vertical taps: next image row of the patch, next weight box
+                            ad += a_sub16; bd += b_box16;
+                            if (CG == 2) umma_f16_run_2sm(d_tmem, ad, a_hi, bd, b_hi, idesc, 1u, a_step, n_k);
+                            else umma_f16_run(d_tmem, ad, a_hi, bd, b_hi, idesc, 1u, a_step, n_k);
+                            ad += a_sub16; bd += b_box16;
+                            if (CG == 2) umma_f16_run_2sm(d_tmem, ad, a_hi, bd, b_hi, idesc, 1u, a_step, n_k);
+                            else umma_f16_run(d_tmem, ad, a_hi, bd, b_hi, idesc, 1u, a_step, n_k);
                         }
                     }
                     if (CG == 2) {  // release the stage / publish the accumulator in both CTAs of the pair
@@ -493,9 +506,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 __syncwarp();
+                a_cur += a_stage16;
+                b_cur += b_stage16;
                 if (++stage == stages) {
                     stage = 0;
                     phase ^= 1;
+                    a_cur = a_lo0;
+                    b_cur = b_lo0;
                 }
             }
             acc ^= 1;
@@ -590,7 +607,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     dst[1] = __ldg(side_ptr + 2 * chunk + 1);
                 }
             };
-            if (side_ptr) {
+            if (side_ptr && !(p.dbg_skip & 8)) {
                 if (c_first < n_chunks) load_side(c_first, sb0);
                 if (c_first + c_step < n_chunks) load_side(c_first + c_step, sb1);
                 if (c_first + 2 * c_step < n_chunks) load_side(c_first + 2 * c_step, sb2);
@@ -608,7 +625,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int ggroup = -1;
             float b1 = 0.f, b2 = 0.f, bmean = 0.f, brstd = 0.f;
             int bgroup = -1;
-            for (int c = c_first; c < n_chunks; c += c_step) {
+            for (int c = c_first; c < ((p.dbg_skip & 8) ? 0 : n_chunks); c += c_step) {
                 const int j0 = c * 16;
                 const int n = n0 + j0;
                 uint4 side_cur[2];
@@ -1167,7 +1184,7 @@ int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream) {
     int grid = total * cg < sms ? total * cg : (sms / cg) * cg;
     char pname[160];
     if (g_prof_on)
-        snprintf(pname, sizeof(pname), "tapgemm:N=%d,BN=%d,taps=%d,cpt=%d,aC=%d,f32=%d,reuse=%d,side=%d,gns=%d,cg=%d", p.N, p.BN,
+        snprintf(pname, sizeof(pname), "tapgemm[%.11s]:N=%d,BN=%d,taps=%d,cpt=%d,aC=%d,f32=%d,reuse=%d,side=%d,gns=%d,cg=%d", op->tag, p.N, p.BN,
                  p.n_taps, p.cpt, p.a_C, p.out_fp32, p.reuse, p.residual ? 1 : (p.rowdot ? 2 : (p.gnb_red ? 3 : 0)),
                  p.gn_sums ? 1 : 0, cg);
     ProfScope prof_scope(g_prof_on ? pname : "", stream);
@@ -1180,7 +1197,17 @@ int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream) {
         tg_dbg = (ev && ev[0] == '1') ? 1 : 0;
         if (tg_dbg && cudaMalloc(&tg_dbg_buf, 16 * sizeof(long long)) != cudaSuccess) tg_dbg = 0;
     }
+    static int tg_skip = -1;  // WFD_TG_SKIP=<bits>: see TapGemmParams::dbg_skip (row-reuse launches only)
+    if (tg_skip < 0) {
+        const char* ev = getenv("WFD_TG_SKIP");
+        tg_skip = ev ? atoi(ev) : 0;
+    }
     TapGemmOp dbg_op;
+    if (tg_skip && p.reuse) {
+        dbg_op = *op;
+        dbg_op.p.dbg_skip = tg_skip;
+        op = &dbg_op;
+    }
     if (tg_dbg && !p.dbg) {
         dbg_op = *op;
         dbg_op.p.dbg = tg_dbg_buf;

@@ -85,6 +85,8 @@ struct TapGemmParams {
     float gnb_inv_n, gnb_eps;
     int is_bf16;            // 1: bf16 operands/outputs, 0: fp16
     long long* dbg;         // optional [8]: per-role cycle counters of CTA 0 (test hook only)
+    int dbg_skip;           // diagnosis only (WFD_TG_SKIP, results are garbage): bit 0 no activation TMA, bit 1 no weight TMA,
+                            // bit 2 no MMA, bit 3 no epilogue loads/stores - isolates which engine bounds a launch
     // ---- raw views (used only by the CUDA-core checking kernel)
     const void* a_ptr; int a_C, a_W, a_H, a_B; long long a_ld;
     const void* b_ptr; long long ldb, b_zstride; int b_rows, b_Z;
@@ -95,6 +97,7 @@ struct TapGemmOp {
     TapGemmParams p;
     int stages;
     size_t smem_bytes;
+    char tag[12];  // launch class for the per-launch profile (dense, g4, g16, g64, conv_out, attn, wfc, down); may be empty
 };
 
 // Encodes the two tensor maps and fills stages/smem. Returns 0 or a negative error (message via set_error).

@@ -262,6 +262,7 @@ int Wfc::forward(const void* in, int is_logits, int B, int H, int W, float stren
         p.kc_list = kc_list;
         p.kc_cnt = kc_cnt;
         CK(tapgemm_prepare(&op));
+        snprintf(op.tag, sizeof(op.tag), "wfc");
         op_wave = wave;
         op_a = v.a;
         op_B = B;

@@ -51,6 +51,70 @@ class WaveFunctionDiffusionPipeline:
         self.wfc_loss = WFCLossEinsum(wfc_mat_x, wfc_mat_y)
         self.config = {"wfc_data_path": wfc_data_path, "requires_safety_checker": requires_safety_checker}
 
+    # ------------------------------------------------------------------ loading (reference README.md:60-64, ui.py:188-192)
+    COMPONENTS = ("vae", "text_encoder", "tokenizer", "tile_vae", "unet", "scheduler", "safety_checker", "feature_extractor")
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, tile_vae=None, wfc_data_path=None, **kwargs):
+        """`WaveFunctionDiffusionPipeline.from_pretrained(path, tile_vae=tilenet, wfc_data_path=npz)` as the reference's
+        README and web UI call it. The reference inherits this from `diffusers.DiffusionPipeline`; here the pipeline
+        folder's `model_index.json` is read directly: every component that is not handed in as a keyword is loaded with
+        `<library>.<class>.from_pretrained(path/<name>)` from the library the index names (`diffusers`, `transformers` -
+        third-party stages, used as they are), the tile VAE by this package's AutoencoderTile. A Hugging Face hub id is
+        resolved with `huggingface_hub.snapshot_download` when that package is importable."""
+        import importlib
+        import json
+        import os
+
+        root = pretrained_model_name_or_path
+        if not os.path.isdir(root):
+            try:
+                from huggingface_hub import snapshot_download
+            except ImportError as e:
+                raise FileNotFoundError(f"{root!r} is not a local pipeline folder and huggingface_hub is not installed") from e
+            root = snapshot_download(root)
+        with open(os.path.join(root, "model_index.json")) as f:
+            index = json.load(f)
+        if wfc_data_path is None:
+            wfc_data_path = index.get("wfc_data_path")
+        if wfc_data_path is None:
+            raise ValueError("wfc_data_path is required (the tileset's wfc/*.npz, reference pipeline_wfd.py:180-182)")
+        torch_dtype = kwargs.pop("torch_dtype", None)
+        parts = {}
+        for name in cls.COMPONENTS:
+            if name == "tile_vae" and tile_vae is not None:
+                parts[name] = tile_vae
+                continue
+            if name in kwargs:
+                parts[name] = kwargs.pop(name)
+                continue
+            spec = index.get(name)
+            if not spec or spec[0] is None or spec[1] is None:
+                if name in ("safety_checker", "feature_extractor"):
+                    parts[name] = None
+                    continue
+                raise ValueError(f"model_index.json of {root} names no {name!r} and none was passed")
+            lib_name, class_name = spec
+            sub = os.path.join(root, name)
+            if class_name == "AutoencoderTile":
+                from .wf_vae import AutoencoderTile
+
+                parts[name] = AutoencoderTile.from_pretrained(sub)
+                continue
+            try:
+                module = importlib.import_module(lib_name)
+            except ImportError as e:
+                raise ImportError(f"component {name!r} of {root} needs the {lib_name!r} package ({class_name}); install it "
+                                  f"or pass {name}=... to from_pretrained") from e
+            klass = getattr(module, class_name)
+            parts[name] = klass.from_pretrained(sub, torch_dtype=torch_dtype) if torch_dtype is not None else klass.from_pretrained(sub)
+        requires = kwargs.pop("requires_safety_checker", index.get("requires_safety_checker", True))
+        if kwargs:
+            raise TypeError(f"from_pretrained got unexpected keyword arguments {sorted(kwargs)}")
+        return cls(parts["vae"], parts["text_encoder"], parts["tokenizer"], parts["tile_vae"], parts["unet"],
+                   parts["scheduler"], parts["safety_checker"], parts["feature_extractor"], wfc_data_path=wfc_data_path,
+                   requires_safety_checker=requires)
+
     # ------------------------------------------------------------------ plumbing shared with diffusers pipelines
     @property
     def device(self):
