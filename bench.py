@@ -185,64 +185,153 @@ def load_workload(args):
     return mx, my, T, t_pad, cfg
 
 
-def cpu_oracle_maps_per_s(args, cfg, mx, my, repeats, maps=1):
-    """The reference algorithm (oracle port, fp32) on the host cores: best of `repeats` after one warm-up."""
+def reference_cpu_step_fn(args, cfg, mx, my):
+    """One guidance step of ONE map on the host cores, fp32: (callable, kind). kind "reference" = the UNMODIFIED
+    reference modules (imported through oracle/reference_loader.py from /root/reference or the offline install under
+    baseline/_ref) executing pipeline_wfd.py:609-613; kind "port" = the oracle restatement when neither is present."""
     import torch
 
     from oracle import wfd_oracle as orc
-    from wavefunctiondiffusion_b200.wf_diffusers.wf_vae import AutoencoderTile
+    from oracle.reference_loader import load_reference, reference_root
 
     torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(1234)
+    lat = torch.randn(1, 4, args.latent, args.latent, generator=g)
+    if reference_root() is not None:
+        vae, losses = load_reference()
+        torch.manual_seed(0)
+        net = vae.AutoencoderTile(**cfg).eval()
+        lossm = losses.WFCLossEinsum(mx, my)
+
+        def step():
+            with torch.enable_grad():
+                _latents = lat.detach().requires_grad_()
+                wave = net.decode(1 / LATENT_SCALE * _latents).sample.softmax(axis=1)
+                _loss = lossm(wave) * STRENGTH
+                (grad,) = torch.autograd.grad(_loss.sum(), _latents)
+            return _loss.detach(), grad
+
+        return step, "reference"
+    from wavefunctiondiffusion_b200.wf_diffusers.wf_vae import AutoencoderTile
+
     torch.manual_seed(0)
     sd = AutoencoderTile(**cfg).state_dict()
-    g = torch.Generator().manual_seed(1234)
-    lat = torch.randn(maps, 4, args.latent, args.latent, generator=g)
-    orc.guidance_step(sd, cfg, mx, my, lat, STRENGTH, torch.float32)
+
+    def step():
+        r = orc.guidance_step(sd, cfg, mx, my, lat, STRENGTH, torch.float32)
+        return r["loss"], r["grad"]
+
+    return step, "port"
+
+
+def cpu_oracle_maps_per_s(args, cfg, mx, my, repeats, maps=1):
+    """The reference's CPU path on the host cores: best of `repeats` after one warm-up."""
+    import torch
+
+    step, kind = reference_cpu_step_fn(args, cfg, mx, my)
+    step()
     best = float("inf")
     for _ in range(repeats):
         t0 = time.time()
-        orc.guidance_step(sd, cfg, mx, my, lat, STRENGTH, torch.float32)
+        step()
         best = min(best, time.time() - t0)
-    return maps / best, torch.get_num_threads(), best
+    return 1.0 / best, torch.get_num_threads(), best, kind
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path. /root/reference (pure Python on diffusers) cannot travel to the GPU
-    box, so the timed code is the oracle port of the same arithmetic (validated against the unmodified reference by
-    tests/golden), with all host threads, one map of the batch per step as the bounded sample."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores, all threads, fp32
+    (set_precision is a no-op on CPU, pipeline_wfd.py:205-206). The timed code is the UNMODIFIED reference
+    (baseline/_ref install or /root/reference, through the stub-diffusers loader) when present, else the oracle port.
+    One step = ONE map of the batch (maps are independent and the metric is per map): the bounded sample that keeps
+    `--steps K` within minutes on a host whose step costs ~1 s per map."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
 
-    from oracle import wfd_oracle as orc
-    from wavefunctiondiffusion_b200.wf_diffusers.wf_vae import AutoencoderTile
-
     mx, my, T, t_pad, cfg = load_workload(args)
-    torch.set_num_threads(os.cpu_count() or 1)
-    torch.manual_seed(0)
-    sd = AutoencoderTile(**cfg).state_dict()
-    g = torch.Generator().manual_seed(1234)
-    lat = torch.randn(1, 4, args.latent, args.latent, generator=g)
+    step, kind = reference_cpu_step_fn(args, cfg, mx, my)
     for _ in range(max(1, min(args.warmup, 2))):
-        orc.guidance_step(sd, cfg, mx, my, lat, STRENGTH, torch.float32)
-    steps = min(args.steps, 12)
+        step()
+    steps = args.steps
     t0 = time.time()
     for _ in range(steps):
-        orc.guidance_step(sd, cfg, mx, my, lat, STRENGTH, torch.float32)
+        loss, _ = step()
     dt = time.time() - t0
     v = steps / dt
-    sample = "1 map of the batch per step (fp32 oracle port, %d of the requested %d steps)" % (steps, args.steps)
+    sample = ("each step = 1 map of the batch of %d (fp32, %s), %d steps, %.2f s per map-step"
+              % (args.batch, "unmodified reference modules" if kind == "reference" else "oracle port", steps, dt / steps))
     print(json.dumps({
         "impl": "reference", "metric": "wfc_guidance_map_steps_per_s", "value": v, "unit": "maps/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(args, T, t_pad, per_gpu_batch=args.batch),
-                       reference_sample="each step runs ONE map of the batch of %d (maps are independent; the metric is "
-                                        "per map)" % args.batch),
-        "cpu_baseline": {"value": v, "unit": "maps/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "config": workload_config(args, T, t_pad, per_gpu_batch=args.batch),
+        "cpu_baseline": {"value": v, "unit": "maps/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "loss_check": [float(x) for x in loss.reshape(-1)[:1]],
     }))
+
+
+def gpu_eager_baseline(args, cfg, mx, my, B, dev, ours_loss, ours_grad, lat):
+    """The reference's own eager PyTorch path on THIS B200 (what a user of the reference runs today): the unmodified
+    modules in fp32 and after `.half()` (set_precision("half"), pipeline_wfd.py:207-212), same weights and latents as the
+    CUDA arm. Reports ms per step, maps/s, and the deviations SURVEY 7.4 asks for: ours vs the reference's fp32, and the
+    reference's own fp16 vs its fp32 (its half-precision backward underflows at random init)."""
+    import torch
+
+    from oracle.reference_loader import load_reference, reference_root
+
+    if reference_root() is None:
+        return None
+    vae, losses = load_reference()
+    torch.manual_seed(0)
+    net = vae.AutoencoderTile(**cfg).eval().to(dev)
+    lossm = losses.WFCLossEinsum(mx, my).to(dev)
+    out = {"code": "unmodified reference modules (stub diffusers), lines pipeline_wfd.py:609-613, batch %d" % B}
+
+    def step(x):
+        with torch.enable_grad():
+            _latents = x.detach().requires_grad_()
+            wave = net.decode(1 / LATENT_SCALE * _latents).sample.softmax(axis=1)
+            _loss = lossm(wave) * STRENGTH
+            (grad,) = torch.autograd.grad(_loss.sum(), _latents)
+        return _loss.detach().float(), grad.float()
+
+    def rel(a, b):
+        return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
+    ref32 = None
+    for tag in ("fp32", "fp16"):
+        if tag == "fp16":
+            net.half()
+            lossm.half()
+        x = lat if tag == "fp32" else lat.half()
+        try:
+            step(x)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            n = 3
+            for _ in range(n):
+                l, g = step(x)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / n
+        except Exception as e:  # e.g. out of memory on a smaller part
+            out[tag] = {"error": str(e)[:200]}
+            continue
+        rec = {"ms_per_step": ms, "maps_per_s": B / (ms / 1e3)}
+        if tag == "fp32":
+            ref32 = (l, g)
+            rec["ours_vs_this"] = {"loss_rel_max": ((ours_loss - l).abs() / l.abs()).max().item(), "grad_rel_l2": rel(ours_grad, g)}
+        elif ref32 is not None:
+            rec["this_vs_reference_fp32"] = {"loss_rel_max": ((l - ref32[0]).abs() / ref32[0].abs()).max().item(),
+                                             "grad_rel_l2": rel(g, ref32[1]),
+                                             "grad_zero_fraction": (g == 0).float().mean().item()}
+        out[tag] = rec
+    del net, lossm
+    torch.cuda.empty_cache()
+    return out
 
 
 def workload_config(args, T, t_pad, per_gpu_batch):
@@ -442,9 +531,13 @@ def run_native(args):
         print("  profiled total %.3f ms/step, tapgemm %.3f ms" % (all_ms, tg_ms), file=sys.stderr)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, cores, sec = cpu_oracle_maps_per_s(args, cfg, mx, my, repeats=3)
-        cpu = {"value": v, "unit": "maps/s", "cores": cores, "kind": "port",
-               "sample": "1 map of the batch (fp32 oracle port), 1 warm-up + best of 3, %.2f s per map-step" % sec}
+        v, cores, sec, kind = cpu_oracle_maps_per_s(args, cfg, mx, my, repeats=3)
+        cpu = {"value": v, "unit": "maps/s", "cores": cores, "kind": kind,
+               "sample": "1 map of the batch (fp32, %s), 1 warm-up + best of 3, %.2f s per map-step"
+                         % ("unmodified reference modules" if kind == "reference" else "oracle port", sec)}
+    eager = None
+    if world == 1 and not args.no_eager_baseline:
+        eager = gpu_eager_baseline(args, cfg, mx, my, B, dev, loss.clone(), dz.clone(), lat)
     out = {
         "metric": "wfc_guidance_map_steps_per_s", "value": value, "unit": "maps/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -458,6 +551,7 @@ def run_native(args):
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "gpu_eager_baseline": eager,
         "loss_check": [float(x) for x in loss.cpu()[:2]],
         "profile_top": [{"kernel": n, "launches_per_step": c, "ms_per_step": t} for n, (c, t) in top],
     }
@@ -632,6 +726,8 @@ def main():
     ap.add_argument("--arch", default="64x64", choices=["64x64", "32x32"])
     ap.add_argument("--latent", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true",
+                    help="skip timing the reference's eager PyTorch path on the GPU (gpu_eager_baseline)")
     ap.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--top", type=int, default=12, help="kernels listed in profile_top")

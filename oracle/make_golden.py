@@ -5,7 +5,7 @@
 
 Fixtures (all small; weights are NOT stored — they are re-created from torch.manual_seed(seed) by the product's
 AutoencoderTile, whose initialisation order is checked to be bit-identical to the reference's in this script):
-  wfc_mats/<tileset>.npz   sparse coordinates of the shipped wfc_mats (the adjacency input data of the path) + KATs
+  (package) data/wfc_mats/<tileset>.npz   sparse coordinates of the shipped wfc_mats (the adjacency input data of the path) + KATs
   tiny_step.npz            reference decode+softmax+loss+grad on a small config, fp64 and fp32
   tiny_down_step.npz       same with a DownDecoderBlock2D (the 32x32-style config)
   ice_c1_step.npz          BASELINE config 1: ice 64x64, batch 1, tilenet_sc_space_64x64, strength 5
@@ -86,8 +86,11 @@ def small_fixture(vae, losses, name, cfg, hw, B, T, seed):
     print(name, "loss", out["loss_f64"], "grad norm", np.linalg.norm(out["grad_f64"]))
 
 
+WFC_DATA = os.path.join(ROOT, "wavefunctiondiffusion_b200", "data", "wfc_mats")  # input data of the path: ships with the package
+
+
 def wfc_mats_fixtures():
-    os.makedirs(os.path.join(GOLD, "wfc_mats"), exist_ok=True)
+    os.makedirs(WFC_DATA, exist_ok=True)
     for path in sorted(glob.glob(REFERENCE_ROOT + "/wfd/scmap/tile_data/wfc/*.npz")):
         name = os.path.basename(path)[:-4]
         z = np.load(path)
@@ -98,7 +101,7 @@ def wfc_mats_fixtures():
         xs = np.argwhere(m[0]).astype(np.int16)
         ys = np.argwhere(m[1]).astype(np.int16)
         kat = (2.0 * T * T - len(xs) - len(ys)) / (2.0 * t_pad * t_pad)
-        np.savez_compressed(os.path.join(GOLD, "wfc_mats", name + ".npz"), T=T, T_pad=t_pad, x=xs, y=ys, uniform_kat=kat)
+        np.savez_compressed(os.path.join(WFC_DATA, name + ".npz"), T=T, T_pad=t_pad, x=xs, y=ys, uniform_kat=kat)
         print(name, T, t_pad, len(xs), len(ys), "%.8f" % kat)
 
 

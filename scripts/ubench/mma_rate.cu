@@ -8,16 +8,19 @@
 using namespace wfd;
 
 template <int CG>
-__global__ void __launch_bounds__(128, 1) mma_rate_k(int N, int n_mma, int reps, int a_stride16, long long* out) {
+__global__ void __launch_bounds__(128, 1) mma_rate_k(int N, int n_mma, int reps, int a_stride16, long long* out, int commit_every, int fill) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t bar;
+    __shared__ uint64_t bar2;  // receives the intermediate commits (never waited on)
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
-    for (int i = threadIdx.x; i < 128 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+    for (int i = threadIdx.x; i < 208 * 1024 / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(smem)[i] = fill ? (0x3f803f80u ^ ((i * 2654435761u) & 0x007f007fu)) : 0u;  // bf16 values near 1
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
+        mbar_init(&bar2, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -37,7 +40,36 @@ __global__ void __launch_bounds__(128, 1) mma_rate_k(int N, int n_mma, int reps,
         uint32_t phase = 0;
         for (int r = 0; r < reps; ++r) {
             const long long t0 = clock64();
-            if (elect_one()) {
+            if (fill >= 5 || elect_one()) {
+                int since = 0;
+                if (fill >= 2) {
+                    // the patch schedule's issue sequence: per tile 3 vertical offsets x 3 horizontal x n_k = 3 K steps, the
+                    // A start on an arbitrary 128-byte row with SBO = 1280 (fill == 3: SBO = 1024, aligned starts)
+                    const uint32_t a_hi = (uint32_t)(make_kmajor_desc_sbo(0, fill == 3 ? 1024u : 1280u) >> 32);
+                    const uint32_t b_hi = (uint32_t)(make_kmajor_desc(0, 128) >> 32);
+                    const uint32_t a_lo0 = (uint32_t)make_kmajor_desc(a_base, 128), b_lo0 = (uint32_t)make_kmajor_desc(b_base, 128);
+                    const uint32_t bbox16 = (uint32_t)(N / CG) * 8u;
+                    for (int tile = 0; tile < n_mma / 27; ++tile) {
+                        const uint32_t d_tmem = tmem_base + (tile & 1) * 256u;
+                        const uint32_t a_st = a_lo0 + (uint32_t)(tile % 3) * 1472u;  // 23552-byte stages
+                        for (int d = 0; d < 3; ++d) {
+                            if (fill >= 4) tc_fence_after();           // as the kernel does after every full-barrier wait
+                            if (fill >= 5) { __syncwarp(); if (!elect_one()) continue; }
+                            const uint32_t ad = a_st + (fill == 3 ? d * 64u : d * 80u), bd = b_lo0 + d * 3u * bbox16;
+                            if (CG == 2) {
+                                umma_f16_run_2sm(d_tmem, ad, a_hi, bd, b_hi, idesc, d > 0 ? 1u : 0u, 2u, commit_every);
+                                umma_f16_run_2sm(d_tmem, ad + (fill == 3 ? 0u : 8u), a_hi, bd + bbox16, b_hi, idesc, 1u, 2u, commit_every);
+                                umma_f16_run_2sm(d_tmem, ad + (fill == 3 ? 0u : 16u), a_hi, bd + 2u * bbox16, b_hi, idesc, 1u, 2u, commit_every);
+                                umma_commit_2sm(&bar2);
+                            } else {
+                                umma_f16_run(d_tmem, ad, a_hi, bd, b_hi, idesc, d > 0 ? 1u : 0u, 2u, commit_every);
+                                umma_f16_run(d_tmem, ad + (fill == 3 ? 0u : 8u), a_hi, bd + bbox16, b_hi, idesc, 1u, 2u, commit_every);
+                                umma_f16_run(d_tmem, ad + (fill == 3 ? 0u : 16u), a_hi, bd + 2u * bbox16, b_hi, idesc, 1u, 2u, commit_every);
+                                umma_commit(&bar2);
+                            }
+                        }
+                    }
+                } else
                 for (int i = 0; i < n_mma; ++i) {
                     // operand addresses walk through a 48 KB window like the stages of the real kernel
                     const uint32_t off = (uint32_t)((i * a_stride16) & 0xBFF) << 4;
@@ -45,6 +77,11 @@ __global__ void __launch_bounds__(128, 1) mma_rate_k(int N, int n_mma, int reps,
                     const uint64_t bdesc = make_kmajor_desc(b_base + (off & 0x1FFF), 128);
                     if (CG == 2) umma_f16_2sm(tmem_base, adesc, bdesc, idesc, i > 0 ? 1u : 0u);
                     else umma_f16(tmem_base, adesc, bdesc, idesc, i > 0 ? 1u : 0u);
+                    if (++since == commit_every && i + 1 < n_mma) {  // (no runtime modulo: a division costs ~200 cycles here)
+                        since = 0;
+                        if (CG == 2) umma_commit_2sm(&bar2);
+                        else umma_commit(&bar2);
+                    }
                 }
                 if (CG == 2) umma_commit_2sm(&bar);
                 else umma_commit(&bar);
@@ -75,14 +112,14 @@ __global__ void __launch_bounds__(128, 1) mma_rate_k(int N, int n_mma, int reps,
 }
 
 template <int CG>
-static long long run(int N, int n_mma, int a_stride16, int grid) {
+static long long run(int N, int n_mma, int a_stride16, int grid, int commit_every = 0, int fill = 0) {
     long long* d;
     cudaMalloc(&d, 8);
-    cudaFuncSetAttribute(mma_rate_k<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
+    cudaFuncSetAttribute(mma_rate_k<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(128);
-    cfg.dynamicSmemBytes = 130 * 1024;
+    cfg.dynamicSmemBytes = 210 * 1024;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG;
@@ -90,7 +127,7 @@ static long long run(int N, int n_mma, int a_stride16, int grid) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, mma_rate_k<CG>, N, n_mma, 20, a_stride16, d);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, mma_rate_k<CG>, N, n_mma, 20, a_stride16, d, commit_every, fill);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     long long h = -1;
     if (e != cudaSuccess) printf("error: %s\n", cudaGetErrorString(e));
@@ -115,5 +152,16 @@ int main() {
     // A rows read with a large stride between consecutive MMAs (different swizzle atoms) vs the same 32 bytes
     for (int s : {0, 2, 64, 130})
         printf("cg=2 N=48 a_stride16=%d: %.1f cyc/mma\n", s, (double)run<2>(48, 256, s, 148) / 256);
+    // patch-schedule pattern: commit_every carries n_k (MMAs per run); cycles per ISSUED MMA = total / (n_mma / 27 * 9 * n_k)
+    for (int fill : {2, 4})
+        for (int nk : {3, 4})
+            printf("pattern fill=%d n_k=%d: cg=2 N=48 %.1f cyc/mma | cg=1 N=48 %.1f | cg=2 N=96 %.1f | cg=2 N=192 %.1f\n", fill, nk,
+                   (double)run<2>(48, 270, 2, 148, nk, fill) / (90 * nk), (double)run<1>(48, 270, 2, 148, nk, fill) / (90 * nk),
+                   (double)run<2>(96, 270, 2, 148, nk, fill) / (90 * nk), (double)run<2>(192, 270, 2, 148, nk, fill) / (90 * nk));
+    for (int fill : {0})
+        for (int ce : {0, 9})
+            printf("cg=2 N=48 fill=%d commit_every=%d: %.1f cyc/mma | cg=1: %.1f | cg=2 N=192: %.1f\n", fill, ce,
+                   (double)run<2>(48, 270, 2, 148, ce, fill) / 270, (double)run<1>(48, 270, 2, 148, ce, fill) / 270,
+                   (double)run<2>(192, 270, 2, 148, ce, fill) / 270);
     return 0;
 }

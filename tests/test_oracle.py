@@ -56,7 +56,9 @@ def test_uniform_and_one_hot_known_answers(tileset):
     mx, my = load_wfc_mats(tileset)
     T = mx.shape[0]
     t_pad = round_up_channels(T)
-    kat = float(np.load(os.path.join(GOLD, "wfc_mats", tileset + ".npz"))["uniform_kat"])
+    from wavefunctiondiffusion_b200.utils.tilesets import WFC_DATA_DIR
+
+    kat = float(np.load(os.path.join(WFC_DATA_DIR, tileset + ".npz"))["uniform_kat"])
     assert abs(orc.uniform_wave_loss(mx, my, t_pad) - kat) < 1e-12
     H = W = 6
     wave = torch.full((1, t_pad, H, W), 1.0 / t_pad, dtype=torch.float64)

@@ -98,7 +98,8 @@ def test_shared_a_z_batch(use_ref):
 
 def _pack_conv(w, groups, BN, bwd=False, reuse=False):
     """Python restatement of the C++ packer for the test: returns (Bm [n_tiles*BN, taps*cpt*64], a_c0, cpt, N).
-    reuse=True stores the 64-wide chunks in the (dx, cc, dy) order of the row-reuse schedule."""
+    reuse=1 stores the 64-wide chunks in the (dx, cc, dy) order of the row-reuse schedule, reuse=2 in the (cc, dy, dx)
+    order of the patch schedule."""
     cout, cin_g, k, _ = w.shape
     cin = cin_g * groups
     cout_g = cout // groups
@@ -126,7 +127,9 @@ def _pack_conv(w, groups, BN, bwd=False, reuse=False):
                 vals = wf[n, kk, :]
             else:
                 vals = wf[g * cout_g + kk, n - g * cin_g, :]
-            if reuse:
+            if reuse == 2:
+                chunk = torch.tensor([cc * 9 + (dy + 1) * 3 + (dx + 1) for dy, dx in offs])
+            elif reuse:
                 chunk = torch.tensor([((dx + 1) * cpt + cc) * 3 + (dy + 1) for dy, dx in offs])
             else:
                 chunk = torch.arange(taps) * cpt + cc
@@ -134,13 +137,15 @@ def _pack_conv(w, groups, BN, bwd=False, reuse=False):
     return Bm, torch.tensor(c0, dtype=torch.int32), cpt, N
 
 
-@pytest.mark.parametrize("reuse", [0, 1])
+@pytest.mark.parametrize("reuse", [0, 1, 2])
 @pytest.mark.parametrize("use_ref", [1, 0])
 @pytest.mark.parametrize("cin,cout,groups,BN,H,W", [(64, 64, 1, 64, 16, 16), (192, 96, 4, 48, 8, 64), (96, 192, 2, 96, 32, 32),
-                                                   (384, 384, 1, 192, 64, 64)])
+                                                   (384, 384, 1, 192, 64, 64), (3072, 3072, 64, 48, 32, 16)])
 def test_conv3x3_forward_and_backward_data(cin, cout, groups, BN, H, W, use_ref, reuse):
-    if reuse and BN > 96:
+    if reuse == 1 and BN > 96:
         pytest.skip("row-reuse schedule is used for tiles that leave >= 3 stages")
+    if reuse == 2 and (H % 16 or W % 8):
+        pytest.skip("the patch schedule tiles the plane into 16 x 8 pixel patches")
     torch.manual_seed(3)
     Bn = 2
     x = torch.randn(Bn, cin, H, W, device="cuda").bfloat16()
@@ -149,8 +154,10 @@ def test_conv3x3_forward_and_backward_data(cin, cout, groups, BN, H, W, use_ref,
     x_nhwc = x.permute(0, 2, 3, 1).contiguous()
     w_box = min(W, 128)
     h_box = 128 // w_box
+    if reuse == 2:
+        w_box, h_box = 8, 16
     # forward
-    Bm, c0, cpt, N = _pack_conv(w, groups, BN, reuse=bool(reuse))
+    Bm, c0, cpt, N = _pack_conv(w, groups, BN, reuse=reuse)
     Bm = Bm.cuda().bfloat16()
     c0 = c0.cuda()
     out = torch.zeros(Bn, H, W, cout, device="cuda", dtype=torch.bfloat16)
@@ -177,7 +184,7 @@ def test_conv3x3_forward_and_backward_data(cin, cout, groups, BN, H, W, use_ref,
     dy = torch.randn(Bn, cout, H, W, device="cuda").bfloat16()
     dy_nhwc = dy.permute(0, 2, 3, 1).contiguous()
     BNb = BN if (cin // groups) % 16 == 0 and (cin // groups) <= 256 and BN % (cin // groups) == 0 else 64
-    Bm2, c02, cpt2, N2 = _pack_conv(w, groups, BNb, bwd=True, reuse=bool(reuse))
+    Bm2, c02, cpt2, N2 = _pack_conv(w, groups, BNb, bwd=True, reuse=reuse)
     Bm2 = Bm2.cuda().bfloat16()
     c02 = c02.cuda()
     dx = torch.zeros(Bn, H, W, cin, device="cuda", dtype=torch.bfloat16)

@@ -76,7 +76,7 @@ void PackedB::release() {
 // w: [cout][cin/groups][k][k] fp32 (torch Conv2d / Linear layout). mode 0: forward, pad (k-1)/2; mode 1: backward-data of
 // mode 0; mode 2: forward of the stride-2 downsample conv applied after F.pad(x, (0,1,0,1)) (resnet.py:185-190).
 int pack_conv(const float* w, int cout, int cin, int groups, int k, int mode, bool bf16, int bn_override, PackedB* out,
-              const std::vector<TapSel>* tap_sel, bool reuse) {
+              const std::vector<TapSel>* tap_sel, int reuse) {
     const bool bwd = (mode == 1);
     const int cin_g = cin / groups, cout_g = cout / groups;
     const int N = bwd ? cin : cout;
@@ -118,7 +118,7 @@ int pack_conv(const float* w, int cout, int cin, int groups, int k, int mode, bo
                 tdy[tap] = dy;
             }
     }
-    if (reuse && (taps != 9 || mode == 2)) {
+    if (reuse && (taps != 9 || mode == 2 || k != 3)) {
         set_error("pack_conv: the row-reuse chunk order needs a 3x3 stride-1 tap set");
         return -3;
     }
@@ -131,9 +131,10 @@ int pack_conv(const float* w, int cout, int cin, int groups, int k, int mode, bo
                 const int c = g * kpg + kk;
                 const int pos = c - c0[t];
                 const int cc = pos / TG_KC, within = pos % TG_KC;
-                // chunk order: plain = (tap, cc); row reuse = (dx, cc, dy), see b_chunk_index() in tapgemm.cu
-                const long long chunk = reuse ? (static_cast<long long>(tdx[tap] + 1) * cpt + cc) * 3 + (tdy[tap] + 1)
-                                              : static_cast<long long>(tap) * cpt + cc;
+                // chunk order: plain = (tap, cc); row reuse = (dx, cc, dy); patch = (cc, dy, dx), see b_chunk_index()
+                const long long chunk = reuse == 2 ? static_cast<long long>(cc) * 9 + (tdy[tap] + 1) * 3 + (tdx[tap] + 1)
+                                        : reuse ? (static_cast<long long>(tdx[tap] + 1) * cpt + cc) * 3 + (tdy[tap] + 1)
+                                                : static_cast<long long>(tap) * cpt + cc;
                 float v;
                 if (!bwd) {
                     v = w[(static_cast<long long>(n) * cin_g + kk) * wtaps + wt];
@@ -154,7 +155,7 @@ int pack_conv(const float* w, int cout, int cin, int groups, int k, int mode, bo
     out->ldb = ldb;
     out->rows = static_cast<int>(rows);
     out->in_stride = (mode == 2) ? 2 : 1;
-    out->reuse = reuse ? 1 : 0;
+    out->reuse = reuse;
     out->kk_last = kk_last;
     for (int t = 0; t < taps; ++t) {
         out->dx[t] = tdx[t];
@@ -230,6 +231,8 @@ int Decoder::init(const wfd_decoder_config& c, int h_, int w_, int Bmax, int dty
         use_reuse = (e && e[0] == '1') ? 0 : 1;
         const char* f = getenv("WFD_NO_FUSE_GN");
         fuse_gn = (f && f[0] == '1') ? 0 : 1;
+        const char* np = getenv("WFD_NO_PATCH");
+        use_patch = (np && np[0] == '1') ? 0 : 1;
         const char* ng = getenv("WFD_CONV_NGROUP");
         conv_n_group = ng ? atoi(ng) : 0;
         const char* m = getenv("WFD_FUSE_BWD_MAX_C");
@@ -410,13 +413,17 @@ int Decoder::pack_named_conv(const std::string& name, int cout, int cin, int gro
     cw.cin = cin;
     cw.cout = cout;
     // the row-reuse schedule pays off when a stage (patch with halo rows + three weight boxes) leaves >= 3 stages
-    auto want_reuse = [&](int rows_per_group) {
-        if (k != 3 || fwd_mode != 0 || !use_reuse || ph <= 0) return false;
+    // K-loop schedule of a 3x3 stride-1 conv: the patch schedule whenever the plane tiles into 16 x 8 pixel patches (one
+    // activation box per 64-channel chunk serves all nine taps); else row reuse when a stage leaves room for 3 stages
+    auto want_reuse = [&](int rows_per_group) -> int {
+        if (k != 3 || fwd_mode != 0 || ph <= 0) return 0;
+        if (use_patch && pw % 8 == 0 && ph % 16 == 0) return 2;
+        if (!use_reuse) return 0;
         int wb = 0, hb = 0;
-        if (!pick_box(pw, ph, &wb, &hb) || wb < 8) return false;
+        if (!pick_box(pw, ph, &wb, &hb) || wb < 8) return 0;
         const int BN = choose_bn(rows_per_group);
         const size_t per_stage = static_cast<size_t>(hb + 2) * wb * 128 + 3 * static_cast<size_t>(BN) * 128;
-        return per_stage * 3 <= 216 * 1024;
+        return per_stage * 3 <= 216 * 1024 ? 1 : 0;
     };
     // dense (groups == 1) layers may use a narrower N tile when the plan has few 128-pixel tiles
     const long long m_tiles = ph > 0 ? static_cast<long long>(B_max) * ((static_cast<long long>(ph) * pw) / TG_BM)
@@ -480,7 +487,7 @@ int Decoder::finalize_weights() {
                 ConvW& cw = convs[std::string(buf) + ".bwd" + std::to_string(py * 2 + px)];
                 cw.cin = cch;
                 cw.cout = cch;
-                CK(pack_conv(wv->data(), cch, cch, grp, 3, 1, bf16 != 0, 0, &cw.bwd, &sel, false));
+                CK(pack_conv(wv->data(), cch, cch, grp, 3, 1, bf16 != 0, 0, &cw.bwd, &sel, 0));
             }
     }
     // attention: q,k,v merged into one [3C, C] matrix (+ backward form), v alone as an A operand, proj
@@ -506,8 +513,8 @@ int Decoder::finalize_weights() {
         ConvW& cq = convs["attn.qkv"];
         cq.cin = Cm;
         cq.cout = 3 * Cm;
-        CK(pack_conv(wq.data(), 3 * Cm, Cm, 1, 1, 0, bf16 != 0, Cm % 192 == 0 ? 192 : 0, &cq.fwd, nullptr, false));
-        CK(pack_conv(wq.data(), 3 * Cm, Cm, 1, 1, 1, bf16 != 0, 0, &cq.bwd, nullptr, false));
+        CK(pack_conv(wq.data(), 3 * Cm, Cm, 1, 1, 0, bf16 != 0, Cm % 192 == 0 ? 192 : 0, &cq.fwd, nullptr, 0));
+        CK(pack_conv(wq.data(), 3 * Cm, Cm, 1, 1, 1, bf16 != 0, 0, &cq.bwd, nullptr, 0));
         CK(upload_f32(bq, &cq.bias));
         CK(pack_named_conv(a + "proj_attn", Cm, Cm, 1, 1, true, 0, 0, 0));
     }
@@ -588,7 +595,10 @@ int Decoder::conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int 
         // fewer halo rows from L2 (3 x 2.0 of the activation bytes at 64 x 2, 3 x 1.25 at 16 x 8). Measured on B200
         // (WFD_REUSE_HBOX = 2 / 4 / 8: 1.00 / 1.14 / 1.12 ms for the five 3072-channel groups=64 launches): no gain, so
         // L2 delivery is not what bounds them and the default stays the widest patch.
-        if (pk.reuse && reuse_hbox > hb) {
+        if (pk.reuse == 2) {  // patch schedule: 16 rows x 8 pixels
+            wb = 8;
+            hb = 16;
+        } else if (pk.reuse && reuse_hbox > hb) {
             const int hb2 = reuse_hbox, wb2 = TG_BM / reuse_hbox;
             if (wb2 >= 8 && wb2 * hb2 == TG_BM && Wout % wb2 == 0 && Hout % hb2 == 0) {
                 wb = wb2;

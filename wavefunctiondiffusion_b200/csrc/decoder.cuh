@@ -36,8 +36,9 @@ struct GnBwdFuse {  // GroupNorm(+SiLU) backward reduction fused into the produc
 struct OutStrides {  // element strides of a strided output plane (downsample backward writes every other pixel)
     long long sx, sy, sb;
 };
+// reuse: chunk order of the packed weights = K-loop schedule of the contraction (0 plain, 1 row reuse, 2 patch; tapgemm.cuh)
 int pack_conv(const float* w, int cout, int cin, int groups, int k, int mode, bool bf16, int bn_override, PackedB* out,
-              const std::vector<TapSel>* tap_sel, bool reuse);
+              const std::vector<TapSel>* tap_sel, int reuse);
 
 struct ConvW {
     PackedB fwd, bwd;
@@ -70,6 +71,7 @@ struct Decoder {
     bool mmajor_a = true;  // attention backward reads P / dS as stored (M-major A operand) instead of transposed copies
     int reuse_hbox = 0;    // preferred patch height of the row-reuse contractions (WFD_REUSE_HBOX: 0 = widest patch, 2, 4, 8, 16)
     int use_reuse = 1;  // row-reuse schedule for 3x3 convs whose stage fits (WFD_NO_REUSE=1 disables, for A/B runs)
+    int use_patch = 1;  // patch schedule for 3x3 convs on planes that tile into 16 x 8 patches (WFD_NO_PATCH=1 disables)
     // row bands (one map split along y over band_R ranks): h is the local band height, h_total the map's
     bool band = false;
     int band_R = 1, band_r = 0, h_total = 0;
@@ -135,8 +137,11 @@ struct WfcSavedHeader {  // host-side record of the last forward (what backward 
 
 struct Wfc {
     int T = 0, T_pad = 0, bf16 = 1;
-    WfcSavedHeader hdr_host;
+    WfcSavedHeader hdr_host;         // of the last forward
     void* hdr_saved = nullptr;
+    // one record per `saved` block that a forward has filled: several forwards may be outstanding before their backwards
+    // run (loss(a) + loss(b)), each backward must see the shapes of ITS forward
+    std::map<void*, WfcSavedHeader> saved_hdrs;
     uint16_t* Bm = nullptr;
     uint8_t* rules = nullptr;  // device copy of the 0/1 rule matrices [2][T][T] (x then y) for count_violations
     int* kc_list = nullptr;  // K chunks of each N tile that hold at least one allowed pair (see Wfc::init)

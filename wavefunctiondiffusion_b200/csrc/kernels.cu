@@ -254,7 +254,9 @@ gn_bwd_reduce_k(const uint4* __restrict__ dy, const uint4* __restrict__ x, const
                 ga[j] = __ldg(gamma + col * 8 + j);
                 be[j] = __ldg(beta + col * 8 + j);
             }
-            float s1 = 0.f, s2 = 0.f;
+            // every 8-channel vector goes to fixed point on its own (as in gn_stats_k): the sums then do not depend on how the
+            // pixels are split over threads, blocks or row bands, nor on the batch size that sizes the grid
+            unsigned long long i1 = 0ull, i2 = 0ull;
             const long long base = (static_cast<long long>(b) * HW) * m.nv + col;
             for (int p = p0 + trow; p < p1; p += U * m.R) {
                 uint4 rx[U], rd[U];
@@ -270,6 +272,7 @@ gn_bwd_reduce_k(const uint4* __restrict__ dy, const uint4* __restrict__ x, const
                     float fx[8], fd[8];
                     unpack8<BF16>(rx[u], fx);
                     unpack8<BF16>(rd[u], fd);
+                    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float xh = (fx[j] - mean) * rstd;
@@ -283,10 +286,12 @@ gn_bwd_reduce_k(const uint4* __restrict__ dy, const uint4* __restrict__ x, const
                         s1 += t;
                         s2 += t * xh;
                     }
+                    i1 += to_fx(s1, WFD_FX_GRAD);
+                    i2 += to_fx(s2, WFD_FX_GRAD);
                 }
             }
-            atomicAdd(&sh[2 * g], to_fx(s1, WFD_FX_GRAD));
-            atomicAdd(&sh[2 * g + 1], to_fx(s2, WFD_FX_GRAD));
+            atomicAdd(&sh[2 * g], i1);
+            atomicAdd(&sh[2 * g + 1], i2);
         }
     }
     __syncthreads();

@@ -111,6 +111,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// L2 prefetch of a tensor box (no shared-memory destination, no barrier): hides DRAM latency of boxes needed a few tiles ahead
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
 // ---------------------------------------------------------------- CTA pairs (cta_group::2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -208,47 +215,203 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 // advance by a_step / 2 (16-byte units) inside the asm block, so the issuing thread spends two 32-bit adds per MMA instead
 // of rebuilding both descriptors (the issue loop, not the tensor pipe, bounds narrow-N contractions: ~4 cycles per
 // dependent uniform instruction, profiles/r02_summary.md). acc_first: accumulate flag of the first MMA; the rest accumulate.
-#define WFD_UMMA_RUN_BODY(GROUP)                                                                     \
-    asm volatile(                                                                                     \
-        "{\n\t"                                                                                       \
-        ".reg .pred p, t;\n\t"                                                                        \
-        ".reg .b32 al, bl;\n\t"                                                                       \
-        ".reg .b64 a, b;\n\t"                                                                         \
-        "setp.ne.b32 p, %6, 0;\n\t"                                                                   \
-        "setp.eq.u32 t, 0, 0;\n\t"                                                                    \
-        "mov.b64 a, {%1, %2};\n\t"                                                                    \
-        "mov.b64 b, {%3, %4};\n\t"                                                                    \
-        "tcgen05.mma.cta_group::" GROUP ".kind::f16 [%0], a, b, %5, p;\n\t"                           \
-        "setp.gt.s32 p, %8, 1;\n\t"                                                                   \
-        "add.u32 al, %1, %7;\n\t"                                                                     \
-        "add.u32 bl, %3, 2;\n\t"                                                                      \
-        "mov.b64 a, {al, %2};\n\t"                                                                    \
-        "mov.b64 b, {bl, %4};\n\t"                                                                    \
-        "@p tcgen05.mma.cta_group::" GROUP ".kind::f16 [%0], a, b, %5, t;\n\t"                        \
-        "setp.gt.s32 p, %8, 2;\n\t"                                                                   \
-        "add.u32 al, al, %7;\n\t"                                                                     \
-        "add.u32 bl, bl, 2;\n\t"                                                                      \
-        "mov.b64 a, {al, %2};\n\t"                                                                    \
-        "mov.b64 b, {bl, %4};\n\t"                                                                    \
-        "@p tcgen05.mma.cta_group::" GROUP ".kind::f16 [%0], a, b, %5, t;\n\t"                        \
-        "setp.gt.s32 p, %8, 3;\n\t"                                                                   \
-        "add.u32 al, al, %7;\n\t"                                                                     \
-        "add.u32 bl, bl, 2;\n\t"                                                                      \
-        "mov.b64 a, {al, %2};\n\t"                                                                    \
-        "mov.b64 b, {bl, %4};\n\t"                                                                    \
-        "@p tcgen05.mma.cta_group::" GROUP ".kind::f16 [%0], a, b, %5, t;\n\t"                        \
-        "}\n" ::"r"(d_tmem),                                                                          \
-        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first), "r"(a_step), "r"(n_k)  \
-        : "memory")
-// n_k in 1..4 MMAs (K steps of one 64-element chunk)
-// descriptors are passed as (low word, high word): only the address field in the low word moves
+// (one asm block per run length: a predicated-off tcgen05.mma still costs ~30 cycles of the issuing thread, measured with
+// scripts/ubench/mma_rate.cu, so the run length is a uniform branch instead of a predicate)
+__device__ __forceinline__ void umma_f16_run1(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t acc_first, uint32_t a_step) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, t;\n\t"
+        ".reg .b32 al, bl;\n\t"
+        ".reg .b64 a, b;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.u32 t, 0, 0;\n\t"
+        "mov.b64 a, {%1, %2};\n\t"
+        "mov.b64 b, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, p;\n\t"
+        "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first), "r"(a_step)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_run2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t acc_first, uint32_t a_step) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, t;\n\t"
+        ".reg .b32 al, bl;\n\t"
+        ".reg .b64 a, b;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.u32 t, 0, 0;\n\t"
+        "mov.b64 a, {%1, %2};\n\t"
+        "mov.b64 b, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, p;\n\t"
+        "add.u32 al, %1, %7;\n\t"
+        "add.u32 bl, %3, 2;\n\t"
+        "mov.b64 a, {al, %2};\n\t"
+        "mov.b64 b, {bl, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, t;\n\t"
+        "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first), "r"(a_step)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_run3(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t acc_first, uint32_t a_step) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, t;\n\t"
+        ".reg .b32 al, bl;\n\t"
+        ".reg .b64 a, b;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.u32 t, 0, 0;\n\t"
+        "mov.b64 a, {%1, %2};\n\t"
+        "mov.b64 b, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, p;\n\t"
+        "add.u32 al, %1, %7;\n\t"
+        "add.u32 bl, %3, 2;\n\t"
+        "mov.b64 a, {al, %2};\n\t"
+        "mov.b64 b, {bl, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, t;\n\t"
+        "add.u32 al, al, %7;\n\t"
+        "add.u32 bl, bl, 2;\n\t"
+        "mov.b64 a, {al, %2};\n\t"
+        "mov.b64 b, {bl, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, t;\n\t"
+        "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first), "r"(a_step)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_run4(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t acc_first, uint32_t a_step) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, t;\n\t"
+        ".reg .b32 al, bl;\n\t"
+        ".reg .b64 a, b;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.u32 t, 0, 0;\n\t"
+        "mov.b64 a, {%1, %2};\n\t"
+        "mov.b64 b, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, p;\n\t"
+        "add.u32 al, %1, %7;\n\t"
+        "add.u32 bl, %3, 2;\n\t"
+        "mov.b64 a, {al, %2};\n\t"
+        "mov.b64 b, {bl, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, t;\n\t"
+        "add.u32 al, al, %7;\n\t"
+        "add.u32 bl, bl, 2;\n\t"
+        "mov.b64 a, {al, %2};\n\t"
+        "mov.b64 b, {bl, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, t;\n\t"
+        "add.u32 al, al, %7;\n\t"
+        "add.u32 bl, bl, 2;\n\t"
+        "mov.b64 a, {al, %2};\n\t"
+        "mov.b64 b, {bl, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, t;\n\t"
+        "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first), "r"(a_step)
+        : "memory");
+}
+// descriptors are passed as (low word, high word): only the address field in the low word moves; n_k in 1..4
 __device__ __forceinline__ void umma_f16_run(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                              uint32_t idesc, uint32_t acc_first, uint32_t a_step, int n_k) {
-    WFD_UMMA_RUN_BODY("1");
+    if (n_k == 4) umma_f16_run4(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, acc_first, a_step);
+    else if (n_k == 3) umma_f16_run3(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, acc_first, a_step);
+    else if (n_k == 2) umma_f16_run2(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, acc_first, a_step);
+    else umma_f16_run1(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, acc_first, a_step);
 }
+__device__ __forceinline__ void umma_f16_run1_2sm(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t acc_first, uint32_t a_step) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, t;\n\t"
+        ".reg .b32 al, bl;\n\t"
+        ".reg .b64 a, b;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.u32 t, 0, 0;\n\t"
+        "mov.b64 a, {%1, %2};\n\t"
+        "mov.b64 b, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %5, p;\n\t"
+        "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first), "r"(a_step)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_run2_2sm(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t acc_first, uint32_t a_step) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, t;\n\t"
+        ".reg .b32 al, bl;\n\t"
+        ".reg .b64 a, b;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.u32 t, 0, 0;\n\t"
+        "mov.b64 a, {%1, %2};\n\t"
+        "mov.b64 b, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %5, p;\n\t"
+        "add.u32 al, %1, %7;\n\t"
+        "add.u32 bl, %3, 2;\n\t"
+        "mov.b64 a, {al, %2};\n\t"
+        "mov.b64 b, {bl, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %5, t;\n\t"
+        "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first), "r"(a_step)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_run3_2sm(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t acc_first, uint32_t a_step) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, t;\n\t"
+        ".reg .b32 al, bl;\n\t"
+        ".reg .b64 a, b;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.u32 t, 0, 0;\n\t"
+        "mov.b64 a, {%1, %2};\n\t"
+        "mov.b64 b, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %5, p;\n\t"
+        "add.u32 al, %1, %7;\n\t"
+        "add.u32 bl, %3, 2;\n\t"
+        "mov.b64 a, {al, %2};\n\t"
+        "mov.b64 b, {bl, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %5, t;\n\t"
+        "add.u32 al, al, %7;\n\t"
+        "add.u32 bl, bl, 2;\n\t"
+        "mov.b64 a, {al, %2};\n\t"
+        "mov.b64 b, {bl, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %5, t;\n\t"
+        "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first), "r"(a_step)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_run4_2sm(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t acc_first, uint32_t a_step) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, t;\n\t"
+        ".reg .b32 al, bl;\n\t"
+        ".reg .b64 a, b;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.u32 t, 0, 0;\n\t"
+        "mov.b64 a, {%1, %2};\n\t"
+        "mov.b64 b, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %5, p;\n\t"
+        "add.u32 al, %1, %7;\n\t"
+        "add.u32 bl, %3, 2;\n\t"
+        "mov.b64 a, {al, %2};\n\t"
+        "mov.b64 b, {bl, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %5, t;\n\t"
+        "add.u32 al, al, %7;\n\t"
+        "add.u32 bl, bl, 2;\n\t"
+        "mov.b64 a, {al, %2};\n\t"
+        "mov.b64 b, {bl, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %5, t;\n\t"
+        "add.u32 al, al, %7;\n\t"
+        "add.u32 bl, bl, 2;\n\t"
+        "mov.b64 a, {al, %2};\n\t"
+        "mov.b64 b, {bl, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], a, b, %5, t;\n\t"
+        "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc_first), "r"(a_step)
+        : "memory");
+}
+// descriptors are passed as (low word, high word): only the address field in the low word moves; n_k in 1..4
 __device__ __forceinline__ void umma_f16_run_2sm(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                                 uint32_t idesc, uint32_t acc_first, uint32_t a_step, int n_k) {
-    WFD_UMMA_RUN_BODY("2");
+                                             uint32_t idesc, uint32_t acc_first, uint32_t a_step, int n_k) {
+    if (n_k == 4) umma_f16_run4_2sm(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, acc_first, a_step);
+    else if (n_k == 3) umma_f16_run3_2sm(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, acc_first, a_step);
+    else if (n_k == 2) umma_f16_run2_2sm(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, acc_first, a_step);
+    else umma_f16_run1_2sm(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, acc_first, a_step);
 }
 // Arrives on the mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -287,6 +450,19 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_
     d |= static_cast<uint64_t>(sbo & 0x3FFF) << 32;
     d |= static_cast<uint64_t>(1) << 46;           // descriptor version 1 (sm_100)
     d |= layout << 61;
+    return d;
+}
+
+// Same with an explicit stride between 8-row groups (SBO): the patch schedule reads 8-pixel row segments of a halo patch
+// whose rows are (w_box + 2) pixels apart. The start address may sit anywhere on a 128-byte row boundary: the 128-byte
+// swizzle is a function of the shared-memory address bits, which is also what makes the usual +32-byte K advance work.
+__device__ __forceinline__ uint64_t make_kmajor_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= 2ull << 61;
     return d;
 }
 

@@ -173,6 +173,8 @@ __device__ __forceinline__ TileCoord decode_tile(const TapGemmParams& p, int t, 
 // position (in 64-element chunks) of the (tap, cc) chunk inside a packed Bm row
 __device__ __host__ __forceinline__ int b_chunk_index(const TapGemmParams& p, int tap, int cc) {
     if (!p.reuse) return tap * p.cpt + cc;
+    // patch order: (cc, dy, dx) - the nine taps of a 64-channel chunk are adjacent
+    if (p.reuse == 2) return cc * 9 + (p.tap_dy[tap] + 1) * 3 + (p.tap_dx[tap] + 1);
     // row-reuse order: (dx, cc, dy) so that the three vertical taps of one horizontal shift are adjacent
     return ((p.tap_dx[tap] + 1) * p.cpt + cc) * 3 + (p.tap_dy[tap] + 1);
 }
@@ -191,16 +193,21 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle atoms.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int a_rows = p.reuse ? (p.h_box + 2) * p.w_box : TG_BM;
-    const uint32_t a_stage_bytes = static_cast<uint32_t>(a_rows) * 128;
+    const bool patch = p.reuse == 2;
+    const int a_rows = patch ? (p.h_box + 2) * (p.w_box + 2) : (p.reuse ? (p.h_box + 2) * p.w_box : TG_BM);
+    const uint32_t a_box_bytes = static_cast<uint32_t>(a_rows) * 128;        // what one activation TMA lands
+    const uint32_t a_stage_bytes = (a_box_bytes + 1023u) & ~1023u;           // ring pitch (swizzle atoms are 1024 bytes)
     const uint32_t b_box_bytes = static_cast<uint32_t>(p.BN / CG) * 128;  // with CG == 2 each CTA holds half of the B rows
-    // resident weights (row-reuse schedule with a small weight set): all 9*cpt chunks of the current N tile stay in
-    // shared memory and only the activation boxes stream through the stage ring
-    const bool b_res = (CG == 1) && p.b_resident;
-    const uint32_t b_stage_bytes = b_res ? 0u : (p.reuse ? 3 * b_box_bytes : b_box_bytes);
+    // resident weights (small weight set): all 9*cpt chunks of the current N tile stay in shared memory and only the
+    // activation boxes stream through a ring
+    const bool b_res = p.b_resident && (CG == 1 || patch);
+    const uint32_t b_stage_bytes = b_res ? 0u : (patch ? p.b_taps * b_box_bytes : (p.reuse ? 3 * b_box_bytes : b_box_bytes));
     const uint32_t b_res_bytes = b_res ? 9u * p.cpt * b_box_bytes : 0u;
+    // the patch schedule keeps two rings: activation boxes (a_stages deep) and weight boxes (`stages` deep, one vertical
+    // tap row = three taps per stage); the other schedules pair one activation box with one weight stage
+    const int a_stages = patch ? p.a_stages : stages;
     uint8_t* smA = smem;
-    uint8_t* smB = smem + static_cast<size_t>(stages) * a_stage_bytes;
+    uint8_t* smB = smem + static_cast<size_t>(a_stages) * a_stage_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smB + static_cast<size_t>(stages) * b_stage_bytes + b_res_bytes);
     uint64_t* full_bar = bars;                 // [stages]
     uint64_t* empty_bar = bars + stages;       // [stages]
@@ -209,7 +216,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* bres_full = bars + 2 * stages + 4;   // resident weights landed
     uint64_t* tdone_bar = bars + 2 * stages + 5;   // all MMAs of a tile completed (resident weights may be replaced)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 6);
-    float* bias_s = reinterpret_cast<float*>(bars + 2 * stages + 8);  // [2][256]
+    uint64_t* afull_bar = bars + 2 * stages + 8;   // [a_stages] patch schedule only
+    uint64_t* aempty_bar = afull_bar + a_stages;   // [a_stages]
+    float* bias_s = reinterpret_cast<float*>(bars + 2 * stages + 8 + (patch ? 2 * a_stages : 0));  // [2][256]
     float* gam_s = bias_s + 512;                                      // [2][256] GroupNorm-backward gamma
     float* bet_s = gam_s + 512;                                       // [2][256] GroupNorm-backward beta
     // per-CTA partial sums of the fused GroupNorm statistics / backward reductions, flushed once at kernel end: thousands
@@ -227,22 +236,34 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
     const int lane = threadIdx.x & 31;
     const int total_tiles = (p.m_tiles / CG) * p.n_tiles * p.z_count;  // pair tiles when CG == 2
-    const int k_iters = p.reuse ? 3 * p.cpt : p.n_taps * p.cpt;
+    const int k_iters = patch ? p.cpt : (p.reuse ? 3 * p.cpt : p.n_taps * p.cpt);
     const int rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
-    const int first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG;
+    // tile ids of this CTA (pair): strided over the grid, or one contiguous range (tile_chunked)
+    int first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG, tile_end = total_tiles;
+    if (p.tile_chunked) {
+        const long long q = blockIdx.x / CG, Q = gridDim.x / CG;
+        first_tile = static_cast<int>(total_tiles * q / Q);
+        tile_end = static_cast<int>(total_tiles * (q + 1) / Q);
+        tile_step = 1;
+    }
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < stages; ++s) {
-            mbar_init(&full_bar[s], b_res ? 1 : 2);
+            mbar_init(&full_bar[s], (b_res || patch) ? 1 : 2);
             mbar_init(&empty_bar[s], 1);
         }
+        if (patch)
+            for (int s = 0; s < a_stages; ++s) {
+                mbar_init(&afull_bar[s], 1);
+                mbar_init(&aempty_bar[s], 1);
+            }
         mbar_init(bres_full, 1);
         mbar_init(tdone_bar, 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], (p.epi_split ? TG_EPI_THREADS / 2 : TG_EPI_THREADS) * CG);
+            mbar_init(&tempty_bar[a], (p.epi_split ? TG_EPI_THREADS / 64 : TG_EPI_THREADS / 32) * CG);  // one arrival per epilogue warp
         }
         fence_barrier_init();
     }
@@ -269,6 +290,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // warp 0 streams the activation boxes, the last warp the weight boxes; both arrive on the stage's full barrier
         const bool load_a = (warp == 0);
         {
+            // the ring this warp feeds: patch schedule = activations and weights have separate rings and barriers
+            const int ring = (patch && load_a) ? a_stages : stages;
+            uint64_t* const fbar = (patch && load_a) ? afull_bar : full_bar;
+            uint64_t* const ebar = (patch && load_a) ? aempty_bar : empty_bar;
             int stage = 0;
             uint32_t phase = 0;
             long long w_empty = 0, w_issue = 0;
@@ -276,12 +301,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const long long t_begin = clock64();
             // Tile coordinates cost several integer divisions and one global load (a_c0): each lane decodes a different
             // upcoming tile, the warp then walks through them with shuffles (32 tiles per batch).
-            for (int base = first_tile; base < total_tiles; base += 32 * tile_step) {
+            for (int base = first_tile; base < tile_end; base += 32 * tile_step) {
                 const int my_t = base + lane * tile_step;
-                TileCoord mine = decode_tile(p, my_t < total_tiles ? my_t : base, CG, rank);
+                TileCoord mine = decode_tile(p, my_t < tile_end ? my_t : base, CG, rank);
                 int my_c0 = 0;
-                if (p.a_c0 && my_t < total_tiles) my_c0 = __ldg(p.a_c0 + mine.n_tile);
-                const int batch = min(32, (total_tiles - base + tile_step - 1) / tile_step);
+                if (p.a_c0 && my_t < tile_end) my_c0 = __ldg(p.a_c0 + mine.n_tile);
+                const int batch = min(32, (tile_end - base + tile_step - 1) / tile_step);
                 for (int l = 0; l < batch; ++l) {
                     TileCoord tc;
                     tc.z = __shfl_sync(0xffffffffu, mine.z, l);
@@ -292,19 +317,39 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int c0 = __shfl_sync(0xffffffffu, my_c0, l);
                     if (b_res && !load_a) {
                         // weight warp, resident mode: reload only when the N tile changes, after every MMA that reads the
-                        // old weights has completed (tdone is waited tile by tile, so its parity never aliases)
-                        if (tiles_seen > 0) mbar_wait(tdone_bar, (tiles_seen - 1) & 1);
+                        // old weights has completed
                         if (tc.n_tile != res_n_tile) {
+                            // the MMA thread commits on tdone when it has issued the last tile that reads the old weights
+                            // (it knows the next tile's N tile too): one phase per reload, so the parity never aliases
+                            if (res_n_tile >= 0) {
+                                mbar_wait(tdone_bar, static_cast<uint32_t>(tiles_seen & 1));
+                                ++tiles_seen;  // counts reloads that waited
+                            }
                             res_n_tile = tc.n_tile;
+                            const int n0r = tc.n_tile * p.BN + rank * (p.BN / CG);
                             if (elect_one()) {
-                                mbar_expect_tx(bres_full, b_res_bytes);
-                                for (int it = 0; it < 3 * p.cpt; ++it)
-                                    tma_load_3d(smB + static_cast<size_t>(it) * 3 * b_box_bytes, &tmB, bres_full, 0,
-                                                tc.n_tile * p.BN, it * 3);
+                                if (CG == 2) {  // each CTA loads its half of the rows; the leader's barrier counts all bytes
+                                    if (rank == 0) mbar_expect_tx(bres_full, 2 * b_res_bytes);
+                                    if (patch) {
+                                        for (int cc = 0; cc < p.cpt; ++cc)
+                                            tma_load_3d_2sm(smB + static_cast<size_t>(cc) * 9 * b_box_bytes, &tmB, bres_full, 0, n0r, cc * 9);
+                                    } else {
+                                        for (int it = 0; it < 3 * p.cpt; ++it)
+                                            tma_load_3d_2sm(smB + static_cast<size_t>(it) * 3 * b_box_bytes, &tmB, bres_full, 0, n0r, it * 3);
+                                    }
+                                } else {
+                                    mbar_expect_tx(bres_full, b_res_bytes);
+                                    if (patch) {
+                                        for (int cc = 0; cc < p.cpt; ++cc)
+                                            tma_load_3d(smB + static_cast<size_t>(cc) * 9 * b_box_bytes, &tmB, bres_full, 0, n0r, cc * 9);
+                                    } else {
+                                        for (int it = 0; it < 3 * p.cpt; ++it)
+                                            tma_load_3d(smB + static_cast<size_t>(it) * 3 * b_box_bytes, &tmB, bres_full, 0, n0r, it * 3);
+                                    }
+                                }
                             }
                             __syncwarp();
                         }
-                        ++tiles_seen;
                         continue;
                     }
                     const int x0 = tc.tx * p.w_box * p.in_stride;
@@ -318,15 +363,15 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     auto slot_wait = [&]() {
                         if (p.dbg) {
                             const long long w0 = clock64();
-                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                            mbar_wait(&ebar[stage], phase ^ 1);
                             w_empty += clock64() - w0;
                         } else {
-                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                            mbar_wait(&ebar[stage], phase ^ 1);
                         }
                     };
                     auto slot_next = [&]() {
                         __syncwarp();
-                        if (++stage == stages) {
+                        if (++stage == ring) {
                             stage = 0;
                             phase ^= 1;
                         }
@@ -335,15 +380,15 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         slot_wait();
                         const long long i0 = p.dbg ? clock64() : 0;
                         if (p.dbg_skip & 1) {
-                            if (elect_one() && rank == 0) mbar_arrive(&full_bar[stage]);
+                            if (elect_one() && rank == 0) mbar_arrive(&fbar[stage]);
                         } else if (elect_one()) {
                             if (CG == 2) {  // both CTAs load into their own shared memory; the leader's barrier counts all bytes
-                                if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * a_stage_bytes);
-                                tma_load_4d_2sm(smA + static_cast<size_t>(stage) * a_stage_bytes, &tmA, &full_bar[stage], ca,
+                                if (rank == 0) mbar_expect_tx(&fbar[stage], 2 * a_box_bytes);
+                                tma_load_4d_2sm(smA + static_cast<size_t>(stage) * a_stage_bytes, &tmA, &fbar[stage], ca,
                                                 xx, yy, ab);
                             } else {
-                                mbar_expect_tx(&full_bar[stage], a_stage_bytes);
-                                tma_load_4d(smA + static_cast<size_t>(stage) * a_stage_bytes, &tmA, &full_bar[stage], ca, xx, yy, ab);
+                                mbar_expect_tx(&fbar[stage], a_box_bytes);
+                                tma_load_4d(smA + static_cast<size_t>(stage) * a_stage_bytes, &tmA, &fbar[stage], ca, xx, yy, ab);
                             }
                         }
                         if (p.dbg) w_issue += clock64() - i0;
@@ -366,7 +411,26 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (p.dbg) w_issue += clock64() - i0;
                         slot_next();
                     };
-                    if (p.kc_list) {
+                    if (patch) {
+                        // one halo patch per 64-channel chunk; weights: one vertical tap row (three taps) per stage
+                        if (load_a) {
+                            if (p.a_prefetch > 0 && l + p.a_prefetch < batch) {
+                                // the tile a few slots ahead: pull its patch into L2 now (DRAM latency off the critical path)
+                                const int lp = l + p.a_prefetch;
+                                const int px0 = __shfl_sync(0xffffffffu, mine.tx, lp) * p.w_box;
+                                const int py0 = __shfl_sync(0xffffffffu, mine.ty, lp) * p.h_box + p.a_y_off;
+                                const int pab = __shfl_sync(0xffffffffu, mine.bb, lp);
+                                const int pc0 = __shfl_sync(0xffffffffu, my_c0, lp);
+                                if (elect_one())
+                                    for (int cc = 0; cc < p.cpt; ++cc) tma_prefetch_4d(&tmA, pc0 + cc * TG_KC, px0 - 1, py0 - 1, pab);
+                                __syncwarp();
+                            }
+                            for (int cc = 0; cc < p.cpt; ++cc) issue_a(c0 + cc * TG_KC, x0 - 1, y0 - 1);
+                        } else {
+                            for (int cc = 0; cc < p.cpt; ++cc)
+                                for (int d = 0; d < 9; d += p.b_taps) issue_b(0, cc * 9 + d);
+                        }
+                    } else if (p.kc_list) {
                         // skip list (plain schedule): packed entries dx+1 | (dy+1) << 2 | chunk-in-tap << 4 | chunk << 16,
                         // fetched 32 at a time (one per lane) and handed round by shuffle
                         const int n_list = __ldg(p.kc_cnt + tc.n_tile);
@@ -448,13 +512,19 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int stage = 0;
         uint32_t phase = 0;
         uint32_t a_cur = a_lo0, b_cur = b_lo0;  // low descriptor words of the current stage
+        // patch schedule: 8-row groups of the A operand are one patch row (w_box + 2 pixels) apart
+        const uint32_t patch_row16 = static_cast<uint32_t>(p.w_box + 2) * 8u;
+        const uint32_t a_hi_patch = static_cast<uint32_t>(make_kmajor_desc_sbo(0, static_cast<uint32_t>(p.w_box + 2) * 128u) >> 32);
+        int a_st = 0;
+        uint32_t a_ph = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         long long w_tempty = 0, w_full = 0;
         const long long t_begin = clock64();
         int res_n_tile = -1;
         uint32_t res_phase = 0;
-        for (int t = first_tile; t < total_tiles; t += tile_step) {
+        for (int t = first_tile; t < tile_end; t += tile_step) {
+            bool res_last = false;  // this tile is the last one that reads the resident weights of its N tile
             if (b_res) {
                 const int nt = decode_tile(p, t, CG, rank).n_tile;
                 if (nt != res_n_tile) {
@@ -463,12 +533,88 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     res_phase ^= 1;
                     tc_fence_after();
                 }
+                res_last = (t + tile_step < tile_end) && decode_tile(p, t + tile_step, CG, rank).n_tile != nt;
             }
             long long w0 = p.dbg ? clock64() : 0;
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             if (p.dbg) w_tempty += clock64() - w0;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
+            if (patch) {
+                // patch schedule: per 64-channel chunk ONE activation box (halo patch, rows of w_box + 2 pixels) serves the
+                // nine taps through descriptor start offsets; weights come three taps (one vertical offset) per stage, or
+                // are resident. Tap (dy, dx) of output pixel (y, x) reads patch row (y + dy + 1) * (w_box + 2) + x + dx + 1.
+                for (int cc2 = 0; cc2 < p.cpt; ++cc2) {
+                    const int n_k = (cc2 == p.cpt - 1) ? kk_last : TG_KC / 16;
+                    w0 = p.dbg ? clock64() : 0;
+                    mbar_wait(&afull_bar[a_st], a_ph);
+                    if (p.dbg) w_full += clock64() - w0;
+                    // vertical offsets per synchronisation point: all three when the weight stage carries nine taps (narrow N:
+                    // the per-stage waits, fence and election then cost as much as the MMAs themselves), else one
+                    const int d_per = (b_res || p.b_taps == 9) ? 3 : 1;
+                    for (int d0 = 0; d0 < 3; d0 += d_per) {
+                        if (!b_res) {
+                            w0 = p.dbg ? clock64() : 0;
+                            mbar_wait(&full_bar[stage], phase);
+                            if (p.dbg) w_full += clock64() - w0;
+                        }
+                        tc_fence_after();
+                        if (elect_one()) {
+                            if (!skip_mma) {
+                                for (int dd = 0; dd < d_per; ++dd) {
+                                    const int d = d0 + dd;
+                                    const uint32_t ad = a_lo0 + static_cast<uint32_t>(a_st) * a_stage16 + static_cast<uint32_t>(d) * patch_row16;
+                                    const uint32_t bd = b_res ? b_lo0 + static_cast<uint32_t>(cc2 * 9 + d * 3) * b_box16
+                                                              : b_cur + static_cast<uint32_t>(dd * 3) * b_box16;
+                                    const uint32_t first = (cc2 > 0 || d > 0) ? 1u : 0u;
+                                    if (CG == 2) {
+                                        umma_f16_run_2sm(d_tmem, ad, a_hi_patch, bd, b_hi, idesc, first, 2u, n_k);
+                                        umma_f16_run_2sm(d_tmem, ad + 8u, a_hi_patch, bd + b_box16, b_hi, idesc, 1u, 2u, n_k);
+                                        umma_f16_run_2sm(d_tmem, ad + 16u, a_hi_patch, bd + 2u * b_box16, b_hi, idesc, 1u, 2u, n_k);
+                                    } else {
+                                        umma_f16_run(d_tmem, ad, a_hi_patch, bd, b_hi, idesc, first, 2u, n_k);
+                                        umma_f16_run(d_tmem, ad + 8u, a_hi_patch, bd + b_box16, b_hi, idesc, 1u, 2u, n_k);
+                                        umma_f16_run(d_tmem, ad + 16u, a_hi_patch, bd + 2u * b_box16, b_hi, idesc, 1u, 2u, n_k);
+                                    }
+                                }
+                            }
+                            const bool d_last = d0 + d_per == 3;
+                            const bool last = (cc2 == p.cpt - 1) && d_last;
+                            if (CG == 2) {
+                                if (!b_res) umma_commit_2sm(&empty_bar[stage]);
+                                if (d_last) umma_commit_2sm(&aempty_bar[a_st]);
+                                if (last) {
+                                    umma_commit_2sm(&tfull_bar[acc]);
+                                    if (res_last) umma_commit_2sm(tdone_bar);
+                                }
+                            } else {
+                                if (!b_res) umma_commit(&empty_bar[stage]);
+                                if (d_last) umma_commit(&aempty_bar[a_st]);
+                                if (last) {
+                                    umma_commit(&tfull_bar[acc]);
+                                    if (res_last) umma_commit(tdone_bar);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        if (!b_res) {
+                            b_cur += b_stage16;
+                            if (++stage == stages) {
+                                stage = 0;
+                                phase ^= 1;
+                                b_cur = b_lo0;
+                            }
+                        }
+                    }
+                    if (++a_st == a_stages) {
+                        a_st = 0;
+                        a_ph ^= 1;
+                    }
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+                continue;
+            }
             int cc = 0;  // chunk index within the tap (the last chunk of a tap may hold fewer than 64 useful channels)
             const int k_walk = p.kc_cnt ? __ldg(p.kc_cnt + decode_tile(p, t, CG, rank).n_tile) : k_iters;
             for (int kc = 0; kc < k_walk; ++kc) {
@@ -501,7 +647,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         umma_commit(&empty_bar[stage]);
                         if (kc == k_walk - 1) {
                             umma_commit(&tfull_bar[acc]);
-                            if (b_res) umma_commit(tdone_bar);
+                            if (res_last) umma_commit(tdone_bar);
                         }
                     }
                 }
@@ -537,14 +683,15 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int eset = split ? TG_EPI_THREADS / 2 : TG_EPI_THREADS;
         const int c_first = split ? 0 : half, c_step = split ? 1 : 2;
         int acc = 0, my_tiles = 0;
+        int staged_nt[2] = {-1, -1};  // N tile whose bias / gamma / beta sit in each of this set's two staging buffers
         uint32_t acc_phase = 0;
         long long w_tfull = 0, e_busy = 0;
         const long long t_begin = clock64();
         const int yy = row / p.w_box, xx = row - yy * p.w_box;
-        for (int base = first_tile; base < total_tiles; base += 32 * tile_step) {
+        for (int base = first_tile; base < tile_end; base += 32 * tile_step) {
           const int my_t = base + lane * tile_step;
-          const TileCoord mine = decode_tile(p, my_t < total_tiles ? my_t : base, CG, rank);
-          const int batch = min(32, (total_tiles - base + tile_step - 1) / tile_step);
+          const TileCoord mine = decode_tile(p, my_t < tile_end ? my_t : base, CG, rank);
+          const int batch = min(32, (tile_end - base + tile_step - 1) / tile_step);
           for (int l = 0; l < batch; ++l) {
             TileCoord tc;
             tc.z = __shfl_sync(0xffffffffu, mine.z, l);
@@ -566,25 +713,36 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // stage this tile's bias in shared memory while the MMAs are still running
             // tile-split mode: a half-set always drains the same accumulator, so its staging buffers alternate with its own
             // tile count instead (four 128-float slices of each 2 x 256 array; BN <= 128 there)
-            const int stage_off = split ? (half * 2 + (my_tiles & 1)) * 128 : acc * 256;
+            const int stage_buf = split ? (my_tiles & 1) : acc;
+            const int stage_off = split ? (half * 2 + stage_buf) * 128 : acc * 256;
             ++my_tiles;
             float* bs = bias_s + stage_off;
-            if (p.bias) {
-                for (int j = etid; j < p.BN; j += eset) bs[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
-            }
             float* gms = gam_s + stage_off;
             float* bts = bet_s + stage_off;
-            if (p.gnb_red) {
-                for (int j = etid; j < p.BN; j += eset) {
-                    gms[j] = (n0 + j < p.N) ? __ldg(p.gnb_gamma + n0 + j) : 0.f;
-                    bts[j] = (n0 + j < p.N) ? __ldg(p.gnb_beta + n0 + j) : 0.f;
+            // consecutive tiles of a CTA mostly share the N tile (M runs fastest): the per-column vectors are staged again
+            // only when it changes. The threads of a set then run unsynchronised between restages, so a restage is
+            // bracketed by two barriers (nobody still reads the buffer / everybody sees the new contents).
+            if ((p.bias || p.gnb_red) && staged_nt[stage_buf] != tc.n_tile) {
+                staged_nt[stage_buf] = tc.n_tile;
+                auto set_sync = [&]() {
+                    if (split) {
+                        if (half == 0) asm volatile("bar.sync 2, %0;" ::"n"(TG_EPI_THREADS / 2) : "memory");
+                        else asm volatile("bar.sync 3, %0;" ::"n"(TG_EPI_THREADS / 2) : "memory");
+                    } else {
+                        asm volatile("bar.sync 1, %0;" ::"n"(TG_EPI_THREADS) : "memory");
+                    }
+                };
+                set_sync();
+                if (p.bias) {
+                    for (int j = etid; j < p.BN; j += eset) bs[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
                 }
-            }
-            if (split) {
-                if (half == 0) asm volatile("bar.sync 2, %0;" ::"n"(TG_EPI_THREADS / 2) : "memory");
-                else asm volatile("bar.sync 3, %0;" ::"n"(TG_EPI_THREADS / 2) : "memory");
-            } else {
-                asm volatile("bar.sync 1, %0;" ::"n"(TG_EPI_THREADS) : "memory");
+                if (p.gnb_red) {
+                    for (int j = etid; j < p.BN; j += eset) {
+                        gms[j] = (n0 + j < p.N) ? __ldg(p.gnb_gamma + n0 + j) : 0.f;
+                        bts[j] = (n0 + j < p.N) ? __ldg(p.gnb_beta + n0 + j) : 0.f;
+                    }
+                }
+                set_sync();
             }
             // one row-wise side input per launch: residual (forward), dot operand (WFC) or saved activation (GroupNorm
             // backward). Its 32-byte pieces are prefetched three chunks deep, the first three before the accumulator wait,
@@ -623,6 +781,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float dot = 0.f;
             float gs = 0.f, gss = 0.f;
             int ggroup = -1;
+            // GroupNorm group of a 16-column chunk without a division per chunk: the group of the tile's first column
+            // (one division per tile) and the first column of the next group; chunks are visited in increasing order
+            const int g_cpg = p.gn_sums ? p.gn_cpg : (p.gnb_red ? p.gnb_cpg : 0);
+            int g_run = g_cpg ? n0 / g_cpg : 0;
+            int g_next = g_cpg ? (g_run + 1) * g_cpg : 0x7fffffff;
             float b1 = 0.f, b2 = 0.f, bmean = 0.f, brstd = 0.f;
             int bgroup = -1;
             for (int c = c_first; c < ((p.dbg_skip & 8) ? 0 : n_chunks); c += c_step) {
@@ -693,8 +856,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         op[0] = make_uint4(w[0], w[1], w[2], w[3]);
                         op[1] = make_uint4(w[4], w[5], w[6], w[7]);
                     }
+                    if (g_cpg) {
+                        while (n >= g_next) {
+                            ++g_run;
+                            g_next += g_cpg;
+                        }
+                    }
                     if (p.gn_sums) {
-                        const int g = n / p.gn_cpg;
+                        const int g = g_run;
                         if (g != ggroup) {
                             if (ggroup >= 0) {
 #pragma unroll
@@ -727,7 +896,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (side_kind == 3) {
                         // fused GroupNorm(+SiLU) backward reduction over the just-stored gradient dy and the saved
                         // forward activation x: sum(du*gamma), sum(du*gamma*xhat), du = dy * act'(xhat*gamma+beta)
-                        const int g = n / p.gnb_cpg;
+                        const int g = g_run;
                         if (g != bgroup) {
                             if (bgroup >= 0) {
 #pragma unroll
@@ -786,8 +955,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             // the accumulator stage is drained: hand it back to the MMA warp before the remaining bookkeeping
             tc_fence_before();
-            if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]);  // the MMA thread lives in the leader CTA
-            else mbar_arrive(&tempty_bar[acc]);
+            __syncwarp();  // every lane's TMEM reads are complete: one lane hands the warp's share back
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]);  // the MMA thread lives in the leader CTA
+                else mbar_arrive(&tempty_bar[acc]);
+            }
             if (p.gn_sums && ggroup >= 0) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
@@ -1018,7 +1190,21 @@ int tapgemm_prepare(TapGemmOp* op) {
         set_error("tapgemm_prepare: a K-chunk skip list needs the plain schedule with whole 64-channel chunks");
         return -3;
     }
-    if (p.reuse && !tapgemm_reuse_ok(p)) {
+    if (p.reuse == 2) {
+        bool ok = p.n_taps == 9 && p.in_stride == 1 && p.z_count == 1 && !p.b_zmul && !p.b_bbmul && p.w_box == 8 &&
+                  p.h_box == 16 && !p.kc_list && !p.a_mn_major && !p.a_zmul;
+        bool seen[9] = {false};
+        for (int t = 0; ok && t < 9; ++t) {
+            const int dx = p.tap_dx[t], dy = p.tap_dy[t];
+            if (dx < -1 || dx > 1 || dy < -1 || dy > 1) ok = false;
+            else seen[(dy + 1) * 3 + dx + 1] = true;
+        }
+        for (bool b : seen) ok = ok && b;
+        if (!ok) {
+            set_error("tapgemm_prepare: the patch schedule needs a full 3x3 stride-1 tap set and 16 x 8 pixel patches");
+            return -3;
+        }
+    } else if (p.reuse && !tapgemm_reuse_ok(p)) {
         set_error("tapgemm_prepare: row-reuse schedule requested for an unsupported tap set / tile");
         return -3;
     }
@@ -1041,6 +1227,39 @@ int tapgemm_prepare(TapGemmOp* op) {
         const bool wide = !p.reuse && p.BN >= 128 && p.BN % 32 == 0;
         const bool narrow_reuse = p.reuse && reuse2 && p.BN % 16 == 0;
         p.cg = (!no2 && p.cg != 1 && (wide || narrow_reuse) && pairs_ok) ? 2 : 1;
+    }
+    const bool patch = p.reuse == 2;
+    if (patch) {
+        // weights of one N tile stay resident when they leave room for >= 3 activation boxes (grouped layers); the CTAs
+        // then walk contiguous tile ranges so that the N tile changes a few times per launch, not every other tile
+        // Measured on B200 (round 2, profiles/r02_summary.md): resident weights + contiguous tile ranges are SLOWER than
+        // streaming the weight boxes through their ring (batch-8 step 12.44 vs 12.12 ms; groups=64 convs 2.71 vs 2.35 ms),
+        // so the mode is opt-in (WFD_PATCH_RESIDENT=1).
+        static int want_res = -1;
+        if (want_res < 0) {
+            const char* e = getenv("WFD_PATCH_RESIDENT");
+            want_res = (e && e[0] == '1') ? 1 : 0;
+        }
+        const size_t res_bytes = 9 * static_cast<size_t>(p.cpt) * (p.BN / p.cg) * 128;
+        p.b_resident = (want_res && res_bytes <= 120 * 1024) ? 1 : 0;
+        static int chunked = -1, prefetch = -1;
+        if (chunked < 0) {
+            const char* e = getenv("WFD_PATCH_CHUNKED");
+            chunked = (e && e[0] == '0') ? 0 : 1;
+            const char* f = getenv("WFD_PATCH_PREFETCH");
+            prefetch = f ? atoi(f) : 0;
+        }
+        p.tile_chunked = (p.b_resident && p.n_group <= 1 && chunked) ? 1 : 0;
+        p.a_prefetch = prefetch;
+        // weight stage = all nine taps of a 64-channel chunk when two such stages fit beside three activation boxes
+        // (narrow N tiles: one synchronisation point per chunk instead of three), else one vertical offset (three taps)
+        static int taps9 = -1;
+        if (taps9 < 0) {
+            const char* e = getenv("WFD_PATCH_TAPS9");
+            taps9 = (e && e[0] == '0') ? 0 : 1;
+        }
+        const size_t box_b = static_cast<size_t>(p.BN / p.cg) * 128;
+        p.b_taps = (taps9 && 2 * 9 * box_b + 3 * 24 * 1024 <= 196 * 1024) ? 9 : 3;
     }
     const CUtensorMapDataType dt = p.is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     if (p.a_mn_major) {
@@ -1067,6 +1286,7 @@ int tapgemm_prepare(TapGemmOp* op) {
         cuuint32_t box[4] = {TG_KC, (cuuint32_t)((p.w_box - 1) * p.in_stride + 1),
                              (cuuint32_t)((p.h_box - 1) * p.in_stride + 1), 1};
         if (p.reuse) box[2] = (cuuint32_t)(p.h_box + 2);
+        if (patch) box[1] = (cuuint32_t)(p.w_box + 2);
         cuuint32_t estr[4] = {1, (cuuint32_t)p.in_stride, (cuuint32_t)p.in_stride, 1};
         CUresult r = enc(&op->tmA, dt, 4, const_cast<void*>(p.a_ptr), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1081,7 +1301,7 @@ int tapgemm_prepare(TapGemmOp* op) {
         // weights as (64 elements, rows, chunk): one box fetches the three vertical-tap chunks of a (dx, cc) pair
         cuuint64_t dims[3] = {(cuuint64_t)TG_KC, (cuuint64_t)p.b_rows, (cuuint64_t)(9 * p.cpt)};
         cuuint64_t strides[2] = {(cuuint64_t)p.ldb * 2, (cuuint64_t)TG_KC * 2};
-        cuuint32_t box[3] = {TG_KC, (cuuint32_t)(p.BN / p.cg), 3};
+        cuuint32_t box[3] = {TG_KC, (cuuint32_t)(p.BN / p.cg), (cuuint32_t)((patch && p.b_resident) ? 9 : (patch ? p.b_taps : 3))};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(&op->tmB, dt, 3, const_cast<void*>(p.b_ptr), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1107,12 +1327,13 @@ int tapgemm_prepare(TapGemmOp* op) {
             return -5;
         }
     }
-    const size_t a_stage = p.reuse ? static_cast<size_t>(p.h_box + 2) * p.w_box * 128 : TG_BM * 128;
+    const size_t a_stage = patch ? ((static_cast<size_t>(p.h_box + 2) * (p.w_box + 2) * 128 + 1023) & ~size_t(1023))
+                                 : (p.reuse ? static_cast<size_t>(p.h_box + 2) * p.w_box * 128 : TG_BM * 128);
     // weights of one N tile resident in shared memory when they are small (grouped layers with few channels per group)
-    const size_t b_res_bytes = 9 * static_cast<size_t>(p.cpt) * p.BN * 128;
-    {
-        // measured on B200 (round 1): 0.27 ms vs 0.21 ms per 3072-channel groups=64 conv with / without resident weights,
-        // so the mode is opt-in (WFD_RESIDENT_B=1) until the stall is understood
+    const size_t b_res_bytes = 9 * static_cast<size_t>(p.cpt) * (p.BN / p.cg) * 128;
+    if (!patch) {
+        // row-reuse schedule, measured on B200 (round 1): 0.27 ms vs 0.21 ms per 3072-channel groups=64 conv with / without
+        // resident weights, so the mode is opt-in there (WFD_RESIDENT_B=1)
         static int res = -1;
         if (res < 0) {
             const char* e = getenv("WFD_RESIDENT_B");
@@ -1120,21 +1341,56 @@ int tapgemm_prepare(TapGemmOp* op) {
         }
         p.b_resident = (res && p.reuse && p.cg == 1 && b_res_bytes <= 64 * 1024) ? 1 : 0;
     }
-    const size_t b_stage = p.b_resident ? 0 : (p.reuse ? 3 : 1) * static_cast<size_t>(p.BN / p.cg) * 128;
-    const size_t per_stage = a_stage + b_stage;
-    int stages = static_cast<int>((196 * 1024 - (p.b_resident ? b_res_bytes : 0)) / per_stage);
-    if (stages > 8) stages = 8;
-    {
-        static int cap = -1;  // WFD_MAX_STAGES: experiment knob
-        if (cap < 0) {
-            const char* e = getenv("WFD_MAX_STAGES");
-            cap = e ? atoi(e) : 0;
+    const size_t b_stage = p.b_resident ? 0 : (patch ? p.b_taps : (p.reuse ? 3 : 1)) * static_cast<size_t>(p.BN / p.cg) * 128;
+    const size_t budget = 196 * 1024;
+    int stages, a_stages = 0;
+    if (patch) {
+        if (p.b_resident) {
+            a_stages = static_cast<int>((budget - b_res_bytes) / a_stage);
+            if (a_stages > 6) a_stages = 6;
+            stages = 1;  // the weight ring is not used
+        } else {
+            a_stages = 3;
+            stages = static_cast<int>((budget - a_stages * a_stage) / b_stage);
+            if (stages > 8) stages = 8;
+            if (stages >= 6 && budget - a_stages * a_stage - stages * b_stage >= a_stage) a_stages = 4;
+            static int a_over = -1, b_over = -1;  // WFD_PATCH_ASTAGES / WFD_PATCH_BSTAGES: experiment knobs
+            if (a_over < 0) {
+                const char* e = getenv("WFD_PATCH_ASTAGES");
+                a_over = e ? atoi(e) : 0;
+                const char* f = getenv("WFD_PATCH_BSTAGES");
+                b_over = f ? atoi(f) : 0;
+            }
+            if (a_over > 0 || b_over > 0) {
+                int as = a_over > 0 ? a_over : a_stages, bs = b_over > 0 ? b_over : stages;
+                while (bs > 2 && as * a_stage + bs * b_stage > budget) --bs;
+                while (as > 2 && as * a_stage + bs * b_stage > budget) --as;
+                a_stages = as;
+                stages = bs;
+            }
         }
-        if (cap > 0 && stages > cap) stages = cap;
+        if (a_stages < 2 || stages < 1 || (!p.b_resident && stages < 2)) {
+            set_error("tapgemm_prepare: the patch schedule does not fit shared memory (BN=%d cpt=%d)", p.BN, p.cpt);
+            return -3;
+        }
+    } else {
+        const size_t per_stage = a_stage + b_stage;
+        stages = static_cast<int>((budget - (p.b_resident ? b_res_bytes : 0)) / per_stage);
+        if (stages > 8) stages = 8;
+        {
+            static int cap = -1;  // WFD_MAX_STAGES: experiment knob
+            if (cap < 0) {
+                const char* e = getenv("WFD_MAX_STAGES");
+                cap = e ? atoi(e) : 0;
+            }
+            if (cap > 0 && stages > cap) stages = cap;
+        }
+        if (stages < 2) stages = 2;
     }
-    if (stages < 2) stages = 2;
+    p.a_stages = a_stages;
     op->stages = stages;
-    op->smem_bytes = 1024 + stages * per_stage + (p.b_resident ? b_res_bytes : 0) + (2 * stages + 8) * sizeof(uint64_t) +
+    op->smem_bytes = 1024 + (patch ? a_stages * a_stage + stages * b_stage : stages * (a_stage + b_stage)) +
+                     (p.b_resident ? b_res_bytes : 0) + (2 * stages + 8 + 2 * a_stages) * sizeof(uint64_t) +
                      6 * 256 * sizeof(float) + 2 * TG_STAT_SLOTS * sizeof(unsigned long long) + 16;
     return 0;
 }

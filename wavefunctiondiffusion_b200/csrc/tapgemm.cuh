@@ -58,6 +58,14 @@ struct TapGemmParams {
     int cg;                 // CTA group: 0 = let tapgemm_prepare choose, 1 = single CTA, 2 = CTA pair (cta_group::2)
     int b_resident;         // set by tapgemm_prepare: weights of the current N tile stay resident in shared memory
     int reuse;              // 1: row-reuse schedule (3x3 stride-1 taps; Bm chunks in (dx, cc, dy) order)
+                            // 2: patch schedule (3x3 stride-1 taps; Bm chunks in (cc, dy, dx) order): ONE activation box per
+                            //    64-channel chunk carries the whole (h_box+2) x (w_box+2) halo patch (w_box = 8) and serves all
+                            //    nine taps through descriptor start offsets (a row pitch of w_box+2 pixels = the SBO field)
+    int a_stages;           // set by tapgemm_prepare (patch schedule): depth of the activation ring (weights have their own)
+    int b_taps;             // set by tapgemm_prepare (patch schedule): taps per weight stage, 3 (one vertical offset) or 9 (all)
+    int a_prefetch;         // patch schedule: activation boxes of the tile this many tile slots ahead are prefetched into L2 (0 = off)
+    int tile_chunked;       // set by tapgemm_prepare: every CTA (pair) walks ONE contiguous range of tile ids instead of a
+                            // strided one, so consecutive tiles share the N tile and resident weights are loaded once
     int a_zmul;             // A dim-3 coordinate = bb + z * a_zmul
     int b_zmul, b_bbmul;    // B dim-2 coordinate = z * b_zmul + bb * b_bbmul
     // ---- epilogue

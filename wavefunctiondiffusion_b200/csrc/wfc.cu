@@ -197,6 +197,8 @@ int Wfc::forward(const void* in, int is_logits, int B, int H, int W, float stren
     hdr_host.coef = strength / static_cast<float>(Hm * (W - 1) + (Hm - 1) * W);
     hdr_host.wave = wave;
     hdr_saved = saved;
+    if (saved_hdrs.size() > 256) saved_hdrs.clear();  // blocks that were never differentiated (inference-only callers)
+    saved_hdrs[saved] = hdr_host;
     if (is_logits) CK(wave_softmax(in, v.wave, v.rowsum, static_cast<long long>(rows), T_pad, T, bf16, s));
     else CK(wave_rowsum(in, v.rowsum, static_cast<long long>(rows), T_pad, T, bf16, s));
     CUDA_CK(cudaMemsetAsync(v.rowdot, 0, rows * sizeof(acc_t), s));
@@ -301,10 +303,12 @@ int Wfc::forward(const void* in, int is_logits, int B, int H, int W, float stren
 }
 
 int Wfc::backward(void* saved, const float* dloss, void* dout, cudaStream_t s) {
-    if (saved != hdr_saved || hdr_host.B == 0) {
-        set_error("wfc: backward called with a `saved` block that is not the one of the last forward");
+    auto it = saved_hdrs.find(saved);
+    if (it == saved_hdrs.end() || it->second.B == 0) {
+        set_error("wfc: backward called with a `saved` block that no forward of this handle has filled");
         return -3;
     }
+    const WfcSavedHeader hdr_host = it->second;  // shapes of the forward that filled THIS block
     const size_t rows = static_cast<size_t>(hdr_host.B) * hdr_host.H * hdr_host.W;
     const size_t halo_wave = band ? align256(static_cast<size_t>(hdr_host.W) * T_pad * 2) : 0;
     const size_t halo_sum = band ? align256(static_cast<size_t>(hdr_host.W) * 4) : 0;

@@ -1,15 +1,15 @@
 """Tileset adjacency data: the `wfc_mats` arrays of the reference's wfd/scmap/tile_data/wfc/*.npz
 (written by wfd/wfdf/datasets.py:124-146, read by pipeline_wfd.py:180-182).
 
-`load_wfc_mats` accepts either a reference npz (key `wfc_mats`, bool (2, T, T)) or the compact coordinate form kept
-under tests/golden/wfc_mats/ (keys T, x, y) so that benchmarks and tests can run where the reference tree is absent.
+`load_wfc_mats` accepts either a reference npz (key `wfc_mats`, bool (2, T, T)) or the compact coordinate form shipped
+with this package under data/wfc_mats/ (keys T, x, y: the same matrices as the reference's nine npz files, bit for bit,
+written by oracle/make_golden.py) so that the tileset names resolve where the reference tree is absent.
 """
 import os
 
 import numpy as np
 
-_GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests", "golden",
-                       "wfc_mats")
+WFC_DATA_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "wfc_mats")
 
 
 def round_up_channels(t, multiple=128):
@@ -21,7 +21,7 @@ def load_wfc_mats(path_or_name):
     """-> (mat_x, mat_y) bool (T, T). `path_or_name`: an npz path, or a tileset name like 'ice_64x64'."""
     path = path_or_name
     if not os.path.exists(path):
-        path = os.path.join(_GOLDEN, path_or_name + ".npz")
+        path = os.path.join(WFC_DATA_DIR, path_or_name + ".npz")
     if not os.path.exists(path):
         raise FileNotFoundError("no wfc data for %r" % (path_or_name,))
     z = np.load(path)

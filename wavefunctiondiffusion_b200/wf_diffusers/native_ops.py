@@ -225,15 +225,24 @@ class WfcHandle:
         self._saved_ptr = (self._saved.data_ptr() + 255) // 256 * 256
         return C.c_void_p(self._saved_ptr)
 
-    def forward(self, in_ptr, is_logits, B, H, W, strength):
+    def new_saved(self, B, H, W):
+        """A fresh `saved` block for ONE forward, owned by the caller (the autograd context): several forwards of the
+        same handle may then be outstanding before their backwards run. Returns (tensor, aligned pointer)."""
+        n = nat.lib().wfd_wfc_saved_bytes(self.handle, B, H, W)
+        t = torch.empty(n + 256, dtype=torch.uint8, device=self.device)
+        return t, (t.data_ptr() + 255) // 256 * 256
+
+    def forward(self, in_ptr, is_logits, B, H, W, strength, saved_ptr=None):
+        """saved_ptr=None uses (and overwrites) the handle's own block - the fused guidance path and wave_view()."""
         loss = torch.empty(B, dtype=torch.float32, device=self.device)
+        saved = self.saved_ptr(B, H, W) if saved_ptr is None else C.c_void_p(saved_ptr)
         nat.check(nat.lib().wfd_wfc_forward(self.handle, C.c_void_p(in_ptr), int(is_logits), B, H, W, float(strength),
-                                            self.saved_ptr(B, H, W), C.c_void_p(loss.data_ptr()), nat.stream_ptr()),
+                                            saved, C.c_void_p(loss.data_ptr()), nat.stream_ptr()),
                   "wfd_wfc_forward")
         return loss
 
-    def backward(self, dloss, out_ptr):
-        nat.check(nat.lib().wfd_wfc_backward(self.handle, C.c_void_p(self._saved_ptr),
+    def backward(self, dloss, out_ptr, saved_ptr=None):
+        nat.check(nat.lib().wfd_wfc_backward(self.handle, C.c_void_p(self._saved_ptr if saved_ptr is None else saved_ptr),
                                              None if dloss is None else C.c_void_p(dloss.data_ptr()),
                                              C.c_void_p(out_ptr), nat.stream_ptr()), "wfd_wfc_backward")
 
@@ -297,8 +306,11 @@ class WfcLossFunction(torch.autograd.Function):
         x = to_nhwc16(t, handle.dtype16)
         if not x.is_contiguous():
             x = x.contiguous()
-        loss = handle.forward(x.data_ptr(), softmax, B, H, W, 1.0)
-        ctx.handle, ctx.x, ctx.like = handle, x, t
+        # the block backward needs belongs to THIS call (ctx keeps it alive): loss(a) + loss(b) differentiates both
+        # against their own waves, and the handle's shared block (wave_view) is left to the fused guidance path
+        saved, saved_ptr = handle.new_saved(B, H, W)
+        loss = handle.forward(x.data_ptr(), softmax, B, H, W, 1.0, saved_ptr=saved_ptr)
+        ctx.handle, ctx.x, ctx.like, ctx.saved, ctx.saved_ptr = handle, x, t, saved, saved_ptr
         return loss.to(t.dtype) if t.dtype != torch.float32 else loss
 
     @staticmethod
@@ -306,7 +318,7 @@ class WfcLossFunction(torch.autograd.Function):
         h = ctx.handle
         x = ctx.x
         dout = torch.empty_like(x)
-        h.backward(dloss.float().contiguous(), dout.data_ptr())
+        h.backward(dloss.float().contiguous(), dout.data_ptr(), saved_ptr=ctx.saved_ptr)
         return from_nhwc16(dout, ctx.like, h.dtype16), None, None
 
 
@@ -329,7 +341,9 @@ class GraphedGuidanceStep:
         self.z = torch.zeros((B, 4, h, w), dtype=zdtype, device=device)
         self.loss = torch.empty(B, dtype=torch.float32, device=device)
         self.dz = torch.empty((B, 4, h, w), dtype=torch.float32, device=device)
-        self.plan, self.handle = plan, handle
+        import weakref
+
+        self._plan, self.handle = weakref.ref(plan), handle  # the plan owns this object (plan._graphs): no cycle
         saved = handle.saved_ptr(B, plan.H, plan.W)
         zcode = _z_dtype_code(self.z)
 
@@ -356,12 +370,9 @@ class GraphedGuidanceStep:
 
     def __call__(self, z):
         self.z.copy_(z)
-        self.plan.generation += 1
+        self._plan().generation += 1
         self.graph.replay()
         return self.loss, self.dz
-
-
-_GRAPH_CACHE = {}
 
 
 class GuidanceLossFunction(torch.autograd.Function):
@@ -377,13 +388,16 @@ class GuidanceLossFunction(torch.autograd.Function):
         plan = native.plan(mb, h, w, latents.device)
         z = latents.contiguous()
         if cuda_graphs_enabled() and B <= mb and not torch.cuda.is_current_stream_capturing():
-            key = (id(plan), id(handle), B, z.dtype, float(in_scale), float(strength), torch.cuda.current_stream().cuda_stream)
-            g = _GRAPH_CACHE.get(key)
-            if g is None or not g.valid() or g.plan is not plan:
-                if len(_GRAPH_CACHE) > 16:
-                    _GRAPH_CACHE.clear()
+            # captured steps live ON the plan (they die with it: NativeDecoder.invalidate() after .to()/.half()/
+            # load_state_dict frees their workspace too); an entry keeps its handle alive, so id(handle) cannot be reused
+            cache = plan.__dict__.setdefault("_graphs", {})
+            key = (id(handle), B, z.dtype, float(in_scale), float(strength), torch.cuda.current_stream().cuda_stream)
+            g = cache.get(key)
+            if g is None or not g.valid() or g.handle is not handle:
+                if len(cache) > 8:
+                    cache.clear()
                 g = GraphedGuidanceStep(plan, handle, B, h, w, z.dtype, in_scale, strength, z.device)
-                _GRAPH_CACHE[key] = g
+                cache[key] = g
             loss_s, dz_s = g(z)
             ctx.save_for_backward(dz_s.clone())
             ctx.zdtype = latents.dtype
@@ -393,6 +407,7 @@ class GuidanceLossFunction(torch.autograd.Function):
         esz = z.element_size() * 4 * h * w
         for lo in range(0, B, mb):
             n = min(mb, B - lo)
+            plan.generation += 1  # the plan's activation workspace is overwritten: an earlier decode cannot run backward
             nat.check(nat.lib().wfd_guidance_step(plan.handle, handle.handle, C.c_void_p(z.data_ptr() + lo * esz),
                                                   _z_dtype_code(z), n, float(in_scale), float(strength),
                                                   handle.saved_ptr(n, plan.H, plan.W), C.c_void_p(loss.data_ptr() + 4 * lo),

@@ -316,6 +316,25 @@ class AutoencoderTile(nn.Module):
             self._native.invalidate()
         return r
 
+    # ---- copies and pickles carry parameters only; the native caches (ctypes handles, device workspaces, a weak
+    # reference to the owner) are rebuilt for the new object on its first decode
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_native", None)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._native = NativeDecoder(self)
+
+    def __deepcopy__(self, memo):
+        import copy
+
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        new.__setstate__({k: copy.deepcopy(v, memo) for k, v in self.__getstate__().items()})
+        return new
+
     def refresh_native(self):
         """Call after mutating decoder weights in place; the packed device copy is rebuilt on the next decode."""
         self._native.invalidate()

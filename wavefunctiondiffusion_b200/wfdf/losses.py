@@ -28,6 +28,20 @@ class WFCLossEinsum(torch.nn.Module):
         self.count = cx.size(0)
         self._handles = {}
 
+    # copies and pickles carry the buffers only; native handles are rebuilt on first use
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_handles"] = {}
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        new.__dict__.update({k: copy.deepcopy(v, memo) for k, v in self.__getstate__().items()})
+        return new
+
     def _mats(self):
         ax = (self.cx[0, :, :, 0, 0] < 0.5).to("cpu").numpy()
         ay = (self.cy[0, :, :, 0, 0] < 0.5).to("cpu").numpy()
