@@ -118,6 +118,19 @@ WFD_API void* wfd_wfc_saved_wave(const wfd_wfc* h, void* saved, int B, int H, in
 WFD_API int wfd_guidance_step(wfd_decoder* d, wfd_wfc* h, const void* z, int z_dtype, int B, float in_scale, float strength,
                       void* wfc_saved, float* loss, float* dz, void* stream);
 
+/* n_steps guided updates of the latents for a scheduler whose step is affine in the sample, prev = a x + b eps (DDIM
+ * eta = 0, PNDM/PLMS): the whole body of the reference's guidance block, pipeline_wfd.py:605-615, and with n_steps = 20
+ * its final-stage loop :626-639 (same eps and t every iteration), without leaving the library:
+ *     eps  = eps_uncond + cfg_scale * (eps_text - eps_uncond)        (:601-603; eps_text == NULL: eps = eps_uncond)
+ *     z    = a * lat + b * eps                                       (:611 scheduler.step(...).prev_sample)
+ *     loss = strength * wfc_loss(softmax(decode(z * in_scale)))       (:612)
+ *     lat -= a * d(sum_b loss_b)/dz                                   (:613-614; a = d prev / d sample)
+ * lat: fp32 NCHW [B,4,h,w], updated in place; eps_*: fp32, same shape; loss_out: [n_steps][B]; z_scratch / dz_scratch:
+ * fp32 buffers of lat's size. A fixed launch sequence: capture it once, replay it per call. */
+WFD_API int wfd_guidance_loop(wfd_decoder* d, wfd_wfc* h, float* lat, const float* eps_uncond, const float* eps_text,
+                              float cfg_scale, float a, float b, int B, float in_scale, float strength, int n_steps,
+                              void* wfc_saved, float* loss_out, float* z_scratch, float* dz_scratch, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Row bands: ONE large map (BASELINE config 4, 256x256) split along y over R GPUs, one band of h/R rows per rank.
  * The reference runs such a map on one device (pipeline_wfd.py:283-290 only widens width/height); cutting the plane
@@ -163,6 +176,20 @@ WFD_API int wfd_argmax_tiles(const void* x, int dtype, long long rows, int n, lo
 WFD_API double wfd_wfc_kc_kept(const wfd_wfc* h);
 WFD_API int wfd_wfc_count_violations(const wfd_wfc* h, const long long* tiles, int B, int H, int W, long long* out,
                                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Tile post-processing on the device (what wfd/webui/ui.py:228-243 does on the host after the argmax):
+ *   optional mirror symmetry   tiles' = [tiles | symm[tiles[:, ::-1]]]          wfd/scmap/data_processing.py:191-196
+ *   id chain                   sc = gen_to_sc[shrink_to_gen[tiles']]            wfd/scmap/map_display.py:55,
+ *                                                                                 data_processing.py:206-211
+ * tiles int64 [B, H, W] (device); symm (may be NULL), shrink_to_gen (may be NULL = identity), gen_to_sc: int32 tables on
+ * the device; tiles_out int64 [B, H, W'] and sc_out uint16 [B, H, W'] (either may be NULL), W' = 2 W with symmetry.
+ * *bad (device int64) counts ids outside a table (an argmax over padded channels): they come out as 0xFFFF, where the
+ * reference's numpy indexing would raise. So only a (H, W') uint16 map has to leave the GPU, not 52 MB of wave.
+ * ---------------------------------------------------------------------------------------------------------------- */
+WFD_API int wfd_tiles_finish(const long long* tiles, int B, int H, int W, const int* symm, int n_symm,
+                             const int* shrink_to_gen, int n_shrink, const int* gen_to_sc, int n_gen,
+                             long long* tiles_out, uint16_t* sc_out, long long* bad, void* stream);
 
 /* layout helpers used by the Python layer: NCHW (fp32/fp16) <-> nhwc16, 16-bit -> fp32 */
 WFD_API int wfd_nchw_to_nhwc16(const void* in, int in_dtype, void* out, int B, int C, int HW, int dtype16, void* stream);

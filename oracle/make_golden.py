@@ -9,6 +9,7 @@ AutoencoderTile, whose initialisation order is checked to be bit-identical to th
   tiny_step.npz            reference decode+softmax+loss+grad on a small config, fp64 and fp32
   tiny_down_step.npz       same with a DownDecoderBlock2D (the 32x32-style config)
   ice_c1_step.npz          BASELINE config 1: ice 64x64, batch 1, tilenet_sc_space_64x64, strength 5
+  tiles_post.npz           the reference's add_symmetry + gen_to_sc[shrink_to_gen[.]] on random ice tiles (with the tables)
   ice_c2_step.npz          BASELINE config 2's benchmarked shape: the same weights, batch 8 (slot 0 = the C1 latents)
 """
 import glob
@@ -133,6 +134,29 @@ def full_fixture(vae, losses):
     np.savez_compressed(os.path.join(GOLD, "ice_c1_step.npz"), **out)
 
 
+def tiles_post_fixture():
+    """Post-argmax integer work on the ice tileset: the reference's own add_symmetry (wfd/scmap/data_processing.py:191-196,
+    executed from where it lies) and the id chain gen_to_sc[shrink_to_gen[.]] (map_display.py:55) on the shipped tables."""
+    import importlib
+    import types
+
+    for name, path in (("ref_wfd", "/wfd"), ("ref_wfd.scmap", "/wfd/scmap")):
+        m = types.ModuleType(name)
+        m.__path__ = [REFERENCE_ROOT + path]  # packages without running their __init__
+        sys.modules[name] = m
+    dp = importlib.import_module("ref_wfd.scmap.data_processing")
+    consts = np.load(REFERENCE_ROOT + "/wfd/scmap/tile_data/wfc/ice_64x64.npz")
+    symm_path = REFERENCE_ROOT + "/wfd/scmap/tile_data/symmetry/ice.npz"
+    rng = np.random.RandomState(5)
+    tiles = rng.randint(0, int(consts["shrink_count"]), size=(12, 9))
+    mirrored = dp.add_symmetry(tiles, symmetry_path=symm_path)
+    sc = consts["gen_to_sc"][consts["shrink_to_gen"][mirrored]]           # map_display.py:55
+    np.savez_compressed(os.path.join(GOLD, "tiles_post.npz"), tiles=tiles, mirrored=mirrored, sc=sc,
+                        mapping=np.load(symm_path)["mapping"], shrink_to_gen=consts["shrink_to_gen"],
+                        gen_to_sc=consts["gen_to_sc"])
+    print("tiles_post", mirrored.shape, sc[0, :6])
+
+
 def batch8_fixture(vae, losses):
     """BASELINE config 2's shape (ice 64x64, batch 8): slot 0 carries the C1 latents, slots 1-7 are fresh draws, slot 5
     repeats slot 2 (identical maps must give identical results). loss (8,) and latent gradient, fp64 and fp32."""
@@ -162,10 +186,14 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     vae, losses = load_reference()
+    if "--only-tiles" in sys.argv:
+        tiles_post_fixture()
+        sys.exit(0)
     if "--only-c2" in sys.argv:
         batch8_fixture(vae, losses)
         sys.exit(0)
     wfc_mats_fixtures()
+    tiles_post_fixture()
     small_fixture(vae, losses, "tiny_step.npz", TINY, 16, 2, 100, 7)
     small_fixture(vae, losses, "tiny_down_step.npz", TINY_DOWN, 32, 2, 100, 11)
     if "--skip-full" not in sys.argv:

@@ -171,6 +171,17 @@ def argmax_tiles(wave_nhwc):
     return np.argmax(np.asarray(wave_nhwc), axis=-1)
 
 
+def add_symmetry(tile_result, mapping):
+    """Mirror symmetry of a tile map (reference wfd/scmap/data_processing.py:191-196): (H, W) -> (H, 2 W)."""
+    tile_result = np.asarray(tile_result)
+    return np.concatenate([tile_result, np.asarray(mapping)[tile_result[:, ::-1]]], axis=1)
+
+
+def tiles_to_sc(tile_result, shrink_to_gen, gen_to_sc):
+    """Shrink ids -> StarCraft tile ids (reference wfd/scmap/map_display.py:55, data_processing.py:206-211)."""
+    return np.asarray(gen_to_sc)[np.asarray(shrink_to_gen)[np.asarray(tile_result)]]
+
+
 def ddim_coefficients(num_inference_steps=50, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012):
     """a_i, b_i of prev = a_i * x + b_i * eps for DDIM(eta=0) on SD's scaled-linear betas: the affine scheduler.step
     stand-in of the synthetic 50-step loop. d prev / d x = a_i is the chain factor the guidance block

@@ -114,6 +114,14 @@ def test_oracle_matches_reference_ice_c2_batch8_slot():
     assert np.linalg.norm(r["grad"].numpy() - g) <= 1e-3 * np.linalg.norm(g)
 
 
+def test_tile_post_processing_against_the_reference():
+    """add_symmetry and the id chain of the oracle against outputs of the reference's own functions (tiles_post.npz)."""
+    z = np.load(os.path.join(GOLD, "tiles_post.npz"))
+    mirrored = orc.add_symmetry(z["tiles"], z["mapping"])
+    assert mirrored.shape == (12, 18) and np.array_equal(mirrored, z["mirrored"])
+    assert np.array_equal(orc.tiles_to_sc(mirrored, z["shrink_to_gen"], z["gen_to_sc"]), z["sc"])
+
+
 def test_ddim_coefficients_shape():
     a, b = orc.ddim_coefficients(50)
     assert a.shape == (50,) and b.shape == (50,) and (a > 1.0).all() and a[0] > a[-1] and (b < 0).all()

@@ -313,3 +313,42 @@ def test_rule_violation_count_of_tile_maps():
     assert got.tolist() == [[2, 1]]
     # (H, W) input is treated as a batch of one
     assert loss.count_violations(torch.zeros(4, 4, dtype=torch.int64, device="cuda")).shape == (1, 2)
+
+
+def test_tile_post_processing_is_bit_exact():
+    """Integer work after the argmax (ui.py:228-243): mirror symmetry + gen_to_sc[shrink_to_gen[.]] on the device against
+    the oracle's numpy restatement, including ids in the padded channels (counted, mapped to 0xFFFF) and ragged sizes."""
+    from wavefunctiondiffusion_b200.scmap_ops import TileTables, finish_tiles, wave_to_map
+
+    rng = np.random.RandomState(3)
+    T, T_gen = 307, 449
+    s2g = rng.permutation(T_gen)[:T].astype(np.int64)
+    g2s = rng.randint(0, 32624, size=T_gen).astype(np.int32)
+    mapping = rng.permutation(T).astype(np.int64)
+    tables = TileTables(s2g, g2s, mapping, "cuda")
+    for (B, H, W) in ((1, 1, 1), (2, 7, 5), (3, 64, 64)):
+        tiles = rng.randint(0, T, size=(B, H, W)).astype(np.int64)
+        t_out, sc, bad = finish_tiles(torch.from_numpy(tiles).cuda(), tables, symmetry=False)
+        assert bad.item() == 0 and torch.equal(t_out.cpu(), torch.from_numpy(tiles))
+        assert np.array_equal(sc.cpu().numpy().astype(np.int64), np.stack([orc.tiles_to_sc(t, s2g, g2s) for t in tiles]))
+        t_out, sc, bad = finish_tiles(torch.from_numpy(tiles).cuda(), tables, symmetry=True)
+        want_t = np.stack([orc.add_symmetry(t, mapping) for t in tiles])
+        assert bad.item() == 0 and np.array_equal(t_out.cpu().numpy(), want_t) and t_out.shape == (B, H, 2 * W)
+        assert np.array_equal(sc.cpu().numpy().astype(np.int64), np.stack([orc.tiles_to_sc(t, s2g, g2s) for t in want_t]))
+    # the shipped ice tables and outputs of the reference's own add_symmetry / id chain (oracle/make_golden.py)
+    z = np.load(os.path.join(GOLD, "tiles_post.npz"))
+    ice = TileTables(z["shrink_to_gen"], z["gen_to_sc"], z["mapping"], "cuda")
+    t_out, sc, bad = finish_tiles(torch.from_numpy(z["tiles"].astype(np.int64)).cuda(), ice, symmetry=True)
+    assert bad.item() == 0 and np.array_equal(t_out[0].cpu().numpy(), z["mirrored"])
+    assert np.array_equal(sc[0].cpu().numpy().astype(np.int64), z["sc"].astype(np.int64))
+    # an id from the padded channels: numpy would raise, the kernel flags it
+    tiles = np.zeros((1, 2, 3), dtype=np.int64)
+    tiles[0, 1, 2] = T + 3
+    _, sc, bad = finish_tiles(torch.from_numpy(tiles).cuda(), tables)
+    assert bad.item() == 1 and sc[0, 1, 2].item() == 0xFFFF and sc[0, 0, 0].item() == g2s[s2g[0]]
+    # fused: wave -> argmax over the first T channels -> map
+    wave = torch.rand(2, 8, 8, 384, device="cuda").bfloat16()
+    t_out, sc, bad = wave_to_map(wave, tables, count=T)
+    want = np.argmax(wave[..., :T].float().cpu().numpy(), axis=-1)
+    assert bad.item() == 0 and np.array_equal(t_out.cpu().numpy(), want)
+    assert np.array_equal(sc.cpu().numpy().astype(np.int64), np.stack([orc.tiles_to_sc(t, s2g, g2s) for t in want]))

@@ -53,6 +53,27 @@ def test_guidance_block_applies_the_scheduler_chain_factor(tmp_path):
     assert _rel((lat - new).cpu(), a * want["grad"]) < 5e-2
 
 
+def test_final_stage_loop_as_one_captured_sequence(tmp_path, monkeypatch):
+    """pipeline_wfd.py:626-639 (20 guidance-only iterations on the last noise prediction): the library's fused loop
+    (scheduler step, decode, loss, backward, latent update of every iteration in one captured launch sequence) against
+    the same loop written as the reference writes it (scheduler.step under autograd, one wfc_guidance call per
+    iteration)."""
+    pipe, z, cfg, mats, net = _tiny_pipeline(tmp_path)
+    pipe.scheduler.set_timesteps(50, device="cuda")
+    t = pipe.scheduler.timesteps[-1]
+    lat = torch.from_numpy(z["latents"]).cuda()
+    eps = torch.randn(lat.shape, generator=torch.Generator().manual_seed(5)).cuda()
+    fused = pipe.wfc_guidance_final(lat, eps, t, 10.0, 6)
+    monkeypatch.setenv("WFD_FUSED_FINAL", "0")
+    plain = pipe.wfc_guidance_final(lat, eps, t, 10.0, 6)
+    assert torch.isfinite(fused).all() and (fused - lat).abs().max() > 0
+    assert _rel((fused - lat).cpu(), (plain - lat).cpu()) < 2e-2
+    # one iteration of the loop is the guidance block itself
+    monkeypatch.setenv("WFD_FUSED_FINAL", "1")
+    one = pipe.wfc_guidance_final(lat, eps, t, 10.0, 1)
+    assert _rel((one - lat).cpu(), (pipe.wfc_guidance(lat, eps, t, 10.0) - lat).cpu()) < 2e-2
+
+
 def test_call_signature_outputs_and_errors(tmp_path):
     pipe, z, cfg, mats, net = _tiny_pipeline(tmp_path)
     out = pipe(["a b", "c"], height=128, width=128, num_inference_steps=6, guidance_scale=3.5,

@@ -79,6 +79,9 @@ SIGNATURES = {
     "wfd_wfc_saved_wave": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "wfd_guidance_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wfd_guidance_loop": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                    C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
     "wfd_comm_unique_id": (C.c_int, [C.c_char_p, C.c_void_p]),
     "wfd_comm_create_nccl": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "wfd_loop_group_create": (C.c_void_p, [C.c_int]),
@@ -91,6 +94,8 @@ SIGNATURES = {
     "wfd_wfc_attach_comm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "wfd_wfc_kc_kept": (C.c_double, [C.c_void_p]),
     "wfd_wfc_count_violations": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "wfd_tiles_finish": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                   C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "wfd_argmax_tiles": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "wfd_nchw_to_nhwc16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "wfd_nhwc16_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -308,6 +308,30 @@ int wfd_guidance_step(wfd_decoder* d, wfd_wfc* h, const void* z, int z_dtype, in
 }
 
 double wfd_wfc_kc_kept(const wfd_wfc* h) { return h ? h->w.kc_kept : 0.0; }
+int wfd_guidance_loop(wfd_decoder* d, wfd_wfc* h, float* lat, const float* eps_uncond, const float* eps_text, float cfg_scale,
+                      float a, float b, int B, float in_scale, float strength, int n_steps, void* wfc_saved, float* loss_out,
+                      float* z_scratch, float* dz_scratch, void* stream) {
+    if (!d || !h || !lat || !eps_uncond || !wfc_saved || !loss_out || !z_scratch || !dz_scratch) {
+        set_error("wfd_guidance_loop: null argument");
+        return -1;
+    }
+    if (d->d.band) {
+        set_error("wfd_guidance_loop: row-band plans take the whole plane per call; use wfd_guidance_step");
+        return -3;
+    }
+    const long long n = static_cast<long long>(B) * 4 * d->d.h * d->d.w;
+    for (int s = 0; s < n_steps; ++s) {
+        int rc = guidance_affine(lat, eps_uncond, eps_text, cfg_scale, a, b, z_scratch, n, S(stream));
+        if (rc < 0) return rc;
+        rc = wfd_guidance_step(d, h, z_scratch, 0, B, in_scale, strength, wfc_saved, loss_out + static_cast<size_t>(s) * B,
+                               dz_scratch, stream);
+        if (rc < 0) return rc;
+        rc = guidance_update(lat, dz_scratch, a, n, S(stream));
+        if (rc < 0) return rc;
+    }
+    return 0;
+}
+
 int wfd_wfc_count_violations(const wfd_wfc* h, const long long* tiles, int B, int H, int W, long long* out, void* stream) {
     if (!h || !tiles || !out) {
         set_error("wfd_wfc_count_violations: null argument");
@@ -323,6 +347,17 @@ int wfd_argmax_tiles(const void* x, int dtype, long long rows, int n, long long*
         return -1;
     }
     return argmax_rows(x, dtype, rows, n, out, S(stream));
+}
+
+int wfd_tiles_finish(const long long* tiles, int B, int H, int W, const int* symm, int n_symm, const int* shrink_to_gen,
+                     int n_shrink, const int* gen_to_sc, int n_gen, long long* tiles_out, uint16_t* sc_out, long long* bad,
+                     void* stream) {
+    if (!tiles || !gen_to_sc || !bad) {
+        set_error("wfd_tiles_finish: null argument");
+        return -1;
+    }
+    return tiles_finish(tiles, B, H, W, symm, n_symm, shrink_to_gen, n_shrink, gen_to_sc, n_gen, tiles_out, sc_out, bad,
+                        S(stream));
 }
 
 int wfd_nchw_to_nhwc16(const void* in, int in_dtype, void* out, int B, int C, int HW, int dtype16, void* stream) {

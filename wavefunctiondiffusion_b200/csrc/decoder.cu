@@ -820,7 +820,7 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
     if (!ex.prepare) {
         CUDA_CK(cudaMemsetAsync(ws + o_gn, 0, static_cast<size_t>(n_gn) * B_max * G * 2 * sizeof(acc_t), s));
         CK(latent_in(z, z_f16, in_scale, vecs["post_quant_conv.weight"], vecs["post_quant_conv.bias"],
-                     vecs["decoder.conv_in.weight"], vecs["decoder.conv_in.bias"], x, B, h, w, Cm, bf16, s, band_r * h,
+                     vecs["decoder.conv_in.weight.T"], vecs["decoder.conv_in.bias"], x, B, h, w, Cm, bf16, s, band_r * h,
                      h_total));
     }
     int cur_h = h, cur_w = w;

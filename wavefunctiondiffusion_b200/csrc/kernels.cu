@@ -522,12 +522,14 @@ int gn_bwd(const void* dy, const void* x, const acc_t* sums, const float* gamma,
 }
 
 // ------------------------------------------------------------------------------------------------ latent side
-// One block per (row segment of LI_PIX pixels, sample). u = pq(z*in_scale) is staged with a one-pixel halo.
+// One block per (row segment of LI_PIX pixels, sample). u = pq(z*in_scale) is staged with a one-pixel halo; a thread then
+// owns FOUR output channels and LI_PIX / 2 pixels: per (tap, latent channel) one 16-byte weight load (transposed layout
+// [ky][kx][ci][co]) feeds 4 x 8 accumulators, and every pixel leaves as one 8-byte store.
 constexpr int LI_PIX = 16;
 template <bool BF16>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 latent_in_k(const void* __restrict__ z, int z_f16, float in_scale, const float* __restrict__ pq_w,
-            const float* __restrict__ pq_b, const float* __restrict__ w, const float* __restrict__ bias,
+            const float* __restrict__ pq_b, const float* __restrict__ wt, const float* __restrict__ bias,
             uint16_t* __restrict__ out, int h, int wd, int Cm, int y_off, int h_total) {
     // rows [y_off, y_off + h) of a z plane of h_total rows are produced (row bands); out is the local band
     __shared__ float u[3][LI_PIX + 2][4];
@@ -556,74 +558,112 @@ latent_in_k(const void* __restrict__ z, int z_f16, float in_scale, const float* 
         for (int ci = 0; ci < 4; ++ci) u[r][c][ci] = v[ci];
     }
     __syncthreads();
-    for (int co = threadIdx.x; co < Cm; co += blockDim.x) {
-        float wr[36];
+    const int quads = Cm / 4;
+    constexpr int PH = LI_PIX / 2;
+    for (int item = threadIdx.x; item < 2 * quads; item += blockDim.x) {
+        const int q = item % quads, half = item / quads;
+        const int co = q * 4, px0 = half * PH;
+        const float4 bs = __ldg(reinterpret_cast<const float4*>(bias + co));
+        float acc[PH][4];
 #pragma unroll
-        for (int i = 0; i < 36; ++i) wr[i] = __ldg(w + co * 36 + i);  // [ci][ky][kx]
-        const float bs = __ldg(bias + co);
-        for (int px = 0; px < LI_PIX; ++px) {
-            if (x0 + px >= wd) break;
-            float a = bs;
+        for (int p = 0; p < PH; ++p) {
+            acc[p][0] = bs.x; acc[p][1] = bs.y; acc[p][2] = bs.z; acc[p][3] = bs.w;
+        }
 #pragma unroll
-            for (int ci = 0; ci < 4; ++ci)
+        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) a += wr[ci * 9 + ky * 3 + kx] * u[ky][px + kx][ci];
-            out[((static_cast<long long>(b) * h + y) * wd + x0 + px) * Cm + co] = f_to_u16<BF16>(a);
+                for (int ci = 0; ci < 4; ++ci) {
+                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(wt + ((ky * 3 + kx) * 4 + ci) * Cm + co));
+#pragma unroll
+                    for (int p = 0; p < PH; ++p) {
+                        const float uv = u[ky][px0 + p + kx][ci];
+                        acc[p][0] = fmaf(w4.x, uv, acc[p][0]);
+                        acc[p][1] = fmaf(w4.y, uv, acc[p][1]);
+                        acc[p][2] = fmaf(w4.z, uv, acc[p][2]);
+                        acc[p][3] = fmaf(w4.w, uv, acc[p][3]);
+                    }
+                }
+#pragma unroll
+        for (int p = 0; p < PH; ++p) {
+            if (x0 + px0 + p >= wd) break;
+            uint2 o;
+            o.x = static_cast<uint32_t>(f_to_u16<BF16>(acc[p][0])) | (static_cast<uint32_t>(f_to_u16<BF16>(acc[p][1])) << 16);
+            o.y = static_cast<uint32_t>(f_to_u16<BF16>(acc[p][2])) | (static_cast<uint32_t>(f_to_u16<BF16>(acc[p][3])) << 16);
+            *reinterpret_cast<uint2*>(out + ((static_cast<long long>(b) * h + y) * wd + x0 + px0 + p) * Cm + co) = o;
         }
     }
 }
 
-int latent_in(const void* z, int z_f16, float in_scale, const float* pq_w, const float* pq_b, const float* w,
+// `wt` is the transposed conv_in weight [ky][kx][ci][co] (the layout latent_out reads too)
+int latent_in(const void* z, int z_f16, float in_scale, const float* pq_w, const float* pq_b, const float* wt,
               const float* b, void* out, int B, int h, int wd, int Cm, int bf16, cudaStream_t s, int y_off,
               int h_total) {
     ProfScope prof_scope("latent_in", s);
     if (h_total <= 0) h_total = h;
+    if (Cm % 4) {
+        set_error("latent_in: channel count %d must be a multiple of 4", Cm);
+        return -3;
+    }
     dim3 grid((wd + LI_PIX - 1) / LI_PIX, h, B);
-    WFD_DISPATCH_BF16(bf16, (latent_in_k<BF16><<<grid, 128, 0, s>>>(z, z_f16, in_scale, pq_w, pq_b, w, b,
+    WFD_DISPATCH_BF16(bf16, (latent_in_k<BF16><<<grid, 256, 0, s>>>(z, z_f16, in_scale, pq_w, pq_b, wt, b,
                                                                    static_cast<uint16_t*>(out), h, wd, Cm, y_off, h_total)));
     WFD_CHECK_LAUNCH("latent_in");
     return 0;
 }
 
-// One warp per latent pixel: d_u[ci] = sum_{tap,co} dy[q - off(tap), co] * w[co, ci, tap]; dz = in_scale * pq_w^T d_u.
+// conv_in^T + post_quant_conv^T: one warp per latent pixel, the nine incoming-gradient rows read as 16-byte vectors (8
+// channels per lane), the transposed conv_in weights [tap][ci][co] staged once per block in shared memory; blocks walk the
+// pixels grid-stride. d_u[ci] = sum_{tap,co} dy[q - off(tap), co] * w[co, ci, tap]; dz = in_scale * pq_w^T d_u.
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 latent_out_k(const uint16_t* __restrict__ dy, float in_scale, const float* __restrict__ scale_b,
              const float* __restrict__ pq_w, const float* __restrict__ wt, float* __restrict__ dz, int B, int h, int wd,
              int Cm, int y_off, int h_total) {
     // row bands: dy has valid halo rows -1 and h wherever those rows are inside the h_total-row plane
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    extern __shared__ float w_s[];  // [9][4][Cm]
+    for (int i = threadIdx.x; i < 36 * Cm; i += blockDim.x) w_s[i] = __ldg(wt + i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int total = B * h * wd;
-    if (warp >= total) return;
-    const int b = warp / (h * wd);
-    const int pr = warp - b * h * wd;
-    const int y = pr / wd, x = pr - y * wd;
-    float du[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int ky = 0; ky < 3; ++ky) {
-        const int ys = y - (ky - 1);
-        if (ys + y_off < 0 || ys + y_off >= h_total) continue;
-        for (int kx = 0; kx < 3; ++kx) {
-            const int xs = x - (kx - 1);
-            if (xs < 0 || xs >= wd) continue;
-            const uint16_t* row = dy + ((static_cast<long long>(b) * h + ys) * wd + xs) * Cm;
-            for (int co = lane; co < Cm; co += 32) {
-                const float g = u16_to_f<BF16>(row[co]);
+    const int nv = Cm / 8;
+    for (int pix = blockIdx.x * wpb + wib; pix < total; pix += gridDim.x * wpb) {
+        const int b = pix / (h * wd);
+        const int pr = pix - b * h * wd;
+        const int y = pr / wd, x = pr - y * wd;
+        float du[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int ky = 0; ky < 3; ++ky) {
+            const int ys = y - (ky - 1);
+            if (ys + y_off < 0 || ys + y_off >= h_total) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int xs = x - (kx - 1);
+                if (xs < 0 || xs >= wd) continue;
+                const uint4* row = reinterpret_cast<const uint4*>(dy + ((static_cast<long long>(b) * h + ys) * wd + xs) * Cm);
+                const float* wk = w_s + (ky * 3 + kx) * 4 * Cm;
+                for (int v = lane; v < nv; v += 32) {
+                    float g[8];
+                    unpack8<BF16>(__ldg(row + v), g);
 #pragma unroll
-                for (int ci = 0; ci < 4; ++ci) du[ci] += g * __ldg(wt + ((ky * 3 + kx) * 4 + ci) * Cm + co);
+                    for (int ci = 0; ci < 4; ++ci) {
+                        const float4 wa = *reinterpret_cast<const float4*>(wk + ci * Cm + v * 8);
+                        const float4 wb = *reinterpret_cast<const float4*>(wk + ci * Cm + v * 8 + 4);
+                        du[ci] += g[0] * wa.x + g[1] * wa.y + g[2] * wa.z + g[3] * wa.w + g[4] * wb.x + g[5] * wb.y +
+                                  g[6] * wb.z + g[7] * wb.w;
+                    }
+                }
             }
         }
-    }
 #pragma unroll
-    for (int ci = 0; ci < 4; ++ci) du[ci] = warp_sum(du[ci]);
-    if (lane < 4) {
-        float a = 0.f;
+        for (int ci = 0; ci < 4; ++ci) du[ci] = warp_sum(du[ci]);
+        if (lane < 4) {
+            float a = 0.f;
 #pragma unroll
-        for (int ci = 0; ci < 4; ++ci) a += pq_w[ci * 4 + lane] * du[ci];
-        a *= in_scale;
-        if (scale_b) a *= scale_b[b];
-        dz[((static_cast<long long>(b) * 4 + lane) * h + y) * wd + x] = a;
+            for (int ci = 0; ci < 4; ++ci) a += pq_w[ci * 4 + lane] * du[ci];
+            a *= in_scale;
+            if (scale_b) a *= scale_b[b];
+            dz[((static_cast<long long>(b) * 4 + lane) * h + y) * wd + x] = a;
+        }
     }
 }
 
@@ -631,11 +671,28 @@ int latent_out(const void* dy, float in_scale, const float* scale_b, const float
                int B, int h, int wd, int Cm, int bf16, cudaStream_t s, int y_off, int h_total) {
     ProfScope prof_scope("latent_out", s);
     if (h_total <= 0) h_total = h;
+    if (Cm % 8 || 36 * static_cast<size_t>(Cm) * sizeof(float) > 200 * 1024) {
+        set_error("latent_out: channel count %d must be a multiple of 8 and its weights must fit shared memory", Cm);
+        return -3;
+    }
+    const size_t smem = 36 * static_cast<size_t>(Cm) * sizeof(float);
     const long long warps = static_cast<long long>(B) * h * wd;
     const int threads = 256;
-    const unsigned blocks = static_cast<unsigned>((warps * 32 + threads - 1) / threads);
-    WFD_DISPATCH_BF16(bf16, (latent_out_k<BF16><<<blocks, threads, 0, s>>>(static_cast<const uint16_t*>(dy), in_scale,
-                                                                         scale_b, pq_w, w, dz, B, h, wd, Cm, y_off, h_total)));
+    long long blocks = (warps + threads / 32 - 1) / (threads / 32);
+    const long long cap = static_cast<long long>(num_sms()) * 2;   // two resident blocks per SM share the staged weights
+    if (blocks > cap) blocks = cap;
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[bf16 ? 1 : 0]) {
+        cudaError_t e = bf16 ? cudaFuncSetAttribute(latent_out_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+                             : cudaFuncSetAttribute(latent_out_k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) {
+            set_error("latent_out: %s", cudaGetErrorString(e));
+            return -8;
+        }
+        attr_done[bf16 ? 1 : 0] = true;
+    }
+    WFD_DISPATCH_BF16(bf16, (latent_out_k<BF16><<<static_cast<unsigned>(blocks), threads, smem, s>>>(
+                                static_cast<const uint16_t*>(dy), in_scale, scale_b, pq_w, w, dz, B, h, wd, Cm, y_off, h_total)));
     WFD_CHECK_LAUNCH("latent_out");
     return 0;
 }
@@ -1114,6 +1171,108 @@ int count_violations(const long long* tiles, const uint8_t* mat_x, const uint8_t
     if (bx > 64) bx = 64;
     count_violations_k<<<dim3(bx, B), 256, 0, s>>>(tiles, mat_x, mat_y, T, H, W, reinterpret_cast<unsigned long long*>(out));
     WFD_CHECK_LAUNCH("count_violations");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ guidance-loop glue
+// The elementwise work around the guidance step when scheduler.step is affine in the latents, prev = a x + b eps
+// (DDIM eta = 0, PNDM/PLMS; reference pipeline_wfd.py:601-603, 611-614 and the final-stage twin :630-637):
+//   z    = a * lat + b * (eps_u + g * (eps_t - eps_u))        classifier-free combine + scheduler.step in one pass
+//   lat -= a * dz                                              chain factor of the step applied to d loss / d z, latent update
+__global__ void guidance_affine_k(const float* __restrict__ lat, const float* __restrict__ eps_u,
+                                  const float* __restrict__ eps_t, float g, float a, float b, float* __restrict__ z,
+                                  long long n) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float e = eps_u[i];
+        if (eps_t) e = e + g * (eps_t[i] - e);
+        z[i] = a * lat[i] + b * e;
+    }
+}
+__global__ void guidance_update_k(float* __restrict__ lat, const float* __restrict__ dz, float a, long long n) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        lat[i] = lat[i] - a * dz[i];
+}
+static unsigned ew_blocks_decl(long long n, int threads);
+int guidance_affine(const float* lat, const float* eps_u, const float* eps_t, float g, float a, float b, float* z,
+                    long long n, cudaStream_t s) {
+    ProfScope prof_scope("guidance_affine", s);
+    guidance_affine_k<<<ew_blocks_decl(n, 256), 256, 0, s>>>(lat, eps_u, eps_t, g, a, b, z, n);
+    WFD_CHECK_LAUNCH("guidance_affine");
+    return 0;
+}
+int guidance_update(float* lat, const float* dz, float a, long long n, cudaStream_t s) {
+    ProfScope prof_scope("guidance_update", s);
+    guidance_update_k<<<ew_blocks_decl(n, 256), 256, 0, s>>>(lat, dz, a, n);
+    WFD_CHECK_LAUNCH("guidance_update");
+    return 0;
+}
+
+static unsigned ew_blocks_decl(long long n, int threads) {
+    long long b = (n + threads - 1) / threads;
+    const long long cap = static_cast<long long>(num_sms()) * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return static_cast<unsigned>(b);
+}
+
+// ------------------------------------------------------------------------------------------------ tile post-processing
+// What the reference's callers do on the host after the argmax (wfd/webui/ui.py:228-243): optional mirror symmetry
+// (scmap/data_processing.py:191-196: [tiles | mapping[tiles reversed along x]]) and the id chain
+// gen_to_sc[shrink_to_gen[tile]] (scmap/map_display.py:55, data_processing.py:206-211). Integer gathers, bit-exact.
+__global__ void __launch_bounds__(256)
+tiles_finish_k(const long long* __restrict__ tiles, int B, int H, int W, const int* __restrict__ symm, int n_symm,
+               const int* __restrict__ shrink_to_gen, int n_shrink, const int* __restrict__ gen_to_sc, int n_gen,
+               long long* __restrict__ tiles_out, uint16_t* __restrict__ sc_out, unsigned long long* __restrict__ bad) {
+    const int Wo = symm ? 2 * W : W;
+    const long long total = static_cast<long long>(B) * H * Wo;
+    unsigned int my_bad = 0u;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(i % Wo);
+        const long long row = i / Wo;  // b * H + y
+        long long t;
+        bool ok = true;
+        if (x < W) {
+            t = tiles[row * W + x];
+        } else {
+            const long long src = tiles[row * W + (2 * W - 1 - x)];  // mirrored column
+            ok = src >= 0 && src < n_symm;
+            t = ok ? symm[src] : -1;
+        }
+        if (tiles_out) tiles_out[i] = t;
+        int sc = 0xFFFF;
+        if (ok && t >= 0 && t < n_shrink) {
+            const int g = shrink_to_gen ? shrink_to_gen[t] : static_cast<int>(t);
+            if (g >= 0 && g < n_gen) sc = gen_to_sc[g];
+            else ok = false;
+        } else {
+            ok = false;
+        }
+        if (!ok) ++my_bad;
+        if (sc_out) sc_out[i] = static_cast<uint16_t>(sc);
+    }
+    if (my_bad) atomicAdd(bad, static_cast<unsigned long long>(my_bad));
+}
+int tiles_finish(const long long* tiles, int B, int H, int W, const int* symm, int n_symm, const int* shrink_to_gen,
+                 int n_shrink, const int* gen_to_sc, int n_gen, long long* tiles_out, uint16_t* sc_out, long long* bad,
+                 cudaStream_t s) {
+    ProfScope prof_scope("tiles_finish", s);
+    if (B < 1 || H < 1 || W < 1 || !gen_to_sc || n_gen < 1 || !bad) {
+        set_error("tiles_finish: bad arguments (B=%d H=%d W=%d n_gen=%d)", B, H, W, n_gen);
+        return -3;
+    }
+    if (!shrink_to_gen) n_shrink = n_gen;
+    cudaError_t e = cudaMemsetAsync(bad, 0, sizeof(long long), s);
+    if (e != cudaSuccess) {
+        set_error("tiles_finish: %s", cudaGetErrorString(e));
+        return -8;
+    }
+    const long long total = static_cast<long long>(B) * H * (symm ? 2 * W : W);
+    tiles_finish_k<<<ew_blocks_decl(total, 256), 256, 0, s>>>(tiles, B, H, W, symm, n_symm, shrink_to_gen, n_shrink, gen_to_sc,
+                                                             n_gen, tiles_out, sc_out, reinterpret_cast<unsigned long long*>(bad));
+    WFD_CHECK_LAUNCH("tiles_finish");
     return 0;
 }
 

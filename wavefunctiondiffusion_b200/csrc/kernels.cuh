@@ -70,6 +70,20 @@ int argmax_rows(const void* x, int dtype, long long rows, int n, long long* out,
 int count_violations(const long long* tiles, const uint8_t* mat_x, const uint8_t* mat_y, int T, int B, int H, int W,
                      long long* out, cudaStream_t s);
 
+// ---- what the reference's callers do with the argmax tiles on the host (ui.py:228-243): optional mirror symmetry
+// [tiles | symm[tiles reversed along x]] (data_processing.py:191-196), then sc = gen_to_sc[shrink_to_gen[tile]]
+// (map_display.py:55). tiles int64 [B, H, W]; tiles_out int64 [B, H, W'] / sc_out uint16 [B, H, W'] (either may be
+// null), W' = 2 W with symmetry; *bad counts ids that fall outside a table (padded channels): they map to 0xFFFF.
+int tiles_finish(const long long* tiles, int B, int H, int W, const int* symm, int n_symm, const int* shrink_to_gen,
+                 int n_shrink, const int* gen_to_sc, int n_gen, long long* tiles_out, uint16_t* sc_out, long long* bad,
+                 cudaStream_t s);
+
+// ---- elementwise glue of the guidance loop for affine schedulers (pipeline_wfd.py:601-603, 611-614, 630-637):
+// z = a lat + b (eps_u + g (eps_t - eps_u)) (eps_t may be null: eps = eps_u), and lat -= a dz
+int guidance_affine(const float* lat, const float* eps_u, const float* eps_t, float g, float a, float b, float* z,
+                    long long n, cudaStream_t s);
+int guidance_update(float* lat, const float* dz, float a, long long n, cudaStream_t s);
+
 // ---- layout conversion at the API boundary: NCHW (fp32/fp16) <-> channels-last 16-bit
 int nchw_to_nhwc16(const void* in, int in_f16, void* out, int B, int C, int HW, int bf16, cudaStream_t s);
 int nhwc16_to_nchw(const void* in, void* out, int out_f16, int B, int C, int HW, int bf16, cudaStream_t s);

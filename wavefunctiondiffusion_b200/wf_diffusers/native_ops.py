@@ -375,6 +375,71 @@ class GraphedGuidanceStep:
         return self.loss, self.dz
 
 
+class GraphedGuidanceLoop:
+    """n_steps guided latent updates for an affine scheduler step (prev = a x + b eps) as ONE captured launch sequence:
+    wfd_guidance_loop = the body of the reference's final-stage loop (pipeline_wfd.py:626-639) without a host round trip
+    between its iterations. Static buffers; a, b, strength and n_steps are part of the capture."""
+
+    def __init__(self, plan, handle, B, h, w, a, b, in_scale, strength, n_steps, device):
+        import weakref
+
+        self._plan, self.handle = weakref.ref(plan), handle
+        self.lat = torch.zeros((B, 4, h, w), dtype=torch.float32, device=device)
+        self.eps = torch.zeros_like(self.lat)
+        self.z = torch.empty_like(self.lat)
+        self.dz = torch.empty_like(self.lat)
+        self.loss = torch.empty((n_steps, B), dtype=torch.float32, device=device)
+        saved = handle.saved_ptr(B, plan.H, plan.W)
+
+        def run(steps):
+            nat.check(nat.lib().wfd_guidance_loop(plan.handle, handle.handle, C.c_void_p(self.lat.data_ptr()),
+                                                  C.c_void_p(self.eps.data_ptr()), None, 0.0, float(a), float(b), B,
+                                                  float(in_scale), float(strength), steps, saved,
+                                                  C.c_void_p(self.loss.data_ptr()), C.c_void_p(self.z.data_ptr()),
+                                                  C.c_void_p(self.dz.data_ptr()), nat.stream_ptr()), "wfd_guidance_loop")
+
+        cur = torch.cuda.current_stream(device)
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            run(1)  # warm-up outside capture: function attributes, tensor maps
+        cur.wait_stream(side)
+        torch.cuda.synchronize(device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            run(n_steps)
+        self.saved_owner = handle._saved
+        self.n_steps = n_steps
+
+    def valid(self):
+        return self.saved_owner is self.handle._saved
+
+    def __call__(self, latents, eps):
+        self.lat.copy_(latents)
+        self.eps.copy_(eps)
+        self._plan().generation += 1
+        self.graph.replay()
+        return self.lat.clone(), self.loss
+
+
+def guidance_loop(latents, eps, native, handle, a, b, in_scale, strength, n_steps):
+    """latents, eps: (B, 4, h, w) fp32 on the device -> (new latents, losses (n_steps, B)) after n_steps updates
+    lat -= a * d/dz [strength * wfc_loss(softmax(decode((a lat + b eps) * in_scale)))]."""
+    _require_cuda(latents, "guidance loop")
+    B, _, h, w = latents.shape
+    plan = native.plan(B, h, w, latents.device)
+    cache = plan.__dict__.setdefault("_graphs", {})
+    key = ("loop", id(handle), B, float(a), float(b), float(in_scale), float(strength), int(n_steps),
+           torch.cuda.current_stream().cuda_stream)
+    g = cache.get(key)
+    if g is None or not g.valid() or g.handle is not handle:
+        if len(cache) > 8:
+            cache.clear()
+        g = GraphedGuidanceLoop(plan, handle, B, h, w, a, b, in_scale, strength, n_steps, latents.device)
+        cache[key] = g
+    return g(latents.float(), eps.float())
+
+
 class GuidanceLossFunction(torch.autograd.Function):
     """Fused guidance loss: loss[b] = strength * WFCLossEinsum(softmax(decode(latents * in_scale)))[b]
     (reference pipeline_wfd.py:612 with decode_latents_tile :402-408). One library call computes loss and d loss / d

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from ..wfdf.losses import WFCLossEinsum
-from .native_ops import GuidanceLossFunction
+from .native_ops import GuidanceLossFunction, cuda_graphs_enabled, guidance_loop, max_micro_batch
 
 LATENT_SCALE = 0.18215
 
@@ -229,6 +229,39 @@ class WaveFunctionDiffusionPipeline:
             cond_grad = -torch.autograd.grad(_loss.sum(), _latents)[0]
         return latents.detach() + cond_grad.to(latents.dtype)
 
+    def _affine_step(self, t):
+        """(a, b) with scheduler.step(eps, t, x).prev_sample == a * x + b * eps, for schedulers that state them through a
+        `coefficients(t)` method (DDIM eta = 0, PNDM/PLMS are affine in the sample; a maintainer adds the five lines to
+        theirs); None otherwise - the generic autograd route then applies the chain factor."""
+        f = getattr(self.scheduler, "coefficients", None)
+        if f is None:
+            return None
+        a, b = f(t)
+        return float(a), float(b)
+
+    def wfc_guidance_final(self, latents, noise_pred, t, strength, n_steps):
+        """The final-stage loop (reference :626-639): n_steps guidance updates re-using the last noise prediction and
+        timestep. With an affine scheduler step the whole loop is ONE captured launch sequence inside the library
+        (wfd_guidance_loop: scheduler step, decode, loss, backward and latent update of all n_steps iterations, no host
+        round trip in between); otherwise it is n_steps calls of wfc_guidance."""
+        import os
+
+        ab = self._affine_step(t)
+        fused = (ab is not None and not getattr(self, "_row_bands", None) and latents.is_cuda and cuda_graphs_enabled()
+                 and latents.shape[0] <= max_micro_batch() and os.environ.get("WFD_FUSED_FINAL", "1") != "0"
+                 and not torch.cuda.is_current_stream_capturing())
+        if not fused:
+            with self.progress_bar(total=n_steps) as bar:
+                for _ in range(n_steps):
+                    latents = self.wfc_guidance(latents, noise_pred, t, strength)
+                    bar.update()
+            return latents
+        t_pad = self.tile_vae.config.out_channels
+        handle = self.wfc_loss.native_handle(t_pad, latents.device)
+        new, _ = guidance_loop(latents, noise_pred, self.tile_vae._native, handle, ab[0], ab[1], 1.0 / LATENT_SCALE,
+                               float(strength), int(n_steps))
+        return new.to(latents.dtype)
+
     # ------------------------------------------------------------------ third-party stages, used as handed in
     def _encode_prompt(self, prompt, device, num_images_per_prompt, do_classifier_free_guidance, negative_prompt):
         batch_size = len(prompt) if isinstance(prompt, list) else 1
@@ -377,10 +410,7 @@ class WaveFunctionDiffusionPipeline:
                         callback(i, t, latents)
         # final stage: guidance only, re-using the last noise prediction and timestep (reference :626-639)
         if wfc_guidance_final_steps > 0 and wfc_guidance_final_strength != 0:
-            with self.progress_bar(total=wfc_guidance_final_steps) as bar:
-                for _ in range(wfc_guidance_final_steps):
-                    latents = self.wfc_guidance(latents, noise_pred, t, wfc_guidance_final_strength)
-                    bar.update()
+            latents = self.wfc_guidance_final(latents, noise_pred, t, wfc_guidance_final_strength, wfc_guidance_final_steps)
         return latents
 
     def _finish(self, latents, device, dtype, output_type, return_dict):
