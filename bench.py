@@ -342,6 +342,160 @@ def workload_config(args, T, t_pad, per_gpu_batch):
             "l2": "working set per step (activations + operands, several GB) exceeds the 126 MB L2; no flush needed"}
 
 
+def _timed_ms(fn, steps, warmup, dev, world):
+    """Device time of `steps` calls after `warmup`, barrier + synchronize on both sides, max over ranks; ms per call."""
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        fn()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    barrier()
+    ms = torch.tensor([a.elapsed_time(b)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return ms.item() / steps
+
+
+def _guidance_runner(arch, tileset, B, latent, dev, seed_off=0):
+    """(callable running one guidance step of B maps through the library, F_step per map, loss getter) for a config."""
+    import torch
+
+    from wavefunctiondiffusion_b200.utils.tilesets import load_wfc_mats, round_up_channels, tilenet_config
+    from wavefunctiondiffusion_b200.wf_diffusers.native_ops import GuidanceLossFunction
+    from wavefunctiondiffusion_b200.wf_diffusers.wf_vae import AutoencoderTile
+    from wavefunctiondiffusion_b200.wfdf.losses import WFCLossEinsum
+
+    mx, my = load_wfc_mats(tileset)
+    T = mx.shape[0]
+    t_pad = round_up_channels(T)
+    cfg = tilenet_config(arch, t_pad)
+    torch.manual_seed(0)
+    net = AutoencoderTile(**cfg).eval().to(dev)
+    handle = WFCLossEinsum(mx, my).to(dev).native_handle(t_pad, dev)
+    lat = torch.randn(B, 4, latent, latent, generator=torch.Generator().manual_seed(1234 + seed_off)).to(dev)
+    box = {}
+
+    def step():
+        box["loss"] = GuidanceLossFunction.apply(lat, net._native, handle, 1.0 / LATENT_SCALE, STRENGTH)
+
+    return step, step_flops(cfg, latent, latent, T)["F_step"], (lambda: box["loss"]), net
+
+
+def extra_configs(args, world, rank, dev, peak):
+    """The other BASELINE configs under the driver's own command, as sub-objects of the one JSON line (the headline
+    value stays config 2). One GPU: config 1 (batch 1), config 4's map on a single GPU, config 5 (32x32 architecture,
+    batch 256 in micro-batches). N GPUs: config 3 (8 tilesets x 8 maps, balanced over the ranks by F_step) and config 4
+    in row bands (one 256x256 map over all ranks, strong scaling). Every rank must call this."""
+    import gc
+
+    import torch
+    import torch.distributed as dist
+
+    from wavefunctiondiffusion_b200.utils.sharding import balance_by_cost
+
+    out = {}
+
+    def free():
+        gc.collect()
+        torch.cuda.empty_cache()
+
+    def single(name, arch, tileset, B, latent, steps):
+        step, f_map, get_loss, net = _guidance_runner(arch, tileset, B, latent, dev)
+        ms = _timed_ms(step, steps, 2, dev, 1)
+        out[name] = {"workload": "%s, %s architecture, %dx%d latents, batch %d" % (tileset, arch, latent, latent, B),
+                     "ms_per_step": ms, "maps_per_s": B / (ms / 1e3), "loss_check": float(get_loss()[0]),
+                     "frac_of_ideal": (f_map * B / (peak * 1e12)) / (ms / 1e3)}
+        del step, get_loss, net
+        free()
+
+    if world == 1:
+        single("config1_ice_64x64_batch1", "64x64", "ice_64x64", 1, 64, 10)
+        single("config4_ice_256x256_one_gpu", "64x64", "ice_64x64", 1, 256, 3)
+        single("config5_platform_32x32_batch256", "32x32", "platform_32x32", 256, 64, 2)
+        return out
+    # ---- config 3: 8 tilesets x 8 maps over the ranks, balanced by cost (maps are independent: no data-path collective)
+    names = ["ashworld_64x64", "badlands_64x64", "desert_64x64", "ice_64x64", "install_64x64", "jungle_64x64",
+             "platform_64x64", "twilight_64x64"]
+    from wavefunctiondiffusion_b200.utils.tilesets import load_wfc_mats, round_up_channels, tilenet_config
+
+    costs = []
+    for n in names:
+        T = load_wfc_mats(n)[0].shape[0]
+        f = step_flops(tilenet_config("64x64", round_up_channels(T)), 64, 64, T)["F_step"]
+        costs += [f] * 8
+    assign = balance_by_cost(costs, world)
+    mine = {}
+    for i in assign[rank]:
+        mine[names[i // 8]] = mine.get(names[i // 8], 0) + 1
+    runners = [_guidance_runner("64x64", n, b, 64, dev, seed_off=rank)[0] for n, b in sorted(mine.items())]
+
+    def step3():
+        for r in runners:
+            r()
+
+    ms3 = _timed_ms(step3, 5, 2, dev, world)
+    loads = [sum(costs[i] for i in a) for a in assign]
+    out["config3_all_tilesets_64_maps"] = {
+        "workload": "8 tilesets x 8 maps (64x64), maps assigned to %d ranks by F_step (greedy longest-processing-time)" % world,
+        "ms_per_step": ms3, "maps_per_s": 64 / (ms3 / 1e3), "maps_per_rank": [len(a) for a in assign],
+        "f_step_balance": max(loads) / (sum(loads) / world),
+        "frac_of_ideal": (sum(costs) / world / (peak * 1e12)) / (ms3 / 1e3)}
+    del runners
+    free()
+    # ---- config 4: ONE 256x256 map in row bands over all ranks (strong scaling); rank 0 first times the single plan
+    t1 = torch.zeros(1, device=dev)
+    if rank == 0:
+        step, _, _, net = _guidance_runner("64x64", "ice_64x64", 1, 256, dev)
+        t1[0] = _timed_ms(step, 3, 2, dev, 1)
+        del step, net
+        free()
+    dist.broadcast(t1, 0)
+    rb = _rowband_core(args, 256, 5, 3, world, rank, dev)
+    out["config4_rowband_256"] = dict(rb, one_gpu_ms_per_step=t1.item(), speedup=t1.item() / rb["ms_per_step"],
+                                      efficiency=t1.item() / rb["ms_per_step"] / world)
+    return out
+
+
+def _rowband_core(args, L, steps, warmup, world, rank, dev):
+    """One L x L ice map split into `world` row bands over NCCL; returns ms per step (graph replay) and the loss."""
+    import torch
+
+    from wavefunctiondiffusion_b200.utils.tilesets import load_wfc_mats, round_up_channels, tilenet_config
+    from wavefunctiondiffusion_b200.wf_diffusers.rowband import BandComm, BandGuidance
+    from wavefunctiondiffusion_b200.wf_diffusers.wf_vae import AutoencoderTile
+
+    mx, my = load_wfc_mats("ice_64x64")
+    t_pad = round_up_channels(mx.shape[0])
+    torch.manual_seed(0)
+    net = AutoencoderTile(**tilenet_config("64x64", t_pad)).eval().to(dev)
+    comm = BandComm.from_torch_distributed(dev)
+    lat = torch.randn(1, 4, L, L, generator=torch.Generator().manual_seed(1234)).to(dev)
+    bg = BandGuidance(net, mx, my, L, L, comm, dev)
+    box = {}
+
+    def step():
+        box["loss"], _ = bg.step(lat, 1.0 / LATENT_SCALE, STRENGTH, graph=True)
+
+    ms = _timed_ms(step, steps, max(warmup, 3), dev, world)
+    loss = float(box["loss"][0])
+    bg.close()
+    comm.close()
+    return {"workload": "ONE ice 256x256 map in %d row bands of %d rows over NCCL (halo rows, GroupNorm sums, keys/values, "
+                        "loss), CUDA-graph replay" % (world, L // world), "ms_per_step": ms, "maps_per_s": 1e3 / ms,
+            "loss_check": loss}
+
+
 def run_native(args):
     import numpy as np
     import torch
@@ -445,6 +599,13 @@ def run_native(args):
         launches = launches_per_step * args.steps  # kernels inside the replayed graph
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
+    extras = None
+    if not args.no_extra_configs:
+        try:
+            peak_tf = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1400.0)
+        except Exception:
+            peak_tf = 1400.0
+        extras = extra_configs(args, world, rank, dev, peak_tf)
     # per-kernel CUDA-event profile of a few extra steps (separate from the timed region) for the roofline numbers
     prof = {}
     if rank == 0:
@@ -552,6 +713,7 @@ def run_native(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "gpu_eager_baseline": eager,
+        "other_configs": extras,
         "loss_check": [float(x) for x in loss.cpu()[:2]],
         "profile_top": [{"kernel": n, "launches_per_step": c, "ms_per_step": t} for n, (c, t) in top],
     }
@@ -726,6 +888,9 @@ def main():
     ap.add_argument("--arch", default="64x64", choices=["64x64", "32x32"])
     ap.add_argument("--latent", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true",
+                    help="skip the other BASELINE configs (other_configs: batch 1, 256x256, 32x32 batch 256; N > 1: "
+                         "all tilesets, row bands)")
     ap.add_argument("--no-eager-baseline", action="store_true",
                     help="skip timing the reference's eager PyTorch path on the GPU (gpu_eager_baseline)")
     ap.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")

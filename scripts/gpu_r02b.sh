@@ -5,7 +5,7 @@ nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I wavefunctiondiffu
 cat $O/mma_rate.txt
 run() { # name, env...
   name=$1; shift
-  env "$@" python bench.py --steps 10 --warmup 3 --verbose --top 14 --no-cpu-baseline > $O/bench_$name.json 2> $O/bench_$name.err
+  env "$@" python bench.py --steps 10 --warmup 3 --verbose --top 14 --no-cpu-baseline --no-extra-configs > $O/bench_$name.json 2> $O/bench_$name.err
   python - $O/bench_$name.json $name <<'PY'
 import json,sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])

@@ -3,7 +3,7 @@
 O=gpurun_out/r02c; mkdir -p $O
 run() { # name, env...
   name=$1; shift
-  env "$@" python bench.py --steps 5 --warmup 3 --verbose --top 40 --no-cpu-baseline > $O/bench_$name.json 2> $O/bench_$name.err
+  env "$@" python bench.py --steps 5 --warmup 3 --verbose --top 40 --no-cpu-baseline --no-extra-configs > $O/bench_$name.json 2> $O/bench_$name.err
   echo "== $name"
   grep "reuse=1" $O/bench_$name.err | sort -k2 | head -12
 }

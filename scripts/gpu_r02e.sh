@@ -5,7 +5,7 @@ timeout 600 python -m pytest tests/test_tapgemm_gpu.py -m gpu -q --timeout 300 -
 timeout 900 python -m pytest tests/test_tapgemm_gpu.py tests/test_parity_gpu.py -m gpu -x -q --timeout 600 > $O/pytest.log 2>&1; echo "pytest rc=$?"; tail -6 $O/pytest.log
 run() { # name, env...
   name=$1; shift
-  env "$@" timeout 300 python bench.py --steps 10 --warmup 3 --verbose --top 60 --no-cpu-baseline > $O/bench_$name.json 2> $O/bench_$name.err
+  env "$@" timeout 300 python bench.py --steps 10 --warmup 3 --verbose --top 60 --no-cpu-baseline --no-extra-configs > $O/bench_$name.json 2> $O/bench_$name.err
   python - $O/bench_$name.json $name <<'PY'
 import json,sys
 try:

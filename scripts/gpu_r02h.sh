@@ -3,7 +3,7 @@
 O=gpurun_out/r02h; mkdir -p $O
 run() { # name, env...
   name=$1; shift
-  env "$@" timeout 300 python bench.py --steps 10 --warmup 3 --verbose --top 60 --no-cpu-baseline --no-eager-baseline > $O/bench_$name.json 2> $O/bench_$name.err
+  env "$@" timeout 300 python bench.py --steps 10 --warmup 3 --verbose --top 60 --no-cpu-baseline --no-eager-baseline --no-extra-configs > $O/bench_$name.json 2> $O/bench_$name.err
   python - $O/bench_$name.json $name <<'PY'
 import json,sys
 try:
