@@ -89,6 +89,27 @@ WFD_API void* wfd_decoder_dlogits(wfd_decoder* d);
 WFD_API int wfd_decoder_import_dlogits(wfd_decoder* d, int B, const void* in, int in_dtype, int layout, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Tile-VAE encoder: AutoencoderTile.encode = quant_conv(EncoderTile(x))   (forward only)
+ *   wfd/wf_diffusers/wf_vae.py:68-148 (EncoderTile), :582-590 (encode); img2img wave input
+ *   wfd/wf_diffusers/pipeline_wfd_img2img.py:68-74 (preprocess_wave), :478-486 (prepare_latents)
+ * cfg: the same struct as the decoder (block_out_channels / conv_groups in config order; out_channels = the wave's channel
+ * count T_pad). Only configurations whose encoder blocks keep the resolution ("EvenEncoderBlock2D": block_down all 0).
+ * Weights by state_dict key: encoder.* and quant_conv.* (others are ignored, returns 1).
+ * moments: fp32 NCHW [B, 2 * latent_channels, H, W] = the `parameters` of the reference's DiagonalGaussianDistribution.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct wfd_encoder wfd_encoder;
+WFD_API int wfd_encoder_create(const wfd_decoder_config* cfg, int H, int W, int B_max, int dtype16, wfd_encoder** out);
+WFD_API void wfd_encoder_destroy(wfd_encoder* e);
+WFD_API int wfd_encoder_set_weight(wfd_encoder* e, const char* key, const float* host_data, long long numel);
+WFD_API int wfd_encoder_finalize_weights(wfd_encoder* e);
+WFD_API size_t wfd_encoder_workspace_bytes(const wfd_encoder* e);
+WFD_API int wfd_encoder_bind_workspace(wfd_encoder* e, void* ws, size_t bytes);
+/* wave: NCHW [B, T_pad, H, W], dtype 0 = fp32, 1 = fp16 (any values: one-hot, soft) */
+WFD_API int wfd_encoder_forward_wave(wfd_encoder* e, const void* wave, int dtype, int B, float* moments, void* stream);
+/* tiles: int64 [B, H, W] = the one-hot wave given by its indices (preprocess_wave): conv_in becomes a gather */
+WFD_API int wfd_encoder_forward_tiles(wfd_encoder* e, const long long* tiles, int B, float* moments, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * WFC transition-rule loss: WFCLossEinsum
  *   wfd/wfdf/losses.py:43-75; buffers built from wfc_mats of wfd/scmap/tile_data/wfc/*.npz (pipeline_wfd.py:180-182)
  *   softmax over all T_pad channels: pipeline_wfd.py:405

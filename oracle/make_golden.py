@@ -9,6 +9,7 @@ AutoencoderTile, whose initialisation order is checked to be bit-identical to th
   tiny_step.npz            reference decode+softmax+loss+grad on a small config, fp64 and fp32
   tiny_down_step.npz       same with a DownDecoderBlock2D (the 32x32-style config)
   ice_c1_step.npz          BASELINE config 1: ice 64x64, batch 1, tilenet_sc_space_64x64, strength 5
+  tiny_encode.npz          reference AutoencoderTile.encode moments of a one-hot tile map and of a soft wave (tiny config)
   tiles_post.npz           the reference's add_symmetry + gen_to_sc[shrink_to_gen[.]] on random ice tiles (with the tables)
   ice_c2_step.npz          BASELINE config 2's benchmarked shape: the same weights, batch 8 (slot 0 = the C1 latents)
 """
@@ -134,6 +135,24 @@ def full_fixture(vae, losses):
     np.savez_compressed(os.path.join(GOLD, "ice_c1_step.npz"), **out)
 
 
+def encode_fixture(vae):
+    """AutoencoderTile.encode of the unmodified reference on a one-hot tile map and on a soft wave (tiny config)."""
+    torch.manual_seed(7)
+    rng = np.random.RandomState(17)
+    tiles = rng.randint(0, 100, size=(2, 16, 16))
+    onehot = torch.nn.functional.one_hot(torch.from_numpy(tiles), num_classes=TINY["in_channels"]).permute(0, 3, 1, 2)
+    soft = torch.softmax(torch.randn(2, TINY["in_channels"], 16, 16, generator=torch.Generator().manual_seed(3)) * 2, dim=1)
+    out = {"tiles": tiles, "soft": soft.numpy(), "seed": 7, "cfg_json": json.dumps(TINY)}
+    for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        torch.manual_seed(7)
+        net = vae.AutoencoderTile(**TINY).eval().to(dtype)
+        with torch.no_grad():
+            out["moments_onehot_" + tag] = net.encode(onehot.to(dtype)).latent_dist.parameters.numpy()
+            out["moments_soft_" + tag] = net.encode(soft.to(dtype)).latent_dist.parameters.numpy()
+    np.savez_compressed(os.path.join(GOLD, "tiny_encode.npz"), **out)
+    print("tiny_encode", out["moments_onehot_f64"].shape, float(np.abs(out["moments_onehot_f64"]).mean()))
+
+
 def tiles_post_fixture():
     """Post-argmax integer work on the ice tileset: the reference's own add_symmetry (wfd/scmap/data_processing.py:191-196,
     executed from where it lies) and the id chain gen_to_sc[shrink_to_gen[.]] (map_display.py:55) on the shipped tables."""
@@ -186,6 +205,9 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     vae, losses = load_reference()
+    if "--only-encode" in sys.argv:
+        encode_fixture(vae)
+        sys.exit(0)
     if "--only-tiles" in sys.argv:
         tiles_post_fixture()
         sys.exit(0)
@@ -194,6 +216,7 @@ if __name__ == "__main__":
         sys.exit(0)
     wfc_mats_fixtures()
     tiles_post_fixture()
+    encode_fixture(vae)
     small_fixture(vae, losses, "tiny_step.npz", TINY, 16, 2, 100, 7)
     small_fixture(vae, losses, "tiny_down_step.npz", TINY_DOWN, 32, 2, 100, 11)
     if "--skip-full" not in sys.argv:

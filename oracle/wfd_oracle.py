@@ -82,6 +82,25 @@ def decode(sd, cfg, z, dtype=torch.float64):
                     groups=cfg["conv_init_groups"])
 
 
+def encode(sd, cfg, x, dtype=torch.float64):
+    """AutoencoderTile.encode moments: quant_conv(EncoderTile.forward(x)) (reference wf_vae.py:582-584, 131-148) for the
+    configurations whose encoder blocks keep the resolution. x: (B, T_pad, H, W) wave (one-hot or soft)."""
+    G = cfg["norm_num_groups"]
+    x = x.to(dtype)
+    x = F.conv2d(x, _p(sd, "encoder.conv_in.weight", dtype), _p(sd, "encoder.conv_in.bias", dtype), padding=1,
+                 groups=cfg["conv_init_groups"])
+    for i, kind in enumerate(cfg["down_block_types"]):
+        assert kind == "EvenEncoderBlock2D", kind
+        for j in range(cfg["layers_per_block"]):
+            x = resnet_block(sd, f"encoder.down_blocks.{i}.resnets.{j}", x, cfg["conv_groups"][i], G, dtype)
+    x = resnet_block(sd, "encoder.mid_block.resnets.0", x, 1, G, dtype)
+    x = attention_block(sd, "encoder.mid_block.attentions.0", x, G, dtype)
+    x = resnet_block(sd, "encoder.mid_block.resnets.1", x, 1, G, dtype)
+    x = F.group_norm(x, G, _p(sd, "encoder.conv_norm_out.weight", dtype), _p(sd, "encoder.conv_norm_out.bias", dtype), 1e-6)
+    x = F.conv2d(F.silu(x), _p(sd, "encoder.conv_out.weight", dtype), _p(sd, "encoder.conv_out.bias", dtype), padding=1)
+    return F.conv2d(x, _p(sd, "quant_conv.weight", dtype), _p(sd, "quant_conv.bias", dtype))
+
+
 # ------------------------------------------------------------------------------------------------ WFC loss
 def wfc_loss(wave, mat_x, mat_y):
     """WFCLossEinsum.forward (reference wfd/wfdf/losses.py:63-75): wave (B, C>=T, H, W) -> (B,).

@@ -114,6 +114,23 @@ def test_oracle_matches_reference_ice_c2_batch8_slot():
     assert np.linalg.norm(r["grad"].numpy() - g) <= 1e-3 * np.linalg.norm(g)
 
 
+def test_oracle_encode_matches_reference():
+    """AutoencoderTile.encode (the img2img wave input): oracle restatement against the reference's moments."""
+    z = np.load(os.path.join(GOLD, "tiny_encode.npz"))
+    cfg = json.loads(str(z["cfg_json"]))
+    torch.manual_seed(int(z["seed"]))
+    net = AutoencoderTile(**cfg)
+    onehot = torch.nn.functional.one_hot(torch.from_numpy(z["tiles"]), num_classes=cfg["in_channels"]).permute(0, 3, 1, 2)
+    m = orc.encode(net.state_dict(), cfg, onehot, torch.float64)
+    assert m.shape == (2, 8, 16, 16) and np.allclose(m.numpy(), z["moments_onehot_f64"], rtol=0, atol=1e-10)
+    m = orc.encode(net.state_dict(), cfg, torch.from_numpy(z["soft"]), torch.float64)
+    assert np.allclose(m.numpy(), z["moments_soft_f64"], rtol=0, atol=1e-10)
+    # the product's eager encoder modules (CPU tensors) are the same arithmetic
+    with torch.no_grad():
+        eager = net.encode(onehot.float()).latent_dist.parameters
+    assert np.allclose(eager.numpy(), z["moments_onehot_f32"], atol=1e-5)
+
+
 def test_tile_post_processing_against_the_reference():
     """add_symmetry and the id chain of the oracle against outputs of the reference's own functions (tiles_post.npz)."""
     z = np.load(os.path.join(GOLD, "tiles_post.npz"))

@@ -70,6 +70,14 @@ SIGNATURES = {
     "wfd_decoder_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "wfd_decoder_dlogits": (C.c_void_p, [C.c_void_p]),
     "wfd_decoder_import_dlogits": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "wfd_encoder_create": (C.c_int, [C.POINTER(DecoderConfig), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "wfd_encoder_destroy": (None, [C.c_void_p]),
+    "wfd_encoder_set_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong]),
+    "wfd_encoder_finalize_weights": (C.c_int, [C.c_void_p]),
+    "wfd_encoder_workspace_bytes": (C.c_size_t, [C.c_void_p]),
+    "wfd_encoder_bind_workspace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "wfd_encoder_forward_wave": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "wfd_encoder_forward_tiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "wfd_wfc_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "wfd_wfc_destroy": (None, [C.c_void_p]),
     "wfd_wfc_saved_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int]),

@@ -14,6 +14,9 @@ struct wfd_decoder {
 struct wfd_wfc {
     Wfc w;
 };
+struct wfd_encoder {
+    Encoder e;
+};
 struct wfd_comm {
     Comm* c = nullptr;
     ~wfd_comm() { delete c; }
@@ -157,6 +160,50 @@ int wfd_decoder_backward(wfd_decoder* d, const void* dlogits, int B, const float
         API_CUDA_CK(cudaMemcpyAsync(D.ws + D.o_dlogits, dlogits, n, cudaMemcpyDeviceToDevice, S(stream)));
     }
     return D.backward(nullptr, B, scale_b, dz, S(stream));
+}
+
+int wfd_encoder_create(const wfd_decoder_config* cfg, int H, int W, int B_max, int dtype16, wfd_encoder** out) {
+    if (!cfg || !out) {
+        set_error("wfd_encoder_create: null argument");
+        return -1;
+    }
+    wfd_encoder* p = new (std::nothrow) wfd_encoder();
+    if (!p) {
+        set_error("wfd_encoder_create: out of host memory");
+        return -1;
+    }
+    int rc = p->e.init_enc(*cfg, H, W, B_max, dtype16);
+    if (rc < 0) {
+        delete p;
+        return rc;
+    }
+    *out = p;
+    return 0;
+}
+void wfd_encoder_destroy(wfd_encoder* e) { delete e; }
+int wfd_encoder_set_weight(wfd_encoder* e, const char* key, const float* host_data, long long numel) {
+    if (!e || !key || !host_data) {
+        set_error("wfd_encoder_set_weight: null argument");
+        return -1;
+    }
+    return e->e.set_weight(key, host_data, numel);
+}
+int wfd_encoder_finalize_weights(wfd_encoder* e) { return e ? e->e.finalize_enc() : -1; }
+size_t wfd_encoder_workspace_bytes(const wfd_encoder* e) { return e ? e->e.ws_bytes : 0; }
+int wfd_encoder_bind_workspace(wfd_encoder* e, void* ws, size_t bytes) { return e ? e->e.bind_workspace_enc(ws, bytes) : -1; }
+int wfd_encoder_forward_wave(wfd_encoder* e, const void* wave, int dtype, int B, float* moments, void* stream) {
+    if (!e || !wave || !moments) {
+        set_error("wfd_encoder_forward_wave: null argument");
+        return -1;
+    }
+    return e->e.encode_wave(wave, dtype, B, moments, S(stream));
+}
+int wfd_encoder_forward_tiles(wfd_encoder* e, const long long* tiles, int B, float* moments, void* stream) {
+    if (!e || !tiles || !moments) {
+        set_error("wfd_encoder_forward_tiles: null argument");
+        return -1;
+    }
+    return e->e.encode_tiles(tiles, B, moments, S(stream));
 }
 
 int wfd_wfc_create(const uint8_t* mat_x, const uint8_t* mat_y, int T, int T_pad, int dtype16, wfd_wfc** out) {

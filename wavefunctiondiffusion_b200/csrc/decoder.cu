@@ -168,7 +168,7 @@ int pack_conv(const float* w, int cout, int cin, int groups, int k, int mode, bo
     return 0;
 }
 
-static int upload_f32(const std::vector<float>& v, float** dev) {
+int upload_f32(const std::vector<float>& v, float** dev) {
     if (*dev) cudaFree(*dev);
     *dev = nullptr;
     CUDA_CK(cudaMalloc(dev, std::max<size_t>(v.size(), 1) * sizeof(float)));
@@ -177,7 +177,7 @@ static int upload_f32(const std::vector<float>& v, float** dev) {
 }
 
 // ------------------------------------------------------------------------------------------------ plan construction
-static bool pick_box(int W, int H, int* w_box, int* h_box) {
+bool pick_box(int W, int H, int* w_box, int* h_box) {
     for (int wb = 128; wb >= 1; wb >>= 1) {
         if (W % wb != 0) continue;
         const int hb = TG_BM / wb;
@@ -383,7 +383,9 @@ void Decoder::layout_workspace() {
 
 int Decoder::set_weight(const char* key, const float* data, long long numel) {
     std::string k(key);
-    if (k.rfind("decoder.", 0) != 0 && k.rfind("post_quant_conv.", 0) != 0) return 1;
+    if (encoder_side ? (k.rfind("encoder.", 0) != 0 && k.rfind("quant_conv.", 0) != 0)
+                     : (k.rfind("decoder.", 0) != 0 && k.rfind("post_quant_conv.", 0) != 0))
+        return 1;
     host[k] = std::vector<float>(data, data + numel);
     finalized = false;
     return 0;
@@ -445,6 +447,35 @@ int Decoder::upload_vec(const std::string& key, long long numel) {
     return 0;
 }
 
+// attention weights: q, k, v merged into one [3C, C] matrix (+ backward form when want_bwd), proj
+int Decoder::pack_attention(const std::string& a, bool want_bwd) {
+    CK(upload_vec(a + "group_norm.weight", Cm));
+    CK(upload_vec(a + "group_norm.bias", Cm));
+    const std::vector<float>*q, *k, *v, *qb, *kb, *vb;
+    const long long cc = static_cast<long long>(Cm) * Cm;
+    CK(need(a + "query.weight", cc, &q));
+    CK(need(a + "key.weight", cc, &k));
+    CK(need(a + "value.weight", cc, &v));
+    CK(need(a + "query.bias", Cm, &qb));
+    CK(need(a + "key.bias", Cm, &kb));
+    CK(need(a + "value.bias", Cm, &vb));
+    std::vector<float> wq(3 * cc), bq(3 * Cm);
+    memcpy(wq.data(), q->data(), cc * 4);
+    memcpy(wq.data() + cc, k->data(), cc * 4);
+    memcpy(wq.data() + 2 * cc, v->data(), cc * 4);
+    memcpy(bq.data(), qb->data(), Cm * 4);
+    memcpy(bq.data() + Cm, kb->data(), Cm * 4);
+    memcpy(bq.data() + 2 * Cm, vb->data(), Cm * 4);
+    ConvW& cq = convs[a + "qkv"];
+    cq.cin = Cm;
+    cq.cout = 3 * Cm;
+    CK(pack_conv(wq.data(), 3 * Cm, Cm, 1, 1, 0, bf16 != 0, Cm % 192 == 0 ? 192 : 0, &cq.fwd, nullptr, 0));
+    if (want_bwd) CK(pack_conv(wq.data(), 3 * Cm, Cm, 1, 1, 1, bf16 != 0, 0, &cq.bwd, nullptr, 0));
+    CK(upload_f32(bq, &cq.bias));
+    CK(pack_named_conv(a + "proj_attn", Cm, Cm, 1, 1, want_bwd, 0, 0, 0));
+    return 0;
+}
+
 int Decoder::finalize_weights() {
     CK(upload_vec("post_quant_conv.weight", 16));
     CK(upload_vec("post_quant_conv.bias", 4));
@@ -490,34 +521,7 @@ int Decoder::finalize_weights() {
                 CK(pack_conv(wv->data(), cch, cch, grp, 3, 1, bf16 != 0, 0, &cw.bwd, &sel, 0));
             }
     }
-    // attention: q,k,v merged into one [3C, C] matrix (+ backward form), v alone as an A operand, proj
-    {
-        const std::string a = "decoder.mid_block.attentions.0.";
-        CK(upload_vec(a + "group_norm.weight", Cm));
-        CK(upload_vec(a + "group_norm.bias", Cm));
-        const std::vector<float>*q, *k, *v, *qb, *kb, *vb;
-        const long long cc = static_cast<long long>(Cm) * Cm;
-        CK(need(a + "query.weight", cc, &q));
-        CK(need(a + "key.weight", cc, &k));
-        CK(need(a + "value.weight", cc, &v));
-        CK(need(a + "query.bias", Cm, &qb));
-        CK(need(a + "key.bias", Cm, &kb));
-        CK(need(a + "value.bias", Cm, &vb));
-        std::vector<float> wq(3 * cc), bq(3 * Cm);
-        memcpy(wq.data(), q->data(), cc * 4);
-        memcpy(wq.data() + cc, k->data(), cc * 4);
-        memcpy(wq.data() + 2 * cc, v->data(), cc * 4);
-        memcpy(bq.data(), qb->data(), Cm * 4);
-        memcpy(bq.data() + Cm, kb->data(), Cm * 4);
-        memcpy(bq.data() + 2 * Cm, vb->data(), Cm * 4);
-        ConvW& cq = convs["attn.qkv"];
-        cq.cin = Cm;
-        cq.cout = 3 * Cm;
-        CK(pack_conv(wq.data(), 3 * Cm, Cm, 1, 1, 0, bf16 != 0, Cm % 192 == 0 ? 192 : 0, &cq.fwd, nullptr, 0));
-        CK(pack_conv(wq.data(), 3 * Cm, Cm, 1, 1, 1, bf16 != 0, 0, &cq.bwd, nullptr, 0));
-        CK(upload_f32(bq, &cq.bias));
-        CK(pack_named_conv(a + "proj_attn", Cm, Cm, 1, 1, true, 0, 0, 0));
-    }
+    CK(pack_attention("decoder.mid_block.attentions.0.", true));
     CK(upload_vec("decoder.conv_norm_out.weight", C_last));
     CK(upload_vec("decoder.conv_norm_out.bias", C_last));
     CK(pack_named_conv("decoder.conv_out", T_pad, C_last, cfg.conv_init_groups, 3, true, 0, H_out, W_out));
@@ -630,7 +634,8 @@ int Decoder::conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int 
         p.kk_last = pk.kk_last;
         p.N = pk.N;
         p.out = out;
-        p.out_fp32 = 0;
+        p.out_fp32 = next_out_fp32 ? 1 : 0;
+        next_out_fp32 = false;
         p.out_sx = os ? os->sx : ldc;
         p.out_sy = os ? os->sy : ldc * Wout;
         p.out_sb = os ? os->sb : ldc * Wout * Hout;
@@ -810,25 +815,20 @@ acc_t* Decoder::gn_red_ptr(int idx) const {
     return reinterpret_cast<acc_t*>(ws + o_gn) + static_cast<size_t>(n_gn + idx) * B_max * G * 2;
 }
 
-// ------------------------------------------------------------------------------------------------ forward
-int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
+// ------------------------------------------------------------------------------------------------ shared forward blocks
+static const char* group_tag_of(int groups) {
+    return groups == 1 ? "dense" : groups == 4 ? "g4" : groups == 16 ? "g16" : groups == 64 ? "g64" : "grouped";
+}
+
+// ResnetBlock2D.forward with temb = None (reference resnet.py:458-499). next_gn: index of the GroupNorm that consumes the
+// output (its statistics ride in conv2's epilogue), or -1 when the consumer computes them itself.
+int Decoder::resnet_forward(Exec& ex, int idx, uint8_t* xin, bool stats_ready, int next_gn) {
     const int B = ex.B;
     cudaStream_t s = ex.stream;
     const float eps = 1e-6f;
-    const int hw = h * w;
-    uint8_t* x = ws + o_x0;
-    if (!ex.prepare) {
-        CUDA_CK(cudaMemsetAsync(ws + o_gn, 0, static_cast<size_t>(n_gn) * B_max * G * 2 * sizeof(acc_t), s));
-        CK(latent_in(z, z_f16, in_scale, vecs["post_quant_conv.weight"], vecs["post_quant_conv.bias"],
-                     vecs["decoder.conv_in.weight.T"], vecs["decoder.conv_in.bias"], x, B, h, w, Cm, bf16, s, band_r * h,
-                     h_total));
-    }
-    int cur_h = h, cur_w = w;
-    int ri = 0;
     auto fused_ok = [&](int C) { return fuse_gn && (C / G) % 16 == 0; };
-    static const char* const group_tag[] = {"dense", "g4", "g16", "g64", "grouped"};
-    auto tag_of = [&](int groups) { return group_tag[groups == 1 ? 0 : groups == 4 ? 1 : groups == 16 ? 2 : groups == 64 ? 3 : 4]; };
-    auto resnet = [&](int idx, uint8_t* xin, bool stats_ready) -> int {
+    auto tag_of = [&](int groups) { return group_tag_of(groups); };
+    {
         const ResnetDesc& r = resnets[idx];
         cur_tag = tag_of(r.groups);
         const int phw = r.h * r.w;
@@ -837,10 +837,6 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
         uint8_t* h1 = ws + o_res_h1[idx];
         uint8_t* xout = ws + o_res_out[idx];
         const int gi1 = 2 * idx, gi2 = 2 * idx + 1;
-        const bool last = idx + 1 == static_cast<int>(resnets.size());
-        // stats of the resnet output feed the next GroupNorm: the next resnet's norm1, the attention norm after
-        // mid.resnets.0, or conv_norm_out after the last resnet
-        int next_gn = last ? n_gn - 1 : (idx == 0 ? n_gn - 2 : 2 * (idx + 1));
         int next_cpg = r.cout / G;
         if (!ex.prepare) {
             if (!stats_ready || !fused_ok(r.cin)) CK(gn_stats(xin, gn_sums_ptr(gi1), B, phw, r.cin, G, bf16, s));
@@ -864,20 +860,20 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
             residual = ws + o_sc;
         }
         const ConvW& c2 = convs[r.prefix + ".conv2"];
-        // a block that ends in a downsample conv re-computes stats after it, so skip the fused stats there
-        bool feeds_down = false;
-        if (idx >= 2) {
-            const int blk = (idx - 2) / (cfg.layers_per_block + 1), j = (idx - 2) % (cfg.layers_per_block + 1);
-            feeds_down = down_after[blk] && j == cfg.layers_per_block;
-        }
         CK(conv_gemm(ex, c2.fwd, act2, r.cout, r.h, r.w, r.h, r.w, xout, r.cout, c2.bias, residual,
-                     feeds_down ? nullptr : gn_sums_ptr(next_gn), next_cpg, nullptr, nullptr));
+                     next_gn < 0 ? nullptr : gn_sums_ptr(next_gn), next_cpg, nullptr, nullptr));
         return 0;
-    };
+    }
+}
 
-    // mid block: resnet, attention, resnet (wf_unet_2d_blocks.py:457-464)
-    CK(resnet(0, x, false));  // conv_in is not a tapgemm: its output statistics need the standalone pass
-    x = ws + o_res_out[0];
+// AttentionBlock.forward (reference attention.py:329-380): one head of Cm channels over the h x w plane; x -> ws + o_attn_out.
+// attn_prefix: state_dict prefix of the block ("decoder.mid_block.attentions.0."); next_gn as in resnet_forward.
+int Decoder::attention_forward(Exec& ex, uint8_t* x, const std::string& attn_prefix, int next_gn) {
+    const int B = ex.B;
+    cudaStream_t s = ex.stream;
+    const float eps = 1e-6f;
+    const int hw = h * w;
+    auto fused_ok = [&](int C) { return fuse_gn && (C / G) % 16 == 0; };
     {
         // AttentionBlock.forward (attention.py:329-380), one head of Cm channels. N queries (this band's pixels)
         // attend over Nk keys; in a band plan the q|k|v rows of all bands are gathered into one [Nk, 3*Cm] block
@@ -886,14 +882,14 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
         uint8_t* xn = ws + o_xn;
         uint8_t* qkv_all = ws + o_qkv;
         uint8_t* qkv = qkv_all + static_cast<size_t>(band_r) * N * 3 * Cm * 2;  // this band's rows
-        const std::string a = "decoder.mid_block.attentions.0.";
+        const std::string a = attn_prefix;
         if (!ex.prepare) {
             if (!fused_ok(Cm)) CK(gn_stats(x, gn_sums_ptr(n_gn - 2), B, N, Cm, G, bf16, s));
             CK(sync_sums(ex, gn_sums_ptr(n_gn - 2)));
             CK(gn_apply(x, gn_sums_ptr(n_gn - 2), vecs[a + "group_norm.weight"], vecs[a + "group_norm.bias"], xn, B, N,
                         Cm, G, eps, 0, bf16, s, N * band_R));
         }
-        const ConvW& cq = convs["attn.qkv"];
+        const ConvW& cq = convs[attn_prefix + "qkv"];
         const int bn_c = fit_bn(Cm % 192 == 0 ? 192 : (Cm % 128 == 0 ? 128 : (Cm % 64 == 0 ? 64 : 16)),
                                 static_cast<long long>(B_max) * (N / TG_BM), Cm);
         const int bn_n = Nk % 256 == 0 ? 256 : 128;
@@ -931,10 +927,47 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
         g.A = ws + o_O; g.K = Cm; g.a_ld = Cm; g.rows_per_sample = N; g.a_B = B_max; g.a_shared = false;
         g.Bm = cp.fwd.Bm; g.b_rows = cp.fwd.rows; g.ldb = cp.fwd.ldb; g.b_Z = 1; g.BN = cp.fwd.BN; g.N = Cm;
         g.out = ws + o_attn_out; g.out_fp32 = 0; g.ldc = Cm; g.bias = cp.bias; g.residual = x; g.alpha = 1.f;
-        g.gn_sums = gn_sums_ptr(2); g.gn_cpg = Cm / G;
+        g.gn_sums = next_gn < 0 ? nullptr : gn_sums_ptr(next_gn); g.gn_cpg = Cm / G;
         CK(plain_gemm(ex, g));
-        x = ws + o_attn_out;
+        }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
+    const int B = ex.B;
+    cudaStream_t s = ex.stream;
+    const float eps = 1e-6f;
+    const int hw = h * w;
+    uint8_t* x = ws + o_x0;
+    if (!ex.prepare) {
+        CUDA_CK(cudaMemsetAsync(ws + o_gn, 0, static_cast<size_t>(n_gn) * B_max * G * 2 * sizeof(acc_t), s));
+        CK(latent_in(z, z_f16, in_scale, vecs["post_quant_conv.weight"], vecs["post_quant_conv.bias"],
+                     vecs["decoder.conv_in.weight.T"], vecs["decoder.conv_in.bias"], x, B, h, w, Cm, bf16, s, band_r * h,
+                     h_total));
     }
+    int cur_h = h, cur_w = w;
+    int ri = 0;
+    auto fused_ok = [&](int C) { return fuse_gn && (C / G) % 16 == 0; };
+    static const char* const group_tag[] = {"dense", "g4", "g16", "g64", "grouped"};
+    auto tag_of = [&](int groups) { return group_tag[groups == 1 ? 0 : groups == 4 ? 1 : groups == 16 ? 2 : groups == 64 ? 3 : 4]; };
+    auto resnet = [&](int idx, uint8_t* xin, bool stats_ready) -> int {
+        const bool last = idx + 1 == static_cast<int>(resnets.size());
+        // stats of the resnet output feed the next GroupNorm: the next resnet's norm1, the attention norm after
+        // mid.resnets.0, or conv_norm_out after the last resnet; a block that ends in a downsample conv re-computes
+        // them after it
+        int next_gn = last ? n_gn - 1 : (idx == 0 ? n_gn - 2 : 2 * (idx + 1));
+        if (idx >= 2) {
+            const int blk = (idx - 2) / (cfg.layers_per_block + 1), j = (idx - 2) % (cfg.layers_per_block + 1);
+            if (down_after[blk] && j == cfg.layers_per_block) next_gn = -1;
+        }
+        return resnet_forward(ex, idx, xin, stats_ready, next_gn);
+    };
+    // mid block: resnet, attention, resnet (wf_unet_2d_blocks.py:457-464)
+    CK(resnet(0, x, false));  // conv_in is not a tapgemm: its output statistics need the standalone pass
+    x = ws + o_res_out[0];
+    CK(attention_forward(ex, x, "decoder.mid_block.attentions.0.", 2));
+    x = ws + o_attn_out;
     CK(resnet(1, x, true));
     x = ws + o_res_out[1];
     ri = 2;
@@ -1176,7 +1209,7 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
                                 3 * Cm, N, 2 * Cm, bf16, s));
         }
         // d xn = [dQ | dK | dV] Wqkv
-        const ConvW& cq = convs["attn.qkv"];
+        const ConvW& cq = convs[a + "qkv"];
         memset(&g, 0, sizeof(g));
         g.A = dqkv; g.K = 3 * Cm; g.a_ld = 3 * Cm; g.rows_per_sample = N; g.a_B = B_max;
         g.Bm = cq.bwd.Bm; g.b_rows = cq.bwd.rows; g.ldb = cq.bwd.ldb; g.b_Z = 1; g.BN = cq.bwd.BN; g.N = Cm;

@@ -60,6 +60,8 @@ struct Exec {
 };
 
 struct PlainGemm;
+int upload_f32(const std::vector<float>& v, float** dev);
+bool pick_box(int W, int H, int* w_box, int* h_box);
 
 struct Decoder {
     wfd_decoder_config cfg;
@@ -96,6 +98,8 @@ struct Decoder {
     float last_in_scale = 1.f;
     int last_B = 0;
     std::vector<TapGemmOp> fwd_ops, bwd_ops;
+    bool next_out_fp32 = false;  // the contraction prepared next stores fp32 (the encoder's moments); reset by conv_gemm
+    bool encoder_side = false;   // set_weight keeps encoder.* / quant_conv.* instead of decoder.* / post_quant_conv.*
     const char* cur_tag = "";  // launch class stamped on the contractions prepared next (per-launch profile of bench.py)
 
     ~Decoder();
@@ -112,6 +116,7 @@ struct Decoder {
     int pack_named_conv(const std::string& name, int cout, int cin, int groups, int k, bool want_bwd, int fwd_mode, int ph,
                         int pw);
     int upload_vec(const std::string& key, long long numel);
+    int pack_attention(const std::string& prefix, bool want_bwd);
     int prepare_ops();
     int run_gemm(Exec& ex, TapGemmOp& tmpl, bool z_is_batch);
     int conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int Hin, int Win, int Hout, int Wout, void* out,
@@ -124,8 +129,29 @@ struct Decoder {
     int halo_rows(Exec& ex, void* buf, int rows, int W, int C);
     int gn_backward(Exec& ex, const void* dy, const void* x, int gn_idx, const float* gamma, const float* beta,
                     const void* add, void* dx, int HW, int C, int silu, int do_reduce);
+    int resnet_forward(Exec& ex, int idx, uint8_t* xin, bool stats_ready, int next_gn);
+    int attention_forward(Exec& ex, uint8_t* x, const std::string& attn_prefix, int next_gn);
     int forward_impl(Exec& ex, const void* z, int z_f16, float in_scale);
     int backward_impl(Exec& ex, const void* dlogits, const float* scale_b, float* dz);
+};
+
+// Tile-VAE ENCODER plan (reference wf_vae.py:68-148 EncoderTile + quant_conv :582-590), forward only: the img2img entry of
+// the pipelines (pipeline_wfd_img2img.py:478-486) encodes a one-hot tile map into latent moments. Built on the decoder's
+// machinery (same contractions, GroupNorm kernels and attention block, in the encoder's order); only configurations whose
+// encoder blocks keep the resolution ("EvenEncoderBlock2D") are supported.
+struct Encoder : Decoder {
+    int C_in = 0, C0 = 0;            // wave channels (T_pad), channels after conv_in
+    int cin_g = 0, cout_g = 0;       // conv_in channels per group (in / out)
+    size_t o_wave = 0, o_mom = 0, o_ping[2] = {0, 0}, o_h1 = 0;
+    float* gather = nullptr;         // [C_in][9][cout_g] fp32: conv_in weights by (input tile, tap) for one-hot input
+    ~Encoder();
+    int init_enc(const wfd_decoder_config& c, int H, int W, int B_max, int dtype16);
+    int finalize_enc();
+    int bind_workspace_enc(void* p, size_t bytes);
+    int prepare_enc();
+    int forward_enc(Exec& ex, const void* wave, int wave_dtype, const long long* tiles, float* moments);
+    int encode_wave(const void* wave_nchw, int dtype, int B, float* moments, cudaStream_t s);
+    int encode_tiles(const long long* tiles, int B, float* moments, cudaStream_t s);
 };
 
 // WFC loss handle: packed adjacency operand [T_pad rows][4 * T_pad] = [Ax | Ax^T | Ay | Ay^T] (0/1), see wfc.cu

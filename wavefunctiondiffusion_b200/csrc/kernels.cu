@@ -1174,6 +1174,71 @@ int count_violations(const long long* tiles, const uint8_t* mat_x, const uint8_t
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ encoder ends
+// conv_in of the tile-VAE encoder on a ONE-HOT input (an integer tile map): a grouped 3x3 conv whose input has a single
+// non-zero channel per pixel is a gather - every neighbour (dy, dx) of an output pixel adds the cout_g weights
+// W[g*cout_g + j, tile % cin_g, tap] of its tile's group g = tile / cin_g (reference wf_vae.py:90, img2img :68-74).
+// table: [C_in][9][cout_g] fp32. One block per output pixel; out nhwc16 [B, H*W, C0].
+template <bool BF16>
+__global__ void __launch_bounds__(128)
+onehot_conv_in_k(const long long* __restrict__ tiles, const float* __restrict__ table, const float* __restrict__ bias,
+                 uint16_t* __restrict__ out, int H, int W, int C_in, int C0, int cin_g, int cout_g) {
+    extern __shared__ float acc[];  // [C0]
+    const long long pix = blockIdx.x;
+    const int b = static_cast<int>(pix / (H * W));
+    const int pr = static_cast<int>(pix - static_cast<long long>(b) * H * W);
+    const int y = pr / W, x = pr - y * W;
+    for (int c = threadIdx.x; c < C0; c += blockDim.x) acc[c] = bias[c];
+    __syncthreads();
+    for (int tap = 0; tap < 9; ++tap) {  // taps one after the other: two neighbours may hit the same group
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const long long t = tiles[(static_cast<long long>(b) * H + yy) * W + xx];
+            if (t >= 0 && t < C_in && static_cast<int>(threadIdx.x) < cout_g) {
+                const int g = static_cast<int>(t) / cin_g;
+                acc[g * cout_g + threadIdx.x] += table[(static_cast<long long>(t) * 9 + tap) * cout_g + threadIdx.x];
+            }
+        }
+        __syncthreads();
+    }
+    uint16_t* dst = out + pix * C0;
+    for (int c = threadIdx.x * 2; c < C0; c += blockDim.x * 2)
+        *reinterpret_cast<uint32_t*>(dst + c) = static_cast<uint32_t>(f_to_u16<BF16>(acc[c])) |
+                                                (static_cast<uint32_t>(f_to_u16<BF16>(acc[c + 1])) << 16);
+}
+int onehot_conv_in(const long long* tiles, const float* table, const float* bias, void* out, int B, int H, int W,
+                   int C_in, int C0, int cin_g, int cout_g, int bf16, cudaStream_t s) {
+    ProfScope prof_scope("onehot_conv_in", s);
+    if (cout_g > 128 || C0 % 2 || C0 * sizeof(float) > 48 * 1024) {
+        set_error("onehot_conv_in: unsupported shape (C0=%d cout_g=%d)", C0, cout_g);
+        return -3;
+    }
+    const unsigned blocks = static_cast<unsigned>(static_cast<long long>(B) * H * W);
+    WFD_DISPATCH_BF16(bf16, (onehot_conv_in_k<BF16><<<blocks, 128, C0 * sizeof(float), s>>>(
+                                tiles, table, bias, static_cast<uint16_t*>(out), H, W, C_in, C0, cin_g, cout_g)));
+    WFD_CHECK_LAUNCH("onehot_conv_in");
+    return 0;
+}
+// moments [B, HW, ld] fp32 (channels-last, the first C columns valid) -> NCHW fp32 [B, C, HW]
+__global__ void moments_out_k(const float* __restrict__ in, float* __restrict__ out, int C, int HW, int ld, long long n) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int p = static_cast<int>(i % HW);
+        const long long bc = i / HW;
+        const int c = static_cast<int>(bc % C);
+        const long long b = bc / C;
+        out[i] = in[(b * HW + p) * ld + c];
+    }
+}
+static unsigned ew_blocks_decl(long long n, int threads);
+int moments_out(const float* in, float* out, int B, int C, int HW, int ld, cudaStream_t s) {
+    ProfScope prof_scope("moments_out", s);
+    const long long n = static_cast<long long>(B) * C * HW;
+    moments_out_k<<<ew_blocks_decl(n, 256), 256, 0, s>>>(in, out, C, HW, ld, n);
+    WFD_CHECK_LAUNCH("moments_out");
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ guidance-loop glue
 // The elementwise work around the guidance step when scheduler.step is affine in the latents, prev = a x + b eps
 // (DDIM eta = 0, PNDM/PLMS; reference pipeline_wfd.py:601-603, 611-614 and the final-stage twin :630-637):

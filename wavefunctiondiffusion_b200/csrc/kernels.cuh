@@ -78,6 +78,11 @@ int tiles_finish(const long long* tiles, int B, int H, int W, const int* symm, i
                  int n_shrink, const int* gen_to_sc, int n_gen, long long* tiles_out, uint16_t* sc_out, long long* bad,
                  cudaStream_t s);
 
+// ---- encoder ends: conv_in on a one-hot input as a gather (table [C_in][9][cout_g] fp32), moments export
+int onehot_conv_in(const long long* tiles, const float* table, const float* bias, void* out, int B, int H, int W,
+                   int C_in, int C0, int cin_g, int cout_g, int bf16, cudaStream_t s);
+int moments_out(const float* in, float* out, int B, int C, int HW, int ld, cudaStream_t s);
+
 // ---- elementwise glue of the guidance loop for affine schedulers (pipeline_wfd.py:601-603, 611-614, 630-637):
 // z = a lat + b (eps_u + g (eps_t - eps_u)) (eps_t may be null: eps = eps_u), and lat -= a dz
 int guidance_affine(const float* lat, const float* eps_u, const float* eps_t, float g, float a, float b, float* z,

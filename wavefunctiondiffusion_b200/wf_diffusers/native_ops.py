@@ -169,6 +169,97 @@ class NativeDecoder:
         return p
 
 
+class EncoderPlan:
+    """One wfd_encoder handle + workspace for a fixed (H, W, B_max, dtype16): AutoencoderTile.encode on the device
+    (reference wf_vae.py:582-590). Forward only."""
+
+    def __init__(self, model, H, W, b_max, dtype16, device):
+        lib = nat.lib()
+        cfg = model.config
+        c = nat.DecoderConfig()
+        c.latent_channels = cfg.latent_channels
+        c.out_channels = cfg.in_channels
+        nb = len(cfg.block_out_channels)
+        c.n_blocks = nb
+        for i in range(nb):
+            c.block_out_channels[i] = cfg.block_out_channels[i]
+            c.conv_groups[i] = cfg.conv_groups[i]
+            c.block_down[i] = 0 if cfg.down_block_types[i] == "EvenEncoderBlock2D" else 1
+        c.conv_init_groups = cfg.conv_init_groups
+        c.layers_per_block = cfg.layers_per_block
+        c.norm_num_groups = cfg.norm_num_groups
+        self.handle = C.c_void_p()
+        self.device, self.H, self.W, self.b_max, self.dtype16 = device, H, W, b_max, dtype16
+        self.n_moments = 2 * cfg.latent_channels
+        with torch.cuda.device(device):
+            nat.check(lib.wfd_encoder_create(C.byref(c), H, W, b_max, dtype16, C.byref(self.handle)), "wfd_encoder_create")
+            for key, t in model.state_dict().items():
+                if not (key.startswith("encoder.") or key.startswith("quant_conv.")):
+                    continue
+                host = t.detach().to("cpu", torch.float32).contiguous()
+                nat.check(lib.wfd_encoder_set_weight(self.handle, key.encode(), C.c_void_p(host.data_ptr()), host.numel()),
+                          "wfd_encoder_set_weight(%s)" % key)
+            nat.check(lib.wfd_encoder_finalize_weights(self.handle), "wfd_encoder_finalize_weights")
+            nbytes = lib.wfd_encoder_workspace_bytes(self.handle)
+            self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+            base = (self.workspace.data_ptr() + 255) // 256 * 256
+            nat.check(lib.wfd_encoder_bind_workspace(self.handle, C.c_void_p(base), nbytes), "wfd_encoder_bind_workspace")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                nat.lib().wfd_encoder_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def encode_wave(self, x):
+        """x: (B, T_pad, H, W) fp32 / fp16 on the device -> moments fp32 (B, 2 * latent, H, W)."""
+        x = x.contiguous()
+        if x.dtype not in (torch.float32, torch.float16):
+            x = x.float()
+        out = torch.empty((x.shape[0], self.n_moments, self.H, self.W), dtype=torch.float32, device=self.device)
+        nat.check(nat.lib().wfd_encoder_forward_wave(self.handle, C.c_void_p(x.data_ptr()), 0 if x.dtype == torch.float32 else 1,
+                                                     x.shape[0], C.c_void_p(out.data_ptr()), nat.stream_ptr()),
+                  "wfd_encoder_forward_wave")
+        return out
+
+    def encode_tiles(self, tiles):
+        """tiles: int64 (B, H, W) on the device (the one-hot wave by its indices) -> moments fp32."""
+        t = tiles.to(torch.int64).contiguous()
+        out = torch.empty((t.shape[0], self.n_moments, self.H, self.W), dtype=torch.float32, device=self.device)
+        nat.check(nat.lib().wfd_encoder_forward_tiles(self.handle, C.c_void_p(t.data_ptr()), t.shape[0],
+                                                      C.c_void_p(out.data_ptr()), nat.stream_ptr()), "wfd_encoder_forward_tiles")
+        return out
+
+
+class NativeEncoder:
+    """Per-model cache of EncoderPlans (rebuilt when the weights change)."""
+
+    def __init__(self, model):
+        import weakref
+
+        self._model = weakref.ref(model)
+        self._plans = {}
+
+    def invalidate(self):
+        self._plans.clear()
+
+    @staticmethod
+    def supported(config):
+        return all(k == "EvenEncoderBlock2D" for k in config.down_block_types)
+
+    def plan(self, B, H, W, device):
+        dtype16 = compute_dtype16()
+        key = (H, W, dtype16, str(device))
+        p = self._plans.get(key)
+        if p is None or p.b_max < B:
+            self._plans.pop(key, None)
+            p = EncoderPlan(self._model(), H, W, B, dtype16, device)
+            self._plans[key] = p
+        return p
+
+
 class TileDecodeFunction(torch.autograd.Function):
     """logits = AutoencoderTile._decode(z) (reference wf_vae.py:592-599) with the data gradient wired to autograd."""
 

@@ -2,8 +2,8 @@
 (wfd/wf_diffusers/pipeline_wfd_img2img.py:76-720). Its guidance block (:667-677, :688-700) is the same code as the
 txt2img one and is served by the same library calls; what differs is how the initial latents are made: from an image
 through the SD VAE encoder, or from an integer tile map through the tile-VAE encoder (`image_is_wave=True`,
-`preprocess_wave` :68-74, `prepare_latents` :468-531). The encoders are not on the guidance path: the
-tile-VAE encoder runs as eager torch modules.
+`preprocess_wave` :68-74, `prepare_latents` :468-531). The tile-VAE encoder runs in libwfd_b200.so on a CUDA device
+(SURVEY §8f-1): an integer tile map is encoded by its indices, the one-hot conv_in becoming a gather of weight columns.
 
 Note: the reference's `set_precision("float")` calls `wfc_loss.half()` by mistake (:253); this mirror converts to float.
 """
@@ -52,16 +52,20 @@ class WaveFunctionDiffusionImg2ImgPipeline(WaveFunctionDiffusionPipeline):
 
     def prepare_latents(self, image, timestep, batch_size, num_images_per_prompt, dtype, device, generator=None,
                         image_is_wave=False):
-        image = image.to(device=device, dtype=dtype)
+        # an integer tile map (B, H, W) stays integer: the tile VAE encodes it by its indices (one-hot conv_in = a gather)
+        by_index = image_is_wave and image.dim() == 3 and not image.is_floating_point()
+        image = image.to(device=device) if by_index else image.to(device=device, dtype=dtype)
         batch_size = batch_size * num_images_per_prompt
         if isinstance(generator, list) and len(generator) != batch_size:
             raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an"
                              f" effective batch size of {batch_size}.")
         enc = self.tile_vae if image_is_wave else self.vae
+        encode = enc.encode_tiles if by_index else enc.encode
         if isinstance(generator, list):
-            init = torch.cat([enc.encode(image[i:i + 1]).latent_dist.sample(generator[i]) for i in range(batch_size)])
+            init = torch.cat([encode(image[i:i + 1]).latent_dist.sample(generator[i]) for i in range(batch_size)])
         else:
-            init = enc.encode(image).latent_dist.sample(generator)
+            init = encode(image).latent_dist.sample(generator)
+        init = init.to(dtype)
         init = LATENT_SCALE * init
         if batch_size > init.shape[0]:
             if batch_size % init.shape[0] != 0:
@@ -118,7 +122,11 @@ class WaveFunctionDiffusionImg2ImgPipeline(WaveFunctionDiffusionPipeline):
         do_cfg = guidance_scale > 1.0
         text_embeddings = self._encode_prompt(prompt, device, num_images_per_prompt, do_cfg, negative_prompt)
         if image_is_wave:
-            image = preprocess_wave(image, num_classes=self.tile_vae.in_channels)
+            tiles = image if isinstance(image, torch.Tensor) else torch.as_tensor(np.asarray(image))
+            if not tiles.is_floating_point() and tiles.dim() in (2, 3) and hasattr(self.tile_vae, "encode_tiles"):
+                image = tiles.long() if tiles.dim() == 3 else tiles.long()[None]   # what preprocess_wave would one-hot
+            else:
+                image = preprocess_wave(image, num_classes=self.tile_vae.in_channels)
         else:
             image = preprocess(image)
         self.scheduler.set_timesteps(num_inference_steps, device=device)

@@ -4,8 +4,9 @@ Same constructor arguments, attribute names, state_dict keys/shapes and default 
 (so a reference checkpoint loads unchanged and `torch.manual_seed(s)` yields the same random-init weights), but
 `decode()` does not run torch modules: it goes through the C ABI of libwfd_b200.so (sm_100a kernels) and registers a
 torch.autograd.Function so that `torch.autograd.grad(loss, latents)` of the guidance block (pipeline_wfd.py:613) keeps
-working. The modules below exist to own parameters; only the encoder (not on the guidance path) has an
-eager forward.
+working. `encode()` (the img2img wave input) runs in the library too when the tensor is on a CUDA device
+and the encoder keeps the resolution; its eager torch modules serve the remaining cases. The decoder modules below
+exist to own parameters.
 """
 import json
 import os
@@ -18,7 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .native_ops import NativeDecoder, TileDecodeFunction
+from .native_ops import NativeDecoder, NativeEncoder, TileDecodeFunction
 
 
 # --------------------------------------------------------------------------------------------- output containers
@@ -272,6 +273,7 @@ class AutoencoderTile(nn.Module):
         self.post_quant_conv = nn.Conv2d(latent_channels, latent_channels, 1)
         self.use_slicing = False
         self._native = NativeDecoder(self)
+        self._native_enc = NativeEncoder(self)
 
     # ---- diffusers-like persistence (config.json + diffusion_pytorch_model.bin)
     @classmethod
@@ -308,12 +310,15 @@ class AutoencoderTile(nn.Module):
     def load_state_dict(self, *a, **kw):
         r = super().load_state_dict(*a, **kw)
         self._native.invalidate()
+        self._native_enc.invalidate()
         return r
 
     def _apply(self, fn, *a, **kw):
         r = super()._apply(fn, *a, **kw)
         if hasattr(self, "_native"):
             self._native.invalidate()
+        if hasattr(self, "_native_enc"):
+            self._native_enc.invalidate()
         return r
 
     # ---- copies and pickles carry parameters only; the native caches (ctypes handles, device workspaces, a weak
@@ -321,11 +326,13 @@ class AutoencoderTile(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         state.pop("_native", None)
+        state.pop("_native_enc", None)
         return state
 
     def __setstate__(self, state):
         self.__dict__.update(state)
         self._native = NativeDecoder(self)
+        self._native_enc = NativeEncoder(self)
 
     def __deepcopy__(self, memo):
         import copy
@@ -336,8 +343,9 @@ class AutoencoderTile(nn.Module):
         return new
 
     def refresh_native(self):
-        """Call after mutating decoder weights in place; the packed device copy is rebuilt on the next decode."""
+        """Call after mutating weights in place; the packed device copies are rebuilt on the next decode / encode."""
         self._native.invalidate()
+        self._native_enc.invalidate()
 
     @property
     def device(self):
@@ -348,8 +356,34 @@ class AutoencoderTile(nn.Module):
         return next(self.parameters()).dtype
 
     # ---- reference API
+    def _encode_moments(self, x):
+        """quant_conv(encoder(x)) (reference :583-584). On a CUDA device and for configurations whose encoder blocks keep
+        the resolution this runs in libwfd_b200.so (forward only: the moments carry no autograd graph); the eager torch
+        modules remain for the other cases (CPU tensors, the 32x32 family's upsampling encoder, training)."""
+        native_ok = (x.is_cuda and NativeEncoder.supported(self.config) and not (torch.is_grad_enabled() and x.requires_grad)
+                     and x.shape[2] * x.shape[3] % 128 == 0)
+        if native_ok:
+            plan = self._native_enc.plan(x.shape[0], x.shape[2], x.shape[3], x.device)
+            return plan.encode_wave(x).to(x.dtype if x.dtype.is_floating_point else torch.float32)
+        return self.quant_conv(self.encoder(x))
+
+    def encode_tiles(self, tiles, return_dict: bool = True):
+        """encode(preprocess_wave(tiles)) for an integer tile map (B, H, W) or (H, W) given by its indices (the img2img
+        wave input, reference pipeline_wfd_img2img.py:68-74, 478-486): on the device the one-hot conv_in is a gather of
+        weight columns, so the (B, T_pad, H, W) one-hot tensor is never materialised."""
+        t = tiles if tiles.dim() == 3 else tiles.unsqueeze(0)
+        if t.is_cuda and NativeEncoder.supported(self.config) and t.shape[1] * t.shape[2] % 128 == 0:
+            moments = self._native_enc.plan(t.shape[0], t.shape[1], t.shape[2], t.device).encode_tiles(t).to(self.dtype)
+        else:
+            onehot = F.one_hot(t.long(), num_classes=self.in_channels).permute(0, 3, 1, 2).to(self.dtype)
+            moments = self._encode_moments(onehot)
+        posterior = DiagonalGaussianDistribution(moments)
+        if not return_dict:
+            return (posterior,)
+        return AutoencoderKLOutput(latent_dist=posterior)
+
     def encode(self, x, return_dict: bool = True):
-        moments = self.quant_conv(self.encoder(x))
+        moments = self._encode_moments(x)
         posterior = DiagonalGaussianDistribution(moments)
         if not return_dict:
             return (posterior,)
