@@ -95,6 +95,27 @@ def test_fused_guidance_step_small(ref_gemm, name):
     assert _rel(l2.cpu(), z["loss_f64"]) < TOL_LOSS
 
 
+@pytest.mark.parametrize("name", ["tiny_step.npz", "ice_c1_step.npz"])
+def test_groupnorm_apply_inside_the_conv_matches_the_standalone_pass(name, monkeypatch):
+    """GroupNorm+SiLU in front of a 3x3 conv runs in the conv's operand path (transform warps rewrite the landed
+    activation box in shared memory, reference resnet.py:461-462, 483-489). Same arithmetic, same rounding points as the
+    standalone gn_apply pass (WFD_FUSE_APPLY=0; 2 = every patch-schedule conv): the logits agree bit for bit."""
+    z = np.load(os.path.join(GOLD, name))
+    cfg = json.loads(str(z["cfg_json"]))
+    lat = torch.from_numpy(z["latents"]).cuda()
+    outs = []
+    for flag in ("2", "0"):
+        monkeypatch.setenv("WFD_FUSE_APPLY", flag)
+        torch.manual_seed(int(z["seed"]))
+        net = AutoencoderTile(**cfg).eval().cuda()
+        with torch.no_grad():
+            outs.append(net.decode(lat / 0.18215).sample.float().cpu())
+        del net
+    d = _rel(outs[0], outs[1])
+    print(name, "fused vs standalone GroupNorm apply: logits rel-L2", d, "bitwise equal:", bool(torch.equal(outs[0], outs[1])))
+    assert d < 1e-3
+
+
 def test_ice_config1_against_reference_golden():
     """BASELINE config 1: ice 64x64, batch 1, tilenet_sc_space_64x64, seed-0 weights, strength 5."""
     z = np.load(os.path.join(GOLD, "ice_c1_step.npz"))

@@ -233,6 +233,8 @@ int Decoder::init(const wfd_decoder_config& c, int h_, int w_, int Bmax, int dty
         fuse_gn = (f && f[0] == '1') ? 0 : 1;
         const char* np = getenv("WFD_NO_PATCH");
         use_patch = (np && np[0] == '1') ? 0 : 1;
+        const char* na = getenv("WFD_FUSE_APPLY");
+        fuse_apply = na ? atoi(na) : 1;
         const char* ng = getenv("WFD_CONV_NGROUP");
         conv_n_group = ng ? atoi(ng) : 0;
         const char* m = getenv("WFD_FUSE_BWD_MAX_C");
@@ -582,7 +584,7 @@ int Decoder::run_gemm(Exec& ex, TapGemmOp& tmpl, bool z_is_batch) {
 // conv-style contraction over a channels-last activation
 int Decoder::conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int Hin, int Win, int Hout, int Wout,
                        void* out, long long ldc, const float* bias, const void* residual, acc_t* gn_sums, int gn_cpg,
-                       const OutStrides* os, const GnBwdFuse* gb) {
+                       const OutStrides* os, const GnBwdFuse* gb, const AxForm* ax) {
     TapGemmOp op;
     memset(&op, 0, sizeof(op));
     TapGemmParams& p = op.p;
@@ -665,6 +667,18 @@ int Decoder::conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int 
             p.a_ptr = static_cast<const uint8_t*>(A) - static_cast<size_t>(Win) * a_C * 2;
             p.a_H = Hin + 2;
             p.a_y_off = 1;
+        }
+        if (ax) {
+            p.ax_stats = ax->stats;
+            p.ax_gamma = ax->gamma;
+            p.ax_beta = ax->beta;
+            p.ax_cpg = ax->cpg;
+            p.ax_silu = ax->silu;
+            p.ax_hw = ax->hw;
+            p.ax_eps = ax->eps;
+            // image rows of the A view: everything but the zeroed halo rows at the top / bottom border of the map
+            p.ax_y0 = (band && vertical && band_r == 0) ? 1 : 0;
+            p.ax_y1 = p.a_H - ((band && vertical && band_r == band_R - 1) ? 1 : 0);
         }
         p.a_B = B_max;
         p.a_ld = a_C;
@@ -838,20 +852,28 @@ int Decoder::resnet_forward(Exec& ex, int idx, uint8_t* xin, bool stats_ready, i
         uint8_t* xout = ws + o_res_out[idx];
         const int gi1 = 2 * idx, gi2 = 2 * idx + 1;
         int next_cpg = r.cout / G;
+        const ConvW& c1 = convs[r.prefix + ".conv1"];
+        const ConvW& c2 = convs[r.prefix + ".conv2"];
+        // GroupNorm + SiLU in front of a patch-schedule conv runs inside that conv (transform warps rewrite the landed
+        // activation box in shared memory): the conv then reads the RAW tensor and the standalone gn_apply pass is gone
+        const bool ax1 = apply_fused(c1.fwd), ax2 = apply_fused(c2.fwd);
+        AxForm a1 = {gn_sums_ptr(gi1), vecs[r.prefix + ".norm1.weight"], vecs[r.prefix + ".norm1.bias"], r.cin / G, 1,
+                     phw * band_R, eps};
+        AxForm a2 = {gn_sums_ptr(gi2), vecs[r.prefix + ".norm2.weight"], vecs[r.prefix + ".norm2.bias"], r.cout / G, 1,
+                     phw * band_R, eps};
         if (!ex.prepare) {
             if (!stats_ready || !fused_ok(r.cin)) CK(gn_stats(xin, gn_sums_ptr(gi1), B, phw, r.cin, G, bf16, s));
             CK(sync_sums(ex, gn_sums_ptr(gi1)));
-            CK(gn_apply(xin, gn_sums_ptr(gi1), vecs[r.prefix + ".norm1.weight"], vecs[r.prefix + ".norm1.bias"], act, B,
-                        phw, r.cin, G, eps, 1, bf16, s, phw * band_R));
+            if (!ax1)
+                CK(gn_apply(xin, a1.stats, a1.gamma, a1.beta, act, B, phw, r.cin, G, eps, 1, bf16, s, phw * band_R));
         }
-        const ConvW& c1 = convs[r.prefix + ".conv1"];
-        CK(conv_gemm(ex, c1.fwd, act, r.cin, r.h, r.w, r.h, r.w, h1, r.cout, c1.bias, nullptr, gn_sums_ptr(gi2),
-                     r.cout / G, nullptr, nullptr));
+        CK(conv_gemm(ex, c1.fwd, ax1 ? xin : act, r.cin, r.h, r.w, r.h, r.w, h1, r.cout, c1.bias, nullptr, gn_sums_ptr(gi2),
+                     r.cout / G, nullptr, nullptr, ax1 ? &a1 : nullptr));
         if (!ex.prepare) {
             if (!fused_ok(r.cout)) CK(gn_stats(h1, gn_sums_ptr(gi2), B, phw, r.cout, G, bf16, s));
             CK(sync_sums(ex, gn_sums_ptr(gi2)));
-            CK(gn_apply(h1, gn_sums_ptr(gi2), vecs[r.prefix + ".norm2.weight"], vecs[r.prefix + ".norm2.bias"], act2, B,
-                        phw, r.cout, G, eps, 1, bf16, s, phw * band_R));
+            if (!ax2)
+                CK(gn_apply(h1, a2.stats, a2.gamma, a2.beta, act2, B, phw, r.cout, G, eps, 1, bf16, s, phw * band_R));
         }
         const void* residual = xin;
         if (r.cin != r.cout) {
@@ -859,9 +881,8 @@ int Decoder::resnet_forward(Exec& ex, int idx, uint8_t* xin, bool stats_ready, i
             CK(conv_gemm(ex, cs.fwd, xin, r.cin, r.h, r.w, r.h, r.w, ws + o_sc, r.cout, cs.bias, nullptr, nullptr, 0, nullptr, nullptr));
             residual = ws + o_sc;
         }
-        const ConvW& c2 = convs[r.prefix + ".conv2"];
-        CK(conv_gemm(ex, c2.fwd, act2, r.cout, r.h, r.w, r.h, r.w, xout, r.cout, c2.bias, residual,
-                     next_gn < 0 ? nullptr : gn_sums_ptr(next_gn), next_cpg, nullptr, nullptr));
+        CK(conv_gemm(ex, c2.fwd, ax2 ? h1 : act2, r.cout, r.h, r.w, r.h, r.w, xout, r.cout, c2.bias, residual,
+                     next_gn < 0 ? nullptr : gn_sums_ptr(next_gn), next_cpg, nullptr, nullptr, ax2 ? &a2 : nullptr));
         return 0;
     }
 }
@@ -994,16 +1015,20 @@ int Decoder::forward_impl(Exec& ex, const void* z, int z_f16, float in_scale) {
     x_last = x;
     // conv_norm_out + SiLU + conv_out (wf_vae.py:228-230)
     const bool last_down = down_after[cfg.n_blocks - 1] != 0;
+    const ConvW& co = convs["decoder.conv_out"];
+    const bool axo = apply_fused(co.fwd);
+    AxForm ao = {gn_sums_ptr(n_gn - 1), vecs["decoder.conv_norm_out.weight"], vecs["decoder.conv_norm_out.bias"], C_last / G, 1,
+                 H_out * W_out * band_R, eps};
     if (!ex.prepare) {
         if (!fused_ok(C_last) || last_down) CK(gn_stats(x, gn_sums_ptr(n_gn - 1), B, H_out * W_out, C_last, G, bf16, s));
         CK(sync_sums(ex, gn_sums_ptr(n_gn - 1)));
-        CK(gn_apply(x, gn_sums_ptr(n_gn - 1), vecs["decoder.conv_norm_out.weight"], vecs["decoder.conv_norm_out.bias"],
-                    ws + o_act, B, H_out * W_out, C_last, G, eps, 1, bf16, s, H_out * W_out * band_R));
+        if (!axo)
+            CK(gn_apply(x, ao.stats, ao.gamma, ao.beta, ws + o_act, B, H_out * W_out, C_last, G, eps, 1, bf16, s,
+                        H_out * W_out * band_R));
     }
-    const ConvW& co = convs["decoder.conv_out"];
     cur_tag = "conv_out";
-    CK(conv_gemm(ex, co.fwd, ws + o_act, C_last, H_out, W_out, H_out, W_out, ws + o_logits, T_pad, co.bias, nullptr,
-                 nullptr, 0, nullptr, nullptr));
+    CK(conv_gemm(ex, co.fwd, axo ? x : ws + o_act, C_last, H_out, W_out, H_out, W_out, ws + o_logits, T_pad, co.bias, nullptr,
+                 nullptr, 0, nullptr, nullptr, axo ? &ao : nullptr));
     return 0;
 }
 

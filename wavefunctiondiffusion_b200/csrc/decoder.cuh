@@ -33,6 +33,13 @@ struct GnBwdFuse {  // GroupNorm(+SiLU) backward reduction fused into the produc
     int cpg, silu;
     float inv_n, eps;
 };
+struct AxForm {  // GroupNorm(+SiLU) applied to the A operand inside the consuming contraction (TapGemmParams::ax_*)
+    const acc_t* stats;
+    const float* gamma;
+    const float* beta;
+    int cpg, silu, hw;
+    float eps;
+};
 struct OutStrides {  // element strides of a strided output plane (downsample backward writes every other pixel)
     long long sx, sy, sb;
 };
@@ -74,6 +81,12 @@ struct Decoder {
     int reuse_hbox = 0;    // preferred patch height of the row-reuse contractions (WFD_REUSE_HBOX: 0 = widest patch, 2, 4, 8, 16)
     int use_reuse = 1;  // row-reuse schedule for 3x3 convs whose stage fits (WFD_NO_REUSE=1 disables, for A/B runs)
     int use_patch = 1;  // patch schedule for 3x3 convs on planes that tile into 16 x 8 patches (WFD_NO_PATCH=1 disables)
+    int fuse_apply = 1; // GroupNorm+SiLU applied in the consuming patch-schedule conv's operand path instead of a standalone
+                        // gn_apply pass (WFD_FUSE_APPLY): 0 = never, 1 = where a box's MMAs outlast its transform (N tiles of
+                        // >= 192 columns: the dense and groups=4 layers), 2 = every patch-schedule conv. Measured on B200
+                        // (profiles/r02_summary.md): the transform costs ~2000 issue cycles per 18 x 10 x 64 box whatever the
+                        // number of transform warps (tanh and the 16-bit pack go through the quarter-rate special-function
+                        // unit), more than the MMAs of a narrow-N box take, so mode 2 is slower than the standalone pass
     // row bands (one map split along y over band_R ranks): h is the local band height, h_total the map's
     bool band = false;
     int band_R = 1, band_r = 0, h_total = 0;
@@ -121,7 +134,9 @@ struct Decoder {
     int run_gemm(Exec& ex, TapGemmOp& tmpl, bool z_is_batch);
     int conv_gemm(Exec& ex, const PackedB& pk, const void* A, int a_C, int Hin, int Win, int Hout, int Wout, void* out,
                   long long ldc, const float* bias, const void* residual, acc_t* gn_sums, int gn_cpg,
-                  const OutStrides* os, const GnBwdFuse* gb);
+                  const OutStrides* os, const GnBwdFuse* gb, const AxForm* ax = nullptr);
+    // whether the GroupNorm in front of this 3x3 conv is applied inside the conv (patch schedule) or needs gn_apply
+    bool apply_fused(const PackedB& pk) const { return pk.reuse == 2 && (fuse_apply == 2 || (fuse_apply == 1 && pk.BN >= 192)); }
     int plain_gemm(Exec& ex, const PlainGemm& g);
     acc_t* gn_sums_ptr(int idx) const;
     acc_t* gn_red_ptr(int idx) const;

@@ -89,6 +89,15 @@ __device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) 
                  : "memory");
 }
 
+// 16-byte shared-memory accesses by shared-window address (a pointer derived from the aligned dynamic shared memory base
+// is a generic pointer to the compiler: it would emit generic LD / ST)
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t (&v)[4]) {
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint32_t (&v)[4]) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

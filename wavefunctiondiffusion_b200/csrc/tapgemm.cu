@@ -186,8 +186,13 @@ __device__ __host__ __forceinline__ int b_chunk_index(const TapGemmParams& p, in
 //                [64 ch] loaded ONCE and read by the three vertical taps through descriptor row offsets, + the three
 //                matching B boxes fetched by a single 3-D TMA; 12 MMAs. A third of the TMA instructions, two thirds of
 //                the activation bytes.
-template <bool BF16, int CG>
-__global__ void __launch_bounds__(TG_THREADS, 1)
+//   patch      : (3x3 stride-1 taps, 16 x 8 pixel tiles) ONE activation box per 64-channel chunk carries the whole halo
+//                patch and serves all nine taps through descriptor start offsets. XF = true adds eight transform warps that
+//                apply GroupNorm(+SiLU) to every landed box in shared memory (TapGemmParams::ax_stats); that variant lays
+//                the roles out by warpgroup (tapgemm.cuh) and rebalances registers with setmaxnreg: 640 threads would
+//                otherwise cap every role at 96 registers, and the epilogue needs ~160.
+template <bool BF16, int CG, bool XF>
+__global__ void __launch_bounds__(XF ? TG_THREADS_XF : TG_THREADS, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ TapGemmParams p, const int stages) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -218,12 +223,15 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 6);
     uint64_t* afull_bar = bars + 2 * stages + 8;   // [a_stages] patch schedule only
     uint64_t* aempty_bar = afull_bar + a_stages;   // [a_stages]
-    float* bias_s = reinterpret_cast<float*>(bars + 2 * stages + 8 + (patch ? 2 * a_stages : 0));  // [2][256]
+    uint64_t* aready_bar = aempty_bar + a_stages;  // [a_stages] XF only: the box is transformed (leader CTA's copy is used)
+    // (an even number of 8-byte barriers keeps the float4 accesses of the staging arrays 16-byte aligned)
+    float* bias_s = reinterpret_cast<float*>(bars + 2 * stages + 8 + (patch ? 4 * a_stages : 0));  // [2][256]
     float* gam_s = bias_s + 512;                                      // [2][256] GroupNorm-backward gamma
     float* bet_s = gam_s + 512;                                       // [2][256] GroupNorm-backward beta
     // per-CTA partial sums of the fused GroupNorm statistics / backward reductions, flushed once at kernel end: thousands
     // of tiles would otherwise hammer the same few global addresses with atomics
     unsigned long long* stat_s = reinterpret_cast<unsigned long long*>(bet_s + 512);  // [2][TG_STAT_SLOTS] fixed point
+    float* xf_s = reinterpret_cast<float*>(stat_s + 2 * TG_STAT_SLOTS);  // [512][mean | rstd] per (sample, group), XF only
 
 #ifndef WFD_NO_UNIFORM_WARP
     // The warp index through a shuffle: the compiler then knows it is warp-uniform, the role branches below become uniform
@@ -258,6 +266,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int s = 0; s < a_stages; ++s) {
                 mbar_init(&afull_bar[s], 1);
                 mbar_init(&aempty_bar[s], 1);
+                mbar_init(&aready_bar[s], (TG_XF_THREADS / 32) * CG);  // one arrival per transform warp of the pair
             }
         mbar_init(bres_full, 1);
         mbar_init(tdone_bar, 1);
@@ -267,7 +276,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         fence_barrier_init();
     }
-    for (int i = threadIdx.x; i < 2 * TG_STAT_SLOTS; i += TG_THREADS) stat_s[i] = 0ull;
+    for (int i = threadIdx.x; i < 2 * TG_STAT_SLOTS; i += blockDim.x) stat_s[i] = 0ull;
     if (warp == 1) {
         if (CG == 2) {
             tmem_alloc_2sm(tmem_slot, 512);
@@ -285,7 +294,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // registers instead of going through an ELECT / R2UR.BROADCAST loop per instruction
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-    if (warp == 0 || warp == TG_THREADS / 32 - 1) {
+    // warp roles (XF: warpgroup aligned, see tapgemm.cuh)
+    constexpr int W_TMAB = XF ? 2 : TG_THREADS / 32 - 1;  // weight TMA producer
+    constexpr int W_EPI0 = XF ? 4 : 2;                     // first of the eight epilogue warps
+    constexpr int W_XF0 = 12;                              // first transform warp (XF only)
+    // The roles are written as lambdas so that the XF variant can nest them under one setmaxnreg per warpgroup (ptxas
+    // allocates registers for the code that a setmaxnreg dominates; .aligned wants the whole warpgroup on the same one).
+    auto producer_role = [&]() {
         // ===================================================== TMA producers (warp-uniform loops, one elected lane issues):
         // warp 0 streams the activation boxes, the last warp the weight boxes; both arrive on the stage's full barrier
         const bool load_a = (warp == 0);
@@ -380,9 +395,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         slot_wait();
                         const long long i0 = p.dbg ? clock64() : 0;
                         if (p.dbg_skip & 1) {
-                            if (elect_one() && rank == 0) mbar_arrive(&fbar[stage]);
+                            if (elect_one() && (rank == 0 || XF)) mbar_arrive(&fbar[stage]);
                         } else if (elect_one()) {
-                            if (CG == 2) {  // both CTAs load into their own shared memory; the leader's barrier counts all bytes
+                            if (XF) {  // each CTA's transform warps wait for their own box: the load signals the LOCAL barrier
+                                mbar_expect_tx(&fbar[stage], a_box_bytes);
+                                tma_load_4d(smA + static_cast<size_t>(stage) * a_stage_bytes, &tmA, &fbar[stage], ca, xx, yy, ab);
+                            } else if (CG == 2) {  // both CTAs load into their own shared memory; the leader's barrier counts all bytes
                                 if (rank == 0) mbar_expect_tx(&fbar[stage], 2 * a_box_bytes);
                                 tma_load_4d_2sm(smA + static_cast<size_t>(stage) * a_stage_bytes, &tmA, &fbar[stage], ca,
                                                 xx, yy, ab);
@@ -487,7 +505,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 p.dbg[load_a ? 1 : 9] = w_empty;
             }
         }
-    } else if (warp == 1) {
+    };
+    auto mma_role = [&]() {
       // ===================================================== MMA issuer (one thread; with CG == 2 only in the leader CTA)
       if (rank == 0) {
         const uint32_t idesc = make_idesc_f16(TG_BM * CG, static_cast<uint32_t>(p.BN), BF16 ? 1u : 0u) |
@@ -547,7 +566,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int cc2 = 0; cc2 < p.cpt; ++cc2) {
                     const int n_k = (cc2 == p.cpt - 1) ? kk_last : TG_KC / 16;
                     w0 = p.dbg ? clock64() : 0;
-                    mbar_wait(&afull_bar[a_st], a_ph);
+                    if (XF) {  // the transform warps of both CTAs have rewritten the box (generic proxy + fence.proxy.async)
+                        mbar_wait(&aready_bar[a_st], a_ph);
+                    } else {
+                        mbar_wait(&afull_bar[a_st], a_ph);
+                    }
                     if (p.dbg) w_full += clock64() - w0;
                     // vertical offsets per synchronisation point: all three when the weight stage carries nine taps (narrow N:
                     // the per-stage waits, fence and election then cost as much as the MMAs themselves), else one
@@ -670,16 +693,191 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             p.dbg[4] = w_full;
         }
       }
-    } else {
+    };
+    auto xform_role = [&]() {
+        // ===================================================== operand transform (4 warps, patch schedule only): GroupNorm
+        // (+SiLU) of the raw activation box in shared memory, between the TMA landing and the MMAs. A box is
+        // (h_box + 2) x (w_box + 2) = 18 x 10 pixel rows of 128 bytes (64 channels) under the 128-byte swizzle: thread t
+        // owns the 16-byte chunk of channels 8 * (t & 7) .. + 7 in rows t >> 3, + 16, ... Pixels outside the image keep the
+        // TMA's zero fill: the reference pads the NORMALISED activation (resnet.py:409, 425 padding = 1).
+        const int tx = threadIdx.x - W_XF0 * 32;  // 0 .. 255
+        const int j8 = tx & 7;
+        constexpr int PROW = 10;                  // patch row pitch in pixels (w_box + 2, w_box == 8 in the patch schedule)
+        constexpr int RSTEP = TG_XF_THREADS / 8;  // rows between two chunks of a thread (32)
+        constexpr int RITER = (18 * PROW + RSTEP - 1) / RSTEP;  // 6
+        int a_st = 0;
+        uint32_t a_ph = 0;
+        // mean / rstd of every (sample, group): double-precision math on the integer sums exactly as in gn_apply_k, once per
+        // CTA (the statistics are complete before the launch) into a shared-memory table; plans with more than
+        // XF_TABLE (sample, group) pairs compute them per box instead
+        constexpr int XF_TABLE = 512;
+        const int n_groups = p.a_C / p.ax_cpg;
+        const int n_pairs = p.a_B * n_groups;
+        const bool use_table = n_pairs <= XF_TABLE;
+        const double n_stat = static_cast<double>(p.ax_cpg) * static_cast<double>(p.ax_hw);
+        auto finalize = [&](int pair, float& mean, float& rstd) {
+            const acc_t* st = p.ax_stats + static_cast<long long>(pair) * 2;
+            const double m = static_cast<double>(__ldg(st)) * (1.0 / WFD_FX_STATS) / n_stat;
+            double var = static_cast<double>(__ldg(st + 1)) * (1.0 / WFD_FX_STATS) / n_stat - m * m;
+            if (var < 0) var = 0;
+            mean = static_cast<float>(m);
+            rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.ax_eps)));
+        };
+        if (use_table) {
+            for (int i = tx; i < n_pairs; i += TG_XF_THREADS) {
+                float mean, rstd;
+                finalize(i, mean, rstd);
+                xf_s[2 * i] = mean;
+                xf_s[2 * i + 1] = rstd;
+            }
+            asm volatile("bar.sync 4, %0;" ::"n"(TG_XF_THREADS) : "memory");
+        }
+        const uint32_t smA_u32 = smem_u32(smA);
+        long long x_wait = 0, x_math = 0;
+        const long long x_begin = clock64();
+        // this thread's rows of a box never change: row (tx >> 3) + 16 i, its patch coordinates, its swizzled byte offset
+        const int r0 = tx >> 3;
+        uint32_t rmask = 0;  // rows that exist (the last of the twelve only for the first 4 row lanes)
+#pragma unroll
+        for (int i = 0; i < RITER; ++i)
+            if (r0 + i * RSTEP < 18 * PROW) rmask |= 1u << i;
+        // (r & 7) == (r0 & 7) for every row of the thread (32-row steps): one swizzled chunk offset serves them all
+        const uint32_t chunk_off = static_cast<uint32_t>(r0 * 128 + ((j8 ^ (r0 & 7)) << 4));
+        int ch_cached = -1;
+        float ga[8], be[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ga[j] = be[j] = 0.f;
+        for (int base = first_tile; base < tile_end; base += 32 * tile_step) {
+            const int my_t = base + lane * tile_step;
+            const TileCoord mine = decode_tile(p, my_t < tile_end ? my_t : base, CG, rank);
+            int my_c0 = 0;
+            if (p.a_c0 && my_t < tile_end) my_c0 = __ldg(p.a_c0 + mine.n_tile);
+            const int batch = min(32, (tile_end - base + tile_step - 1) / tile_step);
+            for (int l = 0; l < batch; ++l) {
+                const int bb = __shfl_sync(0xffffffffu, mine.bb, l);
+                const int ty = __shfl_sync(0xffffffffu, mine.ty, l);
+                const int txx = __shfl_sync(0xffffffffu, mine.tx, l);
+                const int c0 = __shfl_sync(0xffffffffu, my_c0, l);
+                const int x_first = txx * p.w_box - 1;
+                const int y_first = ty * p.h_box + p.a_y_off - 1;
+                // rows of the box that are image pixels (bit i: row r0 + 16 i); interior tiles keep every row
+                uint32_t valid = rmask;
+                if (x_first < 0 || x_first + PROW > p.a_W || y_first < p.ax_y0 || y_first + 18 > p.ax_y1) {
+                    valid = 0;
+#pragma unroll
+                    for (int i = 0; i < RITER; ++i) {
+                        const int r = r0 + i * RSTEP;
+                        const int py = r / PROW, px = r - py * PROW;
+                        const int y = y_first + py, x = x_first + px;
+                        if (x >= 0 && x < p.a_W && y >= p.ax_y0 && y < p.ax_y1) valid |= 1u << i;
+                    }
+                    valid &= rmask;
+                }
+                for (int cc = 0; cc < p.cpt; ++cc) {
+                    // scale / shift of this thread's eight channels; gamma / beta are re-read only when the channels change
+                    // (consecutive tiles of a CTA mostly differ in the sample, i.e. in mean / rstd only)
+                    const int ch = c0 + cc * TG_KC + j8 * 8;
+                    float sc[8], sh[8];
+                    if (ch < p.a_C) {
+                        if (ch != ch_cached) {
+                            ch_cached = ch;
+                            const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ax_gamma + ch));
+                            const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.ax_gamma + ch) + 1);
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ax_beta + ch));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.ax_beta + ch) + 1);
+                            ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
+                            be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
+                        }
+                        float mean, rstd;
+                        const int pair = bb * n_groups + ch / p.ax_cpg;
+                        if (use_table) {
+                            const float2 mr = *reinterpret_cast<const float2*>(xf_s + 2 * pair);
+                            mean = mr.x;
+                            rstd = mr.y;
+                        } else {
+                            finalize(pair, mean, rstd);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            sc[j] = rstd * ga[j];
+                            sh[j] = be[j] - mean * rstd * ga[j];
+                        }
+                    } else {  // beyond the tensor: the TMA filled zeros and the weights there are zero; keep them zero
+                        ch_cached = -1;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) sc[j] = sh[j] = 0.f;
+                    }
+                    const long long xw0 = p.dbg ? clock64() : 0;
+                    mbar_wait(&afull_bar[a_st], a_ph);
+                    const long long xw1 = p.dbg ? clock64() : 0;
+                    const uint32_t box = smA_u32 + static_cast<uint32_t>(a_st) * a_stage_bytes + chunk_off;
+                    if (!(p.dbg_skip & 16)) {
+                        // two rows in flight per thread, branch-free math (only the loads and stores are predicated); two
+                        // transform warps share a scheduler, so one warp's FMAs fill the issue slots the other's tanh leaves
+                        constexpr int RU = 2;
+#pragma unroll
+                        for (int i0 = 0; i0 < RITER; i0 += RU) {
+                            uint32_t w[RU][4];
+#pragma unroll
+                            for (int u = 0; u < RU; ++u) {
+                                w[u][0] = w[u][1] = w[u][2] = w[u][3] = 0u;
+                                if (valid & (1u << (i0 + u))) lds128(box + (i0 + u) * RSTEP * 128, w[u]);
+                            }
+                            uint32_t o[RU][4];
+#pragma unroll
+                            for (int u = 0; u < RU; ++u) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float v0 = lo16_to_f<BF16>(w[u][j]) * sc[2 * j] + sh[2 * j];
+                                    float v1 = hi16_to_f<BF16>(w[u][j]) * sc[2 * j + 1] + sh[2 * j + 1];
+                                    if (p.ax_silu) {
+                                        v0 = v0 * fast_sigmoid(v0);
+                                        v1 = v1 * fast_sigmoid(v1);
+                                    }
+                                    o[u][j] = pack2<BF16>(v0, v1);
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < RU; ++u)
+                                if (valid & (1u << (i0 + u))) sts128(box + (i0 + u) * RSTEP * 128, o[u]);
+                        }
+                    }
+                    // the rewritten box must be visible to the tensor core (async proxy) before the MMA thread is told
+                    // (a cluster-scope release on the remote arrive compiles to MEMBAR.ALL.GPU - microseconds per box; the
+                    // proxy fence already orders this thread's shared-memory writes before the arrive)
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (CG == 2) mbar_arrive_leader(&aready_bar[a_st]);
+                        else mbar_arrive(&aready_bar[a_st]);
+                    }
+                    if (p.dbg) {
+                        x_wait += xw1 - xw0;
+                        x_math += clock64() - xw1;
+                    }
+                    if (++a_st == a_stages) {
+                        a_st = 0;
+                        a_ph ^= 1;
+                    }
+                }
+            }
+        }
+        if (p.dbg && blockIdx.x == 0 && tx == 0) {
+            p.dbg[12] = clock64() - x_begin;
+            p.dbg[13] = x_wait;
+            p.dbg[14] = x_math;
+        }
+    };
+    auto epilogue_role = [&]() {
         // ===================================================== epilogue (8 warps: a TMEM lane quarter is shared by two
         // warps that take the even / odd 16-column chunks of the tile)
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        const int half = (warp - 2) >> 2;    // 0: even chunks, 1: odd chunks (tile-split mode: even / odd tiles)
+        const int half = (warp - W_EPI0) >> 2;    // 0: even chunks, 1: odd chunks (tile-split mode: even / odd tiles)
         // Narrow tiles (a few 16-column chunks) are bound by the per-tile bookkeeping of the epilogue, not by its columns:
         // in tile-split mode each half-set of four warps owns one accumulator stage and drains every other tile on its own
         const bool split = p.epi_split != 0;
-        const int etid = split ? (threadIdx.x - 64) & 127 : threadIdx.x - 64;  // index among the threads that share a tile
+        const int etid = split ? (threadIdx.x - W_EPI0 * 32) & 127 : threadIdx.x - W_EPI0 * 32;  // index among the threads that share a tile
         const int eset = split ? TG_EPI_THREADS / 2 : TG_EPI_THREADS;
         const int c_first = split ? 0 : half, c_step = split ? 1 : 2;
         int acc = 0, my_tiles = 0;
@@ -1001,17 +1199,37 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (acc == 0) acc_phase ^= 1;
           }
         }
-        if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) {
+        if (p.dbg && blockIdx.x == 0 && threadIdx.x == W_EPI0 * 32) {
             p.dbg[5] = clock64() - t_begin;
             p.dbg[6] = w_tfull;
             p.dbg[7] = e_busy;
         }
+    };
+    if (XF) {
+        // registers per thread: 96 at launch (640 threads = 61440, the pool setmaxnreg moves registers within); the producer
+        // / MMA warpgroup and the transform warps give part of their share up, the epilogue warps grow to 136
+        // (4 x 40 + 8 x 136 + 8 x 80 warps x 32 lanes = 60416 <= 61440 - a request beyond the pool would wait forever)
+        if (warp < 4) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+            if (warp == 0 || warp == W_TMAB) producer_role();
+            else if (warp == 1) mma_role();
+        } else if (warp >= W_XF0) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+            xform_role();
+        } else {
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+            epilogue_role();
+        }
+    } else {
+        if (warp == 0 || warp == W_TMAB) producer_role();
+        else if (warp == 1) mma_role();
+        else epilogue_role();
     }
 
     tc_fence_before();
     __syncthreads();
     if (p.gn_sums || p.gnb_red) {
-        for (int i = threadIdx.x; i < TG_STAT_SLOTS; i += TG_THREADS) {
+        for (int i = threadIdx.x; i < TG_STAT_SLOTS; i += blockDim.x) {
             if (p.gn_sums) {
                 const unsigned long long v = stat_s[i];
                 if (v != 0ull) atomicAdd(reinterpret_cast<unsigned long long*>(p.gn_sums) + i, v);
@@ -1060,12 +1278,30 @@ __global__ void tapgemm_ref_kernel(const TapGemmParams p) {
         const uint16_t* arow = A + ((static_cast<long long>(ab) * p.a_H + yi) * p.a_W + xi) * p.a_ld;
         if (p.a_mn_major) arow = A + static_cast<long long>(ab) * p.a_C * p.a_ld + xi;  // column xi of the [K][M] sample
         const long long a_kstride = p.a_mn_major ? p.a_ld : 1;
+        const bool ax_pad = p.ax_stats && (yi < p.ax_y0 || yi >= p.ax_y1);  // a zeroed halo row at the map border
         for (int cc = 0; cc < p.cpt; ++cc) {
             const uint16_t* brow = Bm + static_cast<long long>(b_chunk_index(p, tap, cc)) * TG_KC;
             for (int k = 0; k < TG_KC; ++k) {
                 const int c = c0 + cc * TG_KC + k;
                 if (c >= p.a_C) break;
-                acc = fmaf(lo16_to_f<BF16>(arow[c * a_kstride]), lo16_to_f<BF16>(brow[k]), acc);
+                float av = lo16_to_f<BF16>(arow[c * a_kstride]);
+                if (p.ax_stats) {
+                    // operand transform: GroupNorm(+SiLU) of the raw activation, rounded to the operand type as the
+                    // transform warps of the tensor-core kernel store it
+                    const double n_stat = static_cast<double>(p.ax_cpg) * static_cast<double>(p.ax_hw);
+                    const acc_t* st = p.ax_stats + (static_cast<long long>(ab) * (p.a_C / p.ax_cpg) + c / p.ax_cpg) * 2;
+                    const double m = static_cast<double>(st[0]) * (1.0 / WFD_FX_STATS) / n_stat;
+                    double var = static_cast<double>(st[1]) * (1.0 / WFD_FX_STATS) / n_stat - m * m;
+                    if (var < 0) var = 0;
+                    const float mean = static_cast<float>(m);
+                    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.ax_eps)));
+                    const float ga = p.ax_gamma[c];
+                    const float sc = rstd * ga, sh = p.ax_beta[c] - mean * rstd * ga;
+                    float v = av * sc + sh;
+                    if (p.ax_silu) v = v * fast_sigmoid(v);
+                    av = ax_pad ? 0.f : lo16_to_f<BF16>(pack2<BF16>(v, 0.f));
+                }
+                acc = fmaf(av, lo16_to_f<BF16>(brow[k]), acc);
             }
         }
     }
@@ -1188,6 +1424,10 @@ int tapgemm_prepare(TapGemmOp* op) {
     }
     if (p.kc_list && (p.reuse || p.kk_last || !p.kc_cnt || p.b_resident)) {
         set_error("tapgemm_prepare: a K-chunk skip list needs the plain schedule with whole 64-channel chunks");
+        return -3;
+    }
+    if (p.ax_stats && (p.reuse != 2 || !p.ax_gamma || !p.ax_beta || p.ax_cpg < 8 || p.ax_cpg % 8 || p.a_C % p.ax_cpg || p.ax_hw < 1)) {
+        set_error("tapgemm_prepare: the operand transform needs the patch schedule and whole 8-channel vectors per GroupNorm group");
         return -3;
     }
     if (p.reuse == 2) {
@@ -1389,24 +1629,25 @@ int tapgemm_prepare(TapGemmOp* op) {
     }
     p.a_stages = a_stages;
     op->stages = stages;
+    op->threads = p.ax_stats ? TG_THREADS_XF : TG_THREADS;
     op->smem_bytes = 1024 + (patch ? a_stages * a_stage + stages * b_stage : stages * (a_stage + b_stage)) +
-                     (p.b_resident ? b_res_bytes : 0) + (2 * stages + 8 + 2 * a_stages) * sizeof(uint64_t) +
-                     6 * 256 * sizeof(float) + 2 * TG_STAT_SLOTS * sizeof(unsigned long long) + 16;
+                     (p.b_resident ? b_res_bytes : 0) + (2 * stages + 8 + 4 * a_stages) * sizeof(uint64_t) +
+                     6 * 256 * sizeof(float) + 2 * TG_STAT_SLOTS * sizeof(unsigned long long) + (p.ax_stats ? 2 * 512 * sizeof(float) : 0) + 16;
     return 0;
 }
 
-template <bool BF16, int CG>
+template <bool BF16, int CG, bool XF>
 static cudaError_t launch_variant(const TapGemmOp* op, int grid, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BF16, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BF16, CG, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(TG_THREADS);
+    cfg.blockDim = dim3(XF ? TG_THREADS_XF : TG_THREADS);
     cfg.dynamicSmemBytes = op->smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -1416,7 +1657,7 @@ static cudaError_t launch_variant(const TapGemmOp* op, int grid, cudaStream_t st
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, tapgemm_kernel<BF16, CG>, op->tmA, op->tmB, op->p, op->stages);
+    return cudaLaunchKernelEx(&cfg, tapgemm_kernel<BF16, CG, XF>, op->tmA, op->tmB, op->p, op->stages);
 }
 
 int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream) {
@@ -1440,9 +1681,9 @@ int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream) {
     int grid = total * cg < sms ? total * cg : (sms / cg) * cg;
     char pname[160];
     if (g_prof_on)
-        snprintf(pname, sizeof(pname), "tapgemm[%.11s]:N=%d,BN=%d,taps=%d,cpt=%d,aC=%d,f32=%d,reuse=%d,side=%d,gns=%d,cg=%d", op->tag, p.N, p.BN,
+        snprintf(pname, sizeof(pname), "tapgemm[%.11s]:N=%d,BN=%d,taps=%d,cpt=%d,aC=%d,f32=%d,reuse=%d,side=%d,gns=%d,cg=%d,xf=%d", op->tag, p.N, p.BN,
                  p.n_taps, p.cpt, p.a_C, p.out_fp32, p.reuse, p.residual ? 1 : (p.rowdot ? 2 : (p.gnb_red ? 3 : 0)),
-                 p.gn_sums ? 1 : 0, cg);
+                 p.gn_sums ? 1 : 0, cg, p.ax_stats ? 1 : 0);
     ProfScope prof_scope(g_prof_on ? pname : "", stream);
     cudaError_t e;
     // WFD_TG_DBG=1 (diagnosis only): every launch runs with the per-role wait counters of CTA 0 and prints them
@@ -1470,8 +1711,13 @@ int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream) {
         cudaMemsetAsync(tg_dbg_buf, 0, 16 * sizeof(long long), stream);
         op = &dbg_op;
     }
-    if (p.is_bf16) e = (cg == 2) ? launch_variant<true, 2>(op, grid, stream) : launch_variant<true, 1>(op, grid, stream);
-    else e = (cg == 2) ? launch_variant<false, 2>(op, grid, stream) : launch_variant<false, 1>(op, grid, stream);
+    if (p.ax_stats) {
+        if (p.is_bf16) e = (cg == 2) ? launch_variant<true, 2, true>(op, grid, stream) : launch_variant<true, 1, true>(op, grid, stream);
+        else e = (cg == 2) ? launch_variant<false, 2, true>(op, grid, stream) : launch_variant<false, 1, true>(op, grid, stream);
+    } else {
+        if (p.is_bf16) e = (cg == 2) ? launch_variant<true, 2, false>(op, grid, stream) : launch_variant<true, 1, false>(op, grid, stream);
+        else e = (cg == 2) ? launch_variant<false, 2, false>(op, grid, stream) : launch_variant<false, 1, false>(op, grid, stream);
+    }
     if (tg_dbg && op == &dbg_op && e == cudaSuccess) {
         long long h[16];
         cudaStreamSynchronize(stream);
@@ -1479,9 +1725,9 @@ int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream) {
         const TapGemmParams& q = op->p;
         fprintf(stderr,
                 "tgdbg N=%d BN=%d taps=%d cpt=%d aC=%d reuse=%d cg=%d side=%d tiles=%d grid=%d stages=%d | A %lld we %lld is %lld | "
-                "B %lld we %lld is %lld | MMA %lld wte %lld wf %lld | EPI %lld wtf %lld busy %lld\n",
+                "B %lld we %lld is %lld | MMA %lld wte %lld wf %lld | EPI %lld wtf %lld busy %lld | XF %lld wait %lld math %lld\n",
                 q.N, q.BN, q.n_taps, q.cpt, q.a_C, q.reuse, cg, q.residual ? 1 : (q.rowdot ? 2 : (q.gnb_red ? 3 : 0)), total, grid,
-                op->stages, h[0], h[1], h[10], h[8], h[9], h[11], h[2], h[3], h[4], h[5], h[6], h[7]);
+                op->stages, h[0], h[1], h[10], h[8], h[9], h[11], h[2], h[3], h[4], h[5], h[6], h[7], h[12], h[13], h[14]);
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -28,7 +28,12 @@ constexpr float WFD_FX_STATS = 1048576.f;          // 2^20: forward statistics (
 constexpr float WFD_FX_GRAD = 1099511627776.f;     // 2^40: backward reductions and row dots (small magnitudes)
 constexpr int TG_STAT_SLOTS = 1024;  // per-CTA shared-memory slots for fused GroupNorm partial sums ((sample, group) x 2)
 constexpr int TG_EPI_THREADS = 256;                 // warps 2-9: epilogue (two warps per TMEM lane quarter)
-constexpr int TG_THREADS = 64 + TG_EPI_THREADS + 32; // warp 0 TMA (activations), warp 1 MMA, last warp TMA (weights)
+constexpr int TG_THREADS = 64 + TG_EPI_THREADS + 32; // warp 0 TMA (activations), warp 1 MMA, warp 10 TMA (weights)
+// Launches with the operand transform (ax_stats set) use a warpgroup-aligned layout so that setmaxnreg can move registers
+// between the roles: warps 0-3 = TMA (activations), MMA, TMA (weights), idle; warps 4-11 = epilogue; warps 12-19 = transform
+constexpr int TG_XF_THREADS = 256;                  // transform warps (two per scheduler: a single in-order warp cannot overlap
+                                                    // its quarter-rate tanh with its FMAs)
+constexpr int TG_THREADS_XF = 128 + TG_EPI_THREADS + TG_XF_THREADS;  // 640
 
 struct TapGemmParams {
     // ---- tiling
@@ -91,6 +96,18 @@ struct TapGemmParams {
     const float* gnb_beta;
     int gnb_cpg, gnb_silu;
     float gnb_inv_n, gnb_eps;
+    // optional A-operand transform (patch schedule only): the activation tensor holds the RAW input x of a GroupNorm(+SiLU)
+    // layer (reference resnet.py:461-462, 483-489; wf_vae.py:228-229). Four transform warps normalise every landed halo
+    // box in shared memory - y = act((x - mean) * rstd * gamma + beta), zero outside the image (the conv pads y, not x) -
+    // before the MMAs read it, so the normalised activation never exists in HBM.
+    const acc_t* ax_stats;    // forward {sum, sumsq} per (sample, GroupNorm group), fixed point 2^20; nullptr = no transform
+    const float* ax_gamma;    // [a_C]
+    const float* ax_beta;     // [a_C]
+    int ax_cpg, ax_silu;      // channels per GroupNorm group (multiple of 8); 1 = SiLU after the affine map
+    int ax_hw;                // pixels of the whole plane (statistics are over ax_cpg x ax_hw elements)
+    float ax_eps;
+    int ax_y0, ax_y1;         // rows [ax_y0, ax_y1) of the A view are image rows (row-band plans: halo rows of the neighbour
+                              // bands are image rows too, the zeroed halo at the map border is not)
     int is_bf16;            // 1: bf16 operands/outputs, 0: fp16
     long long* dbg;         // optional [8]: per-role cycle counters of CTA 0 (test hook only)
     int dbg_skip;           // diagnosis only (WFD_TG_SKIP, results are garbage): bit 0 no activation TMA, bit 1 no weight TMA,
@@ -104,6 +121,7 @@ struct TapGemmOp {
     CUtensorMap tmA, tmB;
     TapGemmParams p;
     int stages;
+    int threads;   // block size: TG_THREADS, + TG_XF_THREADS when the operand transform is on
     size_t smem_bytes;
     char tag[12];  // launch class for the per-launch profile (dense, g4, g16, g64, conv_out, attn, wfc, down); may be empty
 };
