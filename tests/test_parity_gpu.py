@@ -235,6 +235,29 @@ def test_wfc_known_answers_on_device(tileset):
             assert wfc_loss(oh.cuda()).item() == 0.0
 
 
+def test_wfc_loss_accepts_any_channel_count_like_the_reference():
+    """losses.py:63-66 slices the first `count` channels of whatever it is given: a wave with exactly `count` channels (not
+    a multiple of 64) must work, forward and backward, with and without the softmax."""
+    mx, my = load_wfc_mats("install_64x64")
+    T = mx.shape[0]
+    assert T % 64 != 0
+    wfc_loss = WFCLossEinsum(mx, my).cuda()
+    g = torch.Generator().manual_seed(5)
+    logits = torch.randn(2, T, 16, 8, generator=g)
+    wave = logits.softmax(dim=1)
+    want = orc.wfc_loss(wave.double(), mx, my)
+    w = wave.cuda().requires_grad_()
+    got = wfc_loss(w)
+    assert got.shape == (2,) and _rel(got.cpu(), want) < TOL_LOSS
+    (gw,) = torch.autograd.grad(got.sum(), w)
+    assert gw.shape == w.shape
+    wd = wave.double().requires_grad_()
+    (gref,) = torch.autograd.grad(orc.wfc_loss(wd, mx, my).sum(), wd)
+    assert _rel(gw.cpu(), gref) < TOL_GRAD
+    got_sm = wfc_loss(logits.cuda(), softmax=True)
+    assert _rel(got_sm.cpu(), want) < TOL_LOSS
+
+
 def test_wfc_gradient_matches_closed_form():
     mx, my = load_wfc_mats("install_64x64")
     T = mx.shape[0]

@@ -235,6 +235,8 @@ int Decoder::init(const wfd_decoder_config& c, int h_, int w_, int Bmax, int dty
         use_patch = (np && np[0] == '1') ? 0 : 1;
         const char* na = getenv("WFD_FUSE_APPLY");
         fuse_apply = na ? atoi(na) : 1;
+        const char* tl = getenv("WFD_NO_TC_LATENT");
+        tc_latent = (tl && tl[0] == '1') ? 0 : 1;
         const char* ng = getenv("WFD_CONV_NGROUP");
         conv_n_group = ng ? atoi(ng) : 0;
         const char* m = getenv("WFD_FUSE_BWD_MAX_C");
@@ -491,6 +493,20 @@ int Decoder::finalize_weights() {
             for (int ci = 0; ci < 4; ++ci)
                 for (int t = 0; t < 9; ++t) wt[(static_cast<size_t>(t) * 4 + ci) * Cm + co] = (*wv)[(co * 4 + ci) * 9 + t];
         CK(upload_f32(wt, &vecs["decoder.conv_in.weight.T"]));
+    }
+    if (!encoder_side && Cm % 64 == 0) {
+        // conv_in^T as a tensor-core product: row tap*4 + ci of a 48-row matrix holds w[co, ci, tap] over co (rows 36..47
+        // are zero), i.e. a 1x1 "conv" from the Cm gradient channels to the 36 (tap, latent channel) pairs
+        const std::vector<float>* wv;
+        CK(need("decoder.conv_in.weight", static_cast<long long>(Cm) * 36, &wv));
+        std::vector<float> wt(static_cast<size_t>(48) * Cm, 0.f);
+        for (int co = 0; co < Cm; ++co)
+            for (int ci = 0; ci < 4; ++ci)
+                for (int t = 0; t < 9; ++t) wt[static_cast<size_t>(t * 4 + ci) * Cm + co] = (*wv)[(co * 4 + ci) * 9 + t];
+        ConvW& cw = convs["decoder.conv_in.T36"];
+        cw.cin = Cm;
+        cw.cout = 48;
+        CK(pack_conv(wt.data(), 48, Cm, 1, 1, 0, bf16 != 0, 48, &cw.fwd, nullptr, 0));
     }
     for (const ResnetDesc& r : resnets) {
         CK(upload_vec(r.prefix + ".norm1.weight", r.cin));
@@ -1250,6 +1266,23 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         cur = (cur + 1) & 3;
     }
     CK(resnet_bwd(0, ws + o_x0));
+    // conv_in^T + post_quant_conv^T. Single plans contract the Cm gradient channels against the 36 (tap, latent channel)
+    // weight rows on the tensor cores (the fp32 product lands in the idle score buffer) and a small kernel gathers the
+    // nine taps per latent pixel; row-band plans keep the CUDA-core kernel that reads the neighbour bands' halo rows.
+    if (tc_latent && !band && convs.count("decoder.conv_in.T36") != 0) {
+        const ConvW& ct = convs["decoder.conv_in.T36"];
+        cur_tag = "dense";
+        PlainGemm g;
+        memset(&g, 0, sizeof(g));
+        g.A = gbuf(cur); g.K = Cm; g.a_ld = Cm; g.rows_per_sample = hw; g.a_B = B_max;
+        g.Bm = ct.fwd.Bm; g.b_rows = ct.fwd.rows; g.ldb = ct.fwd.ldb; g.b_Z = 1; g.BN = ct.fwd.BN; g.N = 48;
+        g.out = ws + o_S; g.out_fp32 = 1; g.ldc = 48; g.alpha = 1.f;
+        CK(plain_gemm(ex, g));
+        if (!ex.prepare)
+            CK(latent_gather(reinterpret_cast<const float*>(ws + o_S), 48, last_in_scale, scale_b, vecs["post_quant_conv.weight"],
+                             dz, B, h, w, s));
+        return 0;
+    }
     if (!ex.prepare)
     {
         if (band) CK(halo_rows(ex, gbuf(cur), h, w, Cm));  // conv_in^T reads the neighbour bands' edge rows

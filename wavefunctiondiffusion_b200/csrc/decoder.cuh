@@ -80,6 +80,7 @@ struct Decoder {
     bool mmajor_a = true;  // attention backward reads P / dS as stored (M-major A operand) instead of transposed copies
     int reuse_hbox = 0;    // preferred patch height of the row-reuse contractions (WFD_REUSE_HBOX: 0 = widest patch, 2, 4, 8, 16)
     int use_reuse = 1;  // row-reuse schedule for 3x3 convs whose stage fits (WFD_NO_REUSE=1 disables, for A/B runs)
+    int tc_latent = 1;  // conv_in^T contracts its Cm channels on the tensor cores (WFD_NO_TC_LATENT=1: the CUDA-core kernel)
     int use_patch = 1;  // patch schedule for 3x3 convs on planes that tile into 16 x 8 patches (WFD_NO_PATCH=1 disables)
     int fuse_apply = 1; // GroupNorm+SiLU applied in the consuming patch-schedule conv's operand path instead of a standalone
                         // gn_apply pass (WFD_FUSE_APPLY): 0 = never, 1 = where a box's MMAs outlast its transform (N tiles of

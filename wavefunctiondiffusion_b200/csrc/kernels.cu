@@ -697,6 +697,47 @@ int latent_out(const void* dy, float in_scale, const float* scale_b, const float
     return 0;
 }
 
+// Second half of conv_in^T when its contraction over the Cm channels ran on the tensor cores (decoder.cu): `du` holds
+// [B*h*wd][ld] fp32 with column tap*4 + ci = sum_co dy[pixel, co] * w[co, ci, tap]; a latent pixel q gathers the nine taps
+// from its neighbours q - off(tap), applies post_quant_conv^T and the two scales. One thread per latent pixel.
+__global__ void __launch_bounds__(256)
+latent_gather_k(const float* __restrict__ du, int ld, float in_scale, const float* __restrict__ scale_b,
+                const float* __restrict__ pq_w, float* __restrict__ dz, int B, int h, int wd) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= B * h * wd) return;
+    const int b = pix / (h * wd);
+    const int pr = pix - b * h * wd;
+    const int y = pr / wd, x = pr - y * wd;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // same order of the nine taps as latent_out_k
+    for (int ky = 0; ky < 3; ++ky) {
+        const int ys = y - (ky - 1);
+        if (ys < 0 || ys >= h) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+            const int xs = x - (kx - 1);
+            if (xs < 0 || xs >= wd) continue;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(du + (static_cast<long long>(b) * h * wd + ys * wd + xs) * ld) + (ky * 3 + kx));
+            acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+        }
+    }
+    const float sc = in_scale * (scale_b ? scale_b[b] : 1.f);
+#pragma unroll
+    for (int cl = 0; cl < 4; ++cl) {
+        float a = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) a += pq_w[ci * 4 + cl] * acc[ci];
+        dz[((static_cast<long long>(b) * 4 + cl) * h + y) * wd + x] = a * sc;
+    }
+}
+int latent_gather(const float* du, int ld, float in_scale, const float* scale_b, const float* pq_w, float* dz, int B, int h,
+                  int wd, cudaStream_t s) {
+    ProfScope prof_scope("latent_gather", s);
+    const int total = B * h * wd;
+    latent_gather_k<<<(total + 255) / 256, 256, 0, s>>>(du, ld, in_scale, scale_b, pq_w, dz, B, h, wd);
+    WFD_CHECK_LAUNCH("latent_gather");
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ wave softmax
 constexpr int WS_MAXV = 20;  // vectors of 8 per lane -> rows up to 5120 channels stay in registers
 template <bool BF16, bool SOFTMAX>

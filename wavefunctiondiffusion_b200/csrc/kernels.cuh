@@ -37,6 +37,10 @@ int latent_in(const void* z, int z_f16, float in_scale, const float* pq_w, const
 // w must be the conv_in weight re-ordered to [ky][kx][ci][co]
 int latent_out(const void* dy, float in_scale, const float* scale_b, const float* pq_w, const float* w, float* dz,
                int B, int h, int wd, int Cm, int bf16, cudaStream_t s, int y_off = 0, int h_total = 0);
+// gathers the nine taps of conv_in^T from the tensor-core product du[pixel][tap*4 + ci] (row pitch ld floats), applies
+// post_quant_conv^T, in_scale and the per-sample scale
+int latent_gather(const float* du, int ld, float in_scale, const float* scale_b, const float* pq_w, float* dz, int B, int h,
+                  int wd, cudaStream_t s);
 
 // ---- wave softmax over all T_pad channels (reference pipeline_wfd.py:405); rowsum[n] = sum_{i<T} p~[n,i] of the
 // rounded 16-bit values that feed the contraction.

@@ -216,16 +216,21 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smB + static_cast<size_t>(stages) * b_stage_bytes + b_res_bytes);
     uint64_t* full_bar = bars;                 // [stages]
     uint64_t* empty_bar = bars + stages;       // [stages]
-    uint64_t* tfull_bar = bars + 2 * stages;   // [2]
-    uint64_t* tempty_bar = bars + 2 * stages + 2;  // [2]
-    uint64_t* bres_full = bars + 2 * stages + 4;   // resident weights landed
-    uint64_t* tdone_bar = bars + 2 * stages + 5;   // all MMAs of a tile completed (resident weights may be replaced)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 6);
-    uint64_t* afull_bar = bars + 2 * stages + 8;   // [a_stages] patch schedule only
+    // TMEM accumulator stages: 512 columns hold p.acc_stages (2, 4 or 8) accumulators of acc_cols columns each. Narrow N
+    // tiles get more than two: with two, a tile's MMAs cannot start before the epilogue of the tile before last has
+    // drained its stage, and the per-tile time becomes (MMA time + epilogue latency) / 2 instead of the larger of the two
+    const int acc_stages = p.acc_stages;
+    const uint32_t acc_cols = 512u / static_cast<uint32_t>(acc_stages);
+    uint64_t* tfull_bar = bars + 2 * stages;       // [<= 8]
+    uint64_t* tempty_bar = bars + 2 * stages + 8;  // [<= 8]
+    uint64_t* bres_full = bars + 2 * stages + 16;  // resident weights landed
+    uint64_t* tdone_bar = bars + 2 * stages + 17;  // all MMAs of a tile completed (resident weights may be replaced)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 18);
+    uint64_t* afull_bar = bars + 2 * stages + 20;  // [a_stages] patch schedule only
     uint64_t* aempty_bar = afull_bar + a_stages;   // [a_stages]
     uint64_t* aready_bar = aempty_bar + a_stages;  // [a_stages] XF only: the box is transformed (leader CTA's copy is used)
     // (an even number of 8-byte barriers keeps the float4 accesses of the staging arrays 16-byte aligned)
-    float* bias_s = reinterpret_cast<float*>(bars + 2 * stages + 8 + (patch ? 4 * a_stages : 0));  // [2][256]
+    float* bias_s = reinterpret_cast<float*>(bars + 2 * stages + 20 + (patch ? 4 * a_stages : 0));  // [2][256]
     float* gam_s = bias_s + 512;                                      // [2][256] GroupNorm-backward gamma
     float* bet_s = gam_s + 512;                                       // [2][256] GroupNorm-backward beta
     // per-CTA partial sums of the fused GroupNorm statistics / backward reductions, flushed once at kernel end: thousands
@@ -270,7 +275,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         mbar_init(bres_full, 1);
         mbar_init(tdone_bar, 1);
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < acc_stages; ++a) {
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], (p.epi_split ? TG_EPI_THREADS / 64 : TG_EPI_THREADS / 32) * CG);  // one arrival per epilogue warp
         }
@@ -558,7 +563,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             if (p.dbg) w_tempty += clock64() - w0;
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 256u;
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * acc_cols;
             if (patch) {
                 // patch schedule: per 64-channel chunk ONE activation box (halo patch, rows of w_box + 2 pixels) serves the
                 // nine taps through descriptor start offsets; weights come three taps (one vertical offset) per stage, or
@@ -634,8 +639,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         a_ph ^= 1;
                     }
                 }
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                if (++acc == acc_stages) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
                 continue;
             }
             int cc = 0;  // chunk index within the tap (the last chunk of a tap may hold fewer than 64 useful channels)
@@ -684,8 +691,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     b_cur = b_lo0;
                 }
             }
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
+            if (++acc == acc_stages) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
         }
         if (p.dbg && blockIdx.x == 0 && lane == 0) {
             p.dbg[2] = clock64() - t_begin;
@@ -897,9 +906,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc.bb = __shfl_sync(0xffffffffu, mine.bb, l);
             tc.ty = __shfl_sync(0xffffffffu, mine.ty, l);
             tc.tx = __shfl_sync(0xffffffffu, mine.tx, l);
-            if (split && acc != half) {  // the other half-set's tile
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+            if (split && (acc & 1) != half) {  // the other half-set's tile (stages alternate between the half-sets)
+                if (++acc == acc_stages) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
                 continue;
             }
             const long long pixel =
@@ -911,8 +922,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // stage this tile's bias in shared memory while the MMAs are still running
             // tile-split mode: a half-set always drains the same accumulator, so its staging buffers alternate with its own
             // tile count instead (four 128-float slices of each 2 x 256 array; BN <= 128 there)
-            const int stage_buf = split ? (my_tiles & 1) : acc;
-            const int stage_off = split ? (half * 2 + stage_buf) * 128 : acc * 256;
+            const int stage_buf = split ? (my_tiles & 1) : (acc & 1);
+            const int stage_off = split ? (half * 2 + stage_buf) * 128 : (acc & 1) * 256;
             ++my_tiles;
             float* bs = bias_s + stage_off;
             float* gms = gam_s + stage_off;
@@ -975,7 +986,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tc_fence_after();
             const long long e0 = p.dbg ? clock64() : 0;
-            const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * 256u + (static_cast<uint32_t>(q * 32) << 16);
+            const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * acc_cols + (static_cast<uint32_t>(q * 32) << 16);
             float dot = 0.f;
             float gs = 0.f, gss = 0.f;
             int ggroup = -1;
@@ -1195,8 +1206,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.rowdot)
                 atomicAdd(reinterpret_cast<unsigned long long*>(p.rowdot) + pixel, static_cast<unsigned long long>(__float2ll_rn((dot) * WFD_FX_GRAD)));
             if (p.dbg) e_busy += clock64() - e0;
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
+            if (++acc == acc_stages) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
           }
         }
         if (p.dbg && blockIdx.x == 0 && threadIdx.x == W_EPI0 * 32) {
@@ -1468,6 +1481,19 @@ int tapgemm_prepare(TapGemmOp* op) {
         const bool narrow_reuse = p.reuse && reuse2 && p.BN % 16 == 0;
         p.cg = (!no2 && p.cg != 1 && (wide || narrow_reuse) && pairs_ok) ? 2 : 1;
     }
+    {
+        // accumulator stages in TMEM (512 columns): two 256-column ones for wide tiles, four for N tiles of <= 128 columns,
+        // eight for <= 64 (WFD_ACC_STAGES caps it, for A/B runs)
+        static int cap = -1;
+        if (cap < 0) {
+            const char* e = getenv("WFD_ACC_STAGES");
+            cap = e ? atoi(e) : 8;
+            if (cap != 2 && cap != 4 && cap != 8) cap = 8;
+        }
+        int s = p.BN <= 64 ? 8 : (p.BN <= 128 ? 4 : 2);
+        if (s > cap) s = cap;
+        p.acc_stages = s;
+    }
     const bool patch = p.reuse == 2;
     if (patch) {
         // weights of one N tile stay resident when they leave room for >= 3 activation boxes (grouped layers); the CTAs
@@ -1631,7 +1657,7 @@ int tapgemm_prepare(TapGemmOp* op) {
     op->stages = stages;
     op->threads = p.ax_stats ? TG_THREADS_XF : TG_THREADS;
     op->smem_bytes = 1024 + (patch ? a_stages * a_stage + stages * b_stage : stages * (a_stage + b_stage)) +
-                     (p.b_resident ? b_res_bytes : 0) + (2 * stages + 8 + 4 * a_stages) * sizeof(uint64_t) +
+                     (p.b_resident ? b_res_bytes : 0) + (2 * stages + 20 + 4 * a_stages) * sizeof(uint64_t) +
                      6 * 256 * sizeof(float) + 2 * TG_STAT_SLOTS * sizeof(unsigned long long) + (p.ax_stats ? 2 * 512 * sizeof(float) : 0) + 16;
     return 0;
 }

@@ -67,5 +67,12 @@ class WFCLossEinsum(torch.nn.Module):
         if t.dim() != 4 or t.size(1) < self.count:
             raise ValueError(f"wave must be (B, C>={self.count}, H, W), got {tuple(t.shape)}")
         _require_cuda(t, "WFCLossEinsum")
+        # The reference accepts any channel count >= count (losses.py:63-66 slices [:count]); the contraction here walks the
+        # channels in blocks of 64, so other counts (e.g. a wave with exactly `count` channels) are padded with channels
+        # that carry no probability: zeros for a wave, a large negative logit when the softmax is still to come. The pad
+        # is an ordinary differentiable torch op, its backward is the slice.
+        pad = (-t.size(1)) % 64
+        if pad:
+            t = torch.nn.functional.pad(t, (0, 0, 0, 0, 0, pad), value=(-3.0e4 if softmax else 0.0))
         handle = self.native_handle(t.size(1), t.device)
         return WfcLossFunction.apply(t, handle, bool(softmax))
