@@ -235,6 +235,10 @@ int Decoder::init(const wfd_decoder_config& c, int h_, int w_, int Bmax, int dty
         use_patch = (np && np[0] == '1') ? 0 : 1;
         const char* na = getenv("WFD_FUSE_APPLY");
         fuse_apply = na ? atoi(na) : 1;
+        const char* ff = getenv("WFD_NO_FUSE_ATTN_FWD");
+        fuse_attn_fwd = (ff && ff[0] == '1') ? 0 : 1;
+        const char* fa = getenv("WFD_NO_FUSE_ATTN_BWD");
+        fuse_attn_bwd = (fa && fa[0] == '1') ? 0 : 1;
         const char* tl = getenv("WFD_NO_TC_LATENT");
         tc_latent = (tl && tl[0] == '1') ? 0 : 1;
         const char* ng = getenv("WFD_CONV_NGROUP");
@@ -359,7 +363,15 @@ void Decoder::layout_workspace() {
     o_xn = take(B * N * Cm * e);
     o_qkv = take(B * Nk * 3 * Cm * e);
     o_vt = take(B * Cm * Nk * e);
-    o_S = take(B * N * Nk * 4);
+    {
+        // fp32 N x Nk scratch of the unfused attention (scores, then dP). With both softmax directions fused into the
+        // products' epilogues only the row-statistics partials (16 bytes per row and N tile) and the 48-column product of
+        // conv_in^T live here: 17 GB less at 256 x 256
+        const size_t bn_n = Nk % 256 == 0 ? 256 : 128;
+        const size_t fused = std::max(B * N * (Nk / bn_n) * 16, B * hw * 48 * 4);
+        o_S = take((fuse_attn_fwd && fuse_attn_bwd) ? fused : std::max(fused, B * N * Nk * 4));
+    }
+    o_RS = take(B * N * 8);
     o_P = take(B * N * Nk * e);
     o_O = take(B * N * Cm * e);
     // backward-only attention scratch
@@ -367,6 +379,7 @@ void Decoder::layout_workspace() {
     o_dS = take(B * N * Nk * e);
     o_dST = mmajor_a ? 0 : take(B * N * Nk * e);
     o_dO = take(B * N * Cm * e);
+    o_D = take(B * N * 4);
     o_dOT = take(B * Cm * N * e);
     o_KT = take(B * Cm * Nk * e);
     o_QT = take(B * Cm * N * e);
@@ -719,6 +732,8 @@ struct PlainGemm {
     const float* bias; const void* residual; float alpha;
     acc_t* gn_sums; int gn_cpg;
     const GnBwdFuse* gb;
+    const float* sb_d; float sb_scale;   // softmax-backward epilogue: out = residual (= P) * (acc - sb_d[row]) * sb_scale
+    float2* rs_out; const float2* rs_in; // row-softmax passes (TapGemmParams::rs_out / rs_in)
 };
 int Decoder::plain_gemm(Exec& ex, const PlainGemm& g) {
     TapGemmOp op;
@@ -765,6 +780,10 @@ int Decoder::plain_gemm(Exec& ex, const PlainGemm& g) {
         p.bias = g.bias;
         p.residual = g.residual;
         p.alpha = g.alpha;
+        p.sb_d = g.sb_d;
+        p.sb_scale = g.sb_scale;
+        p.rs_out = g.rs_out;
+        p.rs_in = g.rs_in;
         p.gn_sums = (fuse_gn && g.gn_cpg > 0 && g.gn_cpg % 16 == 0) ? g.gn_sums : nullptr;
         p.gn_cpg = g.gn_cpg;
         p.gn_G = G;
@@ -948,9 +967,23 @@ int Decoder::attention_forward(Exec& ex, uint8_t* x, const std::string& attn_pre
         g.A = qkv; g.K = Cm; g.a_ld = 3 * Cm; g.rows_per_sample = N; g.a_B = B_max; g.a_shared = false;
         g.Bm = qkv_all + static_cast<size_t>(Cm) * 2; g.b_rows = Nk; g.ldb = 3 * Cm;
         g.b_zstride = static_cast<long long>(Nk) * 3 * Cm; g.b_Z = B_max; g.b_per_sample = true;
-        g.BN = bn_n; g.N = Nk; g.out = ws + o_S; g.out_fp32 = 1; g.ldc = Nk; g.alpha = 1.f / sqrtf(static_cast<float>(Cm));
-        CK(plain_gemm(ex, g));
-        if (!ex.prepare) CK(attn_softmax(reinterpret_cast<const float*>(ws + o_S), ws + o_P, static_cast<long long>(B) * N, Nk, bf16, s));
+        g.BN = bn_n; g.N = Nk; g.alpha = 1.f / sqrtf(static_cast<float>(Cm));
+        if (fuse_attn_fwd) {
+            // fp32 row softmax without the N x Nk score matrix in memory: the product runs twice, first keeping only
+            // {max, sum exp} per (row, N tile), then writing exp(s - max) / sum as the 16-bit probabilities
+            g.rs_out = reinterpret_cast<float2*>(ws + o_S);
+            CK(plain_gemm(ex, g));
+            if (!ex.prepare)
+                CK(rowstats_combine(ws + o_S, ws + o_RS, static_cast<long long>(B) * N, 2 * ((Nk + bn_n - 1) / bn_n), s));
+            g.rs_out = nullptr;
+            g.rs_in = reinterpret_cast<const float2*>(ws + o_RS);
+            g.out = ws + o_P; g.out_fp32 = 0; g.ldc = Nk;
+            CK(plain_gemm(ex, g));
+        } else {
+            g.out = ws + o_S; g.out_fp32 = 1; g.ldc = Nk;
+            CK(plain_gemm(ex, g));
+            if (!ex.prepare) CK(attn_softmax(reinterpret_cast<const float*>(ws + o_S), ws + o_P, static_cast<long long>(B) * N, Nk, bf16, s));
+        }
         // o = p v
         memset(&g, 0, sizeof(g));
         g.A = ws + o_P; g.K = Nk; g.a_ld = Nk; g.rows_per_sample = N; g.a_B = B_max; g.a_shared = false;
@@ -1214,18 +1247,28 @@ int Decoder::backward_impl(Exec& ex, const void* dlogits_in, const float* scale_
         if (split) { g.out = dkv + static_cast<size_t>(Cm) * 4; g.out_fp32 = 1; g.ldc = 2 * Cm; }
         else { g.out = dqkv + static_cast<size_t>(2 * Cm) * 2; g.ldc = 3 * Cm; }
         CK(plain_gemm(ex, g));
-        // dP = dO V^T (fp32, reuses the score buffer)
+        // dP = dO V^T and the softmax backward dS = P * (dP - rowdot) / sqrt(C). Fused form (default): rowdot[i] =
+        // sum_j dP[i,j] P[i,j] = sum_c dO[i,c] O[i,c] comes from a small [N, C] pass and the product's epilogue writes dS
+        // directly, so the fp32 N x Nk matrix dP is neither written nor read (WFD_NO_FUSE_ATTN_BWD=1: the two-kernel form)
         memset(&g, 0, sizeof(g));
         g.A = ws + o_dO; g.K = Cm; g.a_ld = Cm; g.rows_per_sample = N; g.a_B = B_max;
         g.Bm = qkv_all + static_cast<size_t>(2 * Cm) * 2; g.b_rows = Nk; g.ldb = 3 * Cm;
         g.b_zstride = static_cast<long long>(Nk) * 3 * Cm; g.b_Z = B_max; g.b_per_sample = true;
-        g.BN = bn_n; g.N = Nk; g.out = ws + o_S; g.out_fp32 = 1; g.ldc = Nk; g.alpha = 1.f;
-        CK(plain_gemm(ex, g));
-        if (!ex.prepare) {
-            CK(attn_softmax_bwd(ws + o_P, reinterpret_cast<const float*>(ws + o_S), ws + o_dS, static_cast<long long>(B) * N,
-                                Nk, 1.f / sqrtf(static_cast<float>(Cm)), bf16, s));
-            if (!mmajor_a) CK(transpose16(ws + o_dS, ws + o_dST, B, N, Nk, Nk, static_cast<long long>(N) * Nk, s));
+        g.BN = bn_n; g.N = Nk; g.alpha = 1.f;
+        if (fuse_attn_bwd) {
+            if (!ex.prepare)
+                CK(rowdot16(ws + o_dO, ws + o_O, reinterpret_cast<float*>(ws + o_D), static_cast<long long>(B) * N, Cm, bf16, s));
+            g.out = ws + o_dS; g.out_fp32 = 0; g.ldc = Nk; g.residual = ws + o_P;
+            g.sb_d = reinterpret_cast<const float*>(ws + o_D); g.sb_scale = 1.f / sqrtf(static_cast<float>(Cm));
+            CK(plain_gemm(ex, g));
+        } else {
+            g.out = ws + o_S; g.out_fp32 = 1; g.ldc = Nk;
+            CK(plain_gemm(ex, g));
+            if (!ex.prepare)
+                CK(attn_softmax_bwd(ws + o_P, reinterpret_cast<const float*>(ws + o_S), ws + o_dS, static_cast<long long>(B) * N,
+                                    Nk, 1.f / sqrtf(static_cast<float>(Cm)), bf16, s));
         }
+        if (!ex.prepare && !mmajor_a) CK(transpose16(ws + o_dS, ws + o_dST, B, N, Nk, Nk, static_cast<long long>(N) * Nk, s));
         // dQ = dS K -> dqkv[:, 0:C]
         memset(&g, 0, sizeof(g));
         g.A = ws + o_dS; g.K = Nk; g.a_ld = Nk; g.rows_per_sample = N; g.a_B = B_max;

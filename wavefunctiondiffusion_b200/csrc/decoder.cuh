@@ -80,6 +80,8 @@ struct Decoder {
     bool mmajor_a = true;  // attention backward reads P / dS as stored (M-major A operand) instead of transposed copies
     int reuse_hbox = 0;    // preferred patch height of the row-reuse contractions (WFD_REUSE_HBOX: 0 = widest patch, 2, 4, 8, 16)
     int use_reuse = 1;  // row-reuse schedule for 3x3 convs whose stage fits (WFD_NO_REUSE=1 disables, for A/B runs)
+    int fuse_attn_fwd = 1;  // row softmax inside two passes of the score product (WFD_NO_FUSE_ATTN_FWD=1: fp32 scores + kernel)
+    int fuse_attn_bwd = 1;  // softmax backward in the epilogue of dP = dO V^T (WFD_NO_FUSE_ATTN_BWD=1: separate fp32 dP + kernel)
     int tc_latent = 1;  // conv_in^T contracts its Cm channels on the tensor cores (WFD_NO_TC_LATENT=1: the CUDA-core kernel)
     int use_patch = 1;  // patch schedule for 3x3 convs on planes that tile into 16 x 8 patches (WFD_NO_PATCH=1 disables)
     int fuse_apply = 1; // GroupNorm+SiLU applied in the consuming patch-schedule conv's operand path instead of a standalone
@@ -104,6 +106,8 @@ struct Decoder {
     uint8_t* ws = nullptr;
     size_t ws_bytes = 0;
     size_t o_x0 = 0, o_attn_out = 0, o_xn = 0, o_qkv = 0, o_vt = 0, o_S = 0, o_P = 0, o_O = 0;
+    size_t o_RS = 0;        // float2 [B, N] {row max, 1 / row sum} of the fused forward softmax
+    size_t o_D = 0;         // fp32 [B, N] row dots sum_c dO * O of the softmax backward
     size_t o_PT = 0, o_dS = 0, o_dST = 0, o_dO = 0, o_dOT = 0, o_KT = 0, o_QT = 0, o_dqkv = 0;
     size_t o_act = 0, o_act2 = 0, o_sc = 0, o_g[4] = {0, 0, 0, 0}, o_logits = 0, o_dlogits = 0, o_gn = 0;
     std::vector<size_t> o_res_h1, o_res_out, o_down_out;

@@ -47,6 +47,10 @@ int Encoder::init_enc(const wfd_decoder_config& c, int H_, int W_, int Bmax, int
         fuse_gn = (f && f[0] == '1') ? 0 : 1;
         const char* np = getenv("WFD_NO_PATCH");
         use_patch = (np && np[0] == '1') ? 0 : 1;
+        const char* na = getenv("WFD_FUSE_APPLY");
+        fuse_apply = na ? atoi(na) : 1;
+        const char* ff = getenv("WFD_NO_FUSE_ATTN_FWD");
+        fuse_attn_fwd = (ff && ff[0] == '1') ? 0 : 1;
     }
     const int nb = c.n_blocks;
     if (c.latent_channels != 4 || nb < 1 || nb > 8 || Bmax < 1 || h < 1 || w < 1) {
@@ -131,6 +135,7 @@ int Encoder::init_enc(const wfd_decoder_config& c, int H_, int W_, int Bmax, int
     o_qkv = take(B * hw * 3 * Cm * e);
     o_vt = take(B * Cm * hw * e);
     o_S = take(B * hw * hw * 4);
+    o_RS = take(B * hw * 8);
     o_P = take(B * hw * hw * e);
     o_O = take(B * hw * Cm * e);
     o_act = take(B * hw * maxC * e);

@@ -1026,6 +1026,62 @@ int attn_softmax_bwd(const void* probs, const float* dp, void* ds, long long row
     return 0;
 }
 
+// Row softmax, between the two passes of the score product: the {max, sum exp} partials of a row (one per N tile and
+// epilogue half, empty ones are {-inf, 0}) are merged in index order into {row max, 1 / row sum}. One thread per row.
+__global__ void __launch_bounds__(256)
+rowstats_combine_k(const float2* __restrict__ part, float2* __restrict__ out, long long rows, int n_part) {
+    const long long row = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    const float2* pr = part + row * n_part;
+    float M = -INFINITY;
+    for (int i = 0; i < n_part; ++i) M = fmaxf(M, __ldg(pr + i).x);
+    float L = 0.f;
+    for (int i = 0; i < n_part; ++i) {
+        const float2 v = __ldg(pr + i);
+        if (v.y > 0.f) L += v.y * __expf(v.x - M);
+    }
+    out[row] = make_float2(M, 1.f / L);
+}
+int rowstats_combine(const void* part, void* out, long long rows, int n_part, cudaStream_t s) {
+    ProfScope prof_scope("rowstats_combine", s);
+    rowstats_combine_k<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, s>>>(static_cast<const float2*>(part),
+                                                                               static_cast<float2*>(out), rows, n_part);
+    WFD_CHECK_LAUNCH("rowstats_combine");
+    return 0;
+}
+
+// D[row] = sum_c a[row, c] * b[row, c] in fp32 over two 16-bit [rows, C] matrices (C a multiple of 8): one warp per row.
+// Softmax backward needs sum_n dP[row, n] P[row, n] = sum_c dO[row, c] O[row, c] (O = P V, dP = dO V^T).
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+rowdot16_k(const uint4* __restrict__ a, const uint4* __restrict__ b, float* __restrict__ d, long long rows, int nv) {
+    const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    float acc = 0.f;
+    for (int v = lane; v < nv; v += 32) {
+        float fa[8], fb[8];
+        unpack8<BF16>(__ldg(a + row * nv + v), fa);
+        unpack8<BF16>(__ldg(b + row * nv + v), fb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = fmaf(fa[j], fb[j], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) d[row] = acc;
+}
+int rowdot16(const void* a, const void* b, float* d, long long rows, int C, int bf16, cudaStream_t s) {
+    ProfScope prof_scope("rowdot16", s);
+    if (C % 8) {
+        set_error("rowdot16: C=%d must be a multiple of 8", C);
+        return -3;
+    }
+    const unsigned blocks = static_cast<unsigned>((rows * 32 + 255) / 256);
+    WFD_DISPATCH_BF16(bf16, (rowdot16_k<BF16><<<blocks, 256, 0, s>>>(static_cast<const uint4*>(a), static_cast<const uint4*>(b), d,
+                                                                     rows, C / 8)));
+    WFD_CHECK_LAUNCH("rowdot16");
+    return 0;
+}
+
 __global__ void __launch_bounds__(256)
 transpose16_k(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int R, int C, long long ld_in,
               long long zstride_in) {

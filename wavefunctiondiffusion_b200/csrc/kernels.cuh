@@ -62,6 +62,10 @@ int attn_softmax(const float* scores, void* probs, long long rows, int n, int bf
 // ds = p * (dp - sum_j dp*p) * scale
 int attn_softmax_bwd(const void* probs, const float* dp, void* ds, long long rows, int n, float scale, int bf16,
                      cudaStream_t s);
+// d[row] = sum_c a[row, c] * b[row, c] (fp32) over two 16-bit [rows, C] matrices
+int rowdot16(const void* a, const void* b, float* d, long long rows, int C, int bf16, cudaStream_t s);
+// merges the per-(N tile, half) {max, sum exp} partials of every row into {row max, 1 / row sum} (float2 in, float2 out)
+int rowstats_combine(const void* part, void* out, long long rows, int n_part, cudaStream_t s);
 // batched 16-bit transpose: in [Z, R, C] (row stride ld_in) -> out [Z, C, R]
 int transpose16(const void* in, void* out, int Z, int R, int C, long long ld_in, long long zstride_in, cudaStream_t s);
 

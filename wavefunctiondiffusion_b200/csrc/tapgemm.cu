@@ -965,6 +965,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             else if (side_kind == 3)
                 side_ptr = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.gnb_x) + out_off + n0);
             const int n_chunks = (min(p.BN, p.N - n0) + 15) / 16;
+            const float sb_row = p.sb_d ? __ldg(p.sb_d + pixel + tc.z * static_cast<long long>(p.m_tiles) * TG_BM) : 0.f;
             uint4 sb0[2], sb1[2], sb2[2];
             auto load_side = [&](int chunk, uint4(&dst)[2]) {
                 if (p.wide_io) {
@@ -988,6 +989,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const long long e0 = p.dbg ? clock64() : 0;
             const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * acc_cols + (static_cast<uint32_t>(q * 32) << 16);
             float dot = 0.f;
+            float rs_m = -INFINITY, rs_l = 0.f;                       // pass 1 of the row softmax
+            const float2 rs_row = p.rs_in ? __ldg(p.rs_in + pixel + tc.z * static_cast<long long>(p.m_tiles) * TG_BM) : make_float2(0.f, 0.f);
             float gs = 0.f, gss = 0.f;
             int ggroup = -1;
             // GroupNorm group of a 16-column chunk without a division per chunk: the group of the tile's first column
@@ -1020,7 +1023,17 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
                     }
                 }
-                if (side_kind == 1) {
+                if (side_kind == 1 && p.sb_d) {  // softmax backward: dS = P * (dP - rowdot) * scale
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t w[4] = {side_cur[h].x, side_cur[h].y, side_cur[h].z, side_cur[h].w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            v[h * 8 + 2 * j] = lo16_to_f<BF16>(w[j]) * (v[h * 8 + 2 * j] - sb_row) * p.sb_scale;
+                            v[h * 8 + 2 * j + 1] = hi16_to_f<BF16>(w[j]) * (v[h * 8 + 2 * j + 1] - sb_row) * p.sb_scale;
+                        }
+                    }
+                } else if (side_kind == 1) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const uint32_t w[4] = {side_cur[h].x, side_cur[h].y, side_cur[h].z, side_cur[h].w};
@@ -1041,6 +1054,22 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             dot += v[h * 8 + 2 * j + 1] * hi16_to_f<BF16>(w[j]);
                         }
                     }
+                }
+                if (p.rs_out) {  // row softmax, pass 1: statistics only
+                    float cm = v[0];
+#pragma unroll
+                    for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[j]);
+                    if (cm > rs_m) {
+                        rs_l *= __expf(rs_m - cm);
+                        rs_m = cm;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) rs_l += __expf(v[j] - rs_m);
+                    continue;
+                }
+                if (p.rs_in) {   // row softmax, pass 2: probabilities
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __expf(v[j] - rs_row.x) * rs_row.y;
                 }
                 if (p.out_fp32) {
                     float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + n);
@@ -1168,6 +1197,17 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) {
                 if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]);  // the MMA thread lives in the leader CTA
                 else mbar_arrive(&tempty_bar[acc]);
+            }
+            if (p.rs_out) {
+                // one partial per (row, N tile, half): in chunk-split mode the two warps of a lane quarter saw the even /
+                // odd chunks, in tile-split mode the tile's only warp writes slot 0 and an empty slot 1
+                const long long slot = ((pixel + tc.z * static_cast<long long>(p.m_tiles) * TG_BM) * p.n_tiles + tc.n_tile) * 2;
+                if (split) {
+                    p.rs_out[slot] = make_float2(rs_m, rs_l);
+                    p.rs_out[slot + 1] = make_float2(-INFINITY, 0.f);
+                } else {
+                    p.rs_out[slot + half] = make_float2(rs_m, rs_l);
+                }
             }
             if (p.gn_sums && ggroup >= 0) {
 #pragma unroll
@@ -1322,7 +1362,13 @@ __global__ void tapgemm_ref_kernel(const TapGemmParams p) {
     if (p.bias) v += p.bias[n];
     const long long off = z * p.c_zstride + bb * p.out_sb + static_cast<long long>(y) * p.out_sy +
                           static_cast<long long>(x) * p.out_sx + n;
-    if (p.residual) v += lo16_to_f<BF16>(reinterpret_cast<const uint16_t*>(p.residual)[off]);
+    if (p.rs_in) {
+        const float2 st = p.rs_in[pixel + z * total_rows];
+        v = __expf(v - st.x) * st.y;
+    }
+    if (p.residual && p.sb_d)
+        v = lo16_to_f<BF16>(reinterpret_cast<const uint16_t*>(p.residual)[off]) * (v - p.sb_d[pixel + z * total_rows]) * p.sb_scale;
+    else if (p.residual) v += lo16_to_f<BF16>(reinterpret_cast<const uint16_t*>(p.residual)[off]);
     if (p.rowdot)
         atomicAdd(reinterpret_cast<unsigned long long*>(p.rowdot) + pixel,
                   static_cast<unsigned long long>(__float2ll_rn((v * lo16_to_f<BF16>(reinterpret_cast<const uint16_t*>(p.dotsrc)[pixel * p.ld_dot + n])) * WFD_FX_GRAD)));
@@ -1404,6 +1450,10 @@ int tapgemm_prepare(TapGemmOp* op) {
         p.n_taps < 1 || p.n_taps > TG_MAX_TAPS || p.cpt < 1) {
         set_error("tapgemm_prepare: bad tiling (BN=%d N=%d box=%dx%d taps=%d cpt=%d)", p.BN, p.N, p.w_box, p.h_box,
                   p.n_taps, p.cpt);
+        return -3;
+    }
+    if (p.rs_out && (p.residual || p.rowdot || p.gnb_red || p.gn_sums || p.bias || p.rs_in)) {
+        set_error("tapgemm_prepare: the row-statistics epilogue stores nothing and takes no other epilogue option");
         return -3;
     }
     if ((p.residual ? 1 : 0) + (p.rowdot ? 1 : 0) + (p.gnb_red ? 1 : 0) > 1) {
@@ -1772,8 +1822,56 @@ int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream) {
     return 0;
 }
 
+// checking-kernel counterpart of the row-statistics epilogue (plain one-tap GEMMs only): one thread per (row, N tile)
+template <bool BF16>
+__global__ void tapgemm_ref_rowstats_kernel(const TapGemmParams p) {
+    const long long total_rows = static_cast<long long>(p.m_tiles) * TG_BM;
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total_rows * p.n_tiles * p.z_count) return;
+    const int n_tile = static_cast<int>(idx % p.n_tiles);
+    const long long zr = idx / p.n_tiles;
+    const int z = static_cast<int>(zr / total_rows);
+    const long long pixel = zr - z * total_rows;
+    const long long rows_per_sample = static_cast<long long>(p.H) * p.W;
+    const int bb = static_cast<int>(pixel / rows_per_sample);
+    const int x = static_cast<int>(pixel - bb * rows_per_sample);
+    const int ab = bb + z * p.a_zmul, bz = z * p.b_zmul + bb * p.b_bbmul;
+    const uint16_t* arow = reinterpret_cast<const uint16_t*>(p.a_ptr) + (static_cast<long long>(ab) * p.a_W + x) * p.a_ld;
+    float m = -INFINITY, l = 0.f;
+    for (int n = n_tile * p.BN; n < min(p.N, (n_tile + 1) * p.BN); ++n) {
+        const uint16_t* brow = reinterpret_cast<const uint16_t*>(p.b_ptr) + bz * p.b_zstride + static_cast<long long>(n) * p.ldb;
+        float acc = 0.f;
+        for (int k = 0; k < p.cpt * TG_KC && k < p.a_C; ++k) acc = fmaf(lo16_to_f<BF16>(arow[k]), lo16_to_f<BF16>(brow[k]), acc);
+        const float v = acc * p.alpha;
+        if (v > m) {
+            l *= __expf(m - v);
+            m = v;
+        }
+        l += __expf(v - m);
+    }
+    const long long slot = ((pixel + z * total_rows) * p.n_tiles + n_tile) * 2;
+    p.rs_out[slot] = make_float2(m, l);
+    p.rs_out[slot + 1] = make_float2(-INFINITY, 0.f);
+}
+
 int tapgemm_launch_ref(const TapGemmOp* op, cudaStream_t stream) {
     const TapGemmParams& p = op->p;
+    if (p.rs_out) {
+        if (p.n_taps != 1 || p.a_mn_major || p.a_c0) {
+            set_error("tapgemm_ref: the row-statistics epilogue is checked for plain one-tap GEMMs only");
+            return -3;
+        }
+        const long long n = static_cast<long long>(p.m_tiles) * TG_BM * p.n_tiles * p.z_count;
+        if (n <= 0) return 0;
+        const unsigned nb = static_cast<unsigned>((n + 127) / 128);
+        if (p.is_bf16) tapgemm_ref_rowstats_kernel<true><<<nb, 128, 0, stream>>>(op->p);
+        else tapgemm_ref_rowstats_kernel<false><<<nb, 128, 0, stream>>>(op->p);
+        if (cudaGetLastError() != cudaSuccess) {
+            set_error("tapgemm_ref rowstats launch failed");
+            return -7;
+        }
+        return 0;
+    }
     const long long total = static_cast<long long>(p.m_tiles) * TG_BM * p.N * p.z_count;
     if (total <= 0) return 0;
     const int threads = 256;

@@ -83,6 +83,18 @@ struct TapGemmParams {
     const float* bias;      // [N] or nullptr
     const void* residual;   // same layout/dtype(16-bit) as out, or nullptr
     float alpha;
+    // optional softmax-backward epilogue (attention.py:367 differentiated): `residual` then points at the probabilities P
+    // (layout of the output) and the stored value is P[m,n] * (D[m,n] - sb_d[row m]) * sb_scale, i.e. dS from dP = D without
+    // dP ever reaching memory; sb_d[row] = sum_n dP[row,n] P[row,n] is given as sum_c dO[row,c] O[row,c]
+    const float* sb_d;
+    float sb_scale;
+    // optional row-softmax epilogues (attention.py:367 without the fp32 score matrix in memory). Pass 1, rs_out set: nothing
+    // is stored; per (row, N tile, epilogue half) the running {max, sum exp(. - max)} of the tile's columns goes to
+    // rs_out[(row * n_tiles + n_tile) * 2 + half]. Pass 2, rs_in set: the same product again, stored as
+    // exp(D[m,n] - rs_in[row].x) * rs_in[row].y, i.e. the probabilities, with rs_in = {row max, 1 / row sum} combined from
+    // the partials of pass 1 in a fixed order.
+    float2* rs_out;
+    const float2* rs_in;
     acc_t* rowdot;          // optional: rowdot[pixel] += sum_n D[m,n] * dotsrc[pixel*ld_dot + n] (fixed point 2^40)
     const void* dotsrc;
     long long ld_dot;
