@@ -13,6 +13,7 @@ Rank 0 prints exactly one JSON line.
 import argparse
 import ctypes as C
 import json
+import re
 import os
 import subprocess
 import sys
@@ -97,26 +98,11 @@ def class_flops(cfg, h, w, T, t_pad, kc_kept):
     exe = dict(alg)
     n_tiles = (t_pad + 255) // 256
     exe["wfc"] = 2.0 * px * (n_tiles * 256) * (4 * t_pad) * kc_kept
+    if os.environ.get("WFD_NO_FUSE_ATTN_FWD", "0") != "1":
+        # the fp32 row softmax runs inside TWO passes of the score product (row statistics, then probabilities):
+        # one more N x N x C product is executed than the algorithm needs
+        exe["attn"] += 2.0 * (h * w) ** 2 * cm
     return alg, exe
-
-
-def gn_pass_bytes(cfg, h, w):
-    """Algorithmic HBM bytes per map-step of the standalone GroupNorm passes (16-bit activations): every
-    GN layer reads x and writes y forward; backward reads dy and x (reduce) and dy, x (+ residual gradient), writes dx."""
-    rev = list(reversed(cfg["block_out_channels"]))
-    n_res = cfg["layers_per_block"] + 1
-    hw = h * w
-    elems, px, ch = 0, hw, rev[0]
-    elems += 2 * 2 * rev[0] * hw + rev[0] * hw          # mid resnets (2 x 2 GN) + attention group_norm
-    for i, kind in enumerate(cfg["up_block_types"]):
-        for j in range(n_res):
-            cin = ch if j == 0 else rev[i]
-            elems += (cin + rev[i]) * px
-        ch = rev[i]
-        if kind == "DownDecoderBlock2D":
-            px //= 4
-    elems += ch * px                                      # conv_norm_out
-    return {"gn_apply": 2.0 * 2 * elems, "gn_bwd_apply": 2.0 * 3.5 * elems, "gn_bwd_reduce": 2.0 * 2 * elems}
 
 
 def step_flops(cfg, h, w, T):
@@ -670,12 +656,24 @@ def run_native(args):
                 "whole_step_frac_of_ideal": (fl["F_step"] * B / (peak * 1e12)) / (ms / args.steps / 1e3),
                 "traffic": None}
     hbm_peak = peaks.get("hbm_gbs", 6551.4)
-    gn_bytes = {k: v * B for k, v in gn_pass_bytes(cfg, args.latent, args.latent).items()}
+    # standalone GroupNorm passes: the launches that actually ran carry their shape in the profile name (layers whose
+    # normalisation is applied inside the consuming conv have no gn_apply launch); 16-bit streams per launch: apply reads x
+    # and writes y, the backward reduction reads dy and x, the backward apply reads dy, x (+ the residual gradient), writes dx
+    gn = {}
+    for n, (c, t) in prof.items():
+        m = re.match(r"(gn_apply|gn_bwd_reduce|gn_bwd_apply):C=(\d+),HW=(\d+),B=(\d+)(?:,add=(\d))?", n)
+        if not m:
+            continue
+        streams = {"gn_apply": 2, "gn_bwd_reduce": 2, "gn_bwd_apply": 3 + int(m.group(5) or 0)}[m.group(1)]
+        e = gn.setdefault(m.group(1), {"ms": 0.0, "bytes": 0.0, "launches": 0.0})
+        e["ms"] += t
+        e["launches"] += c
+        e["bytes"] += c * streams * 2.0 * int(m.group(2)) * int(m.group(3)) * int(m.group(4))
     roofline["hbm_kernels"] = {
-        k: {"ms_per_step": prof[k][1], "algorithmic_gb_per_step": gb / 1e9,
-            "gbps": gb / (prof[k][1] / 1e3) / 1e9 if prof[k][1] > 0 else None,
-            "frac": gb / (prof[k][1] / 1e3) / 1e9 / hbm_peak if prof[k][1] > 0 else None}
-        for k, gb in gn_bytes.items() if k in prof}
+        k: {"ms_per_step": e["ms"], "launches_per_step": e["launches"], "algorithmic_gb_per_step": e["bytes"] / 1e9,
+            "gbps": e["bytes"] / (e["ms"] / 1e3) / 1e9 if e["ms"] > 0 else None,
+            "frac": e["bytes"] / (e["ms"] / 1e3) / 1e9 / hbm_peak if e["ms"] > 0 else None}
+        for k, e in gn.items()}
     # DRAM bytes per launch come from the committed ncu capture of the same workload (they cannot be measured live)
     if args.tileset == "ice_64x64" and args.latent == 64 and args.arch == "64x64" and B == 8:
         try:
