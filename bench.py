@@ -677,10 +677,10 @@ def run_native(args):
     # DRAM bytes per launch come from the committed ncu capture of the same workload (they cannot be measured live)
     if args.tileset == "ice_64x64" and args.latent == 64 and args.arch == "64x64" and B == 8:
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01c_tapgemm_dram.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_tapgemm_dram.json")))
             roofline["traffic"] = tr["traffic_bytes_per_launch"]
             roofline["traffic_unit"] = "bytes per launch (dram read + write, mean over the %d launches of one step)" % tr["launches"]
-            roofline["traffic_source"] = "profiles/r01c_tapgemm_dram.json: " + tr["source"]
+            roofline["traffic_source"] = "profiles/r02_tapgemm_dram.json: " + tr["source"]
         except Exception:
             pass
     top = sorted(prof.items(), key=lambda kv: -kv[1][1])[:args.top]

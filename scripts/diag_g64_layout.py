@@ -64,8 +64,3 @@ for name in ("real", "compact"):
              dtype16=1, reuse=2)
     res[name] = timed(d)
     print("%-8s %.4f ms per launch" % (name, res[name]))
-# the same with the output going to a compact tensor too (stores of 96 bytes per row at a 128-byte pitch instead of 6 KB)
-outc = torch.zeros(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
-A = torch.randn(B, H, W, 64, device="cuda").bfloat16()
-c0 = torch.zeros(n_tiles, dtype=torch.int32, device="cuda")
-print("(compact output is not expressible per N tile through the hook: skipped)")

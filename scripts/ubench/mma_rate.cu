@@ -8,12 +8,14 @@
 using namespace wfd;
 
 template <int CG>
-__global__ void __launch_bounds__(128, 1) mma_rate_k(int N, int n_mma, int reps, int a_stride16, long long* out, int commit_every, int fill) {
+__global__ void __launch_bounds__(384, 1) mma_rate_k(int N, int n_mma, int reps, int a_stride16, long long* out, int commit_every, int fill) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t bar;
     __shared__ uint64_t bar2;  // receives the intermediate commits (never waited on)
     __shared__ uint64_t bar3, bar4;
+    __shared__ uint64_t spin_bar;           // fill 13 / 14: never completes; warps 4-11 poll it like idle epilogue warps poll theirs
+    __shared__ volatile int spin_done;
     __shared__ uint64_t rfull[4], rempty[4];  // fill == 11 / 12: a ring between the MMA warp and a helper warp (the producer's role)
     __shared__ uint32_t tmem_slot;
     const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -24,6 +26,8 @@ __global__ void __launch_bounds__(128, 1) mma_rate_k(int N, int n_mma, int reps,
         mbar_init(&bar, 1);
         mbar_init(&bar2, 1);
         mbar_init(&bar3, 1);
+        mbar_init(&spin_bar, 1);
+        spin_done = 0;
         mbar_init(&bar4, 1);
         for (int i = 0; i < 4; ++i) { mbar_init(&rfull[i], 1); mbar_init(&rempty[i], 1); }
         fence_barrier_init();
@@ -136,7 +140,14 @@ __global__ void __launch_bounds__(128, 1) mma_rate_k(int N, int n_mma, int reps,
             const long long dt = clock64() - t0;
             if (dt < best) best = dt;
         }
+        spin_done = 1;
         if (lane == 0 && blockIdx.x == 0) out[0] = best;
+    } else if (warp >= 4 && (fill == 13 || fill == 14)) {
+        // fill 13: eight warps per CTA poll a barrier with try_wait (may suspend), fill 14: with test_wait (pure spin)
+        while (!spin_done) {
+            if (fill == 13) mbar_try_wait(&spin_bar, 0);
+            else mbar_test_wait(&spin_bar, 0);
+        }
     } else if (warp == 2 && rank == 0 && (fill == 11 || fill == 12)) {
         const int ring = fill == 12 ? 2 : 3;
         const int n_tiles = n_mma / 27;
@@ -156,6 +167,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_k(int N, int n_mma, int reps,
             mbar_wait(&bar, phase);
             phase ^= 1;
         }
+        spin_done = 1;
     }
     tc_fence_before();
     __syncthreads();
@@ -174,7 +186,7 @@ static long long run(int N, int n_mma, int a_stride16, int grid, int commit_ever
     cudaFuncSetAttribute(mma_rate_k<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(128);
+    cfg.blockDim = dim3(384);
     cfg.dynamicSmemBytes = 210 * 1024;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -209,7 +221,7 @@ int main() {
     for (int s : {0, 2, 64, 130})
         printf("cg=2 N=48 a_stride16=%d: %.1f cyc/mma\n", s, (double)run<2>(48, 256, s, 148) / 256);
     // patch-schedule pattern: commit_every carries n_k (MMAs per run); cycles per ISSUED MMA = total / (n_mma / 27 * 9 * n_k)
-    for (int fill : {2, 10, 11, 12})
+    for (int fill : {2, 13, 14})
         for (int nk : {3, 4})
             printf("pattern fill=%d n_k=%d: cg=2 N=48 %.1f cyc/mma | cg=1 N=48 %.1f | cg=2 N=96 %.1f | cg=2 N=192 %.1f\n", fill, nk,
                    (double)run<2>(48, 324, 2, 148, nk, fill) / (108 * nk), (double)run<1>(48, 324, 2, 148, nk, fill) / (108 * nk),

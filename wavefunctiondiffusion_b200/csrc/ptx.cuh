@@ -75,6 +75,45 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Non-suspending variant: mbarrier.test_wait returns at once, where try_wait may put the thread to sleep for a
+// system-dependent time when the phase is not complete yet. The single-thread roles of the contraction kernel (TMA
+// producers, MMA issuer) hand short tiles to each other through chains of barriers; a sleep on every hand-over that is a
+// few cycles early costs more than the MMAs of a narrow tile (scripts/diag_g64_layout.py, profiles/r02_summary.md).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+#ifdef WFD_NO_SPIN_WAIT
+    mbar_wait(bar, parity);
+#else
+    if (mbar_test_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    while (!mbar_test_wait(bar, parity)) {
+        if ((++spins & 0xFFFFu) == 0 && clock64() - t0 > 4000000000LL) asm volatile("trap;");
+    }
+#endif
+}
+
+// accumulator wait of the epilogue warps: spins too unless -DWFD_EPI_TRY_WAIT (A/B knob)
+__device__ __forceinline__ void mbar_wait_epi(uint64_t* bar, uint32_t parity) {
+#ifdef WFD_EPI_TRY_WAIT
+    mbar_wait(bar, parity);
+#else
+    mbar_wait_spin(bar, parity);
+#endif
+}
+
 // ---------------------------------------------------------------- 256-bit global accesses (sm_100: LDG/STG.256)
 // One instruction moves a thread's whole 32-byte piece; a row-per-thread epilogue is bound by the number of LSU
 // instructions and line accesses, which this halves against two 16-byte accesses.

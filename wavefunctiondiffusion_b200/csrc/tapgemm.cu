@@ -195,6 +195,17 @@ template <bool BF16, int CG, bool XF>
 __global__ void __launch_bounds__(XF ? TG_THREADS_XF : TG_THREADS, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ TapGemmParams p, const int stages) {
+    // Role counters (p.dbg) and engine switches (p.dbg_skip) are diagnosis tools: compiled in only with -DWFD_TG_DBG_BUILD
+    // (WFD_NVCC_EXTRA=-DWFD_TG_DBG_BUILD=1 python -m wavefunctiondiffusion_b200.build --force). Each test of a kernel
+    // parameter is a constant-bank load in the per-tile path of the single-thread roles - about ten per tile in the MMA
+    // issuer alone, and short tiles pay for them (groups=64 conv: 0.143 -> 0.136 ms per launch).
+#ifdef WFD_TG_DBG_BUILD
+    const bool dbg_on = p.dbg != nullptr;
+    const int dbg_skip = p.dbg_skip;
+#else
+    constexpr bool dbg_on = false;
+    constexpr int dbg_skip = 0;
+#endif
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle atoms.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -342,7 +353,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             // the MMA thread commits on tdone when it has issued the last tile that reads the old weights
                             // (it knows the next tile's N tile too): one phase per reload, so the parity never aliases
                             if (res_n_tile >= 0) {
-                                mbar_wait(tdone_bar, static_cast<uint32_t>(tiles_seen & 1));
+                                mbar_wait_spin(tdone_bar, static_cast<uint32_t>(tiles_seen & 1));
                                 ++tiles_seen;  // counts reloads that waited
                             }
                             res_n_tile = tc.n_tile;
@@ -381,12 +392,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // dependent instructions every few cycles): the three walks below keep their per-chunk work minimal, and
                     // each warp only computes the coordinates of its own operand.
                     auto slot_wait = [&]() {
-                        if (p.dbg) {
+                        if (dbg_on) {
                             const long long w0 = clock64();
-                            mbar_wait(&ebar[stage], phase ^ 1);
+                            mbar_wait_spin(&ebar[stage], phase ^ 1);
                             w_empty += clock64() - w0;
                         } else {
-                            mbar_wait(&ebar[stage], phase ^ 1);
+                            mbar_wait_spin(&ebar[stage], phase ^ 1);
                         }
                     };
                     auto slot_next = [&]() {
@@ -398,8 +409,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     };
                     auto issue_a = [&](int ca, int xx, int yy) {
                         slot_wait();
-                        const long long i0 = p.dbg ? clock64() : 0;
-                        if (p.dbg_skip & 1) {
+                        const long long i0 = dbg_on ? clock64() : 0;
+                        if (dbg_skip & 1) {
                             if (elect_one() && (rank == 0 || XF)) mbar_arrive(&fbar[stage]);
                         } else if (elect_one()) {
                             if (XF) {  // each CTA's transform warps wait for their own box: the load signals the LOCAL barrier
@@ -414,13 +425,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 tma_load_4d(smA + static_cast<size_t>(stage) * a_stage_bytes, &tmA, &fbar[stage], ca, xx, yy, ab);
                             }
                         }
-                        if (p.dbg) w_issue += clock64() - i0;
+                        if (dbg_on) w_issue += clock64() - i0;
                         slot_next();
                     };
                     auto issue_b = [&](int k0, int k2) {  // weights box at (k0, n0, k2)
                         slot_wait();
-                        const long long i0 = p.dbg ? clock64() : 0;
-                        if (p.dbg_skip & 2) {
+                        const long long i0 = dbg_on ? clock64() : 0;
+                        if (dbg_skip & 2) {
                             if (elect_one() && rank == 0) mbar_arrive(&full_bar[stage]);
                         } else if (elect_one()) {
                             if (CG == 2) {
@@ -431,7 +442,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 tma_load_3d(smB + static_cast<size_t>(stage) * b_stage_bytes, &tmB, &full_bar[stage], k0, n0, k2);
                             }
                         }
-                        if (p.dbg) w_issue += clock64() - i0;
+                        if (dbg_on) w_issue += clock64() - i0;
                         slot_next();
                     };
                     if (patch) {
@@ -504,7 +515,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             }
-            if (p.dbg && blockIdx.x == 0 && lane == 0) {
+            if (dbg_on && blockIdx.x == 0 && lane == 0) {
                 p.dbg[load_a ? 10 : 11] = w_issue;
                 p.dbg[load_a ? 0 : 8] = clock64() - t_begin;
                 p.dbg[load_a ? 1 : 9] = w_empty;
@@ -532,7 +543,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t a_stage16 = a_stage_bytes >> 4, b_stage16 = b_stage_bytes >> 4;
         const uint32_t a_sub16 = (static_cast<uint32_t>(p.w_box) * 128u) >> 4;  // one image row of the patch
         const uint32_t b_box16 = b_box_bytes >> 4;
-        const int skip_mma = p.dbg_skip & 4;
+        const int skip_mma = dbg_skip & 4;
         int stage = 0;
         uint32_t phase = 0;
         uint32_t a_cur = a_lo0, b_cur = b_lo0;  // low descriptor words of the current stage
@@ -553,15 +564,15 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int nt = decode_tile(p, t, CG, rank).n_tile;
                 if (nt != res_n_tile) {
                     res_n_tile = nt;
-                    mbar_wait(bres_full, res_phase);
+                    mbar_wait_spin(bres_full, res_phase);
                     res_phase ^= 1;
                     tc_fence_after();
                 }
                 res_last = (t + tile_step < tile_end) && decode_tile(p, t + tile_step, CG, rank).n_tile != nt;
             }
-            long long w0 = p.dbg ? clock64() : 0;
-            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-            if (p.dbg) w_tempty += clock64() - w0;
+            long long w0 = dbg_on ? clock64() : 0;
+            mbar_wait_spin(&tempty_bar[acc], acc_phase ^ 1);
+            if (dbg_on) w_tempty += clock64() - w0;
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * acc_cols;
             if (patch) {
@@ -570,21 +581,21 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // are resident. Tap (dy, dx) of output pixel (y, x) reads patch row (y + dy + 1) * (w_box + 2) + x + dx + 1.
                 for (int cc2 = 0; cc2 < p.cpt; ++cc2) {
                     const int n_k = (cc2 == p.cpt - 1) ? kk_last : TG_KC / 16;
-                    w0 = p.dbg ? clock64() : 0;
+                    w0 = dbg_on ? clock64() : 0;
                     if (XF) {  // the transform warps of both CTAs have rewritten the box (generic proxy + fence.proxy.async)
-                        mbar_wait(&aready_bar[a_st], a_ph);
+                        mbar_wait_spin(&aready_bar[a_st], a_ph);
                     } else {
-                        mbar_wait(&afull_bar[a_st], a_ph);
+                        mbar_wait_spin(&afull_bar[a_st], a_ph);
                     }
-                    if (p.dbg) w_full += clock64() - w0;
+                    if (dbg_on) w_full += clock64() - w0;
                     // vertical offsets per synchronisation point: all three when the weight stage carries nine taps (narrow N:
                     // the per-stage waits, fence and election then cost as much as the MMAs themselves), else one
                     const int d_per = (b_res || p.b_taps == 9) ? 3 : 1;
                     for (int d0 = 0; d0 < 3; d0 += d_per) {
                         if (!b_res) {
-                            w0 = p.dbg ? clock64() : 0;
-                            mbar_wait(&full_bar[stage], phase);
-                            if (p.dbg) w_full += clock64() - w0;
+                            w0 = dbg_on ? clock64() : 0;
+                            mbar_wait_spin(&full_bar[stage], phase);
+                            if (dbg_on) w_full += clock64() - w0;
                         }
                         tc_fence_after();
                         if (elect_one()) {
@@ -650,9 +661,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int kc = 0; kc < k_walk; ++kc) {
                 const int n_k = (cc == p.cpt - 1) ? kk_last : TG_KC / 16;
                 if (++cc == p.cpt) cc = 0;
-                w0 = p.dbg ? clock64() : 0;
-                mbar_wait(&full_bar[stage], phase);
-                if (p.dbg) w_full += clock64() - w0;
+                w0 = dbg_on ? clock64() : 0;
+                mbar_wait_spin(&full_bar[stage], phase);
+                if (dbg_on) w_full += clock64() - w0;
                 tc_fence_after();
                 if (elect_one()) {
                     uint32_t ad = a_cur;
@@ -696,7 +707,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 acc_phase ^= 1;
             }
         }
-        if (p.dbg && blockIdx.x == 0 && lane == 0) {
+        if (dbg_on && blockIdx.x == 0 && lane == 0) {
             p.dbg[2] = clock64() - t_begin;
             p.dbg[3] = w_tempty;
             p.dbg[4] = w_full;
@@ -816,11 +827,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < 8; ++j) sc[j] = sh[j] = 0.f;
                     }
-                    const long long xw0 = p.dbg ? clock64() : 0;
+                    const long long xw0 = dbg_on ? clock64() : 0;
                     mbar_wait(&afull_bar[a_st], a_ph);
-                    const long long xw1 = p.dbg ? clock64() : 0;
+                    const long long xw1 = dbg_on ? clock64() : 0;
                     const uint32_t box = smA_u32 + static_cast<uint32_t>(a_st) * a_stage_bytes + chunk_off;
-                    if (!(p.dbg_skip & 16)) {
+                    if (!(dbg_skip & 16)) {
                         // two rows in flight per thread, branch-free math (only the loads and stores are predicated); two
                         // transform warps share a scheduler, so one warp's FMAs fill the issue slots the other's tanh leaves
                         constexpr int RU = 2;
@@ -860,7 +871,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (CG == 2) mbar_arrive_leader(&aready_bar[a_st]);
                         else mbar_arrive(&aready_bar[a_st]);
                     }
-                    if (p.dbg) {
+                    if (dbg_on) {
                         x_wait += xw1 - xw0;
                         x_math += clock64() - xw1;
                     }
@@ -871,7 +882,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
-        if (p.dbg && blockIdx.x == 0 && tx == 0) {
+        if (dbg_on && blockIdx.x == 0 && tx == 0) {
             p.dbg[12] = clock64() - x_begin;
             p.dbg[13] = x_wait;
             p.dbg[14] = x_math;
@@ -975,18 +986,18 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     dst[1] = __ldg(side_ptr + 2 * chunk + 1);
                 }
             };
-            if (side_ptr && !(p.dbg_skip & 8)) {
+            if (side_ptr && !(dbg_skip & 8)) {
                 if (c_first < n_chunks) load_side(c_first, sb0);
                 if (c_first + c_step < n_chunks) load_side(c_first + c_step, sb1);
                 if (c_first + 2 * c_step < n_chunks) load_side(c_first + 2 * c_step, sb2);
             }
             {
-                const long long w0 = p.dbg ? clock64() : 0;
-                mbar_wait(&tfull_bar[acc], acc_phase);
-                if (p.dbg) w_tfull += clock64() - w0;
+                const long long w0 = dbg_on ? clock64() : 0;
+                mbar_wait_epi(&tfull_bar[acc], acc_phase);
+                if (dbg_on) w_tfull += clock64() - w0;
             }
             tc_fence_after();
-            const long long e0 = p.dbg ? clock64() : 0;
+            const long long e0 = dbg_on ? clock64() : 0;
             const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * acc_cols + (static_cast<uint32_t>(q * 32) << 16);
             float dot = 0.f;
             float rs_m = -INFINITY, rs_l = 0.f;                       // pass 1 of the row softmax
@@ -1000,7 +1011,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int g_next = g_cpg ? (g_run + 1) * g_cpg : 0x7fffffff;
             float b1 = 0.f, b2 = 0.f, bmean = 0.f, brstd = 0.f;
             int bgroup = -1;
-            for (int c = c_first; c < ((p.dbg_skip & 8) ? 0 : n_chunks); c += c_step) {
+            for (int c = c_first; c < ((dbg_skip & 8) ? 0 : n_chunks); c += c_step) {
                 const int j0 = c * 16;
                 const int n = n0 + j0;
                 uint4 side_cur[2];
@@ -1245,14 +1256,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if (p.rowdot)
                 atomicAdd(reinterpret_cast<unsigned long long*>(p.rowdot) + pixel, static_cast<unsigned long long>(__float2ll_rn((dot) * WFD_FX_GRAD)));
-            if (p.dbg) e_busy += clock64() - e0;
+            if (dbg_on) e_busy += clock64() - e0;
             if (++acc == acc_stages) {
                 acc = 0;
                 acc_phase ^= 1;
             }
           }
         }
-        if (p.dbg && blockIdx.x == 0 && threadIdx.x == W_EPI0 * 32) {
+        if (dbg_on && blockIdx.x == 0 && threadIdx.x == W_EPI0 * 32) {
             p.dbg[5] = clock64() - t_begin;
             p.dbg[6] = w_tfull;
             p.dbg[7] = e_busy;
@@ -1768,6 +1779,10 @@ int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream) {
     if (tg_dbg < 0) {
         const char* ev = getenv("WFD_TG_DBG");
         tg_dbg = (ev && ev[0] == '1') ? 1 : 0;
+#ifndef WFD_TG_DBG_BUILD
+        if (tg_dbg || getenv("WFD_TG_SKIP"))
+            fprintf(stderr, "wfd: WFD_TG_DBG / WFD_TG_SKIP need a library built with -DWFD_TG_DBG_BUILD=1 (counters read zero)\n");
+#endif
         if (tg_dbg && cudaMalloc(&tg_dbg_buf, 16 * sizeof(long long)) != cudaSuccess) tg_dbg = 0;
     }
     static int tg_skip = -1;  // WFD_TG_SKIP=<bits>: see TapGemmParams::dbg_skip (row-reuse launches only)
