@@ -175,6 +175,14 @@ WFD_API wfd_loop_group* wfd_loop_group_create(int nranks);
 WFD_API void wfd_loop_group_destroy(wfd_loop_group* g);
 WFD_API int wfd_comm_create_loopback(wfd_loop_group* g, int rank, wfd_comm** out);
 WFD_API void wfd_comm_destroy(wfd_comm* c);
+/* Peer mailboxes (NCCL communicators, one process per GPU on one NVLink / NVSwitch node): the small exchanges of a band
+ * step - halo rows, GroupNorm sums, the loss - become direct stores into the neighbour's memory plus a flag (one short
+ * kernel each, replayable from a CUDA graph) instead of ncclSend / Recv / AllReduce; the attention all-gather and
+ * reduce-scatter stay on NCCL. wfd_comm_peer_handle allocates this rank's mailbox (rows of up to max_row_bytes) and
+ * returns its 64-byte CUDA IPC handle; the caller gathers the handles of all ranks (rank order) and hands them to
+ * wfd_comm_peer_attach on every rank. Exchanges that do not fit the mailbox keep using NCCL. */
+WFD_API int wfd_comm_peer_handle(wfd_comm* c, size_t max_row_bytes, void* handle64);
+WFD_API int wfd_comm_peer_attach(wfd_comm* c, const void* handles);
 /* h is the height of the whole latent plane; batch is 1 */
 WFD_API int wfd_decoder_create_band(const wfd_decoder_config* cfg, int h, int w, int rank, int nranks, int dtype16,
                                     wfd_decoder** out);

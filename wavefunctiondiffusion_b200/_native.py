@@ -96,6 +96,8 @@ SIGNATURES = {
     "wfd_loop_group_destroy": (None, [C.c_void_p]),
     "wfd_comm_create_loopback": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "wfd_comm_destroy": (None, [C.c_void_p]),
+    "wfd_comm_peer_handle": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "wfd_comm_peer_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
     "wfd_decoder_create_band": (C.c_int, [C.POINTER(DecoderConfig), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.POINTER(C.c_void_p)]),
     "wfd_decoder_attach_comm": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -290,6 +290,20 @@ int wfd_comm_create_loopback(wfd_loop_group* g, int rank, wfd_comm** out) {
     return 0;
 }
 void wfd_comm_destroy(wfd_comm* c) { delete c; }
+int wfd_comm_peer_handle(wfd_comm* c, size_t max_row_bytes, void* handle64) {
+    if (!c || !c->c || !handle64) {
+        set_error("wfd_comm_peer_handle: null argument");
+        return -1;
+    }
+    return c->c->peer_local_handle(max_row_bytes, handle64);
+}
+int wfd_comm_peer_attach(wfd_comm* c, const void* handles) {
+    if (!c || !c->c || !handles) {
+        set_error("wfd_comm_peer_attach: null argument");
+        return -1;
+    }
+    return c->c->peer_attach(handles);
+}
 
 int wfd_decoder_create_band(const wfd_decoder_config* cfg, int h, int w, int rank, int nranks, int dtype16,
                             wfd_decoder** out) {

@@ -26,6 +26,12 @@ struct Comm {
     virtual int allgather(void* buf, size_t bytes_per_rank, cudaStream_t s) = 0;
     // in place: every rank holds nranks * n_per_rank partial values; the sum of slice r lands in rank r's slice r
     virtual int reduce_scatter_f32(float* buf, size_t n_per_rank, cudaStream_t s) = 0;
+    // Peer mailboxes (NCCL transport only; see comm.cu): the small exchanges - halo rows, the 16-value GroupNorm sums, the
+    // loss - then go over NVLink as direct stores into the neighbour's memory plus a flag, one short kernel each, instead
+    // of ncclSend/Recv/AllReduce. peer_local_handle allocates this rank's mailbox and returns its CUDA IPC handle (64
+    // bytes); peer_attach maps every rank's mailbox (handles of all ranks, nranks x 64 bytes, in rank order).
+    virtual int peer_local_handle(size_t max_row_bytes, void* handle64) { (void)max_row_bytes; (void)handle64; return -30; }
+    virtual int peer_attach(const void* handles) { (void)handles; return -30; }
 };
 
 int nccl_unique_id(const char* libnccl_path, void* id128);

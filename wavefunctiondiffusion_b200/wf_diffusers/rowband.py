@@ -94,6 +94,29 @@ class BandComm:
     def __init__(self, handle, rank, nranks, keep=None):
         self.handle, self.rank, self.nranks, self._keep = handle, rank, nranks, keep
 
+    def enable_peer_mailboxes(self, max_row_bytes=8 << 20):
+        """Halo rows, GroupNorm sums and the loss as direct NVLink stores + flags instead of NCCL send/recv/all-reduce
+        (include/wfd_b200.h, wfd_comm_peer_*). Every rank's mailbox handle travels over the default process group; a rank
+        that cannot create or map a mailbox makes ALL ranks stay on NCCL (the transports must match)."""
+        import torch.distributed as dist
+
+        mine = C.create_string_buffer(64)
+        ok = nat.lib().wfd_comm_peer_handle(self.handle, C.c_size_t(max_row_bytes), mine) == 0
+        gathered = [None] * self.nranks
+        dist.all_gather_object(gathered, mine.raw if ok else None)
+        if any(g is None for g in gathered):
+            return False
+        blob = C.create_string_buffer(b"".join(gathered), 64 * self.nranks)
+        attached = nat.lib().wfd_comm_peer_attach(self.handle, blob) == 0
+        flags = [None] * self.nranks
+        dist.all_gather_object(flags, attached)
+        if not all(flags):
+            raise nat.WfdError("row bands: peer mailboxes could be mapped on some ranks only; set WFD_BAND_P2P=0")
+        self.peer = True
+        if self.rank == 0 and os.environ.get("WFD_VERBOSE"):
+            print("row bands: halo rows / GroupNorm sums / loss over peer mailboxes (%d ranks)" % self.nranks, file=sys.stderr)
+        return True
+
     @staticmethod
     def unique_id():
         buf = C.create_string_buffer(128)
@@ -108,15 +131,19 @@ class BandComm:
         return BandComm(h, rank, nranks)
 
     @staticmethod
-    def from_torch_distributed(device):
-        """One band per torch.distributed rank; rank 0's NCCL id travels over the default process group."""
+    def from_torch_distributed(device, max_row_bytes=8 << 20):
+        """One band per torch.distributed rank; rank 0's NCCL id travels over the default process group. The small
+        exchanges go through peer mailboxes over NVLink (rows of up to max_row_bytes; WFD_BAND_P2P=0 keeps them on NCCL)."""
         import torch.distributed as dist
 
         rank, nranks = dist.get_rank(), dist.get_world_size()
         box = [BandComm.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         with torch.cuda.device(device):
-            return BandComm.nccl(rank, nranks, box[0])
+            comm = BandComm.nccl(rank, nranks, box[0])
+            if nranks > 1 and os.environ.get("WFD_BAND_P2P", "1") != "0":
+                comm.enable_peer_mailboxes(max_row_bytes)
+            return comm
 
     @staticmethod
     def _loopback(group, rank):
