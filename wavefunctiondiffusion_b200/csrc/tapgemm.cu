@@ -6,6 +6,7 @@
 #include <string.h>
 #include <map>
 #include <string>
+#include <type_traits>
 #include <vector>
 #include <stdlib.h>
 
@@ -964,6 +965,130 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 set_sync();
             }
+            if (p.epi_fast) {
+                // Compile-time specialised drain of the plain conv cases (16-bit store, 256-bit accesses, alpha = 1; optional
+                // bias, residual, fused GroupNorm statistics; at most six chunks per warp). The generic loop below spends
+                // ~260 instructions per 16-column chunk and ~360 per tile on option tests, address arithmetic and the
+                // rotation of its side-input registers; the forward groups=64 convs (residual + statistics) were bound by
+                // exactly that (the MMA thread waited 56% of its time for a free accumulator). Same arithmetic, same order.
+                const int n_chunks_f = (min(p.BN, p.N - n0) + 15) / 16;
+                const int n_mine = split ? n_chunks_f : (n_chunks_f + 1 - half) / 2;
+                uint16_t* outp = reinterpret_cast<uint16_t*>(p.out) + out_off + n0;
+                float gs = 0.f, gss = 0.f;
+                int ggroup = -1;
+                auto flush_stats = [&]() {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        gs += __shfl_xor_sync(0xffffffffu, gs, o);
+                        gss += __shfl_xor_sync(0xffffffffu, gss, o);
+                    }
+                    if (lane == 0) {
+                        const int slot = (tc.bb * p.gn_G + ggroup) * 2;
+                        const unsigned long long v0 = static_cast<unsigned long long>(__float2ll_rn(gs * WFD_FX_STATS));
+                        const unsigned long long v1 = static_cast<unsigned long long>(__float2ll_rn(gss * WFD_FX_STATS));
+                        if (slot + 1 < TG_STAT_SLOTS) {
+                            atomicAdd(stat_s + slot, v0);
+                            atomicAdd(stat_s + slot + 1, v1);
+                        } else {
+                            atomicAdd(reinterpret_cast<unsigned long long*>(p.gn_sums) + slot, v0);
+                            atomicAdd(reinterpret_cast<unsigned long long*>(p.gn_sums) + slot + 1, v1);
+                        }
+                    }
+                };
+                auto drain = [&](auto HAS_BIAS, auto HAS_RES, auto HAS_GNS) {
+                    constexpr bool BIAS = decltype(HAS_BIAS)::value, RES = decltype(HAS_RES)::value, GNS = decltype(HAS_GNS)::value;
+                    const uint16_t* resp = RES ? reinterpret_cast<const uint16_t*>(p.residual) + out_off + n0 : nullptr;
+                    uint4 rs[3][2];
+                    if (RES) {  // the first three residual pieces of this warp are in flight before the accumulator wait
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            if (k < n_mine) ldg256(resp + (c_first + k * c_step) * 16, rs[k][0], rs[k][1]);
+                    }
+                    mbar_wait_epi(&tfull_bar[acc], acc_phase);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * acc_cols + (static_cast<uint32_t>(q * 32) << 16);
+                    const int g_cpg = GNS ? p.gn_cpg : 1;
+                    int g_run = GNS ? n0 / g_cpg : 0;
+                    int g_next = (g_run + 1) * g_cpg;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        if (k < n_mine) {
+                            const int j0 = (c_first + k * c_step) * 16;
+                            uint32_t r[16];
+                            tmem_ld16(taddr + j0, r);
+                            tmem_ld_wait(r);
+                            float v[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                            if (BIAS) {
+#pragma unroll
+                                for (int j = 0; j < 16; j += 4) {
+                                    const float4 b4 = *reinterpret_cast<const float4*>(bs + j0 + j);
+                                    v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                                }
+                            }
+                            if (RES) {
+#pragma unroll
+                                for (int h2 = 0; h2 < 2; ++h2) {
+                                    const uint32_t w4[4] = {rs[k % 3][h2].x, rs[k % 3][h2].y, rs[k % 3][h2].z, rs[k % 3][h2].w};
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        v[h2 * 8 + 2 * j] += lo16_to_f<BF16>(w4[j]);
+                                        v[h2 * 8 + 2 * j + 1] += hi16_to_f<BF16>(w4[j]);
+                                    }
+                                }
+                                // the slot is free: the piece three chunks ahead takes it
+                                if (k + 3 < 6 && k + 3 < n_mine)
+                                    ldg256(resp + (c_first + (k + 3) * c_step) * 16, rs[k % 3][0], rs[k % 3][1]);
+                            }
+                            uint32_t w[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) w[j] = pack2<BF16>(v[2 * j], v[2 * j + 1]);
+                            stg256(outp + j0, make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));
+                            if (GNS) {
+                                const int n = n0 + j0;
+                                while (n >= g_next) {
+                                    ++g_run;
+                                    g_next += g_cpg;
+                                }
+                                if (g_run != ggroup) {
+                                    if (ggroup >= 0) flush_stats();
+                                    ggroup = g_run;
+                                    gs = 0.f;
+                                    gss = 0.f;
+                                }
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float a = lo16_to_f<BF16>(w[j]), b = hi16_to_f<BF16>(w[j]);
+                                    gs += a + b;
+                                    gss += a * a + b * b;
+                                }
+                            }
+                        }
+                    }
+                };
+                using T = std::true_type;
+                using F = std::false_type;
+                const int mode = (p.bias ? 4 : 0) | (p.residual ? 2 : 0) | (p.gn_sums ? 1 : 0);
+                switch (mode) {  // (the combinations the decoder launches; tapgemm_prepare admits no others)
+                    case 0: drain(F{}, F{}, F{}); break;
+                    case 4: drain(T{}, F{}, F{}); break;
+                    case 5: drain(T{}, F{}, T{}); break;
+                    default: drain(T{}, T{}, T{}); break;
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]);
+                    else mbar_arrive(&tempty_bar[acc]);
+                }
+                if (ggroup >= 0) flush_stats();
+                if (++acc == acc_stages) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+                continue;
+            }
             // one row-wise side input per launch: residual (forward), dot operand (WFC) or saved activation (GroupNorm
             // backward). Its 32-byte pieces are prefetched three chunks deep, the first three before the accumulator wait,
             // so that DRAM latency overlaps the MMAs instead of serialising the column loop.
@@ -1716,6 +1841,15 @@ int tapgemm_prepare(TapGemmOp* op) {
     }
     p.a_stages = a_stages;
     op->stages = stages;
+    {
+        // specialised epilogue for the plain conv cases (see tapgemm_kernel); WFD_NO_EPI_FAST=1 keeps the generic loop
+        const int chunks = p.BN / 16;
+        const int per_warp = p.epi_split ? chunks : (chunks + 1) / 2;
+        p.epi_fast = (!p.out_fp32 && p.wide_io && !p.rowdot && !p.gnb_red && !p.rs_out && !p.rs_in && !p.sb_d && p.alpha == 1.f &&
+                      per_warp <= 6 && getenv("WFD_NO_EPI_FAST") == nullptr) ? 1 : 0;
+        const int mode = (p.bias ? 4 : 0) | (p.residual ? 2 : 0) | (p.gn_sums ? 1 : 0);
+        if (mode != 0 && mode != 4 && mode != 5 && mode != 7) p.epi_fast = 0;
+    }
     op->threads = p.ax_stats ? TG_THREADS_XF : TG_THREADS;
     op->smem_bytes = 1024 + (patch ? a_stages * a_stage + stages * b_stage : stages * (a_stage + b_stage)) +
                      (p.b_resident ? b_res_bytes : 0) + (2 * stages + 20 + 4 * a_stages) * sizeof(uint64_t) +
