@@ -986,7 +986,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int slot = (tc.bb * p.gn_G + ggroup) * 2;
                         const unsigned long long v0 = static_cast<unsigned long long>(__float2ll_rn(gs * WFD_FX_STATS));
                         const unsigned long long v1 = static_cast<unsigned long long>(__float2ll_rn(gss * WFD_FX_STATS));
-                        if (slot + 1 < TG_STAT_SLOTS) {
+                        if (p.stat_private) {
+                            // this warp's own copy of the slots (only its lane 0 touches it): plain load + store instead of
+                            // a 64-bit shared-memory atomic, which is a compare-and-swap loop that the eight epilogue
+                            // warps of a CTA fight over (they mostly hit the same sample and group)
+                            unsigned long long* sp = stat_s + (warp - W_EPI0) * 128 + slot;
+                            sp[0] += v0;
+                            sp[1] += v1;
+                        } else if (slot + 1 < TG_STAT_SLOTS) {
                             atomicAdd(stat_s + slot, v0);
                             atomicAdd(stat_s + slot + 1, v1);
                         } else {
@@ -1057,11 +1064,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     gs = 0.f;
                                     gss = 0.f;
                                 }
+                                // statistics of the values before their 16-bit rounding (what the reference's fp32
+                                // GroupNorm sees; measured equally fast as statistics of the re-unpacked stores)
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float a = lo16_to_f<BF16>(w[j]), b = hi16_to_f<BF16>(w[j]);
-                                    gs += a + b;
-                                    gss += a * a + b * b;
+                                for (int j = 0; j < 16; ++j) {
+                                    gs += v[j];
+                                    gss = fmaf(v[j], v[j], gss);
                                 }
                             }
                         }
@@ -1417,7 +1425,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
-    if (p.gn_sums || p.gnb_red) {
+    if (p.gn_sums && p.stat_private) {  // sum the eight per-warp copies (integers: the order does not matter)
+        for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+            unsigned long long v = 0ull;
+            for (int wv = 0; wv < TG_EPI_THREADS / 32; ++wv) v += stat_s[wv * 128 + i];
+            if (v != 0ull) atomicAdd(reinterpret_cast<unsigned long long*>(p.gn_sums) + i, v);
+        }
+    } else if (p.gn_sums || p.gnb_red) {
         for (int i = threadIdx.x; i < TG_STAT_SLOTS; i += blockDim.x) {
             if (p.gn_sums) {
                 const unsigned long long v = stat_s[i];
@@ -1849,6 +1863,11 @@ int tapgemm_prepare(TapGemmOp* op) {
                       per_warp <= 6 && getenv("WFD_NO_EPI_FAST") == nullptr) ? 1 : 0;
         const int mode = (p.bias ? 4 : 0) | (p.residual ? 2 : 0) | (p.gn_sums ? 1 : 0);
         if (mode != 0 && mode != 4 && mode != 5 && mode != 7) p.epi_fast = 0;
+        // per-warp private statistic slots when (samples x GroupNorm groups x 2) of the launch fit 128
+        const int per_sample = p.tiles_x * p.tiles_y;
+        const int samples = per_sample > 0 ? (p.m_tiles + per_sample - 1) / per_sample : 1;
+        p.stat_private = (p.epi_fast && p.gn_sums && !p.gnb_red && p.z_count == 1 && samples * p.gn_G * 2 <= 128 &&
+                          getenv("WFD_NO_STAT_PRIVATE") == nullptr) ? 1 : 0;
     }
     op->threads = p.ax_stats ? TG_THREADS_XF : TG_THREADS;
     op->smem_bytes = 1024 + (patch ? a_stages * a_stage + stages * b_stage : stages * (a_stage + b_stage)) +

@@ -66,6 +66,7 @@ struct TapGemmParams {
                             // 2: patch schedule (3x3 stride-1 taps; Bm chunks in (cc, dy, dx) order): ONE activation box per
                             //    64-channel chunk carries the whole (h_box+2) x (w_box+2) halo patch (w_box = 8) and serves all
                             //    nine taps through descriptor start offsets (a row pitch of w_box+2 pixels = the SBO field)
+    int stat_private;       // set by tapgemm_prepare: the fused statistics use per-warp private shared-memory slots
     int epi_fast;           // set by tapgemm_prepare: the launch qualifies for the specialised conv epilogue
     int acc_stages;         // set by tapgemm_prepare: TMEM accumulator stages (2, 4 or 8; 512 / acc_stages columns each)
     int a_stages;           // set by tapgemm_prepare (patch schedule): depth of the activation ring (weights have their own)
