@@ -965,6 +965,105 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 set_sync();
             }
+            if (p.epi_fast == 2) {
+                // Specialised drain of the attention products whose epilogue IS the softmax work (row statistics /
+                // probabilities / softmax backward; 16-bit or no store, up to eight chunks per warp): with K = 384 a
+                // 256 x 256 tile is 24 MMAs, and the generic loop's ~260 instructions per chunk made the epilogue the
+                // busy role (the MMA thread waited 55-74% of its time for a free accumulator).
+                const int n_chunks_f = (min(p.BN, p.N - n0) + 15) / 16;
+                const int n_mine = split ? n_chunks_f : (n_chunks_f + 1 - half) / 2;
+                const long long grow = pixel + tc.z * static_cast<long long>(p.m_tiles) * TG_BM;
+                auto drain_attn = [&](auto MODE_T) {
+                    constexpr int MODE = decltype(MODE_T)::value;  // 0: row statistics, 1: probabilities, 2: softmax backward
+                    uint16_t* outp = MODE == 0 ? nullptr : reinterpret_cast<uint16_t*>(p.out) + out_off + n0;
+                    const uint16_t* pp = MODE == 2 ? reinterpret_cast<const uint16_t*>(p.residual) + out_off + n0 : nullptr;
+                    const float alpha = p.alpha;
+                    float2 st = make_float2(0.f, 0.f);
+                    float drow = 0.f, sscale = 0.f;
+                    if (MODE == 1) st = __ldg(p.rs_in + grow);
+                    if (MODE == 2) {
+                        drow = __ldg(p.sb_d + grow);
+                        sscale = p.sb_scale;
+                    }
+                    uint4 rs[3][2];
+                    if (MODE == 2) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            if (k < n_mine) ldg256(pp + (c_first + k * c_step) * 16, rs[k][0], rs[k][1]);
+                    }
+                    mbar_wait_epi(&tfull_bar[acc], acc_phase);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * acc_cols + (static_cast<uint32_t>(q * 32) << 16);
+                    float rs_m = -INFINITY, rs_l = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (k < n_mine) {
+                            const int j0 = (c_first + k * c_step) * 16;
+                            uint32_t r[16];
+                            tmem_ld16(taddr + j0, r);
+                            tmem_ld_wait(r);
+                            float v[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * alpha;
+                            if (MODE == 0) {
+                                float cm = v[0];
+#pragma unroll
+                                for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[j]);
+                                if (cm > rs_m) {
+                                    rs_l *= __expf(rs_m - cm);
+                                    rs_m = cm;
+                                }
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) rs_l += __expf(v[j] - rs_m);
+                            } else {
+                                if (MODE == 1) {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) v[j] = __expf(v[j] - st.x) * st.y;
+                                } else {
+#pragma unroll
+                                    for (int h2 = 0; h2 < 2; ++h2) {
+                                        const uint32_t w4[4] = {rs[k % 3][h2].x, rs[k % 3][h2].y, rs[k % 3][h2].z, rs[k % 3][h2].w};
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) {
+                                            v[h2 * 8 + 2 * j] = lo16_to_f<BF16>(w4[j]) * (v[h2 * 8 + 2 * j] - drow) * sscale;
+                                            v[h2 * 8 + 2 * j + 1] = hi16_to_f<BF16>(w4[j]) * (v[h2 * 8 + 2 * j + 1] - drow) * sscale;
+                                        }
+                                    }
+                                    if (k + 3 < 8 && k + 3 < n_mine)
+                                        ldg256(pp + (c_first + (k + 3) * c_step) * 16, rs[k % 3][0], rs[k % 3][1]);
+                                }
+                                uint32_t w[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) w[j] = pack2<BF16>(v[2 * j], v[2 * j + 1]);
+                                stg256(outp + j0, make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));
+                            }
+                        }
+                    }
+                    if (MODE == 0) {
+                        const long long slot = (grow * p.n_tiles + tc.n_tile) * 2;
+                        if (split) {
+                            p.rs_out[slot] = make_float2(rs_m, rs_l);
+                            p.rs_out[slot + 1] = make_float2(-INFINITY, 0.f);
+                        } else {
+                            p.rs_out[slot + half] = make_float2(rs_m, rs_l);
+                        }
+                    }
+                };
+                if (p.rs_out) drain_attn(std::integral_constant<int, 0>{});
+                else if (p.rs_in) drain_attn(std::integral_constant<int, 1>{});
+                else drain_attn(std::integral_constant<int, 2>{});
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]);
+                    else mbar_arrive(&tempty_bar[acc]);
+                }
+                if (++acc == acc_stages) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+                continue;
+            }
             if (p.epi_fast) {
                 // Compile-time specialised drain of the plain conv cases (16-bit store, 256-bit accesses, alpha = 1; optional
                 // bias, residual, fused GroupNorm statistics; at most six chunks per warp). The generic loop below spends
@@ -1857,12 +1956,19 @@ int tapgemm_prepare(TapGemmOp* op) {
     op->stages = stages;
     {
         // specialised epilogue for the plain conv cases (see tapgemm_kernel); WFD_NO_EPI_FAST=1 keeps the generic loop
+        const char* nf = getenv("WFD_NO_EPI_FAST");   // 1: generic loop everywhere, 2: generic loop for the attention modes
+        const bool no_fast = nf && nf[0] == '1', no_attn = nf && (nf[0] == '1' || nf[0] == '2');
         const int chunks = p.BN / 16;
         const int per_warp = p.epi_split ? chunks : (chunks + 1) / 2;
         p.epi_fast = (!p.out_fp32 && p.wide_io && !p.rowdot && !p.gnb_red && !p.rs_out && !p.rs_in && !p.sb_d && p.alpha == 1.f &&
-                      per_warp <= 6 && getenv("WFD_NO_EPI_FAST") == nullptr) ? 1 : 0;
+                      per_warp <= 6 && !no_fast) ? 1 : 0;
         const int mode = (p.bias ? 4 : 0) | (p.residual ? 2 : 0) | (p.gn_sums ? 1 : 0);
         if (mode != 0 && mode != 4 && mode != 5 && mode != 7) p.epi_fast = 0;
+        // ... and for the attention products whose epilogue is the softmax work (up to eight chunks per warp)
+        if (!p.epi_fast && !p.out_fp32 && p.wide_io && !p.rowdot && !p.gnb_red && !p.bias && !p.gn_sums && per_warp <= 8 &&
+            ((p.rs_out ? 1 : 0) + (p.rs_in ? 1 : 0) + (p.sb_d ? 1 : 0)) == 1 && (p.sb_d ? p.residual != nullptr : p.residual == nullptr) &&
+            !no_attn)
+            p.epi_fast = 2;
         // per-warp private statistic slots when (samples x GroupNorm groups x 2) of the launch fit 128
         const int per_sample = p.tiles_x * p.tiles_y;
         const int samples = per_sample > 0 ? (p.m_tiles + per_sample - 1) / per_sample : 1;
