@@ -249,6 +249,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // of tiles would otherwise hammer the same few global addresses with atomics
     unsigned long long* stat_s = reinterpret_cast<unsigned long long*>(bet_s + 512);  // [2][TG_STAT_SLOTS] fixed point
     float* xf_s = reinterpret_cast<float*>(stat_s + 2 * TG_STAT_SLOTS);  // [512][mean | rstd] per (sample, group), XF only
+    float* gnb_tab = xf_s + (XF ? 2 * 512 : 0);  // [256][mean | rstd]: fast GroupNorm-backward epilogue only (never with XF)
 
 #ifndef WFD_NO_UNIFORM_WARP
     // The warp index through a shuffle: the compiler then knows it is warp-uniform, the role branches below become uniform
@@ -907,6 +908,19 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         long long w_tfull = 0, e_busy = 0;
         const long long t_begin = clock64();
         const int yy = row / p.w_box, xx = row - yy * p.w_box;
+        if (p.epi_fast == 3) {
+            // mean / rstd of every (sample, group) of the saved activation, once per CTA (same arithmetic as the generic loop)
+            const int per_sample = p.tiles_x * p.tiles_y;
+            const int n_pairs = (p.m_tiles / per_sample) * p.gn_G;
+            for (int i = threadIdx.x - W_EPI0 * 32; i < n_pairs; i += TG_EPI_THREADS) {
+                const acc_t* st = p.gnb_stats + static_cast<long long>(i) * 2;
+                const double dm = static_cast<double>(__ldg(st)) * (1.0 / WFD_FX_STATS) * p.gnb_inv_n;
+                const double dv = static_cast<double>(__ldg(st + 1)) * (1.0 / WFD_FX_STATS) * p.gnb_inv_n - dm * dm;
+                gnb_tab[2 * i] = static_cast<float>(dm);
+                gnb_tab[2 * i + 1] = rsqrtf(fmaxf(static_cast<float>(dv), 0.f) + p.gnb_eps);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(TG_EPI_THREADS) : "memory");
+        }
         for (int base = first_tile; base < tile_end; base += 32 * tile_step) {
           const int my_t = base + lane * tile_step;
           const TileCoord mine = decode_tile(p, my_t < tile_end ? my_t : base, CG, rank);
@@ -964,6 +978,111 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 set_sync();
+            }
+            if (p.epi_fast == 3) {
+                // Specialised drain of the backward convs with the fused GroupNorm(+SiLU) backward reduction (16-bit store of
+                // dy, then sum(du*gamma), sum(du*gamma*xhat) against the saved activation x; <= six chunks per warp): same
+                // arithmetic as the generic loop without its option tests, gamma / beta as 16-byte shared-memory loads,
+                // mean / rstd from the per-CTA table.
+                const int n_chunks_f = (min(p.BN, p.N - n0) + 15) / 16;
+                const int n_mine = split ? n_chunks_f : (n_chunks_f + 1 - half) / 2;
+                uint16_t* outp = reinterpret_cast<uint16_t*>(p.out) + out_off + n0;
+                const uint16_t* xp = reinterpret_cast<const uint16_t*>(p.gnb_x) + out_off + n0;
+                const bool silu = p.gnb_silu != 0;
+                uint4 rs[3][2];
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (k < n_mine) ldg256(xp + (c_first + k * c_step) * 16, rs[k][0], rs[k][1]);
+                mbar_wait_epi(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc) * acc_cols + (static_cast<uint32_t>(q * 32) << 16);
+                const int g_cpg = p.gnb_cpg;
+                int g_run = n0 / g_cpg, g_next = (g_run + 1) * g_cpg, bgroup = -1;
+                float b1 = 0.f, b2 = 0.f, bmean = 0.f, brstd = 0.f;
+                auto flush_red = [&]() {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        b1 += __shfl_xor_sync(0xffffffffu, b1, o);
+                        b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+                    }
+                    if (lane == 0) {
+                        const int slot = (tc.bb * p.gn_G + bgroup) * 2;
+                        const unsigned long long v0 = static_cast<unsigned long long>(__float2ll_rn(b1 * WFD_FX_GRAD));
+                        const unsigned long long v1 = static_cast<unsigned long long>(__float2ll_rn(b2 * WFD_FX_GRAD));
+                        if (p.stat_private) {  // this warp's own copy (<= 64 (sample, group) pairs)
+                            unsigned long long* sp = stat_s + TG_STAT_SLOTS + (warp - W_EPI0) * 128 + slot;
+                            sp[0] += v0;
+                            sp[1] += v1;
+                        } else {  // <= 256 pairs: the CTA's shared slots
+                            atomicAdd(stat_s + TG_STAT_SLOTS + slot, v0);
+                            atomicAdd(stat_s + TG_STAT_SLOTS + slot + 1, v1);
+                        }
+                    }
+                };
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    if (k < n_mine) {
+                        const int j0 = (c_first + k * c_step) * 16;
+                        uint32_t r[16];
+                        tmem_ld16(taddr + j0, r);
+                        tmem_ld_wait(r);
+                        uint32_t w[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) w[j] = pack2<BF16>(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                        stg256(outp + j0, make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));
+                        const int n = n0 + j0;
+                        while (n >= g_next) {
+                            ++g_run;
+                            g_next += g_cpg;
+                        }
+                        if (g_run != bgroup) {
+                            if (bgroup >= 0) flush_red();
+                            bgroup = g_run;
+                            b1 = 0.f;
+                            b2 = 0.f;
+                            const float2 mr = *reinterpret_cast<const float2*>(gnb_tab + 2 * (tc.bb * p.gn_G + g_run));
+                            bmean = mr.x;
+                            brstd = mr.y;
+                        }
+                        const uint32_t xw[8] = {rs[k % 3][0].x, rs[k % 3][0].y, rs[k % 3][0].z, rs[k % 3][0].w,
+                                                rs[k % 3][1].x, rs[k % 3][1].y, rs[k % 3][1].z, rs[k % 3][1].w};
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const float4 g4 = *reinterpret_cast<const float4*>(gms + j0 + 4 * q4);
+                            const float4 b4 = *reinterpret_cast<const float4*>(bts + j0 + 4 * q4);
+                            const float ga4[4] = {g4.x, g4.y, g4.z, g4.w}, be4[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                            for (int t4 = 0; t4 < 4; ++t4) {
+                                const int col = 4 * q4 + t4;
+                                const float dyv = (col & 1) ? hi16_to_f<BF16>(w[col >> 1]) : lo16_to_f<BF16>(w[col >> 1]);
+                                const float xv = (col & 1) ? hi16_to_f<BF16>(xw[col >> 1]) : lo16_to_f<BF16>(xw[col >> 1]);
+                                const float xh = (xv - bmean) * brstd;
+                                float du = dyv;
+                                if (silu) {
+                                    const float u = fmaf(xh, ga4[t4], be4[t4]);
+                                    const float sg = fast_sigmoid(u);
+                                    du *= sg * fmaf(u, 1.f - sg, 1.f);
+                                }
+                                const float tt = du * ga4[t4];
+                                b1 += tt;
+                                b2 = fmaf(tt, xh, b2);
+                            }
+                        }
+                        if (k + 3 < 6 && k + 3 < n_mine) ldg256(xp + (c_first + (k + 3) * c_step) * 16, rs[k % 3][0], rs[k % 3][1]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_leader(&tempty_bar[acc]);
+                    else mbar_arrive(&tempty_bar[acc]);
+                }
+                if (bgroup >= 0) flush_red();
+                if (++acc == acc_stages) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+                continue;
             }
             if (p.epi_fast == 2) {
                 // Specialised drain of the attention products whose epilogue IS the softmax work (row statistics /
@@ -1524,7 +1643,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
-    if (p.gn_sums && p.stat_private) {  // sum the eight per-warp copies (integers: the order does not matter)
+    if (p.gnb_red && p.epi_fast == 3 && p.stat_private) {  // the fast GroupNorm-backward epilogue's per-warp copies
+        for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+            unsigned long long v = 0ull;
+            for (int wv = 0; wv < TG_EPI_THREADS / 32; ++wv) v += stat_s[TG_STAT_SLOTS + wv * 128 + i];
+            if (v != 0ull) atomicAdd(reinterpret_cast<unsigned long long*>(p.gnb_red) + i, v);
+        }
+    } else if (p.gn_sums && p.stat_private) {  // sum the eight per-warp copies (integers: the order does not matter)
         for (int i = threadIdx.x; i < 128; i += blockDim.x) {
             unsigned long long v = 0ull;
             for (int wv = 0; wv < TG_EPI_THREADS / 32; ++wv) v += stat_s[wv * 128 + i];
@@ -1964,6 +2089,15 @@ int tapgemm_prepare(TapGemmOp* op) {
                       per_warp <= 6 && !no_fast) ? 1 : 0;
         const int mode = (p.bias ? 4 : 0) | (p.residual ? 2 : 0) | (p.gn_sums ? 1 : 0);
         if (mode != 0 && mode != 4 && mode != 5 && mode != 7) p.epi_fast = 0;
+        // ... for the backward convs with the fused GroupNorm-backward reduction (per-CTA mean / rstd table of <= 256 pairs)
+        {
+            const int per_sample = p.tiles_x * p.tiles_y;
+            const int samples = per_sample > 0 ? (p.m_tiles + per_sample - 1) / per_sample : 1;
+            if (!p.epi_fast && !p.out_fp32 && p.wide_io && p.gnb_red && !p.residual && !p.rowdot && !p.bias && !p.gn_sums &&
+                !p.rs_out && !p.rs_in && !p.sb_d && !p.ax_stats && p.alpha == 1.f && per_warp <= 6 && p.z_count == 1 &&
+                samples * p.gn_G <= 256 && p.gnb_cpg % 16 == 0 && !no_fast && !(nf && nf[0] == '3'))
+                p.epi_fast = 3;
+        }
         // ... and for the attention products whose epilogue is the softmax work (up to eight chunks per warp)
         if (!p.epi_fast && !p.out_fp32 && p.wide_io && !p.rowdot && !p.gnb_red && !p.bias && !p.gn_sums && per_warp <= 8 &&
             ((p.rs_out ? 1 : 0) + (p.rs_in ? 1 : 0) + (p.sb_d ? 1 : 0)) == 1 && (p.sb_d ? p.residual != nullptr : p.residual == nullptr) &&
@@ -1972,13 +2106,14 @@ int tapgemm_prepare(TapGemmOp* op) {
         // per-warp private statistic slots when (samples x GroupNorm groups x 2) of the launch fit 128
         const int per_sample = p.tiles_x * p.tiles_y;
         const int samples = per_sample > 0 ? (p.m_tiles + per_sample - 1) / per_sample : 1;
-        p.stat_private = (p.epi_fast && p.gn_sums && !p.gnb_red && p.z_count == 1 && samples * p.gn_G * 2 <= 128 &&
+        p.stat_private = (p.epi_fast && ((p.gn_sums && !p.gnb_red) || p.epi_fast == 3) && p.z_count == 1 && samples * p.gn_G * 2 <= 128 &&
                           getenv("WFD_NO_STAT_PRIVATE") == nullptr) ? 1 : 0;
     }
     op->threads = p.ax_stats ? TG_THREADS_XF : TG_THREADS;
     op->smem_bytes = 1024 + (patch ? a_stages * a_stage + stages * b_stage : stages * (a_stage + b_stage)) +
                      (p.b_resident ? b_res_bytes : 0) + (2 * stages + 20 + 4 * a_stages) * sizeof(uint64_t) +
-                     6 * 256 * sizeof(float) + 2 * TG_STAT_SLOTS * sizeof(unsigned long long) + (p.ax_stats ? 2 * 512 * sizeof(float) : 0) + 16;
+                     6 * 256 * sizeof(float) + 2 * TG_STAT_SLOTS * sizeof(unsigned long long) + (p.ax_stats ? 2 * 512 * sizeof(float) : 0) +
+                     (p.epi_fast == 3 ? 2 * 256 * sizeof(float) : 0) + 16;
     return 0;
 }
 
