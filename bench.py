@@ -405,7 +405,61 @@ def extra_configs(args, world, rank, dev, peak):
         del step, get_loss, net
         free()
 
+    def sparse_loss(B=8, latent=64):
+        """SURVEY 8f-4, reported on its own: the loss contraction as a CUDA-core gather over the allowed pairs
+        (csrc/wfc_sparse.cu) next to the dense tensor-core launch it replaces, on the bench workload's wave. Not part of
+        `value` / `roofline`: the headline path keeps the tensor-core contraction north_star names."""
+        import numpy as np
+
+        from wavefunctiondiffusion_b200 import _native as nat
+        from wavefunctiondiffusion_b200.utils.tilesets import load_wfc_mats, round_up_channels
+        from wavefunctiondiffusion_b200.wfdf.losses import WFCLossEinsum
+
+        mx, my = load_wfc_mats("ice_64x64")
+        T = mx.shape[0]
+        t_pad = round_up_channels(T)
+        nnz4 = 2 * (int(np.count_nonzero(mx)) + int(np.count_nonzero(my)))  # every allowed pair is seen from both cells
+        logits = 3.0 * torch.randn(B, t_pad, latent, latent, generator=torch.Generator(device=dev).manual_seed(7), device=dev)
+        lib = nat.lib()
+        res = {}
+        for name in ("dense", "sparse"):
+            mod = WFCLossEinsum(mx, my).to(dev).set_sparse(name == "sparse")
+            x = logits.clone().requires_grad_()
+            for _ in range(3):
+                loss = mod(x, softmax=True)
+            (g,) = torch.autograd.grad(loss.sum(), x)
+            lib.wfd_profile_enable(1)
+            reps = 10
+            for _ in range(reps):
+                mod(x, softmax=True)
+            torch.cuda.synchronize()
+            buf = C.create_string_buffer(1 << 16)
+            lib.wfd_profile_report(buf, len(buf))
+            lib.wfd_profile_enable(0)
+            ms = 0.0
+            for line in buf.value.decode().splitlines():
+                n, cnt, tot = line.rsplit(" ", 2)
+                if n.startswith("tapgemm") or n.startswith("wfc_sparse"):
+                    ms += float(tot) / reps
+            res[name] = (ms, loss.detach().double().cpu(), g.double().cpu())
+            del mod, x
+        cells = B * latent * latent
+        d_ms, s_ms = res["dense"][0], res["sparse"][0]
+        out["sparse_loss"] = {
+            "workload": "ice 64x64 batch %d wave: a[n,i] of the WFC loss, CUDA-core gather over allowed pairs vs the dense tensor-core launch" % B,
+            "sparse_ms_per_launch": s_ms, "dense_ms_per_launch": d_ms,
+            "allowed_pairs_per_cell": nnz4, "gathered_pairs_per_s": cells * nnz4 / (s_ms / 1e3) if s_ms > 0 else None,
+            "bound": "shared-memory gathers (two 32-bit gathers per pair and four cells)",
+            "hbm_bytes_algorithmic": 2 * cells * t_pad * 2, "hbm_GBps": (2 * cells * t_pad * 2 / 1e9) / (s_ms / 1e3) if s_ms > 0 else None,
+            "loss_rel_vs_dense": float(((res["sparse"][1] - res["dense"][1]).abs() / res["dense"][1].abs()).max()),
+            "grad_rel_l2_vs_dense": float((res["sparse"][2] - res["dense"][2]).norm() / res["dense"][2].norm())}
+        free()
+
     if world == 1:
+        try:
+            sparse_loss()
+        except Exception as e:  # reported, never fatal for the headline line
+            out["sparse_loss"] = {"error": repr(e)[:300]}
         single("config1_ice_64x64_batch1", "64x64", "ice_64x64", 1, 64, 10)
         single("config4_ice_256x256_one_gpu", "64x64", "ice_64x64", 1, 256, 3)
         single("config5_platform_32x32_batch256", "32x32", "platform_32x32", 256, 64, 2)

@@ -206,6 +206,46 @@ WFD_API double wfd_wfc_kc_kept(const wfd_wfc* h);
 WFD_API int wfd_wfc_count_violations(const wfd_wfc* h, const long long* tiles, int B, int H, int W, long long* out,
                                      void* stream);
 
+/* Alternative contraction for the loss: with on != 0 the handle computes a[n, i] through a CUDA-core gather
+ * over the allowed pairs of the adjacency matrices (0.2 % dense for the StarCraft tilesets; sliced-ELL lists, four cells
+ * per CTA) instead of the dense tensor-core product. Same `saved` layout, same finishing kernels, same gradient; fp32
+ * accumulation in a different order, so results agree to rounding, not bitwise. Off by default: north_star asks for the
+ * tensor-core contraction, bench.py reports this one separately. Not available on row-band handles. */
+WFD_API int wfd_wfc_set_sparse(wfd_wfc* h, int on);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Wave-seeded constraint propagation: the information propagation of the reference's prior-distribution
+ * WFC solver (wfd/wfc/wfc_prior_dist.py:136-174 propagate_information, :176-199 double_check) as bit-set arc
+ * consistency over whole maps, on the device.
+ *   allowed  uint32 [B, H, W, Wd], Wd = ceil(T / 32): bit (t & 31) of word (t >> 5) = tile t still possible in the cell
+ *            (map_allowed_tiles, wfc_prior_dist.py:14); bits >= T must be zero
+ *   conn     uint32 [4, T, Wd]: conn[d][s] = tiles allowed at direction d of tile s (connections[s, d, :], :11), d ordered
+ *            as the reference's directions (:25): 0 left, 1 up, 2 right, 3 down
+ *   boundary uint8 [B, H, W] or NULL: non-zero cells take no part (boundary_grids / is_grid_allowed, :41-43)
+ * wfd_propagator_create takes conn from HOST memory and re-encodes it for the device as supporter lists (for direction
+ * d and target tile t the source tiles s with conn[d][s][t] set; the rules are 0.2 % dense, so ~7 16-bit ids per list).
+ * wfd_propagator_run repeats   allowed'[n] = allowed[n] & AND_d OR_{s in allowed[m_d]} conn[d][s]   over every cell n and its
+ * in-map sources m_d = n - direction d (an empty source does not propagate, :152-153), every sweep from the previous
+ * sweep's state, until a sweep changes nothing or max_sweeps ran. Order-free and deterministic; while no cell runs empty
+ * it ends in the state the reference reaches by repeating its raster-order depth-1 propagation until nothing changes
+ * (the update is monotone). The handle owns its device scratch (flags + a second state buffer, grown on demand).
+ * *sweeps_done / *converged are host ints (the call synchronises the stream every few sweeps to read the change
+ * counters). wfd_propagator_entries: list entries after the re-encoding. wfd_wfc_allowed_count: tiles left per cell
+ * (is_fixed / is_zero, :86-90), int32 [B, H, W] on the device.
+ * wfd_wave_to_allowed seeds the sets from a wave: allowed[n, t] = first_tile <= t < T and (wave[n, t] >= threshold or
+ * (keep_argmax and t == argmax over [first_tile, T), first maximum wins)); wave [rows, ld] with dtype 0 fp32 / 1 fp16 /
+ * 2 bf16; first_tile = 1 keeps the null tile out as allow_all_connections_to_null does (:207-212).
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct wfd_propagator wfd_propagator;
+WFD_API int wfd_propagator_create(const uint32_t* conn_bits, int T, wfd_propagator** out);
+WFD_API void wfd_propagator_destroy(wfd_propagator* p);
+WFD_API long long wfd_propagator_entries(const wfd_propagator* p);
+WFD_API int wfd_propagator_run(wfd_propagator* p, uint32_t* allowed, const uint8_t* boundary, int B, int H, int W,
+                               int max_sweeps, int* sweeps_done, int* converged, void* stream);
+WFD_API int wfd_wfc_allowed_count(const uint32_t* allowed, int B, int H, int W, int T, int* count, void* stream);
+WFD_API int wfd_wave_to_allowed(const void* wave, int dtype, long long rows, int ld, int T, int first_tile,
+                                float threshold, int keep_argmax, uint32_t* allowed, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Tile post-processing on the device (what wfd/webui/ui.py:228-243 does on the host after the argmax):
  *   optional mirror symmetry   tiles' = [tiles | symm[tiles[:, ::-1]]]          wfd/scmap/data_processing.py:191-196

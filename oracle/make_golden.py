@@ -12,6 +12,8 @@ AutoencoderTile, whose initialisation order is checked to be bit-identical to th
   tiny_encode.npz          reference AutoencoderTile.encode moments of a one-hot tile map and of a soft wave (tiny config)
   tiles_post.npz           the reference's add_symmetry + gen_to_sc[shrink_to_gen[.]] on random ice tiles (with the tables)
   ice_c2_step.npz          BASELINE config 2's benchmarked shape: the same weights, batch 8 (slot 0 = the C1 latents)
+  wfc_propagate.npz        the reference's WFCGeneratorPriorDist (wfd/wfc/wfc_prior_dist.py) propagated until its state stops
+                           changing: a synthetic tileset learnt from a random map, the ice rules, a contradiction
 """
 import glob
 import json
@@ -201,8 +203,101 @@ def batch8_fixture(vae, losses):
     np.savez_compressed(os.path.join(GOLD, "ice_c2_step.npz"), **out)
 
 
+def propagate_fixture():
+    """The UNMODIFIED reference solver class, imported from where it lies (it needs numpy only): constructor state, then
+    its own depth-1 propagate_information (:136-174) from every allowed cell in raster order - what double_check (:176-199)
+    does - repeated until the state stops changing."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_wfc_prior_dist", REFERENCE_ROOT + "/wfd/wfc/wfc_prior_dist.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    Ref = mod.WFCGeneratorPriorDist
+    from wavefunctiondiffusion_b200.wfc import connections_from_wfc_mats, pack_bits  # bit packing of the fixture only
+    from wavefunctiondiffusion_b200.utils.tilesets import load_wfc_mats
+
+    def closure(gen):
+        rounds = 0
+        while True:
+            before = gen.map_allowed_tiles.copy()
+            ok = True
+            for y in range(gen.max_y):
+                for x in range(gen.max_x):
+                    if gen.is_grid_allowed((y, x)):
+                        ok = gen.propagate_information((y, x), depth=1, verbose=False) and ok
+            rounds += 1
+            if not ok or (before == gen.map_allowed_tiles).all():
+                return ok, rounds
+
+    out = {}
+    rng = np.random.RandomState(11)
+    # A: rules learnt by the reference's own get_probs_from_map from a random map of 47 tiles (+ the null tile 0); every
+    # window of that map satisfies them, so seeds that contain the window's tiles never contradict
+    T = 48
+    src = rng.randint(1, T, size=(20, 22))
+    probe = Ref((4, 4), None, np.ones((T, 4, T), dtype=np.float32))
+    conn_counts, _ = probe.get_probs_from_map(src)
+    H, W = 10, 12
+    boundary = np.zeros((H, W), dtype=bool)
+    boundary[3, 4] = boundary[7, 9] = True
+    gen = Ref((W, H), None, conn_counts.copy(), boundary_grids=boundary.copy())
+    out["a_conn_probs"] = conn_counts
+    out["a_connections"] = gen.connections.copy()
+    out["a_allowed_ctor"] = gen.map_allowed_tiles.copy()
+    window = src[5:5 + H, 6:6 + W]
+    seeds = rng.rand(H, W, T) < 0.35
+    np.put_along_axis(seeds, window[..., None], True, axis=2)
+    gen.map_allowed_tiles &= seeds
+    out["a_boundary"] = boundary
+    out["a_allowed_in"] = gen.map_allowed_tiles.copy()
+    ok, rounds = closure(gen)
+    assert ok
+    out["a_allowed_out"] = gen.map_allowed_tiles.copy()
+    out["a_ok"] = ok
+    print("propagate A: rounds", rounds, "allowed", int(out["a_allowed_in"].sum()), "->", int(out["a_allowed_out"].sum()))
+    # B: the ice rules (T = 3074: 97 words per cell), 6 x 6 map, two decided cells (the first candidates, in id order, that
+    # connect on all four sides and leave the map satisfiable)
+    mx, my = load_wfc_mats("ice_64x64")[:2]
+    conn = connections_from_wfc_mats(mx, my).astype(np.float32)
+    cb = conn > 0
+    cand = [int(t) for t in np.where((cb.sum(axis=2) > 3).all(axis=1))[0] if t > 0]
+    for k in range(len(cand) - 1):
+        gen = Ref((6, 6), None, conn.copy())
+        Ti = gen.tile_count
+        for cell, t in (((2, 3), cand[k]), ((4, 0), cand[k + 1])):
+            gen.map_allowed_tiles[cell] = False
+            gen.map_allowed_tiles[cell][t] = True
+        b_in = gen.map_allowed_tiles.copy()
+        ok, rounds = closure(gen)
+        if ok:
+            break
+    assert ok
+    out["b_allowed_in"] = pack_bits(b_in)
+    out["b_allowed_out"] = pack_bits(gen.map_allowed_tiles)
+    out["b_ok"] = ok
+    print("propagate B (ice): tiles", cand[k], cand[k + 1], "rounds", rounds, "allowed", int(b_in.sum()), "->",
+          int(gen.map_allowed_tiles.sum()), "of", 36 * Ti)
+    # C: a contradiction - two neighbouring cells decided to tiles that the learnt rules never put side by side
+    gen = Ref((5, 4), None, conn_counts.copy())
+    c2 = gen.connections
+    pair = next((s, t) for s in range(1, T) for t in range(1, T) if not c2[s, 2, t])
+    gen.map_allowed_tiles[1, 1] = False
+    gen.map_allowed_tiles[1, 1][pair[0]] = True
+    gen.map_allowed_tiles[1, 2] = False
+    gen.map_allowed_tiles[1, 2][pair[1]] = True
+    out["c_allowed_in"] = gen.map_allowed_tiles.copy()
+    ok, _ = closure(gen)
+    assert not ok
+    out["c_ok"] = ok
+    print("propagate C: contradiction reported by the reference")
+    np.savez_compressed(os.path.join(GOLD, "wfc_propagate.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
+    if "--only-propagate" in sys.argv:
+        propagate_fixture()
+        sys.exit(0)
     torch.set_num_threads(os.cpu_count())
     vae, losses = load_reference()
     if "--only-encode" in sys.argv:
@@ -222,3 +317,4 @@ if __name__ == "__main__":
     if "--skip-full" not in sys.argv:
         full_fixture(vae, losses)
         batch8_fixture(vae, losses)
+    propagate_fixture()

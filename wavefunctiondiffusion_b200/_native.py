@@ -104,6 +104,15 @@ SIGNATURES = {
     "wfd_wfc_attach_comm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "wfd_wfc_kc_kept": (C.c_double, [C.c_void_p]),
     "wfd_wfc_count_violations": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "wfd_wfc_set_sparse": (C.c_int, [C.c_void_p, C.c_int]),
+    "wfd_propagator_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "wfd_propagator_destroy": (None, [C.c_void_p]),
+    "wfd_propagator_entries": (C.c_longlong, [C.c_void_p]),
+    "wfd_propagator_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
+    "wfd_wfc_allowed_count": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "wfd_wave_to_allowed": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                      C.c_void_p, C.c_void_p]),
     "wfd_tiles_finish": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "wfd_argmax_tiles": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwfd_b200.so")
-SOURCES = ["tapgemm.cu", "kernels.cu", "decoder.cu", "encoder.cu", "wfc.cu", "comm.cu", "api.cu"]
+SOURCES = ["tapgemm.cu", "kernels.cu", "decoder.cu", "encoder.cu", "wfc.cu", "wfc_sparse.cu", "propagate.cu", "comm.cu", "api.cu"]
 HEADERS = ["ptx.cuh", "tapgemm.cuh", "kernels.cuh", "decoder.cuh", "comm.cuh", os.path.join("..", "..", "include", "wfd_b200.h"),
            os.path.join("..", "..", "include", "wfd_b200_test.h")]
 NVCC_FLAGS = [

@@ -393,6 +393,14 @@ int wfd_guidance_loop(wfd_decoder* d, wfd_wfc* h, float* lat, const float* eps_u
     return 0;
 }
 
+int wfd_wfc_set_sparse(wfd_wfc* h, int on) {
+    if (!h) {
+        set_error("wfd_wfc_set_sparse: null handle");
+        return -1;
+    }
+    return h->w.set_sparse(on);
+}
+
 int wfd_wfc_count_violations(const wfd_wfc* h, const long long* tiles, int B, int H, int W, long long* out, void* stream) {
     if (!h || !tiles || !out) {
         set_error("wfd_wfc_count_violations: null argument");

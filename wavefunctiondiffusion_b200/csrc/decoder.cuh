@@ -181,8 +181,25 @@ struct WfcSavedHeader {  // host-side record of the last forward (what backward 
     const void* wave = nullptr;  // the wave operand (inside saved, or the caller's pointer when is_logits == 0)
 };
 
+// sliced-ELL lists of the allowed pairs for the CUDA-core form of the contraction (csrc/wfc_sparse.cu)
+struct WfcSparse {
+    int T = 0, T_pad = 0, n_slices = 0;
+    long long nnz = 0, padded = 0;  // allowed pairs over the four directions; list entries including the ELL padding
+    uint16_t* ent = nullptr;
+    int* slice_off = nullptr;
+    uint16_t* row_of = nullptr;
+    uint16_t* len_of = nullptr;
+    ~WfcSparse();
+    int init(const uint8_t* mat_x, const uint8_t* mat_y, int T, int T_pad);
+    size_t smem_bytes() const;
+    int contract(const void* wave, void* a, acc_t* rowdot, int B, int H, int W, int bf16, cudaStream_t s) const;
+};
+
 struct Wfc {
     int T = 0, T_pad = 0, bf16 = 1;
+    WfcSparse sparse;         // built on the first set_sparse(1)
+    bool use_sparse = false;  // wfd_wfc_set_sparse / WFD_WFC_SPARSE=1
+    int set_sparse(int on);
     WfcSavedHeader hdr_host;         // of the last forward
     void* hdr_saved = nullptr;
     // one record per `saved` block that a forward has filled: several forwards may be outstanding before their backwards

@@ -111,6 +111,25 @@ int Wfc::init(const uint8_t* mx, const uint8_t* my, int T_, int T_pad_, int dtyp
         CUDA_CK(cudaMemcpy(kc_list, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice));
         CUDA_CK(cudaMemcpy(kc_cnt, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
+    {
+        const char* e = getenv("WFD_WFC_SPARSE");  // whole-suite runs of the alternative contraction
+        if (e && e[0] == '1') return set_sparse(1);
+    }
+    return 0;
+}
+
+int Wfc::set_sparse(int on) {
+    if (on && band) {
+        set_error("wfc: the sparse contraction does not serve row-band handles");
+        return -3;
+    }
+    if (on && !sparse.ent) {
+        const size_t tt = static_cast<size_t>(T) * T;
+        std::vector<uint8_t> r(2 * tt);
+        CUDA_CK(cudaMemcpy(r.data(), rules, r.size(), cudaMemcpyDeviceToHost));
+        CK(sparse.init(r.data(), r.data() + tt, T, T_pad));
+    }
+    use_sparse = on != 0;
     return 0;
 }
 
@@ -173,7 +192,7 @@ int Wfc::forward(const void* in, int is_logits, int B, int H, int W, float stren
             break;
         }
     }
-    if (!wb) {
+    if (!wb && !use_sparse) {  // the sparse contraction walks strips of four cells: any map shape
         set_error("wfc: map %dx%d cannot be tiled into 128-cell patches", H, W);
         return -3;
     }
@@ -208,6 +227,15 @@ int Wfc::forward(const void* in, int is_logits, int B, int H, int W, float stren
         uint8_t* rs = reinterpret_cast<uint8_t*>(v.rowsum);
         CK(comm->halo(wv - wb_, wv, wv + static_cast<size_t>(H - 1) * wb_, wv + static_cast<size_t>(H) * wb_, wb_, s));
         CK(comm->halo(rs - sb_, rs, rs + static_cast<size_t>(H - 1) * sb_, rs + static_cast<size_t>(H) * sb_, sb_, s));
+    }
+    if (use_sparse) {
+        if (band) {
+            set_error("wfc: the sparse contraction does not serve row-band handles");
+            return -3;
+        }
+        CK(sparse.contract(wave, v.a, v.rowdot, B, H, W, bf16, s));
+        CK(wfc_loss_finish(v.rowsum, v.rowdot, loss, B, H, W, hdr_host.coef, s, y_off, Hm));
+        return 0;
     }
     if (op_wave != wave || op_a != v.a || op_B != B || op_H != H || op_W != W) {
         memset(&op, 0, sizeof(op));

@@ -309,6 +309,12 @@ class WfcHandle:
         except Exception:
             pass
 
+    def set_sparse(self, on):
+        """Alternative contraction: CUDA-core gather over the allowed pairs instead of the dense tensor-core
+        product; same results to rounding. Off by default."""
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().wfd_wfc_set_sparse(self.handle, int(bool(on))), "wfd_wfc_set_sparse")
+
     def saved_ptr(self, B, H, W):
         n = nat.lib().wfd_wfc_saved_bytes(self.handle, B, H, W)
         if self._saved is None or self._saved.numel() < n + 256:

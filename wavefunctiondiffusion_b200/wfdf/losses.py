@@ -27,6 +27,7 @@ class WFCLossEinsum(torch.nn.Module):
         self.register_buffer("cy", (1 - cy)[None, :, :, None, None])
         self.count = cx.size(0)
         self._handles = {}
+        self.sparse_contraction = False  # set_sparse(): the CUDA-core gather over allowed pairs instead of the dense product
 
     # copies and pickles carry the buffers only; native handles are rebuilt on first use
     def __getstate__(self):
@@ -53,8 +54,19 @@ class WFCLossEinsum(torch.nn.Module):
         if h is None:
             ax, ay = self._mats()
             h = WfcHandle(ax, ay, t_pad, key[1], device)
+            if self.sparse_contraction:
+                h.set_sparse(True)
             self._handles[key] = h
         return h
+
+    def set_sparse(self, on=True):
+        """Not part of the reference API: score through the sparse complement form
+        p^T (1 - A) q = sum(p) sum(q) - p^T A q with A as lists of allowed pairs (a CUDA-core gather) instead of the dense
+        tensor-core contraction. Loss and gradient agree with the dense path to rounding."""
+        self.sparse_contraction = bool(on)
+        for h in self._handles.values():
+            h.set_sparse(self.sparse_contraction)
+        return self
 
     def count_violations(self, tiles):
         """Forbidden adjacent pairs of integer tile maps (B, H, W) -> int64 (B, 2) = (horizontal, vertical): the
