@@ -455,11 +455,48 @@ def extra_configs(args, world, rank, dev, peak):
             "grad_rel_l2_vs_dense": float((res["sparse"][2] - res["dense"][2]).norm() / res["dense"][2].norm())}
         free()
 
+    def wave_prior_propagation(B=8, latent=64):
+        """the wave as the prior of the reference's WFC solver - allowed-tile bit sets seeded from a wave on
+        the device and propagated to the fixed point (csrc/propagate.cu), at the bench shape. Integer work; reported per
+        sweep with the state bytes a sweep touches at most (read own + four neighbours, write own)."""
+        from wavefunctiondiffusion_b200.utils.tilesets import load_wfc_mats, round_up_channels
+        from wavefunctiondiffusion_b200.wfc import WFCGeneratorPriorDist
+
+        mx, my = load_wfc_mats("ice_64x64")
+        T = mx.shape[0]
+        t_pad = round_up_channels(T)
+        g = torch.Generator(device=dev).manual_seed(5)
+        cases = {}
+        for name, sharp, thr in (("peaked_wave", 6.0, 2e-3), ("flat_wave", 1.0, 2e-4), ("all_tiles_allowed", 0.0, 1e-4)):
+            wave = torch.softmax(sharp * torch.randn(B, latent, latent, t_pad, generator=g, device=dev), dim=-1).to(torch.bfloat16)
+            gen = WFCGeneratorPriorDist.from_wave(wave, mx, my, threshold=thr)
+            seed = gen.allowed_bits.clone()
+            n0 = gen.count_allowed().float().mean().item()
+            gen.propagate_all(2048)  # warm-up (builds the rule lists)
+            gen.set_allowed_bits(seed.clone())
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ok = gen.propagate_all(2048)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b)
+            cases[name] = {"threshold": thr, "allowed_per_cell_seeded": n0,
+                           "allowed_per_cell_fixed_point": gen.count_allowed().float().mean().item(),
+                           "satisfiable": bool(ok), "sweeps": gen.last_sweeps, "ms_total": ms, "ms_per_sweep": ms / max(1, gen.last_sweeps)}
+            del gen, wave, seed
+        Wd = (T + 31) // 32
+        out["wave_prior_propagation"] = {
+            "workload": "ice 64x64 batch %d: allowed-tile bit sets (%d words per cell) seeded from a bf16 wave, swept to the fixed point" % (B, Wd),
+            "state_bytes_per_full_sweep": B * latent * latent * Wd * 4 * 6, "cases": cases,
+            "bound": "L1/L2-resident supporter lists + launch / barrier latency of one CTA per cell; HBM traffic is the state words"}
+        free()
+
     if world == 1:
-        try:
-            sparse_loss()
-        except Exception as e:  # reported, never fatal for the headline line
-            out["sparse_loss"] = {"error": repr(e)[:300]}
+        for fn, key in ((sparse_loss, "sparse_loss"), (wave_prior_propagation, "wave_prior_propagation")):
+            try:
+                fn()
+            except Exception as e:  # reported, never fatal for the headline line
+                out[key] = {"error": repr(e)[:300]}
         single("config1_ice_64x64_batch1", "64x64", "ice_64x64", 1, 64, 10)
         single("config4_ice_256x256_one_gpu", "64x64", "ice_64x64", 1, 256, 3)
         single("config5_platform_32x32_batch256", "32x32", "platform_32x32", 256, 64, 2)

@@ -244,10 +244,25 @@ int Wfc::forward(const void* in, int is_logits, int B, int H, int W, float stren
         p.n_tiles = (T_pad + WFC_BN - 1) / WFC_BN;
         p.z_count = 1;
         {
-            // band of N tiles swept per wave of CTAs (L2 reuse of the wave tiles); the CTA stride modulo the band width
-            // must walk through every N tile of the band, or CTAs would be stuck with the heavy / light ones only
+            // N tiles swept per wave of CTAs before the next M tiles (L2 reuse of the wave tiles). All of them: measured on
+            // ice 64x64 batch 8 (ncu, DRAM read of the launch / time): band of 2: 2255 MB / 0.763 ms, 4: 1767 / 0.766,
+            // 7: 1014 / 0.833, all 13: 1097 / 0.772 - same time, 0.6x the DRAM reads of the former default (4). An L2
+            // evict_last hint on the adjacency boxes changed neither (1051 vs 1088 MB): what is re-read is the wave.
+            // The persistent CTAs (pairs) stride through the tile ids by the grid size: the band width must be coprime to
+            // that stride, or a CTA would only ever meet some of the N tiles (the heavy or the light ones of the skip list).
             const char* e = getenv("WFD_WFC_NGROUP");
-            p.n_group = e ? atoi(e) : 4;
+            int ng = p.n_tiles;
+            const int stride = num_sms() / 2;
+            auto gcd = [](int a, int b) {
+                while (b) {
+                    const int t = a % b;
+                    a = b;
+                    b = t;
+                }
+                return a;
+            };
+            while (ng > 1 && gcd(ng, stride) != 1) --ng;
+            p.n_group = e ? atoi(e) : ng;
         }
         p.w_box = wb;
         p.h_box = hb;
