@@ -2,11 +2,11 @@
 # round 2 evidence in one call: the bench line (driver command), ncu launch list of the step, DRAM bytes of every
 # tensor-core launch, full ncu sets of selected launches, per-role counters. Tests run separately (scripts/gpu_suite.sh).
 cd "$(dirname "$0")/.."
-O=gpurun_out/r02final; mkdir -p $O
+O=gpurun_out/r02final2; mkdir -p $O
 timeout 900 python bench.py --steps 20 --warmup 3 --verbose --top 100 > $O/bench.json 2> $O/bench.err
 python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/r02final/bench.json').read().strip().splitlines()[-1])
+d=json.loads(open('gpurun_out/r02final2/bench.json').read().strip().splitlines()[-1])
 print("bench: ms/step %.3f value %.1f e2e %.1f roofline %.3f launches %d clocks %s"%(d['ms_per_step'],d['value'],d['e2e']['value'],d['roofline']['frac'],d['gpu_launches'],d['clocks']))
 PY
 timeout 300 python scripts/ncu_step.py 8 > $O/ncu_plain.log 2>&1 &&
