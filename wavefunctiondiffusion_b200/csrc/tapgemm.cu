@@ -192,7 +192,13 @@ __device__ __host__ __forceinline__ int b_chunk_index(const TapGemmParams& p, in
 //                apply GroupNorm(+SiLU) to every landed box in shared memory (TapGemmParams::ax_stats); that variant lays
 //                the roles out by warpgroup (tapgemm.cuh) and rebalances registers with setmaxnreg: 640 threads would
 //                otherwise cap every role at 96 registers, and the epilogue needs ~160.
-template <bool BF16, int CG, bool XF>
+// EPI = p.epi_fast of the launch (tapgemm_prepare): every epilogue form is its own instantiation and compiles only its own
+// drain - 0 the generic column loop (WFC contraction, fp32 outputs, odd shapes), 1 the plain conv drains, 2 the attention
+// drains whose epilogue is the softmax work, 3 the backward convs with the fused GroupNorm-backward reduction. With all
+// of them in one kernel the register allocator paid for every path in every launch (168 registers, 120 - 216 bytes of
+// spills); alone, the plain conv drain needs 151 registers and no spill, and the groups=64 launches - bound by that
+// drain - run 22% faster (batch-8 step 11.83 -> 10.84 / 11.07 ms in one call, `WFD_NO_EPI_SPLIT=1` on the former build).
+template <bool BF16, int CG, bool XF, int EPI>
 __global__ void __launch_bounds__(XF ? TG_THREADS_XF : TG_THREADS, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ TapGemmParams p, const int stages) {
@@ -908,7 +914,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         long long w_tfull = 0, e_busy = 0;
         const long long t_begin = clock64();
         const int yy = row / p.w_box, xx = row - yy * p.w_box;
-        if (p.epi_fast == 3) {
+        if (EPI == 3) {
             // mean / rstd of every (sample, group) of the saved activation, once per CTA (same arithmetic as the generic loop)
             const int per_sample = p.tiles_x * p.tiles_y;
             const int n_pairs = (p.m_tiles / per_sample) * p.gn_G;
@@ -979,7 +985,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 set_sync();
             }
-            if (p.epi_fast == 3) {
+            if (EPI == 3) {
                 // Specialised drain of the backward convs with the fused GroupNorm(+SiLU) backward reduction (16-bit store of
                 // dy, then sum(du*gamma), sum(du*gamma*xhat) against the saved activation x; <= six chunks per warp): same
                 // arithmetic as the generic loop without its option tests, gamma / beta as 16-byte shared-memory loads,
@@ -1084,7 +1090,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 continue;
             }
-            if (p.epi_fast == 2) {
+            if (EPI == 2) {
                 // Specialised drain of the attention products whose epilogue IS the softmax work (row statistics /
                 // probabilities / softmax backward; 16-bit or no store, up to eight chunks per warp): with K = 384 a
                 // 256 x 256 tile is 24 MMAs, and the generic loop's ~260 instructions per chunk made the epilogue the
@@ -1183,7 +1189,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 continue;
             }
-            if (p.epi_fast) {
+            if (EPI == 1) {
                 // Compile-time specialised drain of the plain conv cases (16-bit store, 256-bit accesses, alpha = 1; optional
                 // bias, residual, fused GroupNorm statistics; at most six chunks per warp). The generic loop below spends
                 // ~260 instructions per 16-column chunk and ~360 per tile on option tests, address arithmetic and the
@@ -1643,7 +1649,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
-    if (p.gnb_red && p.epi_fast == 3 && p.stat_private) {  // the fast GroupNorm-backward epilogue's per-warp copies
+    if (EPI == 3 && p.gnb_red && p.stat_private) {  // the fast GroupNorm-backward epilogue's per-warp copies
         for (int i = threadIdx.x; i < 128; i += blockDim.x) {
             unsigned long long v = 0ull;
             for (int wv = 0; wv < TG_EPI_THREADS / 32; ++wv) v += stat_s[TG_STAT_SLOTS + wv * 128 + i];
@@ -2117,11 +2123,11 @@ int tapgemm_prepare(TapGemmOp* op) {
     return 0;
 }
 
-template <bool BF16, int CG, bool XF>
+template <bool BF16, int CG, bool XF, int EPI>
 static cudaError_t launch_variant(const TapGemmOp* op, int grid, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BF16, CG, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BF16, CG, XF, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -2138,7 +2144,7 @@ static cudaError_t launch_variant(const TapGemmOp* op, int grid, cudaStream_t st
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, tapgemm_kernel<BF16, CG, XF>, op->tmA, op->tmB, op->p, op->stages);
+    return cudaLaunchKernelEx(&cfg, tapgemm_kernel<BF16, CG, XF, EPI>, op->tmA, op->tmB, op->p, op->stages);
 }
 
 int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream) {
@@ -2196,13 +2202,26 @@ int tapgemm_launch(const TapGemmOp* op, cudaStream_t stream) {
         cudaMemsetAsync(tg_dbg_buf, 0, 16 * sizeof(long long), stream);
         op = &dbg_op;
     }
-    if (p.ax_stats) {
-        if (p.is_bf16) e = (cg == 2) ? launch_variant<true, 2, true>(op, grid, stream) : launch_variant<true, 1, true>(op, grid, stream);
-        else e = (cg == 2) ? launch_variant<false, 2, true>(op, grid, stream) : launch_variant<false, 1, true>(op, grid, stream);
+    e = cudaErrorInvalidValue;
+#define WFD_TG_LAUNCH(XFV, EPIV)                                                                                            \
+    do {                                                                                                                   \
+        if (p.is_bf16) e = (cg == 2) ? launch_variant<true, 2, XFV, EPIV>(op, grid, stream) : launch_variant<true, 1, XFV, EPIV>(op, grid, stream); \
+        else e = (cg == 2) ? launch_variant<false, 2, XFV, EPIV>(op, grid, stream) : launch_variant<false, 1, XFV, EPIV>(op, grid, stream);       \
+    } while (0)
+    if (p.ax_stats) {  // operand transform: plain conv launches only (tapgemm_prepare)
+        if (p.epi_fast == 1) WFD_TG_LAUNCH(true, 1);
+        else if (p.epi_fast == 0) WFD_TG_LAUNCH(true, 0);
+        else set_error("tapgemm launch: operand transform with epilogue form %d", p.epi_fast);
     } else {
-        if (p.is_bf16) e = (cg == 2) ? launch_variant<true, 2, false>(op, grid, stream) : launch_variant<true, 1, false>(op, grid, stream);
-        else e = (cg == 2) ? launch_variant<false, 2, false>(op, grid, stream) : launch_variant<false, 1, false>(op, grid, stream);
+        switch (p.epi_fast) {
+            case 0: WFD_TG_LAUNCH(false, 0); break;
+            case 1: WFD_TG_LAUNCH(false, 1); break;
+            case 2: WFD_TG_LAUNCH(false, 2); break;
+            case 3: WFD_TG_LAUNCH(false, 3); break;
+            default: set_error("tapgemm launch: unknown epilogue form %d", p.epi_fast); break;
+        }
     }
+#undef WFD_TG_LAUNCH
     if (tg_dbg && op == &dbg_op && e == cudaSuccess) {
         long long h[16];
         cudaStreamSynchronize(stream);
